@@ -1,0 +1,209 @@
+/* libstdadk.so -- C ABI of the B200-native ST-DADK hot path.
+ *
+ * The reference (STLABTW/ST-DADK) is pure Python/PyTorch and has no FFI of its own; the boundary it
+ * exposes for this path is the nn.Module API.  These entry points are what a binding underneath that
+ * API calls; each cites the reference code it replaces (path:line under the upstream repo root).
+ * INTEGRATION.md shows the ctypes stub a maintainer would add to stnf/models/st_interp.py.
+ *
+ * Conventions
+ *  - every pointer is a raw DEVICE address owned by the caller (PyTorch); the library allocates no
+ *    device memory; work is enqueued on `stream` (a cudaStream_t passed as void*) and returns at once;
+ *  - return value: 0 ok, <0 argument error found on the host before launch, >0 cudaError_t of the
+ *    launch; the message is available from stdadk_last_error() (thread local);
+ *  - no CPU fallback and no other backend: a device that is not sm_100 is an error.
+ *
+ * Operand images.  Activations and weights that feed the tensor cores live in HBM as "images":
+ * tiles of 128 rows x 32 fp32 columns (a 16 KB slab), rows 128 bytes long with their eight 16-byte
+ * chunks XOR-swizzled by (row & 7) -- byte for byte the SWIZZLE_128B shared-memory form tcgen05
+ * reads, so a slab moves HBM -> SMEM with one bulk copy and the same slab serves as a K-major
+ * operand (forward, dgrad) and as an MN-major operand (wgrad).  Matrix (rows x cols) image:
+ * [ceil(rows/128)][ceil(cols/32)][128][32] floats; stdadk_image_floats() gives the size.
+ */
+#ifndef STDADK_H
+#define STDADK_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STDADK_VERSION 100
+#define STDADK_MAX_Q 8
+
+enum { STDADK_WENDLAND = 0, STDADK_GAUSSIAN = 1, STDADK_TRIANGULAR = 2 };
+enum { STDADK_LOSS_NONE = 0, STDADK_LOSS_MSE = 1, STDADK_LOSS_PINBALL = 2 };
+
+/* Basis description.  knots4[j] = (cx, cy, theta'^2, 1/theta'), theta' = bandwidth * calibration
+ * (st_interp.py:447-448, CALIBRATION_FACTORS :56-60); tknots2[k] = (c, 1/bw) (st_interp.py:583-596).
+ * Feature order of the first Linear layer: [X (p_cov) | phi (k_s) | psi (k_t)] (st_interp.py:843-846). */
+typedef struct {
+    const float* knots4;
+    const float* tknots2;
+    int32_t k_s, k_t, p_cov, basis_fn;
+} stdadk_basis;
+
+/* Point source: arrays (coords (N,2), t (N,1), xcov (N,p) row-major FP32) or, when grid_nx > 0,
+ * the dense space-time grid n = (k*nx + i)*ny + j, x=i/(nx-1), y=j/(ny-1), t=k/(nt-1) generated on
+ * the device (train_st_interp.py:1233-1248, :1380-1394).  row_begin = first GLOBAL row of this call
+ * (index into the arrays / grid, and the dropout key), n_rows = rows processed. */
+typedef struct {
+    const float* coords;
+    const float* t;
+    const float* xcov;
+    int32_t grid_nx, grid_ny, grid_nt, _pad;
+    int64_t row_begin;
+    int64_t n_rows;
+} stdadk_points;
+
+/* One hidden block Linear -> LayerNorm -> ReLU -> Dropout (st_interp.py:659-666). */
+typedef struct {
+    const float* w_img;  /* image of W (n_out x n_in), K-major forward operand */
+    const float* bias;   /* (n_out) */
+    const float* gamma;  /* (n_out) LayerNorm weight or NULL when layernorm=False */
+    const float* beta;   /* (n_out) */
+    int32_t n_in, n_out;
+    float ln_eps;
+    int32_t layer_id;    /* dropout stream id */
+} stdadk_layer;
+
+typedef struct {
+    float p;             /* 0 => off (eval mode) */
+    uint32_t step;
+    uint64_t seed;
+} stdadk_dropout;
+
+/* Output head + loss (st_interp.py:689 / :849-877 through an effective (Q x d) matrix;
+ * train_st_interp.py:37-50, :620-631).  loss = mean over rows and quantiles; inv_count = 1/(B*Q)
+ * with B the GLOBAL batch so that data-parallel ranks sum to the global mean. */
+typedef struct {
+    const float* w;      /* (q x d) row-major */
+    const float* b;      /* (q) */
+    int32_t q;
+    int32_t loss_type;
+    const float* y;      /* (N) targets, NULL for prediction */
+    float taus[STDADK_MAX_Q];
+    float inv_count;
+    float nc_weight;     /* prediction-level non-crossing penalty weight (train_st_interp.py:53-85) */
+    int32_t nc_power;
+    int32_t _pad;
+    float* yhat;         /* (N x q) out */
+    float* dyhat;        /* (N x q) out, dLoss/dyhat, NULL for prediction */
+    float* loss_acc;     /* (1) += loss contribution of these rows */
+} stdadk_head;
+
+/* Forward of one hidden block.  A operand = basis generated in-kernel (basis != NULL; the N x K
+ * basis matrix is never written to HBM) or the previous block's activation image (a_img). */
+typedef struct {
+    const stdadk_basis* basis;
+    stdadk_points pts;       /* rows; for a_img mode only row_begin/n_rows are used */
+    const float* a_img;
+    stdadk_layer layer;
+    stdadk_dropout drop;
+    float* out_img;          /* image (rows x n_out) of the block output, or NULL */
+    float* stats;            /* (rows x 2) LayerNorm mean, rstd for backward, or NULL */
+    const stdadk_head* head; /* non-NULL on the last hidden block: fuses head (+ loss) */
+} stdadk_fwd_args;
+
+/* Backward of one hidden block: recomputes z = A W^T (for block 1 this recomputes the basis),
+ * forms dh (from the head, or dz_next * W_next on the tensor cores), and writes dz image + bias /
+ * LayerNorm / head gradients (accumulated with atomics into zero-initialised buffers). */
+typedef struct {
+    const stdadk_basis* basis;
+    stdadk_points pts;
+    const float* a_img;
+    stdadk_layer layer;
+    stdadk_dropout drop;
+    const float* stats;        /* from forward */
+    /* upstream gradient: exactly one of (head) or (dz_next_img, wt_next_img) */
+    const stdadk_head* head;   /* uses head->dyhat, head->w */
+    float* d_head_w;           /* (q x d) += */
+    float* d_head_b;           /* (q) += */
+    const float* dz_next_img;  /* image (rows x n_next) */
+    const float* wt_next_img;  /* image of W_next^T (n_out x n_next): dgrad operand */
+    int32_t n_next, _pad;
+    float* dz_img;             /* out: image (rows x n_out) */
+    float* d_bias;             /* (n_out) += */
+    float* d_gamma;            /* (n_out) += or NULL */
+    float* d_beta;             /* (n_out) += or NULL */
+} stdadk_bwd_args;
+
+/* Weight gradient dW (n_out x n_in) += dz^T A, reduction over rows on the tensor cores (both
+ * operands MN-major from the same images the forward wrote).  A = a_img or the recomputed basis.
+ * dW element (o, i) is accumulated at dw[o*stride_o + i*stride_i]. */
+typedef struct {
+    const stdadk_basis* basis;
+    stdadk_points pts;
+    const float* a_img;
+    const float* dz_img;
+    int32_t n_in, n_out;
+    float* dw;
+    int64_t stride_o, stride_i;
+} stdadk_wgrad_args;
+
+/* Gradient of the learnable knots (st_interp.py:94-108, closed form of SURVEY.md 9.1):
+ * G = dz1 * W1[:, p:p+k_s] on the tensor cores, then d_centers (k_s x 2) and d_log_bw (k_s) +=. */
+typedef struct {
+    const stdadk_basis* basis;
+    stdadk_points pts;
+    const float* dz_img;      /* image (rows x n_out) of block-1 dz */
+    const float* w1s_img;     /* image of W1[:, p:p+k_s]^T (k_s x n_out) */
+    int32_t n_out, _pad;
+    float* d_centers;
+    float* d_log_bw;
+} stdadk_knotgrad_args;
+
+/* Fused clip + AdamW + EMA over one flat buffer (train_st_interp.py:696-718, torch.optim.AdamW,
+ * ema.py:52-66).  Groups are contiguous ranges; hyper[g] = (lr, weight_decay, max_norm, unused) is
+ * read from DEVICE memory so a captured graph picks up schedule changes; norms[g] holds the squared
+ * L2 norm written by stdadk_grad_sqnorm; step_count (device int) is incremented by the kernel. */
+typedef struct {
+    float* p;
+    const float* g;
+    float* m;
+    float* v;
+    float* shadow;            /* EMA or NULL */
+    int64_t n;
+    int32_t n_groups, _pad;
+    const int64_t* group_end; /* host array (n_groups): exclusive end offset of each group */
+    const float* hyper;       /* device (n_groups x 4) */
+    const float* sqnorms;     /* device (n_groups) or NULL (no clipping) */
+    int32_t* step_count;      /* device */
+    float beta1, beta2, eps, ema_decay;
+} stdadk_adamw_args;
+
+int stdadk_version(void);
+const char* stdadk_last_error(void);
+/* sizeof() of the argument structs, for bindings to verify their layout:
+ * 0 basis, 1 points, 2 layer, 3 dropout, 4 head, 5 fwd_args, 6 bwd_args, 7 wgrad_args, 8 knotgrad_args, 9 adamw_args */
+size_t stdadk_sizeof(int which);
+
+size_t stdadk_image_floats(int64_t rows, int64_t cols);
+
+/* theta' = bw*calib (or exp(log_bw)*calib when log_bw != NULL) -> knots4 (st_interp.py:144-150, :447-448) */
+int stdadk_knots_prepare(const float* centers, const float* bw, const float* log_bw, float calib, int k,
+                         float* knots4, void* stream);
+int stdadk_tknots_prepare(const float* centers, const float* bw, int k, float* tknots2, void* stream);
+
+/* Unfused basis for parity checks: phi (N x k_s), psi (N x k_t) dense FP32 (st_interp.py:433-491, :583-596) */
+int stdadk_basis_fwd(const stdadk_basis* basis, const stdadk_points* pts, float* phi, float* psi, void* stream);
+
+/* Row-major (strided) matrix -> image with TF32 rounding, and back (testing) */
+int stdadk_pack_image(const float* src, int64_t row_stride, int64_t col_stride, int64_t rows, int64_t cols,
+                      float* img, void* stream);
+int stdadk_unpack_image(const float* img, int64_t rows, int64_t cols, float* dst, void* stream);
+
+int stdadk_layer_fwd(const stdadk_fwd_args* a, void* stream);
+int stdadk_layer_bwd(const stdadk_bwd_args* a, void* stream);
+int stdadk_wgrad(const stdadk_wgrad_args* a, void* stream);
+int stdadk_knot_grad(const stdadk_knotgrad_args* a, void* stream);
+
+/* sqnorms[g] = sum of squares of g over each group (sqnorms zeroed by the call) */
+int stdadk_grad_sqnorm(const float* g, int64_t n, int n_groups, const int64_t* group_end, float* sqnorms,
+                       void* stream);
+int stdadk_adamw_ema_step(const stdadk_adamw_args* a, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

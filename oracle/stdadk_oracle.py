@@ -190,20 +190,27 @@ def philox4x32(c0, c1, c2, c3, k0, k1):
 
 def dropout_keep_mask(n_rows: int, n_cols: int, p: float, seed: int, step: int, layer: int,
                       row_offset: int = 0) -> np.ndarray:
-    """Keep mask (n_rows, n_cols) the kernels draw for hidden layer `layer` at optimizer `step`.
+    """Keep mask (n_rows, n_cols) the kernels draw for hidden block `layer` at optimizer `step`.
 
-    counter = (global_row, col // 4, layer, step), key = (seed_lo, seed_hi); element
-    col % 4 of the 4 outputs; keep iff u32 >= floor(p * 2^32).  Keyed on the GLOBAL row
-    index so the mask does not depend on how rows are sharded over ranks.
+    One Philox4x32-10 call per (row, block of 8 columns): counter = (row_lo, block, layer | row_hi<<8,
+    step), key = (seed_lo, seed_hi); column e of the block takes 16 bits of word e>>1 (low half first)
+    and is kept iff u16 >= floor(p * 65536).  Keyed on the GLOBAL row index so the mask does not
+    depend on how rows are sharded over ranks (st_dadk_b200/csrc/common.cuh: dropout_keep8).
     """
     if p <= 0.0:
         return np.ones((n_rows, n_cols), dtype=bool)
-    rows = (np.arange(n_rows, dtype=np.uint64) + np.uint64(row_offset)).astype(np.uint32)[:, None]
-    blocks = np.arange((n_cols + 3) // 4, dtype=np.uint32)[None, :]
-    outs = philox4x32(rows, blocks, np.uint32(layer), np.uint32(step & 0xFFFFFFFF),
-                      seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
-    u = np.stack(outs, axis=-1).reshape(n_rows, -1)[:, :n_cols]
-    thresh = np.uint32(min(int(p * 4294967296.0), 0xFFFFFFFF))
+    rows64 = np.arange(n_rows, dtype=np.uint64) + np.uint64(row_offset)
+    rows_lo = (rows64 & np.uint64(0xFFFFFFFF)).astype(np.uint32)[:, None]
+    rows_hi = (rows64 >> np.uint64(32)).astype(np.uint32)[:, None]
+    blocks = np.arange((n_cols + 7) // 8, dtype=np.uint32)[None, :]
+    c2 = (np.uint32(layer) | (rows_hi << np.uint32(8))).astype(np.uint32)
+    outs = philox4x32(rows_lo, blocks, c2, np.uint32(step & 0xFFFFFFFF), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    halves = []
+    for w in outs:
+        halves.append(w & np.uint32(0xFFFF))
+        halves.append(w >> np.uint32(16))
+    u = np.stack(halves, axis=-1).reshape(n_rows, -1)[:, :n_cols]
+    thresh = np.uint32(min(max(int(np.float32(p) * np.float32(65536.0)), 0), 65535))
     return u >= thresh
 
 

@@ -1,0 +1,444 @@
+// C ABI of libstdadk.so (see include/stdadk.h): argument validation on the host, kernel launches on the
+// caller's stream.  No device allocation, no CPU fallback.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "layer.cuh"
+#include "misc.cuh"
+#include "sparse.cuh"
+
+using namespace stdadk;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+static int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail((int)e, "%s: %s", what, cudaGetErrorString(e));
+    return 0;
+}
+#define REQUIRE(cond, ...) \
+    do {                   \
+        if (!(cond)) return fail(-1, __VA_ARGS__); \
+    } while (0)
+
+static int g_sm_count = 0;
+static int check_device() {
+    static thread_local int ok_dev = -1;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return fail((int)e, "cudaGetDevice: %s (libstdadk has no CPU fallback)", cudaGetErrorString(e));
+    if (dev == ok_dev) return 0;
+    cudaDeviceProp p;
+    e = cudaGetDeviceProperties(&p, dev);
+    if (e != cudaSuccess) return fail((int)e, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (p.major != 10) return fail(-2, "libstdadk requires an sm_100 (B200) device, found sm_%d%d", p.major, p.minor);
+    g_sm_count = p.multiProcessorCount;
+    ok_dev = dev;
+    return 0;
+}
+static int grid_for(long long work_items, int threads, int per_sm = 8) {
+    long long blocks = (work_items + threads - 1) / threads;
+    long long cap = (long long)(g_sm_count > 0 ? g_sm_count : 148) * per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+static int pow2_cols(int n) {
+    int c = 32;
+    while (c < n) c <<= 1;
+    return c;
+}
+template <typename K>
+static int set_smem(K kernel, uint32_t bytes) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(%u B smem): %s", bytes, cudaGetErrorString(e));
+    return 0;
+}
+
+static BasisP to_basis(const stdadk_basis* b) {
+    BasisP B{};
+    if (b) {
+        B.knots = reinterpret_cast<const float4*>(b->knots4);
+        B.tknots = reinterpret_cast<const float2*>(b->tknots2);
+        B.k_s = b->k_s;
+        B.k_t = b->k_t;
+        B.p_cov = b->p_cov;
+        B.fn = b->basis_fn;
+    }
+    return B;
+}
+static PointsP to_points(const stdadk_points& p) {
+    PointsP P{};
+    P.coords = p.coords;
+    P.t = p.t;
+    P.xcov = p.xcov;
+    P.nx = p.grid_nx;
+    P.ny = p.grid_ny;
+    P.nt = p.grid_nt;
+    P.row_begin = p.row_begin;
+    P.n_rows = p.n_rows;
+    return P;
+}
+static LayerP to_layer(const stdadk_layer& l, const stdadk_dropout& d) {
+    LayerP L{};
+    L.w_img = l.w_img;
+    L.bias = l.bias;
+    L.gamma = l.gamma;
+    L.beta = l.beta;
+    L.n_in = l.n_in;
+    L.n_out = l.n_out;
+    L.layer_id = l.layer_id;
+    L.eps = l.ln_eps;
+    L.drop_p = d.p;
+    L.step = d.step;
+    L.seed = d.seed;
+    return L;
+}
+static HeadP to_head(const stdadk_head* h) {
+    HeadP H{};
+    if (h) {
+        H.w = h->w;
+        H.b = h->b;
+        H.y = h->y;
+        H.yhat = h->yhat;
+        H.dyhat = h->dyhat;
+        H.loss_acc = h->loss_acc;
+        H.q = h->q;
+        H.loss_type = h->loss_type;
+        H.nc_power = h->nc_power;
+        H.inv_count = h->inv_count;
+        H.nc_weight = h->nc_weight;
+        memcpy(H.taus, h->taus, sizeof(H.taus));
+    }
+    return H;
+}
+static int check_basis_points(const stdadk_basis* b, const stdadk_points& p, int n_in) {
+    REQUIRE(b->knots4 || b->k_s == 0, "basis: knots4 is NULL");
+    REQUIRE(b->tknots2 || b->k_t == 0, "basis: tknots2 is NULL");
+    REQUIRE(b->k_s >= 0 && b->k_t >= 0 && b->p_cov >= 0, "basis: negative sizes");
+    REQUIRE(b->basis_fn >= 0 && b->basis_fn <= 2, "basis: unknown basis_fn %d", b->basis_fn);
+    REQUIRE(n_in < 0 || b->p_cov + b->k_s + b->k_t == n_in, "basis: p+k_s+k_t=%d != layer n_in=%d",
+            b->p_cov + b->k_s + b->k_t, n_in);
+    if (p.grid_nx > 0) {
+        REQUIRE(p.grid_ny > 0 && p.grid_nt > 0, "points: grid sizes must all be positive");
+    } else {
+        REQUIRE(p.coords && p.t, "points: coords/t are NULL and no grid was given");
+        REQUIRE((reinterpret_cast<uintptr_t>(p.coords) & 7) == 0, "points: coords must be 8-byte aligned");
+    }
+    REQUIRE(b->p_cov == 0 || p.xcov || p.grid_nx > 0, "points: xcov is NULL but p_cov > 0");
+    return 0;
+}
+
+extern "C" {
+
+int stdadk_version(void) { return STDADK_VERSION; }
+const char* stdadk_last_error(void) { return g_err; }
+
+size_t stdadk_sizeof(int which) {
+    switch (which) {
+        case 0: return sizeof(stdadk_basis);
+        case 1: return sizeof(stdadk_points);
+        case 2: return sizeof(stdadk_layer);
+        case 3: return sizeof(stdadk_dropout);
+        case 4: return sizeof(stdadk_head);
+        case 5: return sizeof(stdadk_fwd_args);
+        case 6: return sizeof(stdadk_bwd_args);
+        case 7: return sizeof(stdadk_wgrad_args);
+        case 8: return sizeof(stdadk_knotgrad_args);
+        case 9: return sizeof(stdadk_adamw_args);
+        default: return 0;
+    }
+}
+
+size_t stdadk_image_floats(int64_t rows, int64_t cols) {
+    return (size_t)(ceil_div64(rows, TILE_M) * ceil_div64(cols, SLAB_K)) * SLAB_FLOATS;
+}
+
+int stdadk_knots_prepare(const float* centers, const float* bw, const float* log_bw, float calib, int k,
+                         float* knots4, void* stream) {
+    if (int r = check_device()) return r;
+    REQUIRE(k >= 0 && centers && (bw || log_bw) && knots4, "knots_prepare: bad arguments");
+    REQUIRE((reinterpret_cast<uintptr_t>(knots4) & 15) == 0, "knots_prepare: knots4 must be 16-byte aligned");
+    if (k == 0) return 0;
+    knots_prepare_kernel<<<(k + 127) / 128, 128, 0, (cudaStream_t)stream>>>(centers, bw, log_bw, calib, k,
+                                                                             reinterpret_cast<float4*>(knots4));
+    return check_launch("knots_prepare");
+}
+
+int stdadk_tknots_prepare(const float* centers, const float* bw, int k, float* tknots2, void* stream) {
+    if (int r = check_device()) return r;
+    REQUIRE(k >= 0 && centers && bw && tknots2, "tknots_prepare: bad arguments");
+    if (k == 0) return 0;
+    tknots_prepare_kernel<<<(k + 127) / 128, 128, 0, (cudaStream_t)stream>>>(centers, bw, k,
+                                                                              reinterpret_cast<float2*>(tknots2));
+    return check_launch("tknots_prepare");
+}
+
+int stdadk_basis_fwd(const stdadk_basis* basis, const stdadk_points* pts, float* phi, float* psi, void* stream) {
+    if (int r = check_device()) return r;
+    REQUIRE(basis && pts, "basis_fwd: NULL descriptor");
+    if (int r = check_basis_points(basis, *pts, -1)) return r;
+    if (pts->n_rows <= 0) return 0;
+    long long total = pts->n_rows * (long long)(basis->k_s + basis->k_t);
+    if (total == 0) return 0;
+    basis_fwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(to_basis(basis), to_points(*pts), phi,
+                                                                              psi);
+    return check_launch("basis_fwd");
+}
+
+int stdadk_pack_image(const float* src, int64_t row_stride, int64_t col_stride, int64_t rows, int64_t cols,
+                      float* img, void* stream) {
+    if (int r = check_device()) return r;
+    REQUIRE(src && img && rows > 0 && cols > 0, "pack_image: bad arguments");
+    REQUIRE((reinterpret_cast<uintptr_t>(img) & 127) == 0, "pack_image: image must be 128-byte aligned");
+    int slabs = (int)ceil_div64(cols, SLAB_K);
+    long long chunks = (long long)ceil_div64(rows, TILE_M) * slabs * (SLAB_FLOATS / 4);
+    pack_image_kernel<<<grid_for(chunks, 256), 256, 0, (cudaStream_t)stream>>>(src, row_stride, col_stride, rows, cols,
+                                                                                img, chunks, slabs);
+    return check_launch("pack_image");
+}
+
+int stdadk_unpack_image(const float* img, int64_t rows, int64_t cols, float* dst, void* stream) {
+    if (int r = check_device()) return r;
+    REQUIRE(dst && img && rows > 0 && cols > 0, "unpack_image: bad arguments");
+    int slabs = (int)ceil_div64(cols, SLAB_K);
+    unpack_image_kernel<<<grid_for(rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(img, rows, cols, dst, slabs);
+    return check_launch("unpack_image");
+}
+
+static int check_layer(const stdadk_layer& l, const char* who) {
+    REQUIRE(l.w_img && l.bias, "%s: weight image / bias is NULL", who);
+    REQUIRE(l.n_out >= 1 && l.n_out <= MAX_N, "%s: n_out=%d outside [1,%d] (one UMMA N / LayerNorm row per thread)", who,
+            l.n_out, MAX_N);
+    REQUIRE(l.n_in >= 1, "%s: n_in=%d", who, l.n_in);
+    REQUIRE((l.gamma == nullptr) == (l.beta == nullptr), "%s: gamma and beta must both be given or both NULL", who);
+    REQUIRE((reinterpret_cast<uintptr_t>(l.w_img) & 127) == 0, "%s: weight image must be 128-byte aligned", who);
+    return 0;
+}
+
+int stdadk_layer_fwd(const stdadk_fwd_args* a, void* stream) {
+    if (int r = check_device()) return r;
+    REQUIRE(a, "layer_fwd: NULL args");
+    if (int r = check_layer(a->layer, "layer_fwd")) return r;
+    REQUIRE((a->basis != nullptr) != (a->a_img != nullptr), "layer_fwd: give exactly one of basis / a_img");
+    if (a->basis)
+        if (int r = check_basis_points(a->basis, a->pts, a->layer.n_in)) return r;
+    REQUIRE(a->drop.p >= 0.0f && a->drop.p < 1.0f, "layer_fwd: dropout p=%f", a->drop.p);
+    if (a->head) {
+        REQUIRE(a->head->q >= 1 && a->head->q <= STDADK_MAX_Q, "layer_fwd: head q=%d outside [1,%d]", a->head->q,
+                STDADK_MAX_Q);
+        REQUIRE(a->head->w && a->head->b && a->head->yhat, "layer_fwd: head w/b/yhat NULL");
+        REQUIRE(a->head->loss_type == STDADK_LOSS_NONE || (a->head->y && a->head->loss_acc),
+                "layer_fwd: loss requested without y / loss_acc");
+    } else {
+        REQUIRE(a->out_img, "layer_fwd: out_img is NULL and there is no head");
+    }
+    if (a->pts.n_rows <= 0) return 0;
+    FwdK K{};
+    K.basis = to_basis(a->basis);
+    K.pts = to_points(a->pts);
+    K.L = to_layer(a->layer, a->drop);
+    K.head = to_head(a->head);
+    K.a_img = a->a_img;
+    K.out_img = a->out_img;
+    K.stats = a->stats;
+    K.has_head = a->head ? 1 : 0;
+    K.k_slabs = pad32(a->layer.n_in) / SLAB_K;
+    K.n_pad = pad32(a->layer.n_out);
+    K.tmem_cols = pow2_cols(K.n_pad);
+    K.thresh16 = dropout_thresh16(a->drop.p);
+    K.drop_scale = a->drop.p > 0.0f ? 1.0f / (1.0f - a->drop.p) : 1.0f;
+    const bool basis = a->basis != nullptr;
+    SmemPlan sp = plan_smem(K.n_pad, K.has_head ? K.head.q : 0, basis ? K.basis.k_s : 0, basis ? K.basis.k_t : 0, false);
+    REQUIRE(sp.total <= 227 * 1024, "layer_fwd: needs %u B of shared memory (> 227 KB): too many knots for the dense path",
+            sp.total);
+    int tiles = (int)ceil_div64(a->pts.n_rows, TILE_M);
+    if (basis) {
+        if (int r = set_smem(layer_fwd_kernel<true>, sp.total)) return r;
+        layer_fwd_kernel<true><<<tiles, NTHREADS, sp.total, (cudaStream_t)stream>>>(K);
+    } else {
+        if (int r = set_smem(layer_fwd_kernel<false>, sp.total)) return r;
+        layer_fwd_kernel<false><<<tiles, NTHREADS, sp.total, (cudaStream_t)stream>>>(K);
+    }
+    return check_launch("layer_fwd");
+}
+
+int stdadk_layer_bwd(const stdadk_bwd_args* a, void* stream) {
+    if (int r = check_device()) return r;
+    REQUIRE(a, "layer_bwd: NULL args");
+    if (int r = check_layer(a->layer, "layer_bwd")) return r;
+    REQUIRE((a->basis != nullptr) != (a->a_img != nullptr), "layer_bwd: give exactly one of basis / a_img");
+    if (a->basis)
+        if (int r = check_basis_points(a->basis, a->pts, a->layer.n_in)) return r;
+    REQUIRE((a->head != nullptr) != (a->dz_next_img != nullptr), "layer_bwd: give exactly one of head / dz_next_img");
+    REQUIRE(a->dz_img && a->d_bias, "layer_bwd: dz_img / d_bias NULL");
+    REQUIRE(!a->layer.gamma || (a->d_gamma && a->d_beta && a->stats), "layer_bwd: LayerNorm needs d_gamma/d_beta/stats");
+    if (a->head) {
+        REQUIRE(a->head->q >= 1 && a->head->q <= STDADK_MAX_Q && a->head->w && a->head->dyhat && a->d_head_w &&
+                    a->d_head_b,
+                "layer_bwd: head arguments incomplete");
+    } else {
+        REQUIRE(a->wt_next_img && a->n_next >= 1 && a->n_next <= MAX_N, "layer_bwd: wt_next_img / n_next invalid");
+    }
+    if (a->pts.n_rows <= 0) return 0;
+    BwdK K{};
+    K.basis = to_basis(a->basis);
+    K.pts = to_points(a->pts);
+    K.L = to_layer(a->layer, a->drop);
+    K.head = to_head(a->head);
+    K.a_img = a->a_img;
+    K.stats = a->stats;
+    K.dz_next_img = a->dz_next_img;
+    K.wt_next_img = a->wt_next_img;
+    K.dz_img = a->dz_img;
+    K.d_bias = a->d_bias;
+    K.d_gamma = a->d_gamma;
+    K.d_beta = a->d_beta;
+    K.d_head_w = a->d_head_w;
+    K.d_head_b = a->d_head_b;
+    K.has_head = a->head ? 1 : 0;
+    K.k_slabs = pad32(a->layer.n_in) / SLAB_K;
+    K.k_slabs2 = a->head ? 0 : pad32(a->n_next) / SLAB_K;
+    K.n_pad = pad32(a->layer.n_out);
+    K.tmem_cols = 2 * pow2_cols(K.n_pad);
+    K.thresh16 = dropout_thresh16(a->drop.p);
+    K.drop_scale = a->drop.p > 0.0f ? 1.0f / (1.0f - a->drop.p) : 1.0f;
+    const bool basis = a->basis != nullptr;
+    SmemPlan sp = plan_smem(K.n_pad, K.has_head ? K.head.q : 0, basis ? K.basis.k_s : 0, basis ? K.basis.k_t : 0, true);
+    REQUIRE(sp.total <= 227 * 1024, "layer_bwd: needs %u B of shared memory (> 227 KB)", sp.total);
+    int tiles = (int)ceil_div64(a->pts.n_rows, TILE_M);
+    if (basis) {
+        if (int r = set_smem(layer_bwd_kernel<true>, sp.total)) return r;
+        layer_bwd_kernel<true><<<tiles, NTHREADS, sp.total, (cudaStream_t)stream>>>(K);
+    } else {
+        if (int r = set_smem(layer_bwd_kernel<false>, sp.total)) return r;
+        layer_bwd_kernel<false><<<tiles, NTHREADS, sp.total, (cudaStream_t)stream>>>(K);
+    }
+    return check_launch("layer_bwd");
+}
+
+int stdadk_wgrad(const stdadk_wgrad_args* a, void* stream) {
+    if (int r = check_device()) return r;
+    REQUIRE(a, "wgrad: NULL args");
+    REQUIRE((a->basis != nullptr) != (a->a_img != nullptr), "wgrad: give exactly one of basis / a_img");
+    REQUIRE(a->dz_img && a->dw, "wgrad: dz_img / dw NULL");
+    REQUIRE(a->n_out >= 1 && a->n_out <= MAX_N && a->n_in >= 1, "wgrad: bad sizes n_in=%d n_out=%d", a->n_in, a->n_out);
+    if (a->basis)
+        if (int r = check_basis_points(a->basis, a->pts, a->n_in)) return r;
+    if (a->pts.n_rows <= 0) return 0;
+    WgradK K{};
+    K.basis = to_basis(a->basis);
+    K.pts = to_points(a->pts);
+    K.a_img = a->a_img;
+    K.dz_img = a->dz_img;
+    K.dw = a->dw;
+    K.stride_o = a->stride_o;
+    K.stride_i = a->stride_i;
+    K.n_in = a->n_in;
+    K.n_out = a->n_out;
+    K.a_slabs = pad32(a->n_in) / SLAB_K;
+    K.dz_slabs = pad32(a->n_out) / SLAB_K;
+    K.n_row_tiles = (int)ceil_div64(a->pts.n_rows, TILE_M);
+    int n_tiles_n = (K.a_slabs + 7) / 8;
+    K.nt_slabs = (K.a_slabs + n_tiles_n - 1) / n_tiles_n;
+    K.tmem_cols = pow2_cols(K.nt_slabs * SLAB_K);
+    int m_tiles = (K.dz_slabs + 3) / 4;
+    int per = m_tiles * n_tiles_n;
+    int sms = g_sm_count > 0 ? g_sm_count : 148;
+    int splits = sms / per;
+    if (splits < 1) splits = 1;
+    if (splits > K.n_row_tiles) splits = K.n_row_tiles;
+    const bool basis = a->basis != nullptr;
+    uint32_t smem = wgrad_smem_bytes(basis ? K.basis.k_s : 0, basis ? K.basis.k_t : 0);
+    REQUIRE(smem <= 227 * 1024, "wgrad: needs %u B of shared memory (> 227 KB)", smem);
+    dim3 grid(splits, m_tiles, n_tiles_n);
+    if (basis) {
+        if (int r = set_smem(wgrad_kernel<true>, smem)) return r;
+        wgrad_kernel<true><<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(K);
+    } else {
+        if (int r = set_smem(wgrad_kernel<false>, smem)) return r;
+        wgrad_kernel<false><<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(K);
+    }
+    return check_launch("wgrad");
+}
+
+int stdadk_knot_grad(const stdadk_knotgrad_args* a, void* stream) {
+    if (int r = check_device()) return r;
+    REQUIRE(a && a->basis && a->dz_img && a->w1s_img && a->d_centers && a->d_log_bw, "knot_grad: NULL argument");
+    if (int r = check_basis_points(a->basis, a->pts, -1)) return r;
+    REQUIRE(a->n_out >= 1 && a->n_out <= MAX_N, "knot_grad: n_out=%d", a->n_out);
+    if (a->pts.n_rows <= 0 || a->basis->k_s == 0) return 0;
+    KnotGradK K{};
+    K.basis = to_basis(a->basis);
+    K.pts = to_points(a->pts);
+    K.dz_img = a->dz_img;
+    K.w1s_img = a->w1s_img;
+    K.d_centers = a->d_centers;
+    K.d_log_bw = a->d_log_bw;
+    K.n_out = a->n_out;
+    K.k_slabs = pad32(a->n_out) / SLAB_K;
+    SmemPlan sp = plan_smem(TILE_M, 0, 0, 0, false);
+    if (int r = set_smem(knotgrad_kernel, sp.total)) return r;
+    dim3 grid((unsigned)ceil_div64(a->pts.n_rows, TILE_M), (unsigned)((a->basis->k_s + TILE_M - 1) / TILE_M));
+    knotgrad_kernel<<<grid, NTHREADS, sp.total, (cudaStream_t)stream>>>(K);
+    return check_launch("knot_grad");
+}
+
+static int make_groups(int n_groups, const int64_t* group_end, int64_t n, GroupsP* G) {
+    REQUIRE(n_groups >= 1 && n_groups <= 8 && group_end, "optimizer: 1..8 parameter groups supported, got %d", n_groups);
+    int64_t prev = 0;
+    for (int i = 0; i < n_groups; ++i) {
+        REQUIRE(group_end[i] >= prev, "optimizer: group_end must be non-decreasing");
+        G->end[i] = prev = group_end[i];
+    }
+    REQUIRE(prev == n, "optimizer: last group_end (%lld) != n (%lld)", (long long)prev, (long long)n);
+    G->n = n_groups;
+    return 0;
+}
+
+int stdadk_grad_sqnorm(const float* g, int64_t n, int n_groups, const int64_t* group_end, float* sqnorms,
+                       void* stream) {
+    if (int r = check_device()) return r;
+    REQUIRE(g && sqnorms && n > 0, "grad_sqnorm: bad arguments");
+    GroupsP G{};
+    if (int r = make_groups(n_groups, group_end, n, &G)) return r;
+    cudaError_t e = cudaMemsetAsync(sqnorms, 0, sizeof(float) * n_groups, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail((int)e, "grad_sqnorm memset: %s", cudaGetErrorString(e));
+    sqnorm_kernel<<<grid_for(n, 256, 4), 256, 0, (cudaStream_t)stream>>>(g, n, G, sqnorms);
+    return check_launch("grad_sqnorm");
+}
+
+__global__ void step_inc_kernel(int* c) { *c += 1; }
+
+int stdadk_adamw_ema_step(const stdadk_adamw_args* a, void* stream) {
+    if (int r = check_device()) return r;
+    REQUIRE(a && a->p && a->g && a->m && a->v && a->hyper && a->step_count && a->n > 0, "adamw: bad arguments");
+    AdamK K{};
+    if (int r = make_groups(a->n_groups, a->group_end, a->n, &K.G)) return r;
+    K.p = a->p;
+    K.g = a->g;
+    K.m = a->m;
+    K.v = a->v;
+    K.shadow = a->shadow;
+    K.n = a->n;
+    K.hyper = a->hyper;
+    K.sqnorms = a->sqnorms;
+    K.step_count = a->step_count;
+    K.beta1 = a->beta1;
+    K.beta2 = a->beta2;
+    K.eps = a->eps;
+    K.ema_decay = a->ema_decay;
+    step_inc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(a->step_count);
+    adamw_ema_kernel<<<grid_for(a->n, 256, 4), 256, 0, (cudaStream_t)stream>>>(K);
+    return check_launch("adamw_ema_step");
+}
+
+}  // extern "C"

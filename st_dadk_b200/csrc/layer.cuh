@@ -1,0 +1,944 @@
+// tcgen05 kernels for one hidden block  Linear -> LayerNorm -> ReLU -> Dropout  (st_interp.py:659-666).
+//
+//   layer_fwd_kernel : z = A W^T on the tensor cores (TF32 in, FP32 accumulate in TMEM); A is either
+//                      the previous block's activation image (bulk-copied HBM->SMEM) or, for block 1,
+//                      the basis features [X|phi|psi] generated slab by slab straight into the
+//                      swizzled SMEM operand (the N x K basis matrix never exists in HBM).
+//                      Epilogue: bias + LayerNorm + ReLU + dropout (+ output head + loss) from TMEM.
+//   layer_bwd_kernel : recomputes z the same way (=> recomputes the basis), forms dh = dz_next W_next
+//                      in a second TMEM accumulator (or from the head), applies the dropout/ReLU/
+//                      LayerNorm backward and writes the dz image + bias/LN/head gradients.
+//   wgrad_kernel     : dW += dz^T A, reduction over rows, both operands MN-major from the same images.
+//
+// One CTA = one 128-row tile (128 TMEM lanes).  Warps 0-3: workers (operand generation, epilogue; thread
+// = row), warp 4: producer (bulk copies), warp 5: MMA issuer (one elected thread).
+#pragma once
+#include "common.cuh"
+
+namespace stdadk {
+
+constexpr int NSTAGE = 2;
+constexpr int NWORK = 128;
+constexpr int NTHREADS = 192;
+
+// ---------------------------------------------------------------- shared-memory carve-up
+struct SmemPlan {
+    uint32_t a_off, b_off, bar_off, tmem_off, vec_off, headw_off, knots_off, tknots_off, colsum_off, total;
+};
+__host__ __device__ inline SmemPlan plan_smem(int n_pad, int q, int k_s, int k_t, bool bwd) {
+    SmemPlan s;
+    uint32_t o = 0;
+    s.a_off = o; o += NSTAGE * SLAB_BYTES;
+    s.b_off = o; o += NSTAGE * (uint32_t)n_pad * 128u;
+    s.bar_off = o; o += 64;
+    s.tmem_off = o; o += 16;
+    s.vec_off = o; o += 3u * n_pad * 4u;                 // bias, gamma, beta
+    s.headw_off = o; o += (uint32_t)(q > 0 ? (q * n_pad + STDADK_MAX_Q) * 4 : 0);
+    o = (o + 15u) & ~15u;
+    s.knots_off = o; o += (uint32_t)k_s * 16u;
+    s.tknots_off = o; o += (uint32_t)k_t * 8u;
+    o = (o + 15u) & ~15u;
+    s.colsum_off = o; o += bwd ? (uint32_t)((3 + q) * n_pad + STDADK_MAX_Q) * 4u : 0u;
+    s.total = o + 1024;                                   // slack for manual 1024-byte alignment
+    return s;
+}
+
+struct FwdK {
+    BasisP basis;
+    PointsP pts;
+    LayerP L;
+    HeadP head;
+    const float* a_img;
+    float* out_img;
+    float* stats;
+    int has_head, k_slabs, n_pad, tmem_cols;
+    unsigned int thresh16;
+    float drop_scale;
+};
+
+struct BwdK {
+    BasisP basis;
+    PointsP pts;
+    LayerP L;
+    HeadP head;
+    const float* a_img;
+    const float* stats;
+    const float* dz_next_img;
+    const float* wt_next_img;
+    float* dz_img;
+    float* d_bias;
+    float* d_gamma;
+    float* d_beta;
+    float* d_head_w;
+    float* d_head_b;
+    int has_head, k_slabs, k_slabs2, n_pad, tmem_cols, _pad;
+    unsigned int thresh16;
+    float drop_scale;
+};
+
+// Generate one 128-row x 32-feature operand slab (this thread = row r) into swizzled SMEM.
+__device__ __forceinline__ void gen_basis_slab(const BasisP& B, const float4* sk, const float2* st, int slab,
+                                               float x, float y, float t, const float* xrow, uint32_t slab_saddr,
+                                               uint32_t r) {
+#pragma unroll 1
+    for (int c = 0; c < 8; ++c) {
+        int f = slab * SLAB_K + c * 4;
+        float v0 = to_tf32(feature_value(B, sk, st, f + 0, x, y, t, xrow));
+        float v1 = to_tf32(feature_value(B, sk, st, f + 1, x, y, t, xrow));
+        float v2 = to_tf32(feature_value(B, sk, st, f + 2, x, y, t, xrow));
+        float v3 = to_tf32(feature_value(B, sk, st, f + 3, x, y, t, xrow));
+        st_shared_v4(slab_saddr + swz_off(r, c), v0, v1, v2, v3);
+    }
+}
+
+// Producer: B slab (n_pad rows of the weight image, split over its 128-row tiles) [+ A slab].
+__device__ __forceinline__ void issue_slab_copies(const float* w_img, int w_slabs, int slab, int n_pad,
+                                                  const float* a_tile_img, float* sA, float* sB, uint64_t* bar) {
+    uint32_t bytes = (uint32_t)n_pad * 128u + (a_tile_img ? (uint32_t)SLAB_BYTES : 0u);
+    mbar_arrive_expect_tx(bar, bytes);
+    for (int r0 = 0; r0 < n_pad; r0 += TILE_M) {
+        int rows = min(TILE_M, n_pad - r0);
+        const float* src = w_img + ((size_t)(r0 / TILE_M) * w_slabs + slab) * SLAB_FLOATS;
+        bulk_g2s(sB + (size_t)r0 * SLAB_K, src, (uint32_t)rows * 128u, bar);
+    }
+    if (a_tile_img) bulk_g2s(sA, a_tile_img + (size_t)slab * SLAB_FLOATS, SLAB_BYTES, bar);
+}
+
+// MMA issuer: one 128-byte K slab = 4 MMAs of K=8 (TF32), advancing 32 bytes inside the swizzle atom.
+__device__ __forceinline__ void issue_slab_mma(uint32_t tmem_acc, const float* sA, const float* sB, uint32_t idesc,
+                                               bool first) {
+    uint64_t ad = umma_desc_sw128(smem_u32(sA), 16, 1024);
+    uint64_t bd = umma_desc_sw128(smem_u32(sB), 16, 1024);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_tf32(tmem_acc, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc,
+                                          (first && k == 0) ? 0u : 1u);
+}
+
+__device__ __forceinline__ uint8_t* align_smem(uint8_t* p) {
+    return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023));
+}
+
+// Pinball / MSE loss on one row: fills dy[q] (already scaled) and returns the row's loss contribution.
+__device__ __forceinline__ float row_loss(const HeadP& H, const float* yh, float yt, float* dy) {
+    float loss = 0.0f;
+    const int q = H.q;
+    if (H.loss_type == STDADK_LOSS_MSE) {
+#pragma unroll
+        for (int k = 0; k < STDADK_MAX_Q; ++k)
+            if (k < q) {
+                float e = yh[k] - yt;
+                loss += e * e;
+                dy[k] = 2.0f * e * H.inv_count;
+            }
+        loss *= H.inv_count;
+    } else {
+#pragma unroll
+        for (int k = 0; k < STDADK_MAX_Q; ++k)
+            if (k < q) {
+                float tau = H.taus[k];
+                float err = yt - yh[k];
+                loss += fmaxf((tau - 1.0f) * err, tau * err);
+                float g = err > 0.0f ? -tau : (err < 0.0f ? 1.0f - tau : 0.5f - tau);
+                dy[k] = g * H.inv_count;
+            }
+        loss *= H.inv_count;
+        if (H.nc_weight > 0.0f && q > 1) {  // sum_k relu(q_k - q_{k+1})^power, mean over rows
+            float inv_rows = H.inv_count * (float)q;
+            float pen = 0.0f;
+#pragma unroll
+            for (int k = 0; k < STDADK_MAX_Q - 1; ++k)
+                if (k + 1 < q) {
+                    float d = yh[k] - yh[k + 1];
+                    if (d > 0.0f) {
+                        float gd = (H.nc_power == 2 ? 2.0f * d : 1.0f) * H.nc_weight * inv_rows;
+                        pen += (H.nc_power == 2 ? d * d : d);
+                        dy[k] += gd;
+                        dy[k + 1] -= gd;
+                    }
+                }
+            loss += pen * H.nc_weight * inv_rows;
+        }
+    }
+    return loss;
+}
+
+// =============================================================================================
+// Forward
+// =============================================================================================
+template <bool BASIS>
+__global__ void __launch_bounds__(NTHREADS) layer_fwd_kernel(const __grid_constant__ FwdK P) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = align_smem(smem_raw);
+    const SmemPlan sp = plan_smem(P.n_pad, P.has_head ? P.head.q : 0, BASIS ? P.basis.k_s : 0,
+                                  BASIS ? P.basis.k_t : 0, false);
+    float* sA = reinterpret_cast<float*>(smem + sp.a_off);
+    float* sB = reinterpret_cast<float*>(smem + sp.b_off);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + sp.bar_off);
+    uint64_t* empty = full + NSTAGE;
+    uint64_t* accf = full + 2 * NSTAGE;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + sp.tmem_off);
+    float* sbias = reinterpret_cast<float*>(smem + sp.vec_off);
+    float* sgam = sbias + P.n_pad;
+    float* sbet = sgam + P.n_pad;
+    float* shw = reinterpret_cast<float*>(smem + sp.headw_off);
+    float* shb = shw + (P.has_head ? P.head.q * P.n_pad : 0);
+    float4* sk = reinterpret_cast<float4*>(smem + sp.knots_off);
+    float2* st = reinterpret_cast<float2*>(smem + sp.tknots_off);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tile = blockIdx.x;
+    const int n_pad = P.n_pad, n_out = P.L.n_out;
+    const bool has_ln = P.L.gamma != nullptr;
+    const size_t b_stage_floats = (size_t)n_pad * SLAB_K;
+
+    if (tid == NWORK) {
+        for (int s = 0; s < NSTAGE; ++s) {
+            mbar_init(&full[s], BASIS ? 1 + NWORK : 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(accf, 1);
+        mbar_fence_init();
+    }
+    if (warp == 4) {
+        __syncwarp();
+        tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
+    }
+    for (int i = tid; i < n_pad; i += NTHREADS) {
+        bool ok = i < n_out;
+        sbias[i] = ok ? P.L.bias[i] : 0.0f;
+        sgam[i] = (ok && has_ln) ? P.L.gamma[i] : 1.0f;
+        sbet[i] = (ok && has_ln) ? P.L.beta[i] : 0.0f;
+    }
+    if (P.has_head) {
+        for (int i = tid; i < P.head.q * n_pad; i += NTHREADS) {
+            int k = i / n_pad, c = i - k * n_pad;
+            shw[i] = c < n_out ? P.head.w[(size_t)k * n_out + c] : 0.0f;
+        }
+        if (tid < P.head.q) shb[tid] = P.head.b[tid];
+    }
+    if (BASIS) {
+        for (int i = tid; i < P.basis.k_s; i += NTHREADS) sk[i] = P.basis.knots[i];
+        for (int i = tid; i < P.basis.k_t; i += NTHREADS) st[i] = P.basis.tknots[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        // ---------------- producer
+        if (lane == 0) {
+            const float* a_tile = BASIS ? nullptr : P.a_img + (size_t)tile * P.k_slabs * SLAB_FLOATS;
+            for (int s = 0; s < P.k_slabs; ++s) {
+                int stage = s % NSTAGE, it = s / NSTAGE;
+                if (it > 0) mbar_wait(&empty[stage], (it - 1) & 1);
+                issue_slab_copies(P.L.w_img, P.k_slabs, s, n_pad, a_tile, sA + (size_t)stage * SLAB_FLOATS,
+                                  sB + stage * b_stage_floats, &full[stage]);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 5) {
+        // ---------------- MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32((uint32_t)n_pad, 0, 0);
+            for (int s = 0; s < P.k_slabs; ++s) {
+                int stage = s % NSTAGE, it = s / NSTAGE;
+                mbar_wait(&full[stage], it & 1);
+                tc_fence_after();
+                issue_slab_mma(tmem_base, sA + (size_t)stage * SLAB_FLOATS, sB + stage * b_stage_floats, idesc,
+                               s == 0);
+                umma_commit(&empty[stage]);
+            }
+            umma_commit(accf);
+        }
+        __syncwarp();
+    } else {
+        // ---------------- workers: thread = row
+        const long long lrow = (long long)tile * TILE_M + tid;
+        const bool rvalid = lrow < P.pts.n_rows;
+        const long long grow = P.pts.row_begin + lrow;
+        if (BASIS) {
+            float x = 0.f, y = 0.f, t = 0.f;
+            const float* xrow = nullptr;
+            if (rvalid) {
+                load_point(P.pts, grow, x, y, t);
+                if (P.basis.p_cov > 0 && P.pts.xcov) xrow = P.pts.xcov + grow * P.basis.p_cov;
+            }
+            for (int s = 0; s < P.k_slabs; ++s) {
+                int stage = s % NSTAGE, it = s / NSTAGE;
+                if (it > 0) mbar_wait(&empty[stage], (it - 1) & 1);
+                gen_basis_slab(P.basis, sk, st, s, x, y, t, xrow, smem_u32(sA + (size_t)stage * SLAB_FLOATS),
+                               (uint32_t)tid);
+                fence_proxy_async_smem();
+                mbar_arrive(&full[stage]);
+            }
+        }
+        // ---------------- epilogue
+        mbar_wait(accf, 0);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+        float v[32];
+        float mean = 0.0f, rstd = 1.0f;
+        if (has_ln) {
+            float shift = 0.0f, s1 = 0.0f, s2 = 0.0f;
+            for (int c0 = 0; c0 < n_pad; c0 += 32) {
+                tmem_ld32(trow + c0, v);
+                if (c0 == 0) shift = v[0] + sbias[0];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    if (c0 + i < n_out) {
+                        float d = v[i] + sbias[c0 + i] - shift;
+                        s1 += d;
+                        s2 = fmaf(d, d, s2);
+                    }
+                }
+            }
+            float inv_n = 1.0f / (float)n_out;
+            float m1 = s1 * inv_n;
+            mean = shift + m1;
+            float var = fmaxf(s2 * inv_n - m1 * m1, 0.0f);
+            rstd = 1.0f / sqrtf(var + P.L.eps);
+            if (P.stats && rvalid) {
+                P.stats[2 * lrow] = mean;
+                P.stats[2 * lrow + 1] = rstd;
+            }
+        }
+        float yh[STDADK_MAX_Q];
+#pragma unroll
+        for (int k = 0; k < STDADK_MAX_Q; ++k) yh[k] = 0.0f;
+        const bool drop = P.L.drop_p > 0.0f;
+        for (int c0 = 0; c0 < n_pad; c0 += 32) {
+            tmem_ld32(trow + c0, v);
+            uint32_t keep = 0xFFFFFFFFu;
+            if (drop) {
+                keep = 0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    keep |= dropout_keep8(P.L.seed, P.L.step, (uint32_t)P.L.layer_id, (unsigned long long)grow,
+                                          (uint32_t)(c0 / 8 + b), P.thresh16)
+                            << (8 * b);
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int col = c0 + i;
+                float x = v[i] + sbias[col];
+                float yv = has_ln ? fmaf((x - mean) * rstd, sgam[col], sbet[col]) : x;
+                float a = fmaxf(yv, 0.0f);
+                if (drop) a = ((keep >> i) & 1u) ? a * P.drop_scale : 0.0f;
+                if (col >= n_out || !rvalid) a = 0.0f;
+                v[i] = a;
+            }
+            if (P.has_head) {
+#pragma unroll
+                for (int k = 0; k < STDADK_MAX_Q; ++k)
+                    if (k < P.head.q) {
+                        float acc = yh[k];
+                        const float* wk = shw + k * n_pad + c0;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) acc = fmaf(v[i], wk[i], acc);
+                        yh[k] = acc;
+                    }
+            }
+            if (P.out_img) {
+                float* dst = P.out_img + ((size_t)tile * (n_pad / SLAB_K) + (c0 / SLAB_K)) * SLAB_FLOATS;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    float4 o = make_float4(to_tf32(v[4 * c]), to_tf32(v[4 * c + 1]), to_tf32(v[4 * c + 2]),
+                                           to_tf32(v[4 * c + 3]));
+                    *reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(dst) + swz_off((uint32_t)tid, c)) = o;
+                }
+            }
+        }
+        if (P.has_head) {
+            float loss = 0.0f;
+            if (rvalid) {
+                float dy[STDADK_MAX_Q];
+#pragma unroll
+                for (int k = 0; k < STDADK_MAX_Q; ++k)
+                    if (k < P.head.q) {
+                        yh[k] += shb[k];
+                        P.head.yhat[lrow * P.head.q + k] = yh[k];
+                    }
+                if (P.head.loss_type != STDADK_LOSS_NONE) {
+                    loss = row_loss(P.head, yh, P.head.y[grow], dy);
+                    if (P.head.dyhat) {
+#pragma unroll
+                        for (int k = 0; k < STDADK_MAX_Q; ++k)
+                            if (k < P.head.q) P.head.dyhat[lrow * P.head.q + k] = dy[k];
+                    }
+                }
+            }
+            if (P.head.loss_type != STDADK_LOSS_NONE) {
+                loss = warp_sum(loss);
+                if (lane == 0) atomicAdd(P.head.loss_acc, loss);
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+}
+
+// =============================================================================================
+// Backward
+// =============================================================================================
+template <bool BASIS>
+__global__ void __launch_bounds__(NTHREADS, 1) layer_bwd_kernel(const __grid_constant__ BwdK P) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = align_smem(smem_raw);
+    const int q = P.has_head ? P.head.q : 0;
+    const SmemPlan sp = plan_smem(P.n_pad, q, BASIS ? P.basis.k_s : 0, BASIS ? P.basis.k_t : 0, true);
+    float* sA = reinterpret_cast<float*>(smem + sp.a_off);
+    float* sB = reinterpret_cast<float*>(smem + sp.b_off);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + sp.bar_off);
+    uint64_t* empty = full + NSTAGE;
+    uint64_t* accf = full + 2 * NSTAGE;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + sp.tmem_off);
+    float* sbias = reinterpret_cast<float*>(smem + sp.vec_off);
+    float* sgam = sbias + P.n_pad;
+    float* sbet = sgam + P.n_pad;
+    float* shw = reinterpret_cast<float*>(smem + sp.headw_off);
+    float4* sk = reinterpret_cast<float4*>(smem + sp.knots_off);
+    float2* st = reinterpret_cast<float2*>(smem + sp.tknots_off);
+    float* cs_bias = reinterpret_cast<float*>(smem + sp.colsum_off);
+    float* cs_gam = cs_bias + P.n_pad;
+    float* cs_bet = cs_gam + P.n_pad;
+    float* cs_hw = cs_bet + P.n_pad;
+    float* cs_hb = cs_hw + q * P.n_pad;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tile = blockIdx.x;
+    const int n_pad = P.n_pad, n_out = P.L.n_out;
+    const bool has_ln = P.L.gamma != nullptr;
+    const size_t b_stage_floats = (size_t)n_pad * SLAB_K;
+    const int total_slabs = P.k_slabs + P.k_slabs2;
+    const uint32_t acc1_off = (uint32_t)(P.tmem_cols / 2);
+
+    if (tid == NWORK) {
+        for (int s = 0; s < NSTAGE; ++s) {
+            mbar_init(&full[s], BASIS ? 1 + NWORK : 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(accf, 1);
+        mbar_fence_init();
+    }
+    if (warp == 4) {
+        __syncwarp();
+        tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
+    }
+    for (int i = tid; i < n_pad; i += NTHREADS) {
+        bool ok = i < n_out;
+        sbias[i] = ok ? P.L.bias[i] : 0.0f;
+        sgam[i] = (ok && has_ln) ? P.L.gamma[i] : 1.0f;
+        sbet[i] = (ok && has_ln) ? P.L.beta[i] : 0.0f;
+    }
+    for (int i = tid; i < (3 + q) * n_pad + STDADK_MAX_Q; i += NTHREADS) cs_bias[i] = 0.0f;
+    if (P.has_head) {
+        for (int i = tid; i < q * n_pad; i += NTHREADS) {
+            int k = i / n_pad, c = i - k * n_pad;
+            shw[i] = c < n_out ? P.head.w[(size_t)k * n_out + c] : 0.0f;
+        }
+    }
+    if (BASIS) {
+        for (int i = tid; i < P.basis.k_s; i += NTHREADS) sk[i] = P.basis.knots[i];
+        for (int i = tid; i < P.basis.k_t; i += NTHREADS) st[i] = P.basis.tknots[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            const float* a_tile = BASIS ? nullptr : P.a_img + (size_t)tile * P.k_slabs * SLAB_FLOATS;
+            const float* dzn_tile = P.k_slabs2 ? P.dz_next_img + (size_t)tile * P.k_slabs2 * SLAB_FLOATS : nullptr;
+            for (int s = 0; s < total_slabs; ++s) {
+                int stage = s % NSTAGE, it = s / NSTAGE;
+                if (it > 0) mbar_wait(&empty[stage], (it - 1) & 1);
+                float* a_dst = sA + (size_t)stage * SLAB_FLOATS;
+                float* b_dst = sB + stage * b_stage_floats;
+                if (s < P.k_slabs)
+                    issue_slab_copies(P.L.w_img, P.k_slabs, s, n_pad, a_tile, a_dst, b_dst, &full[stage]);
+                else
+                    issue_slab_copies(P.wt_next_img, P.k_slabs2, s - P.k_slabs, n_pad, dzn_tile, a_dst, b_dst,
+                                      &full[stage]);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 5) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32((uint32_t)n_pad, 0, 0);
+            for (int s = 0; s < total_slabs; ++s) {
+                int stage = s % NSTAGE, it = s / NSTAGE;
+                mbar_wait(&full[stage], it & 1);
+                tc_fence_after();
+                bool second = s >= P.k_slabs;
+                issue_slab_mma(tmem_base + (second ? acc1_off : 0u), sA + (size_t)stage * SLAB_FLOATS,
+                               sB + stage * b_stage_floats, idesc, s == 0 || s == P.k_slabs);
+                umma_commit(&empty[stage]);
+            }
+            umma_commit(accf);
+        }
+        __syncwarp();
+    } else {
+        const long long lrow = (long long)tile * TILE_M + tid;
+        const bool rvalid = lrow < P.pts.n_rows;
+        const long long grow = P.pts.row_begin + lrow;
+        if (BASIS) {
+            float x = 0.f, y = 0.f, t = 0.f;
+            const float* xrow = nullptr;
+            if (rvalid) {
+                load_point(P.pts, grow, x, y, t);
+                if (P.basis.p_cov > 0 && P.pts.xcov) xrow = P.pts.xcov + grow * P.basis.p_cov;
+            }
+            for (int s = 0; s < total_slabs; ++s) {
+                int stage = s % NSTAGE, it = s / NSTAGE;
+                if (it > 0) mbar_wait(&empty[stage], (it - 1) & 1);
+                if (s < P.k_slabs) {
+                    gen_basis_slab(P.basis, sk, st, s, x, y, t, xrow, smem_u32(sA + (size_t)stage * SLAB_FLOATS),
+                                   (uint32_t)tid);
+                    fence_proxy_async_smem();
+                }
+                mbar_arrive(&full[stage]);
+            }
+        }
+        mbar_wait(accf, 0);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+        float mean = 0.0f, rstd = 1.0f;
+        if (has_ln && rvalid) {
+            mean = P.stats[2 * lrow];
+            rstd = P.stats[2 * lrow + 1];
+        }
+        float dyh[STDADK_MAX_Q];
+#pragma unroll
+        for (int k = 0; k < STDADK_MAX_Q; ++k)
+            dyh[k] = (P.has_head && rvalid && k < q) ? P.head.dyhat[lrow * q + k] : 0.0f;
+        const bool drop = P.L.drop_p > 0.0f;
+        const float inv_n = 1.0f / (float)n_out;
+        uint32_t actbits[MAX_N / 32];
+        float Sa = 0.0f, Sb = 0.0f;
+        float z[32], g[32], tmp[32];
+
+        // pass A: g = dL/dy (after dropout+ReLU backward); LN row sums; dgamma/dbeta/head column sums
+        for (int c0 = 0; c0 < n_pad; c0 += 32) {
+            tmem_ld32(trow + c0, z);
+            if (!P.has_head) tmem_ld32(trow + acc1_off + c0, g);
+            uint32_t keep = 0xFFFFFFFFu;
+            if (drop) {
+                keep = 0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    keep |= dropout_keep8(P.L.seed, P.L.step, (uint32_t)P.L.layer_id, (unsigned long long)grow,
+                                          (uint32_t)(c0 / 8 + b), P.thresh16)
+                            << (8 * b);
+            }
+            uint32_t act = 0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int col = c0 + i;
+                float x = z[i] + sbias[col];
+                float xh = has_ln ? (x - mean) * rstd : x;
+                float yv = has_ln ? fmaf(xh, sgam[col], sbet[col]) : x;
+                bool on = (yv > 0.0f) && ((keep >> i) & 1u) && (col < n_out) && rvalid;
+                act |= (on ? 1u : 0u) << i;
+                float dh;
+                if (P.has_head) {
+                    dh = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < STDADK_MAX_Q; ++k)
+                        if (k < q) dh = fmaf(dyh[k], shw[k * n_pad + col], dh);
+                } else {
+                    dh = g[i];
+                }
+                float h = on ? yv * P.drop_scale : 0.0f;  // forward activation (for the head gradient)
+                g[i] = on ? dh * P.drop_scale : 0.0f;
+                z[i] = xh;
+                tmp[i] = h;
+            }
+            actbits[c0 / 32] = act;
+            if (P.has_head) {
+                for (int k = 0; k < q; ++k) {
+                    float hv[32];
+                    const float dk = dyh[k];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) hv[i] = dk * tmp[i];
+                    float s = warp_transpose_sum(hv, lane);
+                    atomicAdd(&cs_hw[k * n_pad + c0 + lane], s);
+                }
+            }
+            if (has_ln) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    float gy = g[i] * sgam[c0 + i];
+                    Sa += gy;
+                    Sb = fmaf(gy, z[i], Sb);
+                    tmp[i] = g[i] * z[i];
+                }
+                float s = warp_transpose_sum(tmp, lane);
+                atomicAdd(&cs_gam[c0 + lane], s);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) tmp[i] = g[i];
+                s = warp_transpose_sum(tmp, lane);
+                atomicAdd(&cs_bet[c0 + lane], s);
+            } else {
+                float* dst = P.dz_img + ((size_t)tile * (n_pad / SLAB_K) + (c0 / SLAB_K)) * SLAB_FLOATS;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    float4 o = make_float4(to_tf32(g[4 * c]), to_tf32(g[4 * c + 1]), to_tf32(g[4 * c + 2]),
+                                           to_tf32(g[4 * c + 3]));
+                    *reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(dst) + swz_off((uint32_t)tid, c)) = o;
+                }
+                float s = warp_transpose_sum(g, lane);
+                atomicAdd(&cs_bias[c0 + lane], s);
+            }
+        }
+        if (P.has_head) {
+            for (int k = 0; k < q; ++k) {
+                float s = warp_sum(dyh[k]);
+                if (lane == 0) atomicAdd(&cs_hb[k], s);
+            }
+        }
+        // pass B (LayerNorm): dz = rstd * (gy - mean(gy) - xh * mean(gy * xh))
+        if (has_ln) {
+            const float ma = Sa * inv_n, mb = Sb * inv_n;
+            for (int c0 = 0; c0 < n_pad; c0 += 32) {
+                tmem_ld32(trow + c0, z);
+                if (!P.has_head) tmem_ld32(trow + acc1_off + c0, g);
+                const uint32_t act = actbits[c0 / 32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int col = c0 + i;
+                    float xh = (z[i] + sbias[col] - mean) * rstd;
+                    float dh;
+                    if (P.has_head) {
+                        dh = 0.0f;
+#pragma unroll
+                        for (int k = 0; k < STDADK_MAX_Q; ++k)
+                            if (k < q) dh = fmaf(dyh[k], shw[k * n_pad + col], dh);
+                    } else {
+                        dh = g[i];
+                    }
+                    float gy = ((act >> i) & 1u) ? dh * P.drop_scale * sgam[col] : 0.0f;
+                    float dz = rstd * (gy - ma - xh * mb);
+                    g[i] = (col < n_out && rvalid) ? dz : 0.0f;
+                }
+                float* dst = P.dz_img + ((size_t)tile * (n_pad / SLAB_K) + (c0 / SLAB_K)) * SLAB_FLOATS;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    float4 o = make_float4(to_tf32(g[4 * c]), to_tf32(g[4 * c + 1]), to_tf32(g[4 * c + 2]),
+                                           to_tf32(g[4 * c + 3]));
+                    *reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(dst) + swz_off((uint32_t)tid, c)) = o;
+                }
+                float s = warp_transpose_sum(g, lane);
+                atomicAdd(&cs_bias[c0 + lane], s);
+            }
+        }
+        tc_fence_before();
+        // flush the CTA's column sums
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int c = tid; c < n_out; c += NWORK) {
+            atomicAdd(&P.d_bias[c], cs_bias[c]);
+            if (has_ln) {
+                atomicAdd(&P.d_gamma[c], cs_gam[c]);
+                atomicAdd(&P.d_beta[c], cs_bet[c]);
+            }
+            for (int k = 0; k < q; ++k) atomicAdd(&P.d_head_w[(size_t)k * n_out + c], cs_hw[k * n_pad + c]);
+        }
+        if (tid < q) atomicAdd(&P.d_head_b[tid], cs_hb[tid]);
+    }
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+}
+
+// =============================================================================================
+// Weight gradient: dW[o, i] += sum_rows dz[row, o] * A[row, i]
+// =============================================================================================
+struct WgradK {
+    BasisP basis;
+    PointsP pts;
+    const float* a_img;
+    const float* dz_img;
+    float* dw;
+    long long stride_o, stride_i;
+    int n_in, n_out, a_slabs, dz_slabs, n_row_tiles, nt_slabs, tmem_cols, _pad;
+};
+constexpr int WG_HALF_ROWS = 64;
+constexpr int WG_CHUNK_BYTES = WG_HALF_ROWS * 128;           // 8 KB: 64 rows of one slab
+constexpr int WG_A_BYTES = 4 * WG_CHUNK_BYTES;               // M = 128 = 4 chunks of 32
+constexpr int WG_B_BYTES = 8 * WG_CHUNK_BYTES;               // N <= 256
+constexpr int WG_STAGE_BYTES = WG_A_BYTES + WG_B_BYTES;
+
+__host__ __device__ inline uint32_t wgrad_smem_bytes(int k_s, int k_t) {
+    return NSTAGE * WG_STAGE_BYTES + 64 + 16 + 16 + (uint32_t)k_s * 16u + (uint32_t)k_t * 8u + 16 + 1024;
+}
+
+template <bool BASIS>
+__global__ void __launch_bounds__(NTHREADS, 1) wgrad_kernel(const __grid_constant__ WgradK P) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = align_smem(smem_raw);
+    uint8_t* stage_base = smem;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + NSTAGE * WG_STAGE_BYTES);
+    uint64_t* empty = full + NSTAGE;
+    uint64_t* accf = full + 2 * NSTAGE;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + NSTAGE * WG_STAGE_BYTES + 64);
+    float4* sk = reinterpret_cast<float4*>(smem + NSTAGE * WG_STAGE_BYTES + 96);
+    float2* st = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(sk) + (size_t)(BASIS ? P.basis.k_s : 0) * 16);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int split = blockIdx.x, n_split = gridDim.x, mi = blockIdx.y, ni = blockIdx.z;
+    const int m_chunks = min(4, P.dz_slabs - mi * 4);
+    const int n_chunks = min(P.nt_slabs, P.a_slabs - ni * P.nt_slabs);
+    const int n_mma = n_chunks * SLAB_K;
+    int my_tiles = 0;
+    for (int rt = split; rt < P.n_row_tiles; rt += n_split) ++my_tiles;
+    const int n_iter = my_tiles * 2;
+
+    if (tid == NWORK) {
+        for (int s = 0; s < NSTAGE; ++s) {
+            mbar_init(&full[s], BASIS ? 1 + NWORK : 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(accf, 1);
+        mbar_fence_init();
+    }
+    if (warp == 4) {
+        __syncwarp();
+        tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
+    }
+    // unused M chunks must read as zeros (they are never overwritten)
+    if (m_chunks < 4) {
+        for (int s = 0; s < NSTAGE; ++s) {
+            float4* zp = reinterpret_cast<float4*>(stage_base + s * WG_STAGE_BYTES + m_chunks * WG_CHUNK_BYTES);
+            int n16 = (4 - m_chunks) * WG_CHUNK_BYTES / 16;
+            for (int i = tid; i < n16; i += NTHREADS) zp[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        fence_proxy_async_smem();
+    }
+    if (BASIS) {
+        for (int i = tid; i < P.basis.k_s; i += NTHREADS) sk[i] = P.basis.knots[i];
+        for (int i = tid; i < P.basis.k_t; i += NTHREADS) st[i] = P.basis.tknots[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (n_iter > 0) {
+        if (warp == 4) {
+            if (lane == 0) {
+                int itn = 0;
+                for (int rt = split; rt < P.n_row_tiles; rt += n_split)
+                    for (int half = 0; half < 2; ++half, ++itn) {
+                        int stage = itn % NSTAGE, it = itn / NSTAGE;
+                        if (it > 0) mbar_wait(&empty[stage], (it - 1) & 1);
+                        uint8_t* sa = stage_base + stage * WG_STAGE_BYTES;
+                        uint8_t* sb = sa + WG_A_BYTES;
+                        uint32_t bytes = (uint32_t)(m_chunks + (BASIS ? 0 : n_chunks)) * WG_CHUNK_BYTES;
+                        mbar_arrive_expect_tx(&full[stage], bytes);
+                        for (int c = 0; c < m_chunks; ++c)
+                            bulk_g2s(sa + c * WG_CHUNK_BYTES,
+                                     P.dz_img + ((size_t)rt * P.dz_slabs + mi * 4 + c) * SLAB_FLOATS +
+                                         half * WG_HALF_ROWS * SLAB_K,
+                                     WG_CHUNK_BYTES, &full[stage]);
+                        if (!BASIS)
+                            for (int c = 0; c < n_chunks; ++c)
+                                bulk_g2s(sb + c * WG_CHUNK_BYTES,
+                                         P.a_img + ((size_t)rt * P.a_slabs + ni * P.nt_slabs + c) * SLAB_FLOATS +
+                                             half * WG_HALF_ROWS * SLAB_K,
+                                         WG_CHUNK_BYTES, &full[stage]);
+                    }
+            }
+            __syncwarp();
+        } else if (warp == 5) {
+            if (lane == 0) {
+                const uint32_t idesc = umma_idesc_tf32((uint32_t)n_mma, 1, 1);
+                for (int itn = 0; itn < n_iter; ++itn) {
+                    int stage = itn % NSTAGE, it = itn / NSTAGE;
+                    mbar_wait(&full[stage], it & 1);
+                    tc_fence_after();
+                    uint32_t sa = smem_u32(stage_base + stage * WG_STAGE_BYTES);
+                    uint32_t sb = sa + WG_A_BYTES;
+#pragma unroll
+                    for (int k8 = 0; k8 < WG_HALF_ROWS / 8; ++k8) {
+                        uint64_t ad = umma_desc_sw128(sa + k8 * 1024, WG_CHUNK_BYTES, 1024);
+                        uint64_t bd = umma_desc_sw128(sb + k8 * 1024, WG_CHUNK_BYTES, 1024);
+                        umma_tf32(tmem_base, ad, bd, idesc, (itn == 0 && k8 == 0) ? 0u : 1u);
+                    }
+                    umma_commit(&empty[stage]);
+                }
+                umma_commit(accf);
+            }
+            __syncwarp();
+        } else {
+            if (BASIS) {
+                const int row64 = tid & 63, par = tid >> 6;
+                int itn = 0;
+                for (int rt = split; rt < P.n_row_tiles; rt += n_split)
+                    for (int half = 0; half < 2; ++half, ++itn) {
+                        int stage = itn % NSTAGE, it = itn / NSTAGE;
+                        long long lrow = (long long)rt * TILE_M + half * WG_HALF_ROWS + row64;
+                        float x = 0.f, y = 0.f, t = 0.f;
+                        const float* xrow = nullptr;
+                        if (lrow < P.pts.n_rows) {
+                            long long grow = P.pts.row_begin + lrow;
+                            load_point(P.pts, grow, x, y, t);
+                            if (P.basis.p_cov > 0 && P.pts.xcov) xrow = P.pts.xcov + grow * P.basis.p_cov;
+                        }
+                        if (it > 0) mbar_wait(&empty[stage], (it - 1) & 1);
+                        uint32_t sb = smem_u32(stage_base + stage * WG_STAGE_BYTES + WG_A_BYTES);
+                        for (int c = par; c < n_chunks; c += 2)
+                            gen_basis_slab(P.basis, sk, st, ni * P.nt_slabs + c, x, y, t, xrow,
+                                           sb + c * WG_CHUNK_BYTES, (uint32_t)row64);
+                        fence_proxy_async_smem();
+                        mbar_arrive(&full[stage]);
+                    }
+            }
+            mbar_wait(accf, 0);
+            tc_fence_after();
+            const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+            const int o = mi * TILE_M + tid;
+            float v[32];
+            for (int c0 = 0; c0 < n_mma; c0 += 32) {
+                tmem_ld32(trow + c0, v);
+                if (o < P.n_out) {
+                    float* dst = P.dw + (long long)o * P.stride_o;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        int col = ni * P.nt_slabs * SLAB_K + c0 + i;
+                        if (col < P.n_in) atomicAdd(dst + (long long)col * P.stride_i, v[i]);
+                    }
+                }
+            }
+            tc_fence_before();
+        }
+    }
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+}
+
+}  // namespace stdadk
+
+// =============================================================================================
+// Gradient of learnable knots (centres, log-bandwidths): G^T = W1s dz1^T on the tensor cores
+// (M = 128 knots, N = 128 points, K = n_out), then the closed-form chain rule per (knot, point).
+// =============================================================================================
+namespace stdadk {
+
+struct KnotGradK {
+    BasisP basis;
+    PointsP pts;
+    const float* dz_img;
+    const float* w1s_img;
+    float* d_centers;
+    float* d_log_bw;
+    int n_out, k_slabs, _p0, _p1;
+};
+
+__global__ void __launch_bounds__(NTHREADS) knotgrad_kernel(const __grid_constant__ KnotGradK P) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = align_smem(smem_raw);
+    const SmemPlan sp = plan_smem(TILE_M, 0, 0, 0, false);
+    float* sA = reinterpret_cast<float*>(smem + sp.a_off);
+    float* sB = reinterpret_cast<float*>(smem + sp.b_off);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + sp.bar_off);
+    uint64_t* empty = full + NSTAGE;
+    uint64_t* accf = full + 2 * NSTAGE;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + sp.tmem_off);
+    float2* spt = reinterpret_cast<float2*>(smem + sp.vec_off);  // 128 points (x, y): 1 KB <= 3*128*4
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ptile = blockIdx.x, ktile = blockIdx.y;
+    if (tid == NWORK) {
+        for (int s = 0; s < NSTAGE; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(accf, 1);
+        mbar_fence_init();
+    }
+    if (warp == 4) {
+        __syncwarp();
+        tmem_alloc(tmem_slot, TILE_M);
+    }
+    if (tid < TILE_M) {
+        long long lrow = (long long)ptile * TILE_M + tid;
+        float x = 0.f, y = 0.f, t = 0.f;
+        if (lrow < P.pts.n_rows) load_point(P.pts, P.pts.row_begin + lrow, x, y, t);
+        spt[tid] = make_float2(x, y);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            const float* a_tile = P.w1s_img + (size_t)ktile * P.k_slabs * SLAB_FLOATS;
+            for (int s = 0; s < P.k_slabs; ++s) {
+                int stage = s % NSTAGE, it = s / NSTAGE;
+                if (it > 0) mbar_wait(&empty[stage], (it - 1) & 1);
+                mbar_arrive_expect_tx(&full[stage], 2 * SLAB_BYTES);
+                bulk_g2s(sA + (size_t)stage * SLAB_FLOATS, a_tile + (size_t)s * SLAB_FLOATS, SLAB_BYTES, &full[stage]);
+                bulk_g2s(sB + (size_t)stage * SLAB_FLOATS,
+                         P.dz_img + ((size_t)ptile * P.k_slabs + s) * SLAB_FLOATS, SLAB_BYTES, &full[stage]);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 5) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32(TILE_M, 0, 0);
+            for (int s = 0; s < P.k_slabs; ++s) {
+                int stage = s % NSTAGE, it = s / NSTAGE;
+                mbar_wait(&full[stage], it & 1);
+                tc_fence_after();
+                issue_slab_mma(tmem_base, sA + (size_t)stage * SLAB_FLOATS, sB + (size_t)stage * SLAB_FLOATS, idesc,
+                               s == 0);
+                umma_commit(&empty[stage]);
+            }
+            umma_commit(accf);
+        }
+        __syncwarp();
+    } else {
+        mbar_wait(accf, 0);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const int j = ktile * TILE_M + tid;
+        const bool kvalid = j < P.basis.k_s;
+        float4 kn = kvalid ? P.basis.knots[j] : make_float4(0.f, 0.f, 1.f, 1.f);
+        const long long rows_left = P.pts.n_rows - (long long)ptile * TILE_M;
+        float gcx = 0.f, gcy = 0.f, glb = 0.f;
+        float v[32];
+        for (int c0 = 0; c0 < TILE_M; c0 += 32) {
+            tmem_ld32(trow + c0, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                if (c0 + i < rows_left) {
+                    float2 pt = spt[c0 + i];
+                    float dx = pt.x - kn.x, dy = pt.y - kn.y;
+                    float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+                    bool in = (P.basis.fn == STDADK_GAUSSIAN) || (d2 < kn.z);
+                    if (in && d2 > 0.0f) {
+                        float d = sqrtf(d2);
+                        float r = d * kn.w;
+                        float coef = v[i] * phi_dr(P.basis.fn, r);
+                        float s = coef * kn.w / d;  // coef / (d * theta')
+                        gcx = fmaf(-dx, s, gcx);
+                        gcy = fmaf(-dy, s, gcy);
+                        glb = fmaf(-r, coef, glb);
+                    }
+                }
+            }
+        }
+        if (kvalid) {
+            atomicAdd(&P.d_centers[2 * j], gcx);
+            atomicAdd(&P.d_centers[2 * j + 1], gcy);
+            atomicAdd(&P.d_log_bw[j], glb);
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem_base, TILE_M);
+}
+
+}  // namespace stdadk

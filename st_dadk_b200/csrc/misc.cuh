@@ -1,0 +1,179 @@
+// Elementwise / streaming kernels: operand-image packing, knot tables, unfused basis (parity checks),
+// gradient norm and the fused clip + AdamW + EMA update.  All are HBM-bound; grids are sized in
+// multiples of the SM count and accesses are 16-byte vectors where the layout allows.
+#pragma once
+#include "common.cuh"
+
+namespace stdadk {
+
+// ---------------------------------------------------------------- images
+// One thread per 16-byte chunk of the image.
+__global__ void pack_image_kernel(const float* __restrict__ src, long long row_stride, long long col_stride,
+                                  long long rows, long long cols, float* __restrict__ img, long long n_chunks,
+                                  int slabs) {
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n_chunks;
+         idx += (long long)gridDim.x * blockDim.x) {
+        int chunk = (int)(idx & 7);
+        int row = (int)((idx >> 3) & 127);
+        long long ts = idx >> 10;  // tile * slabs + slab
+        int slab = (int)(ts % slabs);
+        long long tile = ts / slabs;
+        long long r = tile * TILE_M + row;
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            long long c = (long long)slab * SLAB_K + chunk * 4 + e;
+            v[e] = (r < rows && c < cols) ? to_tf32(src[r * row_stride + c * col_stride]) : 0.0f;
+        }
+        float* dst = img + ts * SLAB_FLOATS;
+        *reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(dst) + swz_off((uint32_t)row, (uint32_t)chunk)) =
+            make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+__global__ void unpack_image_kernel(const float* __restrict__ img, long long rows, long long cols,
+                                    float* __restrict__ dst, int slabs) {
+    long long n = rows * cols;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n;
+         idx += (long long)gridDim.x * blockDim.x) {
+        long long r = idx / cols, c = idx - r * cols;
+        long long tile = r / TILE_M;
+        uint32_t row = (uint32_t)(r - tile * TILE_M);
+        int slab = (int)(c / SLAB_K);
+        int cc = (int)(c - (long long)slab * SLAB_K);
+        const uint8_t* base = reinterpret_cast<const uint8_t*>(img + (tile * slabs + slab) * SLAB_FLOATS);
+        dst[idx] = *reinterpret_cast<const float*>(base + swz_off(row, (uint32_t)(cc >> 2)) + (cc & 3) * 4);
+    }
+}
+
+// ---------------------------------------------------------------- knot tables
+__global__ void knots_prepare_kernel(const float* __restrict__ centers, const float* __restrict__ bw,
+                                     const float* __restrict__ log_bw, float calib, int k,
+                                     float4* __restrict__ out) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= k) return;
+    float b = log_bw ? expf(log_bw[j]) : bw[j];
+    float th = __fmul_rn(b, calib);
+    out[j] = make_float4(centers[2 * j], centers[2 * j + 1], __fmul_rn(th, th), 1.0f / th);
+}
+__global__ void tknots_prepare_kernel(const float* __restrict__ centers, const float* __restrict__ bw, int k,
+                                      float2* __restrict__ out) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= k) return;
+    out[j] = make_float2(centers[j], 1.0f / bw[j]);
+}
+
+// ---------------------------------------------------------------- unfused basis (debug / parity)
+// phi (N x k_s) and psi (N x k_t) dense FP32; thread = (row, feature), consecutive threads = features.
+__global__ void basis_fwd_kernel(BasisP B, PointsP P, float* __restrict__ phi, float* __restrict__ psi) {
+    const int kf = B.k_s + B.k_t;
+    const long long total = P.n_rows * (long long)kf;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        long long r = idx / kf;
+        int f = (int)(idx - r * kf);
+        float x, y, t;
+        load_point(P, P.row_begin + r, x, y, t);
+        if (f < B.k_s) {
+            if (phi) {
+                float4 kn = B.knots[f];
+                phi[r * B.k_s + f] = phi_eval(B.fn, x - kn.x, y - kn.y, kn.z, kn.w);
+            }
+        } else if (psi) {
+            float2 tk = B.tknots[f - B.k_s];
+            psi[r * B.k_t + (f - B.k_s)] = psi_eval(t, tk.x, tk.y);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- gradient norm + AdamW + EMA
+struct GroupsP {
+    long long end[8];
+    int n;
+};
+__device__ __forceinline__ int group_of(const GroupsP& G, long long i) {
+    int g = 0;
+#pragma unroll
+    for (int k = 0; k < 7; ++k)
+        if (k + 1 < G.n && i >= G.end[k]) g = k + 1;
+    return g;
+}
+
+__global__ void sqnorm_kernel(const float* __restrict__ g, long long n, GroupsP G, float* __restrict__ out) {
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.0f;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        float v = g[i];
+        int gi = group_of(G, i);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (k == gi) acc[k] = fmaf(v, v, acc[k]);
+    }
+    __shared__ float red[8];
+    if (threadIdx.x < 8) red[threadIdx.x] = 0.0f;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (k < G.n) {
+            float s = warp_sum(acc[k]);
+            if ((threadIdx.x & 31) == 0) atomicAdd(&red[k], s);
+        }
+    __syncthreads();
+    if (threadIdx.x < G.n) atomicAdd(&out[threadIdx.x], red[threadIdx.x]);
+}
+
+struct AdamK {
+    float* p;
+    const float* g;
+    float* m;
+    float* v;
+    float* shadow;
+    long long n;
+    GroupsP G;
+    const float* hyper;    // (n_groups x 4): lr, weight_decay, max_norm (<=0: no clipping), unused
+    const float* sqnorms;  // (n_groups) or null
+    const int* step_count; // device; holds the 1-based step index of THIS update
+    float beta1, beta2, eps, ema_decay;
+};
+// torch.optim.AdamW (decoupled decay, bias correction) + clip_grad_norm_ coefficient + ModelEMA.update
+// in one pass: 20 B read + 16 B written per parameter (28 B without EMA).
+__global__ void adamw_ema_kernel(AdamK A) {
+    const int step = *A.step_count;
+    const float bc1 = 1.0f - powf(A.beta1, (float)step);
+    const float bc2 = 1.0f - powf(A.beta2, (float)step);
+    const float inv_sqrt_bc2 = 1.0f / sqrtf(bc2);
+    float lr[8], wd[8], clip[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        lr[k] = wd[k] = 0.0f;
+        clip[k] = 1.0f;
+        if (k < A.G.n) {
+            lr[k] = A.hyper[4 * k];
+            wd[k] = A.hyper[4 * k + 1];
+            float mx = A.hyper[4 * k + 2];
+            if (A.sqnorms && mx > 0.0f) clip[k] = fminf(1.0f, mx / (sqrtf(A.sqnorms[k]) + 1e-6f));
+        }
+    }
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < A.n;
+         i += (long long)gridDim.x * blockDim.x) {
+        int gi = group_of(A.G, i);
+        float l = lr[0], w = wd[0], c = clip[0];
+#pragma unroll
+        for (int k = 1; k < 8; ++k)
+            if (k == gi) { l = lr[k]; w = wd[k]; c = clip[k]; }
+        float g = A.g[i] * c;
+        float p = A.p[i] * (1.0f - l * w);
+        float m = A.beta1 * A.m[i] + (1.0f - A.beta1) * g;
+        float v = A.beta2 * A.v[i] + (1.0f - A.beta2) * g * g;
+        float denom = sqrtf(v) * inv_sqrt_bc2 + A.eps;
+        p -= (l / bc1) * (m / denom);
+        A.p[i] = p;
+        A.m[i] = m;
+        A.v[i] = v;
+        if (A.shadow) A.shadow[i] = A.ema_decay * A.shadow[i] + (1.0f - A.ema_decay) * p;
+    }
+}
+
+}  // namespace stdadk

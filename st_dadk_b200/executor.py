@@ -1,0 +1,282 @@
+"""Forward / backward chains of the ST-DADK network on libstdadk kernels.
+
+`NetSpec` is a view of the model's tensors (owned by the nn.Module or by the trainer's flat buffer);
+`Executor` owns the operand images, activation workspaces and the flat gradient buffer, and issues
+the kernel sequence
+
+    forward : layer_fwd(basis -> h1) -> layer_fwd(h1 -> h2) -> ... -> layer_fwd(h_{L-1} -> head [+loss])
+    backward: layer_bwd(L) -> ... -> layer_bwd(1), then wgrad(l) for every block, then knot_grad
+
+mirroring STInterpMLP.forward (stnf/models/st_interp.py:827-882) and its autograd.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+from . import ops
+
+
+@dataclass
+class NetSpec:
+    centers: torch.Tensor                      # (K_s, 2)
+    bandwidths: Optional[torch.Tensor]         # (K_s,) fixed basis
+    log_bandwidths: Optional[torch.Tensor]     # (K_s,) learnable basis (theta = exp(.))
+    t_centers: torch.Tensor
+    t_bandwidths: torch.Tensor
+    weights: List[torch.Tensor]                # hidden Linear weights, logical shape (out, in), any strides
+    biases: List[torch.Tensor]
+    gammas: List[Optional[torch.Tensor]]
+    betas: List[Optional[torch.Tensor]]
+    head_w: torch.Tensor                       # (Q, d) effective head
+    head_b: torch.Tensor                       # (Q,)
+    basis_fn: str = "wendland"
+    p_cov: int = 0
+    dropout: float = 0.0
+    ln_eps: float = 1e-5
+    learnable_basis: bool = False
+
+    @property
+    def n_hidden(self):
+        return len(self.weights)
+
+    @property
+    def q(self):
+        return self.head_w.shape[0]
+
+
+@dataclass
+class LossSpec:
+    kind: str = "mse"                          # "mse" | "pinball"
+    taus: Sequence[float] = ()
+    nc_weight: float = 0.0
+    nc_power: int = 1
+
+
+class _Workspace:
+    def __init__(self, spec: NetSpec, n_rows: int, device):
+        self.n_rows = n_rows
+        self.h = [ops.new_image(n_rows, w.shape[0], device) for w in spec.weights[:-1]]
+        self.dz = [ops.new_image(n_rows, w.shape[0], device) for w in spec.weights]
+        self.stats = [torch.empty(n_rows, 2, dtype=torch.float32, device=device) if g is not None else None
+                      for g in spec.gammas]
+        self.yhat = torch.empty(n_rows, spec.q, dtype=torch.float32, device=device)
+        self.dyhat = torch.empty(n_rows, spec.q, dtype=torch.float32, device=device)
+
+
+class Executor:
+    MAX_WORKSPACES = 4
+
+    def __init__(self, spec: NetSpec):
+        self.spec = spec
+        dev = spec.centers.device
+        if dev.type != "cuda":
+            raise RuntimeError("st_dadk_b200.Executor needs CUDA tensors: the hot path has no CPU implementation")
+        self.device = dev
+        self._ws: Dict[int, _Workspace] = {}
+        self._ctx = None
+        self._pack_key = None
+        self.w_img: List[torch.Tensor] = [None] * spec.n_hidden
+        self.wt_img: List[torch.Tensor] = [None] * spec.n_hidden
+        self.w1s_img = None
+        self.knots4 = torch.empty(max(spec.centers.shape[0], 1), 4, dtype=torch.float32, device=dev)
+        self.tknots2 = torch.empty(max(spec.t_centers.shape[0], 1), 2, dtype=torch.float32, device=dev)
+        self.loss_acc = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._grad_flat = None
+        self.grads = None
+
+    # ------------------------------------------------------------------ operand preparation
+    def rebind(self, spec: NetSpec):
+        self.spec = spec
+        self._pack_key = None
+
+    def _key(self):
+        s = self.spec
+        ts = [s.centers, s.bandwidths, s.log_bandwidths, *s.weights]
+        return tuple((t.data_ptr(), t._version) for t in ts if t is not None)
+
+    def prepare(self, force: bool = True, for_backward: bool = False):
+        """(Re)build knot tables and weight images.  Training calls this every step (weights move);
+        evaluation may reuse them while the parameter storage is unchanged."""
+        s = self.spec
+        key = (self._key(), for_backward)
+        if not force and key == self._pack_key:
+            return
+        ops.knots_prepare(s.centers, s.bandwidths if s.log_bandwidths is None else None, s.log_bandwidths,
+                          s.basis_fn, out=self.knots4)
+        ops.tknots_prepare(s.t_centers, s.t_bandwidths, out=self.tknots2)
+        for l, w in enumerate(s.weights):
+            self.w_img[l] = ops.pack_image(w, out=self.w_img[l])
+            if for_backward and l > 0:
+                self.wt_img[l] = ops.pack_image(w.t(), out=self.wt_img[l])
+        if for_backward and s.learnable_basis:
+            w1s = s.weights[0][:, s.p_cov:s.p_cov + s.centers.shape[0]].t()   # (K_s, n_out)
+            self.w1s_img = ops.pack_image(w1s, out=self.w1s_img)
+        self._pack_key = key
+
+    def _workspace(self, n_rows: int) -> _Workspace:
+        ws = self._ws.get(n_rows)
+        if ws is None:
+            if len(self._ws) >= self.MAX_WORKSPACES:
+                self._ws.pop(next(iter(self._ws)))
+            ws = self._ws[n_rows] = _Workspace(self.spec, n_rows, self.device)
+        return ws
+
+    def _basis(self) -> L.Basis:
+        s = self.spec
+        return ops.make_basis(self.knots4, self.tknots2, s.centers.shape[0], s.t_centers.shape[0], s.p_cov, s.basis_fn)
+
+    def _layer(self, l: int) -> L.Layer:
+        s = self.spec
+        w = s.weights[l]
+        return ops.make_layer(self.w_img[l], s.biases[l], s.gammas[l], s.betas[l], w.shape[1], w.shape[0], s.ln_eps, l)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, pts: L.Points, train: bool = False, step: int = 0, seed: int = 0,
+                y: Optional[torch.Tensor] = None, loss: Optional[LossSpec] = None, inv_count: float = 0.0,
+                out: Optional[torch.Tensor] = None, save: bool = False, prepared: bool = False):
+        """Returns yhat (n_rows, Q).  With `y`/`loss`, also accumulates the loss into self.loss_acc and
+        leaves dLoss/dyhat in the workspace for `backward()`.  `save=True` keeps what backward needs."""
+        s = self.spec
+        n = int(pts.n_rows)
+        if not prepared:
+            self.prepare(force=train or save, for_backward=save)
+        ws = self._workspace(n)
+        yhat = out if out is not None else ws.yhat
+        basis = self._basis()
+        drop = L.Dropout(s.dropout if train else 0.0, step & 0xFFFFFFFF, seed)
+        head = None
+        for l in range(s.n_hidden):
+            a = L.FwdArgs()
+            a.pts = pts
+            if l == 0:
+                a.basis = C.pointer(basis)
+            else:
+                a.a_img = ws.h[l - 1].data_ptr()
+            a.layer = self._layer(l)
+            a.drop = drop
+            if save and ws.stats[l] is not None:
+                a.stats = ws.stats[l].data_ptr()
+            if l < s.n_hidden - 1:
+                a.out_img = ws.h[l].data_ptr()
+            else:
+                if loss is not None:
+                    code = L.LOSS_MSE if loss.kind == "mse" else L.LOSS_PINBALL
+                    head = ops.make_head(s.head_w, s.head_b, s.q, yhat, code, y, list(loss.taus), inv_count,
+                                         ws.dyhat, self.loss_acc, loss.nc_weight, loss.nc_power)
+                else:
+                    head = ops.make_head(s.head_w, s.head_b, s.q, yhat)
+                a.head = C.pointer(head)
+            ops.layer_fwd(a)
+        if save:
+            self._ctx = (pts, drop, ws)
+        return yhat
+
+    # ------------------------------------------------------------------ backward
+    def alloc_grads(self, flat: Optional[torch.Tensor] = None, views: Optional[dict] = None):
+        """Gradient buffers.  Linear weight gradients are stored (in, out)-contiguous and exposed as
+        the transposed (out, in) view so the wgrad epilogue's atomics are coalesced."""
+        s = self.spec
+        if views is not None:
+            self._grad_flat, self.grads = flat, views
+            return
+        shapes = []
+        for w in s.weights:
+            shapes.append(w.shape[0] * w.shape[1])
+        sizes = shapes + [b.numel() for b in s.biases] + \
+            [g.numel() if g is not None else 0 for g in s.gammas] * 2 + \
+            [s.head_w.numel(), s.head_b.numel(), s.centers.numel(), s.centers.shape[0]]
+        flat = torch.zeros(sum(sizes), dtype=torch.float32, device=self.device)
+        o = 0
+        g = {"weights": [], "biases": [], "gammas": [], "betas": []}
+        for w in s.weights:
+            n = w.shape[0] * w.shape[1]
+            g["weights"].append(flat[o:o + n].view(w.shape[1], w.shape[0]).t())
+            o += n
+        for b in s.biases:
+            g["biases"].append(flat[o:o + b.numel()])
+            o += b.numel()
+        for name in ("gammas", "betas"):
+            for gm in s.gammas:
+                n = gm.numel() if gm is not None else 0
+                g[name].append(flat[o:o + n] if n else None)
+                o += n
+        g["head_w"] = flat[o:o + s.head_w.numel()].view_as(s.head_w)
+        o += s.head_w.numel()
+        g["head_b"] = flat[o:o + s.head_b.numel()]
+        o += s.head_b.numel()
+        g["centers"] = flat[o:o + s.centers.numel()].view(-1, 2)
+        o += s.centers.numel()
+        g["log_bandwidths"] = flat[o:o + s.centers.shape[0]]
+        self._grad_flat, self.grads = flat, g
+
+    def backward(self, dyhat: Optional[torch.Tensor] = None, zero: bool = True) -> dict:
+        """Gradients of every parameter for the rows of the last `forward(save=True)`.  `dyhat`
+        overrides the loss gradient left by the fused loss (used by the autograd bridge)."""
+        if self._ctx is None:
+            raise RuntimeError("Executor.backward called without a saved forward")
+        s = self.spec
+        pts, drop, ws = self._ctx
+        if self.grads is None:
+            self.alloc_grads()
+        if zero:
+            self._grad_flat.zero_()
+        g = self.grads
+        if dyhat is not None:
+            ws.dyhat.copy_(dyhat)
+        basis = self._basis()
+        nh = s.n_hidden
+        head = ops.make_head(s.head_w, s.head_b, s.q, ws.yhat, dyhat=ws.dyhat)
+        for l in reversed(range(nh)):
+            a = L.BwdArgs()
+            a.pts = pts
+            if l == 0:
+                a.basis = C.pointer(basis)
+            else:
+                a.a_img = ws.h[l - 1].data_ptr()
+            a.layer = self._layer(l)
+            a.drop = drop
+            if ws.stats[l] is not None:
+                a.stats = ws.stats[l].data_ptr()
+                a.d_gamma = g["gammas"][l].data_ptr()
+                a.d_beta = g["betas"][l].data_ptr()
+            if l == nh - 1:
+                a.head = C.pointer(head)
+                a.d_head_w = g["head_w"].data_ptr()
+                a.d_head_b = g["head_b"].data_ptr()
+            else:
+                a.dz_next_img = ws.dz[l + 1].data_ptr()
+                a.wt_next_img = self.wt_img[l + 1].data_ptr()
+                a.n_next = s.weights[l + 1].shape[0]
+            a.dz_img = ws.dz[l].data_ptr()
+            a.d_bias = g["biases"][l].data_ptr()
+            ops.layer_bwd(a)
+        for l in range(nh):
+            w = s.weights[l]
+            gw = g["weights"][l]
+            a = L.WgradArgs()
+            a.pts = pts
+            if l == 0:
+                a.basis = C.pointer(basis)
+            else:
+                a.a_img = ws.h[l - 1].data_ptr()
+            a.dz_img = ws.dz[l].data_ptr()
+            a.n_in, a.n_out = w.shape[1], w.shape[0]
+            a.dw = gw.data_ptr()
+            a.stride_o, a.stride_i = gw.stride(0), gw.stride(1)
+            ops.wgrad(a)
+        if s.learnable_basis:
+            a = L.KnotGradArgs()
+            a.basis = C.pointer(basis)
+            a.pts = pts
+            a.dz_img = ws.dz[0].data_ptr()
+            a.w1s_img = self.w1s_img.data_ptr()
+            a.n_out = s.weights[0].shape[0]
+            a.d_centers = g["centers"].data_ptr()
+            a.d_log_bw = g["log_bandwidths"].data_ptr()
+            ops.knot_grad(a)
+        return g

@@ -1,0 +1,154 @@
+"""Tensor-level wrappers over the C ABI.  PyTorch supplies device memory and the stream; every
+arithmetic step runs in libstdadk.so.  All functions require CUDA tensors and raise otherwise."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib as L
+
+TILE_M, SLAB_K, SLAB_FLOATS = 128, 32, 4096
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("st_dadk_b200: expected a CUDA tensor (there is no CPU path)")
+    return t.data_ptr()
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"st_dadk_b200: `{name}` must be a CUDA tensor (there is no CPU path)")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def pad32(x: int) -> int:
+    return (x + 31) & ~31
+
+
+def image_floats(rows: int, cols: int) -> int:
+    return ((rows + TILE_M - 1) // TILE_M) * ((cols + SLAB_K - 1) // SLAB_K) * SLAB_FLOATS
+
+
+def new_image(rows: int, cols: int, device) -> torch.Tensor:
+    return torch.empty(image_floats(rows, cols), dtype=torch.float32, device=device)
+
+
+def pack_image(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(rows x cols) strided FP32 matrix -> TF32-rounded swizzled operand image."""
+    assert src.dim() == 2 and src.dtype == torch.float32
+    rows, cols = src.shape
+    if out is None:
+        out = new_image(rows, cols, src.device)
+    L.check(L.lib().stdadk_pack_image(_ptr(src), src.stride(0), src.stride(1), rows, cols, _ptr(out), _stream()),
+            "pack_image")
+    return out
+
+
+def unpack_image(img: torch.Tensor, rows: int, cols: int) -> torch.Tensor:
+    out = torch.empty(rows, cols, dtype=torch.float32, device=img.device)
+    L.check(L.lib().stdadk_unpack_image(_ptr(img), rows, cols, _ptr(out), _stream()), "unpack_image")
+    return out
+
+
+def knots_prepare(centers: torch.Tensor, bandwidths: Optional[torch.Tensor], log_bandwidths: Optional[torch.Tensor],
+                  basis_fn: str, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    k = centers.shape[0]
+    centers = _f32c(centers, "centers")
+    bw = _f32c(bandwidths, "bandwidths") if bandwidths is not None else None
+    lbw = _f32c(log_bandwidths, "log_bandwidths") if log_bandwidths is not None else None
+    if out is None:
+        out = torch.empty(max(k, 1), 4, dtype=torch.float32, device=centers.device)
+    L.check(L.lib().stdadk_knots_prepare(_ptr(centers), _ptr(bw), _ptr(lbw), L.CALIBRATION[basis_fn], k, _ptr(out),
+                                         _stream()), "knots_prepare")
+    return out
+
+
+def tknots_prepare(centers: torch.Tensor, bandwidths: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    k = centers.shape[0]
+    if out is None:
+        out = torch.empty(max(k, 1), 2, dtype=torch.float32, device=centers.device)
+    L.check(L.lib().stdadk_tknots_prepare(_ptr(_f32c(centers, "t_centers")), _ptr(_f32c(bandwidths, "t_bandwidths")),
+                                          k, _ptr(out), _stream()), "tknots_prepare")
+    return out
+
+
+def make_basis(knots4: torch.Tensor, tknots2: torch.Tensor, k_s: int, k_t: int, p_cov: int, basis_fn: str) -> L.Basis:
+    return L.Basis(_ptr(knots4), _ptr(tknots2), k_s, k_t, p_cov, L.BASIS_CODE[basis_fn])
+
+
+def make_points(coords: Optional[torch.Tensor] = None, t: Optional[torch.Tensor] = None,
+                xcov: Optional[torch.Tensor] = None, grid: Optional[Sequence[int]] = None, row_begin: int = 0,
+                n_rows: Optional[int] = None) -> L.Points:
+    """Array point source (coords (N,2), t (N,1|N)) or the dense grid (nx, ny, nt)."""
+    if grid is not None:
+        nx, ny, nt = grid
+        if n_rows is None:
+            n_rows = nx * ny * nt - row_begin
+        return L.Points(None, None, None, nx, ny, nt, 0, row_begin, n_rows)
+    if n_rows is None:
+        n_rows = coords.shape[0] - row_begin
+    return L.Points(_ptr(coords), _ptr(t), _ptr(xcov) if xcov is not None and xcov.numel() > 0 else None, 0, 0, 0, 0,
+                    row_begin, n_rows)
+
+
+def basis_fwd(basis: L.Basis, pts: L.Points, device) -> tuple:
+    n = pts.n_rows
+    phi = torch.empty(n, basis.k_s, dtype=torch.float32, device=device)
+    psi = torch.empty(n, basis.k_t, dtype=torch.float32, device=device)
+    L.check(L.lib().stdadk_basis_fwd(C.byref(basis), C.byref(pts), _ptr(phi), _ptr(psi), _stream()), "basis_fwd")
+    return phi, psi
+
+
+def make_layer(w_img, bias, gamma, beta, n_in, n_out, eps, layer_id) -> L.Layer:
+    return L.Layer(_ptr(w_img), _ptr(bias), _ptr(gamma), _ptr(beta), n_in, n_out, eps, layer_id)
+
+
+def make_head(w, b, q, yhat, loss_type=L.LOSS_NONE, y=None, taus=None, inv_count=0.0, dyhat=None, loss_acc=None,
+              nc_weight=0.0, nc_power=1) -> L.Head:
+    h = L.Head()
+    h.w, h.b, h.q, h.loss_type, h.y = _ptr(w), _ptr(b), q, loss_type, _ptr(y)
+    for i, tau in enumerate(taus or []):
+        h.taus[i] = float(tau)
+    h.inv_count, h.nc_weight, h.nc_power = inv_count, nc_weight, nc_power
+    h.yhat, h.dyhat, h.loss_acc = _ptr(yhat), _ptr(dyhat), _ptr(loss_acc)
+    return h
+
+
+def layer_fwd(args: L.FwdArgs):
+    L.check(L.lib().stdadk_layer_fwd(C.byref(args), _stream()), "layer_fwd")
+
+
+def layer_bwd(args: L.BwdArgs):
+    L.check(L.lib().stdadk_layer_bwd(C.byref(args), _stream()), "layer_bwd")
+
+
+def wgrad(args: L.WgradArgs):
+    L.check(L.lib().stdadk_wgrad(C.byref(args), _stream()), "wgrad")
+
+
+def knot_grad(args: L.KnotGradArgs):
+    L.check(L.lib().stdadk_knot_grad(C.byref(args), _stream()), "knot_grad")
+
+
+def grad_sqnorm(g: torch.Tensor, group_end: Sequence[int], out: torch.Tensor):
+    arr = (C.c_int64 * len(group_end))(*group_end)
+    L.check(L.lib().stdadk_grad_sqnorm(_ptr(g), g.numel(), len(group_end), arr, _ptr(out), _stream()), "grad_sqnorm")
+
+
+def adamw_ema_step(p, g, m, v, shadow, group_end: Sequence[int], hyper: torch.Tensor, sqnorms, step_count,
+                   beta1=0.9, beta2=0.999, eps=1e-8, ema_decay=0.0):
+    arr = (C.c_int64 * len(group_end))(*group_end)
+    a = L.AdamWArgs(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(shadow), p.numel(), len(group_end), 0, arr, _ptr(hyper),
+                    _ptr(sqnorms), _ptr(step_count), beta1, beta2, eps, ema_decay)
+    L.check(L.lib().stdadk_adamw_ema_step(C.byref(a), _stream()), "adamw_ema_step")

@@ -1,0 +1,50 @@
+"""CPU: the C-ABI library loads and exports every symbol include/stdadk.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "stdadk.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(stdadk_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported():
+    import __graft_entry__ as g
+    g.build()
+    lib = ctypes.CDLL(os.path.join(ROOT, "st_dadk_b200", "libstdadk.so"))
+    names = _declared()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/stdadk.h but not exported"
+    lib.stdadk_version.restype = ctypes.c_int
+    assert lib.stdadk_version() == 100
+    lib.stdadk_image_floats.restype = ctypes.c_size_t
+    lib.stdadk_image_floats.argtypes = [ctypes.c_int64, ctypes.c_int64]
+    assert lib.stdadk_image_floats(130, 33) == 2 * 2 * 4096
+
+
+def test_ctypes_structs_match_header_sizes():
+    from st_dadk_b200 import _lib as L
+    L.lib()   # raises on any sizeof mismatch between the ctypes structs and the compiled header
+    assert ctypes.sizeof(L.Basis) == 32 and ctypes.sizeof(L.Points) == 56
+    assert ctypes.sizeof(L.Layer) == 48 and ctypes.sizeof(L.Dropout) == 16
+    assert ctypes.sizeof(L.Head) == 24 + 8 + 32 + 16 + 24
+    assert ctypes.sizeof(L.FwdArgs) == 8 + 56 + 8 + 48 + 16 + 24
+
+
+def test_product_never_imports_oracle():
+    """The product path must not route through the CPU oracle (or /root/reference)."""
+    bad = []
+    for base in ("st_dadk_b200", "stnf", "scripts"):
+        for dp, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if f.endswith(".py"):
+                    s = open(os.path.join(dp, f)).read()
+                    if re.search(r"^\s*(from|import)\s+oracle\b", s, flags=re.M) or "/root/reference" in s:
+                        if not f.endswith("selftest.py"):
+                            bad.append(os.path.join(dp, f))
+    assert not bad, bad

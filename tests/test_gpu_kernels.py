@@ -1,0 +1,371 @@
+"""GPU parity tests (B200): every CUDA kernel, called through the C ABI, against the CPU oracle and the
+reference's golden vectors.  Tolerances (stated per test):
+  * knot-support index sets, sharding, grid generation, dropout masks: bit-exact;
+  * basis values: |err| <= 1e-5 * max(phi, 1e-2) against the FP64 reference;
+  * tensor-core GEMMs with operands pre-rounded to TF32: 2e-5 (FP32 accumulation order only);
+  * network outputs / loss / gradients under TF32: 1e-3 (outputs, loss) and 5e-3 (gradients) relative
+    to the largest magnitude of the compared tensor, against the FP64 reference.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import golden, kat, oracle_from_state, state_of, c_spatial_basis, orc
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _mods():
+    from st_dadk_b200 import _lib as L, ops
+    from st_dadk_b200.executor import Executor, NetSpec, LossSpec
+    return L, ops, Executor, NetSpec, LossSpec
+
+
+def T(a):
+    return torch.tensor(np.ascontiguousarray(a), dtype=torch.float32, device=DEV)
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
+
+
+def spec_from_oracle(m, learnable=False, dropout=0.0):
+    L, ops, Executor, NetSpec, LossSpec = _mods()
+    Wh, bh = m.head(np.float64)
+    n_hidden = len(m.ln_gamma)
+    return NetSpec(
+        centers=T(m.centers), bandwidths=None if learnable else T(m.bandwidths),
+        log_bandwidths=T(np.log(m.bandwidths.astype(np.float64))) if learnable else None,
+        t_centers=T(m.t_centers), t_bandwidths=T(m.t_bandwidths),
+        weights=[T(w) for w in m.weights[:n_hidden]], biases=[T(b) for b in m.biases[:n_hidden]],
+        gammas=[T(g) if g is not None else None for g in m.ln_gamma],
+        betas=[T(b) if b is not None else None for b in m.ln_beta],
+        head_w=T(Wh), head_b=T(bh), basis_fn=m.basis_fn, p_cov=m.p, dropout=dropout, ln_eps=m.ln_eps,
+        learnable_basis=learnable)
+
+
+def test_library_loads_on_gpu():
+    L, ops, *_ = _mods()
+    assert L.lib().stdadk_version() == 100
+
+
+def test_pack_unpack_roundtrip():
+    L, ops, *_ = _mods()
+    rng = np.random.default_rng(0)
+    for rows, cols in [(1, 1), (128, 32), (130, 33), (300, 297), (256, 256)]:
+        a = rng.standard_normal((rows, cols)).astype(np.float32)
+        img = ops.pack_image(T(a))
+        assert img.numel() == ops.image_floats(rows, cols)
+        back = ops.unpack_image(img, rows, cols).cpu().numpy()
+        assert np.array_equal(back, orc.tf32_round(a))
+        # strided source (transposed view)
+        img_t = ops.pack_image(T(a).t())
+        back_t = ops.unpack_image(img_t, cols, rows).cpu().numpy()
+        assert np.array_equal(back_t, orc.tf32_round(a.T))
+
+
+@pytest.mark.parametrize("fn", ["wendland", "gaussian", "triangular"])
+def test_basis_fwd_values_and_support(fn):
+    L, ops, *_ = _mods()
+    g = golden("basis_values")
+    kn = golden("knots")
+    c, b = kn["centers"], kn["bandwidths"]
+    rng = np.random.default_rng(3)
+    extra = rng.random((5000, 2)).astype(np.float32)
+    coords = np.concatenate([g["coords"], extra])
+    tt = np.concatenate([g["t"], rng.random((5000, 1)).astype(np.float32)])
+    knots4 = ops.knots_prepare(T(c), T(b), None, fn)
+    tk = ops.tknots_prepare(T(kn["t_centers"]), T(kn["t_bandwidths"]))
+    basis = ops.make_basis(knots4, tk, c.shape[0], kn["t_centers"].shape[0], 0, fn)
+    ct, ttt = T(coords), T(tt)
+    pts = ops.make_points(ct, ttt)
+    phi, psi = ops.basis_fwd(basis, pts, DEV)
+    phi, psi = phi.cpu().numpy(), psi.cpu().numpy()
+    n0 = g["coords"].shape[0]
+    ref = g[f"phi64_{fn}"]
+    assert np.max(np.abs(phi[:n0] - ref) / np.maximum(ref, 1e-2)) < 1e-5
+    ref_all = orc.spatial_basis(coords, c, b, fn)
+    assert np.max(np.abs(phi - ref_all) / np.maximum(ref_all, 1e-2)) < 1e-5
+    psi_ref = orc.temporal_basis(tt, kn["t_centers"], kn["t_bandwidths"])
+    assert np.max(np.abs(psi - psi_ref) / np.maximum(psi_ref, 1e-2)) < 1e-5
+    np.testing.assert_allclose(psi[:n0], g["psi64"], rtol=0, atol=2e-6)
+    # knot-support index sets: bit-exact against the C restatement (and the reference's non-zeros)
+    thetap = (b * np.float32(orc.CALIBRATION[fn])).astype(np.float32)
+    phic, maskc = c_spatial_basis(coords, c, thetap, fn)
+    if fn != "gaussian":
+        assert np.array_equal(phi > 0, phic > 0)
+        assert np.array_equal((phi > 0)[:n0], ref > 0)
+    # KAT points of SURVEY 8(c)
+    if fn == "wendland":
+        for p in kat()["points"]:
+            pp = ops.make_points(T([[p["x"], p["y"]]]), T([[p["t"]]]))
+            ph, ps = ops.basis_fwd(basis, pp, DEV)
+            ph = ph.cpu().numpy()[0]
+            assert np.nonzero(ph > 0)[0].tolist() == p["support"]
+            assert abs(ph.sum() - p["sum_phi"]) < 1e-5 * p["sum_phi"]
+            assert abs(ps.cpu().numpy().sum() - p["sum_psi"]) < 1e-5 * p["sum_psi"]
+
+
+def test_basis_fwd_grid_generator_bit_exact():
+    L, ops, *_ = _mods()
+    kn = golden("knots")
+    knots4 = ops.knots_prepare(T(kn["centers"]), T(kn["bandwidths"]), None, "wendland")
+    tk = ops.tknots_prepare(T(kn["t_centers"]), T(kn["t_bandwidths"]))
+    basis = ops.make_basis(knots4, tk, 227, 70, 0, "wendland")
+    nx, ny, nt = 37, 29, 5
+    begin, end = 1000, 3500
+    phi_g, psi_g = ops.basis_fwd(basis, ops.make_points(grid=(nx, ny, nt), row_begin=begin, n_rows=end - begin), DEV)
+    coords, t = orc.grid_points(nx, ny, nt, begin, end)
+    phi_a, psi_a = ops.basis_fwd(basis, ops.make_points(T(coords), T(t)), DEV)
+    assert torch.equal(phi_g, phi_a) and torch.equal(psi_g, psi_a)
+
+
+def _run_dense(ops, L, A, W, bias, gamma=None, beta=None, eps=1e-5):
+    """relu(LN(A W^T + b)) through the image path of layer_fwd; returns the unpacked output."""
+    rows, n_in = A.shape
+    n_out = W.shape[0]
+    a_img = ops.pack_image(T(A))
+    w_img = ops.pack_image(T(W))
+    out = ops.new_image(rows, n_out, DEV)
+    out.fill_(float("nan"))
+    tb, tg, tbe = T(bias), (T(gamma) if gamma is not None else None), (T(beta) if beta is not None else None)
+    stats = torch.zeros(rows, 2, device=DEV)
+    a = L.FwdArgs()
+    a.pts = ops.make_points(grid=None, coords=None, t=None, row_begin=0, n_rows=rows)
+    a.a_img = a_img.data_ptr()
+    a.layer = ops.make_layer(w_img, tb, tg, tbe, n_in, n_out, eps, 0)
+    a.drop = L.Dropout(0.0, 0, 0)
+    a.out_img = out.data_ptr()
+    a.stats = stats.data_ptr()
+    ops.layer_fwd(a)
+    torch.cuda.synchronize()
+    return ops.unpack_image(out, rows, n_out).cpu().numpy(), stats.cpu().numpy()
+
+
+@pytest.mark.parametrize("rows,n_in,n_out", [(128, 32, 32), (128, 64, 128), (200, 96, 48), (384, 256, 256),
+                                             (1000, 297, 256), (130, 256, 128), (77, 128, 16), (128, 512, 64)])
+def test_dense_gemm_relu_exact_tf32(rows, n_in, n_out):
+    """K-major tcgen05 path: operands pre-rounded to TF32 => products exact, only FP32 summation order differs."""
+    L, ops, *_ = _mods()
+    rng = np.random.default_rng(rows + n_in + n_out)
+    A = orc.tf32_round(rng.standard_normal((rows, n_in)).astype(np.float32))
+    W = orc.tf32_round((rng.standard_normal((n_out, n_in)) / np.sqrt(n_in)).astype(np.float32))
+    bias = rng.standard_normal(n_out).astype(np.float32)
+    got, _ = _run_dense(ops, L, A, W, bias)
+    ref = np.maximum(A.astype(np.float64) @ W.astype(np.float64).T + bias, 0.0)
+    assert np.max(np.abs(got - orc.tf32_round(ref.astype(np.float32)))) < 2e-5 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("rows,n_in,n_out", [(256, 256, 256), (300, 96, 48), (128, 297, 128)])
+def test_dense_layernorm_epilogue(rows, n_in, n_out):
+    L, ops, *_ = _mods()
+    rng = np.random.default_rng(5)
+    A = orc.tf32_round(rng.standard_normal((rows, n_in)).astype(np.float32))
+    W = orc.tf32_round((rng.standard_normal((n_out, n_in)) / np.sqrt(n_in)).astype(np.float32))
+    bias = (rng.standard_normal(n_out) + 3.0).astype(np.float32)   # non-zero mean stresses the variance
+    gamma = (1.0 + 0.2 * rng.standard_normal(n_out)).astype(np.float32)
+    beta = (0.1 * rng.standard_normal(n_out)).astype(np.float32)
+    got, stats = _run_dense(ops, L, A, W, bias, gamma, beta)
+    z = A.astype(np.float64) @ W.astype(np.float64).T + bias
+    mu = z.mean(1, keepdims=True)
+    var = ((z - mu) ** 2).mean(1, keepdims=True)
+    ref = np.maximum((z - mu) / np.sqrt(var + 1e-5) * gamma + beta, 0.0)
+    assert np.max(np.abs(got - ref)) < 1e-3 * np.abs(ref).max()          # output image is TF32-rounded
+    np.testing.assert_allclose(stats[:, 0], mu[:, 0], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(stats[:, 1], 1 / np.sqrt(var[:, 0] + 1e-5), rtol=1e-4)
+
+
+@pytest.mark.parametrize("rows,n_in,n_out", [(128, 32, 32), (256, 256, 256), (1000, 297, 256), (300, 128, 48),
+                                             (4096, 256, 128), (130, 40, 16)])
+def test_wgrad_mn_major_exact_tf32(rows, n_in, n_out):
+    """MN-major tcgen05 path: dW = dz^T A with both operands read from the forward's images."""
+    L, ops, *_ = _mods()
+    rng = np.random.default_rng(rows * 7 + n_in)
+    A = orc.tf32_round(rng.standard_normal((rows, n_in)).astype(np.float32))
+    dz = orc.tf32_round(rng.standard_normal((rows, n_out)).astype(np.float32))
+    a_img, dz_img = ops.pack_image(T(A)), ops.pack_image(T(dz))
+    for transposed_storage in (False, True):
+        dw = torch.zeros(n_in, n_out, device=DEV).t() if transposed_storage else torch.zeros(n_out, n_in, device=DEV)
+        a = L.WgradArgs()
+        a.pts = ops.make_points(grid=None, coords=None, t=None, row_begin=0, n_rows=rows)
+        a.a_img, a.dz_img = a_img.data_ptr(), dz_img.data_ptr()
+        a.n_in, a.n_out = n_in, n_out
+        a.dw, a.stride_o, a.stride_i = dw.data_ptr(), dw.stride(0), dw.stride(1)
+        ops.wgrad(a)
+        ref = dz.astype(np.float64).T @ A.astype(np.float64)
+        assert np.max(np.abs(dw.cpu().numpy() - ref)) < 3e-5 * max(1.0, np.abs(ref).max())
+
+
+CASES = [("small_mse", "wendland", "mse", None), ("small_mq", "wendland", "pinball", [0.1, 0.5, 0.9]),
+         ("small_noln_tri", "triangular", "mse", None), ("small_gauss", "gaussian", "mse", None),
+         ("small_learnable", "wendland", "pinball", [0.1, 0.5, 0.9]),
+         ("small_delta", "wendland", "pinball", [0.1, 0.5, 0.9])]
+
+
+@pytest.mark.parametrize("name,fn,loss,taus", CASES)
+def test_network_forward_backward_vs_reference(name, fn, loss, taus):
+    """Whole chain (basis fused into block 1, tcgen05 blocks, fused head + loss, backward with basis
+    recompute, wgrad, knot gradients) against the reference module's FP64 outputs and autograd."""
+    L, ops, Executor, NetSpec, LossSpec = _mods()
+    g = golden(name)
+    m = oracle_from_state(state_of(g), basis_fn=fn)
+    learn = name == "small_learnable"
+    spec = spec_from_oracle(m, learnable=learn)
+    ex = Executor(spec)
+    coords, t, y = T(g["coords"]), T(g["t"]), T(g["y"].reshape(-1))
+    n = coords.shape[0]
+    pts = ops.make_points(coords, t)
+    ex.loss_acc.zero_()
+    yhat = ex.forward(pts, train=True, y=y, loss=LossSpec(loss, taus or ()), inv_count=1.0 / (n * spec.q), save=True)
+    torch.cuda.synchronize()
+    yh = yhat.cpu().numpy()
+    assert rel_err(yh, g["yhat64"]) < 1e-3
+    assert abs(ex.loss_acc.item() - float(g["loss64"])) < 1e-3 * abs(float(g["loss64"]))
+    grads = ex.backward()
+    torch.cuda.synchronize()
+    ref = {k[5:]: g[k] for k in g.files if k.startswith("grad.")}
+    pre = "mlp_trunk." if m.delta is not None else "mlp."
+    lin = sorted({int(k.split(".")[1]) for k in ref if k.startswith(pre) and ref[k].ndim == 2})
+    tol = 5e-3
+    nh = spec.n_hidden
+    for li in range(nh):
+        k = lin[li]
+        assert rel_err(grads["weights"][li].cpu().numpy(), ref[f"{pre}{k}.weight"]) < tol, f"dW{li}"
+        assert rel_err(grads["biases"][li].cpu().numpy(), ref[f"{pre}{k}.bias"]) < tol, f"db{li}"
+    lns = sorted({int(k.split(".")[1]) for k in ref if k.startswith(pre) and k.endswith("weight") and ref[k].ndim == 1})
+    for li, k in enumerate(lns):
+        assert rel_err(grads["gammas"][li].cpu().numpy(), ref[f"{pre}{k}.weight"]) < tol, f"dgamma{li}"
+        assert rel_err(grads["betas"][li].cpu().numpy(), ref[f"{pre}{k}.bias"]) < tol, f"dbeta{li}"
+    if m.delta is not None:
+        dbeta = np.concatenate([grads["head_b"].cpu().numpy()[:, None], grads["head_w"].cpu().numpy()], axis=1)
+        ddelta = np.cumsum(dbeta[::-1], axis=0)[::-1]
+        for j in range(len(m.delta)):
+            assert rel_err(ddelta[j], ref[f"delta_params.{j}"]) < tol
+    else:
+        assert rel_err(grads["head_w"].cpu().numpy(), ref[f"{pre}{lin[-1]}.weight"]) < tol
+        assert rel_err(grads["head_b"].cpu().numpy(), ref[f"{pre}{lin[-1]}.bias"]) < tol
+    if learn:
+        assert rel_err(grads["centers"].cpu().numpy(), ref["spatial_basis.centers"]) < tol
+        assert rel_err(grads["log_bandwidths"].cpu().numpy(), ref["spatial_basis.log_bandwidths"]) < tol
+
+
+def _default_oracle_model(seed, q=1, fn="wendland", hidden=(256, 256, 128)):
+    kn = golden("knots")
+    rng = np.random.default_rng(seed)
+    dims = [kn["centers"].shape[0] + kn["t_centers"].shape[0], *hidden]
+    ws, bs, gs, be = [], [], [], []
+    for i in range(len(hidden)):
+        bound = 1 / np.sqrt(dims[i])
+        ws.append(rng.uniform(-bound, bound, (dims[i + 1], dims[i])).astype(np.float32))
+        bs.append(rng.uniform(-bound, bound, dims[i + 1]).astype(np.float32))
+        gs.append((1 + 0.1 * rng.standard_normal(dims[i + 1])).astype(np.float32))
+        be.append((0.1 * rng.standard_normal(dims[i + 1])).astype(np.float32))
+    bound = 1 / np.sqrt(dims[-1])
+    ws.append(rng.uniform(-bound, bound, (q, dims[-1])).astype(np.float32))
+    bs.append(rng.uniform(-bound, bound, q).astype(np.float32))
+    return orc.OracleModel(centers=kn["centers"], bandwidths=kn["bandwidths"], t_centers=kn["t_centers"],
+                           t_bandwidths=kn["t_bandwidths"], weights=ws, biases=bs, ln_gamma=gs, ln_beta=be,
+                           basis_fn=fn)
+
+
+@pytest.mark.parametrize("q,loss,taus,p", [(1, "mse", None, 0.0), (5, "pinball", [0.05, 0.25, 0.5, 0.75, 0.95], 0.1)])
+def test_default_size_network_with_dropout_vs_oracle(q, loss, taus, p):
+    """Default architecture 297-256-256-128-Q, ragged batch, dropout masks drawn in-kernel (Philox keyed on the
+    global row) and replayed by the oracle: outputs, loss and all gradients."""
+    L, ops, Executor, NetSpec, LossSpec = _mods()
+    m = _default_oracle_model(42 + q, q=q)
+    m.dropout = p
+    n, row0 = 1000, 0
+    rng = np.random.default_rng(9)
+    coords = rng.random((n, 2)).astype(np.float32)
+    t = (rng.integers(0, 100, (n, 1)) / 99.0).astype(np.float32)
+    y = rng.standard_normal(n).astype(np.float32)
+    seed, step = 0x1234567890ABCDEF, 17
+    masks = [orc.dropout_keep_mask(n, w.shape[0], p, seed, step, l, row0) for l, w in enumerate(m.weights[:-1])]
+    yref, cache = orc.forward(m, None, coords, t, train=True, keep_masks=masks, return_cache=True)
+    lref, dy = orc.loss_and_grad(yref, y, loss, taus)
+    gref = orc.backward(m, cache, dy)
+    spec = spec_from_oracle(m, dropout=p)
+    ex = Executor(spec)
+    ex.loss_acc.zero_()
+    pts = ops.make_points(T(coords), T(t))
+    yhat = ex.forward(pts, train=True, step=step, seed=seed, y=T(y), loss=LossSpec(loss, taus or ()),
+                      inv_count=1.0 / (n * q), save=True)
+    grads = ex.backward()
+    torch.cuda.synchronize()
+    assert rel_err(yhat.cpu().numpy(), yref) < 1e-3
+    assert abs(ex.loss_acc.item() - lref) < 1e-3 * abs(lref)
+    for l in range(3):
+        assert rel_err(grads["weights"][l].cpu().numpy(), gref["weights"][l]) < 5e-3, f"dW{l}"
+        assert rel_err(grads["biases"][l].cpu().numpy(), gref["biases"][l]) < 5e-3
+        assert rel_err(grads["gammas"][l].cpu().numpy(), gref["ln_gamma"][l]) < 5e-3
+        assert rel_err(grads["betas"][l].cpu().numpy(), gref["ln_beta"][l]) < 5e-3
+    assert rel_err(grads["head_w"].cpu().numpy(), gref["weights"][3]) < 5e-3
+    assert rel_err(grads["head_b"].cpu().numpy(), gref["biases"][3]) < 5e-3
+    # eval mode: no dropout
+    ye = ex.forward(pts, train=False).cpu().numpy()
+    assert rel_err(ye, orc.forward(m, None, coords, t)) < 1e-3
+
+
+def test_prediction_sharding_and_grid_bit_exact():
+    """Point-sharded dense-grid prediction: contiguous block partition, outputs of the shards concatenated
+    are bit-identical to the single-shard run (no cross-row op), and grid == explicit arrays."""
+    L, ops, Executor, NetSpec, LossSpec = _mods()
+    m = _default_oracle_model(7, q=5)
+    ex = Executor(spec_from_oracle(m))
+    nx, ny, nt = 50, 40, 3
+    n = nx * ny * nt
+    full = ex.forward(ops.make_points(grid=(nx, ny, nt)), train=False).clone()
+    for world in (2, 3, 8):
+        parts = []
+        for r in range(world):
+            b, e = orc.shard_range(n, r, world)
+            parts.append(ex.forward(ops.make_points(grid=(nx, ny, nt), row_begin=b, n_rows=e - b), train=False).clone())
+        assert torch.equal(torch.cat(parts), full)
+    coords, t = orc.grid_points(nx, ny, nt, 0, n)
+    arr = ex.forward(ops.make_points(T(coords), T(t)), train=False)
+    assert torch.equal(arr, full)
+    assert rel_err(full.cpu().numpy(), orc.forward(m, None, coords, t)) < 1e-3
+
+
+def test_adamw_ema_and_sqnorm_vs_oracle():
+    L, ops, *_ = _mods()
+    rng = np.random.default_rng(1)
+    n = 100_003
+    ends = [60_000, n]
+    p0 = rng.standard_normal(n).astype(np.float32)
+    p, m, v, sh = T(p0), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV), T(p0)
+    pn, mn, vn, shn = p0.astype(np.float64), np.zeros(n), np.zeros(n), p0.astype(np.float64)
+    hyper = T([[2e-2, 5e-4, 10.0, 0], [1e-3, 5e-4, 1.0, 0]])
+    sq = torch.zeros(2, device=DEV)
+    stepc = torch.zeros(1, dtype=torch.int32, device=DEV)
+    for step in range(1, 5):
+        gnp = (rng.standard_normal(n) * (3.0 if step == 2 else 0.01)).astype(np.float32)
+        g = T(gnp)
+        ops.grad_sqnorm(g, ends, sq)
+        ops.adamw_ema_step(p, g, m, v, sh, ends, hyper, sq, stepc, ema_decay=0.95)
+        lo = 0
+        for gi, hi in enumerate(ends):
+            norm, coef = orc.clip_coef([gnp[lo:hi]], float(hyper[gi, 2]))
+            assert abs(np.sqrt(sq[gi].item()) - norm) < 1e-4 * norm
+            orc.adamw_ema_step(pn[lo:hi], gnp[lo:hi].astype(np.float64), mn[lo:hi], vn[lo:hi], shn[lo:hi], step,
+                               float(hyper[gi, 0]), float(hyper[gi, 1]), 0.95, clip=coef)
+            lo = hi
+    assert stepc.item() == 4
+    np.testing.assert_allclose(p.cpu().numpy(), pn, rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(sh.cpu().numpy(), shn, rtol=2e-5, atol=2e-6)
+
+
+def test_errors_are_loud():
+    L, ops, *_ = _mods()
+    with pytest.raises(RuntimeError):
+        ops.pack_image(torch.zeros(4, 4))          # CPU tensor: no CPU path
+    a = L.FwdArgs()
+    with pytest.raises(RuntimeError, match="libstdadk"):
+        ops.layer_fwd(a)                            # NULL weights
