@@ -51,6 +51,9 @@ typedef struct {
     const float* coords;
     const float* t;
     const float* xcov;
+    const int64_t* index;   /* optional gather: row r reads sample index[row_begin + r] of the arrays (and of y):
+                               a mini-batch is a slice of a device-resident permutation, no collate copy
+                               (replaces train_st_interp.py:453-460) */
     int32_t grid_nx, grid_ny, grid_nt, _pad;
     int64_t row_begin;
     int64_t n_rows;
@@ -68,9 +71,10 @@ typedef struct {
 } stdadk_layer;
 
 typedef struct {
-    float p;             /* 0 => off (eval mode) */
-    uint32_t step;
+    float p;                  /* 0 => off (eval mode) */
+    uint32_t step;            /* stream position; masks are keyed by (seed, step, layer, row_begin + r, column) */
     uint64_t seed;
+    const int32_t* step_ptr;  /* if non-NULL the step is read from this DEVICE counter (graph replay) */
 } stdadk_dropout;
 
 /* Output head + loss (st_interp.py:689 / :849-877 through an effective (Q x d) matrix;

@@ -252,14 +252,23 @@ def features(m: OracleModel, X, coords, t, dtype=np.float64):
     return np.concatenate(parts, axis=1)
 
 
+def _ident(x):
+    return x
+
+
 def forward(m: OracleModel, X, coords, t, dtype=np.float64, train: bool = False,
-            keep_masks: Optional[List[np.ndarray]] = None, return_cache: bool = False):
-    """y_hat (N, Q) (st_interp.py:827-882).  `keep_masks[l]` is the dropout keep mask of hidden layer l."""
-    h = features(m, X, coords, t, dtype)
-    cache = {"feat": h, "layers": []}
+            keep_masks: Optional[List[np.ndarray]] = None, return_cache: bool = False, rnd=None):
+    """y_hat (N, Q) (st_interp.py:827-882).  `keep_masks[l]` is the dropout keep mask of hidden layer l.
+
+    `rnd` (e.g. tf32_round) emulates the kernels' operand rounding: it is applied to every matrix that
+    enters a tensor-core product (features, hidden activations, weights) while sums stay in `dtype`;
+    with rnd=None this is the reference's exact arithmetic."""
+    rnd_ = (lambda a: rnd(np.asarray(a, dtype=np.float32)).astype(dtype)) if rnd is not None else _ident
+    h = rnd_(features(m, X, coords, t, dtype))
+    cache = {"feat": h, "layers": [], "rnd": rnd_}
     n_hidden = len(m.weights) - (0 if m.delta is not None else 1)
     for l in range(n_hidden):
-        W, b = m.weights[l].astype(dtype), m.biases[l].astype(dtype)
+        W, b = rnd_(m.weights[l].astype(dtype)), m.biases[l].astype(dtype)
         z = h @ W.T + b
         rec = {"h_in": h, "z": z}
         if m.ln_gamma[l] is not None:
@@ -277,11 +286,12 @@ def forward(m: OracleModel, X, coords, t, dtype=np.float64, train: bool = False,
             keep = keep_masks[l]
             a = np.where(keep, a / dtype(1.0 - m.dropout), 0.0)
             rec["keep"] = keep
-        h = a.astype(dtype)
+        a = a.astype(dtype)
+        h = rnd_(a)               # what the next block's tensor-core product consumes
         cache["layers"].append(rec)
     Wh, bh = m.head(dtype)
-    y_hat = h @ Wh.T + bh
-    cache["h_last"] = h
+    y_hat = a @ Wh.T + bh        # the head is evaluated on the unrounded FP32 activation
+    cache["h_last"] = a
     return (y_hat, cache) if return_cache else y_hat
 
 
@@ -328,6 +338,7 @@ def backward(m: OracleModel, cache, d_yhat, coords=None, want_knot_grads: bool =
     SURVEY.md section 9.1 (phi'(r), dr/dc = -(s-c)/(d theta'), dr/dlog(theta) = -r).
     """
     dtype = d_yhat.dtype.type
+    rnd_ = cache.get("rnd", _ident)
     n_hidden = len(cache["layers"])
     Wh, bh = m.head(dtype)
     h = cache["h_last"]
@@ -355,9 +366,10 @@ def backward(m: OracleModel, cache, d_yhat, coords=None, want_knot_grads: bool =
             dz = rstd * (gy - gy.mean(axis=1, keepdims=True) - xh * (gy * xh).mean(axis=1, keepdims=True))
         else:
             dz = dy
-        g["weights"][l] = dz.T @ rec["h_in"]
+        dz_r = rnd_(dz)
+        g["weights"][l] = dz_r.T @ rec["h_in"]
         g["biases"][l] = dz.sum(axis=0)
-        dh = dz @ m.weights[l].astype(dtype)
+        dh = dz_r @ rnd_(m.weights[l].astype(dtype))
     if want_knot_grads:
         coords = np.asarray(coords, dtype=dtype)
         G = dh[:, m.p:m.p + m.centers.shape[0]]                   # dL/dphi (N, K_s)

@@ -23,7 +23,7 @@ class Basis(C.Structure):
 
 
 class Points(C.Structure):
-    _fields_ = [("coords", fp), ("t", fp), ("xcov", fp), ("grid_nx", C.c_int32), ("grid_ny", C.c_int32),
+    _fields_ = [("coords", fp), ("t", fp), ("xcov", fp), ("index", fp), ("grid_nx", C.c_int32), ("grid_ny", C.c_int32),
                 ("grid_nt", C.c_int32), ("_pad", C.c_int32), ("row_begin", C.c_int64), ("n_rows", C.c_int64)]
 
 
@@ -33,7 +33,7 @@ class Layer(C.Structure):
 
 
 class Dropout(C.Structure):
-    _fields_ = [("p", C.c_float), ("step", C.c_uint32), ("seed", C.c_uint64)]
+    _fields_ = [("p", C.c_float), ("step", C.c_uint32), ("seed", C.c_uint64), ("step_ptr", fp)]
 
 
 class Head(C.Structure):

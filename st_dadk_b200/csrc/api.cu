@@ -80,6 +80,7 @@ static PointsP to_points(const stdadk_points& p) {
     P.coords = p.coords;
     P.t = p.t;
     P.xcov = p.xcov;
+    P.index = reinterpret_cast<const long long*>(p.index);
     P.nx = p.grid_nx;
     P.ny = p.grid_ny;
     P.nt = p.grid_nt;
@@ -100,6 +101,7 @@ static LayerP to_layer(const stdadk_layer& l, const stdadk_dropout& d) {
     L.drop_p = d.p;
     L.step = d.step;
     L.seed = d.seed;
+    L.step_ptr = d.step_ptr;
     return L;
 }
 static HeadP to_head(const stdadk_head* h) {

@@ -26,6 +26,7 @@ struct PointsP {
     const float* coords;
     const float* t;
     const float* xcov;
+    const long long* index;
     int nx, ny, nt, _pad;
     long long row_begin;
     long long n_rows;
@@ -50,7 +51,13 @@ struct LayerP {
     float eps, drop_p;
     unsigned int step, _pad2;
     unsigned long long seed;
+    const int* step_ptr;
 };
+__device__ __forceinline__ unsigned int dropout_step(const LayerP& L) {
+    return L.step_ptr ? (unsigned int)(*L.step_ptr) : L.step;
+}
+// sample index of global row g (identity unless a gather index is given)
+__device__ __forceinline__ long long sample_of(const PointsP& P, long long g) { return P.index ? P.index[g] : g; }
 
 // ---------------------------------------------------------------- basis evaluation
 // Spatial basis value from the coordinate difference; the support predicate d2 < th2 is evaluated
@@ -96,10 +103,11 @@ __device__ __forceinline__ void load_point(const PointsP& P, long long g, float&
         y = P.ny > 1 ? __fdiv_rn((float)j, (float)(P.ny - 1)) : 0.0f;
         t = P.nt > 1 ? __fdiv_rn((float)k, (float)(P.nt - 1)) : 0.0f;
     } else {
-        float2 c = *reinterpret_cast<const float2*>(P.coords + 2 * g);
+        long long sidx = sample_of(P, g);
+        float2 c = *reinterpret_cast<const float2*>(P.coords + 2 * sidx);
         x = c.x;
         y = c.y;
-        t = P.t[g];
+        t = P.t[sidx];
     }
 }
 

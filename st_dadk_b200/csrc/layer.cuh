@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(NTHREADS) layer_fwd_kernel(const __grid_consta
             const float* xrow = nullptr;
             if (rvalid) {
                 load_point(P.pts, grow, x, y, t);
-                if (P.basis.p_cov > 0 && P.pts.xcov) xrow = P.pts.xcov + grow * P.basis.p_cov;
+                if (P.basis.p_cov > 0 && P.pts.xcov) xrow = P.pts.xcov + sample_of(P.pts, grow) * P.basis.p_cov;
             }
             for (int s = 0; s < P.k_slabs; ++s) {
                 int stage = s % NSTAGE, it = s / NSTAGE;
@@ -307,6 +307,7 @@ __global__ void __launch_bounds__(NTHREADS) layer_fwd_kernel(const __grid_consta
 #pragma unroll
         for (int k = 0; k < STDADK_MAX_Q; ++k) yh[k] = 0.0f;
         const bool drop = P.L.drop_p > 0.0f;
+        const unsigned int drop_step = drop ? dropout_step(P.L) : 0u;
         for (int c0 = 0; c0 < n_pad; c0 += 32) {
             tmem_ld32(trow + c0, v);
             uint32_t keep = 0xFFFFFFFFu;
@@ -314,7 +315,7 @@ __global__ void __launch_bounds__(NTHREADS) layer_fwd_kernel(const __grid_consta
                 keep = 0;
 #pragma unroll
                 for (int b = 0; b < 4; ++b)
-                    keep |= dropout_keep8(P.L.seed, P.L.step, (uint32_t)P.L.layer_id, (unsigned long long)grow,
+                    keep |= dropout_keep8(P.L.seed, drop_step, (uint32_t)P.L.layer_id, (unsigned long long)grow,
                                           (uint32_t)(c0 / 8 + b), P.thresh16)
                             << (8 * b);
             }
@@ -360,7 +361,7 @@ __global__ void __launch_bounds__(NTHREADS) layer_fwd_kernel(const __grid_consta
                         P.head.yhat[lrow * P.head.q + k] = yh[k];
                     }
                 if (P.head.loss_type != STDADK_LOSS_NONE) {
-                    loss = row_loss(P.head, yh, P.head.y[grow], dy);
+                    loss = row_loss(P.head, yh, P.head.y[sample_of(P.pts, grow)], dy);
                     if (P.head.dyhat) {
 #pragma unroll
                         for (int k = 0; k < STDADK_MAX_Q; ++k)
@@ -489,7 +490,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) layer_bwd_kernel(const __grid_con
             const float* xrow = nullptr;
             if (rvalid) {
                 load_point(P.pts, grow, x, y, t);
-                if (P.basis.p_cov > 0 && P.pts.xcov) xrow = P.pts.xcov + grow * P.basis.p_cov;
+                if (P.basis.p_cov > 0 && P.pts.xcov) xrow = P.pts.xcov + sample_of(P.pts, grow) * P.basis.p_cov;
             }
             for (int s = 0; s < total_slabs; ++s) {
                 int stage = s % NSTAGE, it = s / NSTAGE;
@@ -515,6 +516,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) layer_bwd_kernel(const __grid_con
         for (int k = 0; k < STDADK_MAX_Q; ++k)
             dyh[k] = (P.has_head && rvalid && k < q) ? P.head.dyhat[lrow * q + k] : 0.0f;
         const bool drop = P.L.drop_p > 0.0f;
+        const unsigned int drop_step = drop ? dropout_step(P.L) : 0u;
         const float inv_n = 1.0f / (float)n_out;
         uint32_t actbits[MAX_N / 32];
         float Sa = 0.0f, Sb = 0.0f;
@@ -529,7 +531,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) layer_bwd_kernel(const __grid_con
                 keep = 0;
 #pragma unroll
                 for (int b = 0; b < 4; ++b)
-                    keep |= dropout_keep8(P.L.seed, P.L.step, (uint32_t)P.L.layer_id, (unsigned long long)grow,
+                    keep |= dropout_keep8(P.L.seed, drop_step, (uint32_t)P.L.layer_id, (unsigned long long)grow,
                                           (uint32_t)(c0 / 8 + b), P.thresh16)
                             << (8 * b);
             }
@@ -653,6 +655,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) layer_bwd_kernel(const __grid_con
 
 // =============================================================================================
 // Weight gradient: dW[o, i] += sum_rows dz[row, o] * A[row, i]
+//
+// The reduction runs over rows, so both operands are MN-major (the contiguous 128 bytes of an image
+// row are 32 values of the M / N dimension).  For 32-bit (TF32) MN-major operands tcgen05 accepts a
+// single shared-memory form, SWIZZLE_128B_BASE32B (32-byte units XOR-ed with row & 3, atoms of 4 rows
+// x 128 B), which differs from the 16-byte-unit swizzle of the K-major images; the workers therefore
+// restage each 64-row half tile HBM -> registers -> SMEM (coalesced 16-byte loads, conflict-free
+// stores) and, for block 1, regenerate the basis straight into that form.
 // =============================================================================================
 struct WgradK {
     BasisP basis;
@@ -671,6 +680,41 @@ constexpr int WG_STAGE_BYTES = WG_A_BYTES + WG_B_BYTES;
 
 __host__ __device__ inline uint32_t wgrad_smem_bytes(int k_s, int k_t) {
     return NSTAGE * WG_STAGE_BYTES + 64 + 16 + 16 + (uint32_t)k_s * 16u + (uint32_t)k_t * 8u + 16 + 1024;
+}
+// byte offset of logical 16-byte chunk `c16` of row `row` in the SWIZZLE_128B_BASE32B form
+__device__ __forceinline__ uint32_t swz32_off(uint32_t row, uint32_t c16) {
+    return row * 128u + ((((c16 >> 1) ^ (row & 3u)) << 5) | ((c16 & 1u) << 4));
+}
+__device__ __forceinline__ uint64_t umma_desc_sw128_32b(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (1ull << 61);
+}
+// Restage `n_chunks` half-slabs (64 rows x 128 B each, image swizzle) into the MN-major SMEM form.
+__device__ __forceinline__ void restage_half_slabs(const float* img_tile, int slab0, int n_chunks, int half,
+                                                   uint32_t sdst, int tid) {
+    const int units = n_chunks * 512;  // 16-byte units
+    for (int u0 = tid; u0 < units; u0 += NWORK * 4) {
+        float4 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int u = u0 + j * NWORK;
+            if (u < units) {
+                int c = u >> 9, w = u & 511;
+                v[j] = __ldg(reinterpret_cast<const float4*>(img_tile + (size_t)(slab0 + c) * SLAB_FLOATS +
+                                                             half * WG_HALF_ROWS * SLAB_K) + w);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int u = u0 + j * NWORK;
+            if (u < units) {
+                int c = u >> 9, w = u & 511;
+                uint32_t r = (uint32_t)(w >> 3), pc = (uint32_t)(w & 7);
+                uint32_t lc = pc ^ (r & 7u);
+                st_shared_v4(sdst + c * WG_CHUNK_BYTES + swz32_off(r, lc), v[j].x, v[j].y, v[j].z, v[j].w);
+            }
+        }
+    }
 }
 
 template <bool BASIS>
@@ -696,7 +740,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_kernel(const __grid_constan
 
     if (tid == NWORK) {
         for (int s = 0; s < NSTAGE; ++s) {
-            mbar_init(&full[s], BASIS ? 1 + NWORK : 1);
+            mbar_init(&full[s], NWORK);
             mbar_init(&empty[s], 1);
         }
         mbar_init(accf, 1);
@@ -725,32 +769,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_kernel(const __grid_constan
     const uint32_t tmem_base = *tmem_slot;
 
     if (n_iter > 0) {
-        if (warp == 4) {
-            if (lane == 0) {
-                int itn = 0;
-                for (int rt = split; rt < P.n_row_tiles; rt += n_split)
-                    for (int half = 0; half < 2; ++half, ++itn) {
-                        int stage = itn % NSTAGE, it = itn / NSTAGE;
-                        if (it > 0) mbar_wait(&empty[stage], (it - 1) & 1);
-                        uint8_t* sa = stage_base + stage * WG_STAGE_BYTES;
-                        uint8_t* sb = sa + WG_A_BYTES;
-                        uint32_t bytes = (uint32_t)(m_chunks + (BASIS ? 0 : n_chunks)) * WG_CHUNK_BYTES;
-                        mbar_arrive_expect_tx(&full[stage], bytes);
-                        for (int c = 0; c < m_chunks; ++c)
-                            bulk_g2s(sa + c * WG_CHUNK_BYTES,
-                                     P.dz_img + ((size_t)rt * P.dz_slabs + mi * 4 + c) * SLAB_FLOATS +
-                                         half * WG_HALF_ROWS * SLAB_K,
-                                     WG_CHUNK_BYTES, &full[stage]);
-                        if (!BASIS)
-                            for (int c = 0; c < n_chunks; ++c)
-                                bulk_g2s(sb + c * WG_CHUNK_BYTES,
-                                         P.a_img + ((size_t)rt * P.a_slabs + ni * P.nt_slabs + c) * SLAB_FLOATS +
-                                             half * WG_HALF_ROWS * SLAB_K,
-                                         WG_CHUNK_BYTES, &full[stage]);
-                    }
-            }
-            __syncwarp();
-        } else if (warp == 5) {
+        if (warp == 5) {
             if (lane == 0) {
                 const uint32_t idesc = umma_idesc_tf32((uint32_t)n_mma, 1, 1);
                 for (int itn = 0; itn < n_iter; ++itn) {
@@ -761,8 +780,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_kernel(const __grid_constan
                     uint32_t sb = sa + WG_A_BYTES;
 #pragma unroll
                     for (int k8 = 0; k8 < WG_HALF_ROWS / 8; ++k8) {
-                        uint64_t ad = umma_desc_sw128(sa + k8 * 1024, WG_CHUNK_BYTES, 1024);
-                        uint64_t bd = umma_desc_sw128(sb + k8 * 1024, WG_CHUNK_BYTES, 1024);
+                        uint64_t ad = umma_desc_sw128_32b(sa + k8 * 1024, WG_CHUNK_BYTES, 512);
+                        uint64_t bd = umma_desc_sw128_32b(sb + k8 * 1024, WG_CHUNK_BYTES, 512);
                         umma_tf32(tmem_base, ad, bd, idesc, (itn == 0 && k8 == 0) ? 0u : 1u);
                     }
                     umma_commit(&empty[stage]);
@@ -770,30 +789,47 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_kernel(const __grid_constan
                 umma_commit(accf);
             }
             __syncwarp();
-        } else {
-            if (BASIS) {
-                const int row64 = tid & 63, par = tid >> 6;
-                int itn = 0;
-                for (int rt = split; rt < P.n_row_tiles; rt += n_split)
-                    for (int half = 0; half < 2; ++half, ++itn) {
-                        int stage = itn % NSTAGE, it = itn / NSTAGE;
+        } else if (warp < 4) {
+            const int row64 = tid & 63, par = tid >> 6;
+            int itn = 0;
+            for (int rt = split; rt < P.n_row_tiles; rt += n_split)
+                for (int half = 0; half < 2; ++half, ++itn) {
+                    int stage = itn % NSTAGE, it = itn / NSTAGE;
+                    float x = 0.f, y = 0.f, t = 0.f;
+                    const float* xrow = nullptr;
+                    if (BASIS) {
                         long long lrow = (long long)rt * TILE_M + half * WG_HALF_ROWS + row64;
-                        float x = 0.f, y = 0.f, t = 0.f;
-                        const float* xrow = nullptr;
                         if (lrow < P.pts.n_rows) {
                             long long grow = P.pts.row_begin + lrow;
                             load_point(P.pts, grow, x, y, t);
-                            if (P.basis.p_cov > 0 && P.pts.xcov) xrow = P.pts.xcov + grow * P.basis.p_cov;
+                            if (P.basis.p_cov > 0 && P.pts.xcov) xrow = P.pts.xcov + sample_of(P.pts, grow) * P.basis.p_cov;
                         }
-                        if (it > 0) mbar_wait(&empty[stage], (it - 1) & 1);
-                        uint32_t sb = smem_u32(stage_base + stage * WG_STAGE_BYTES + WG_A_BYTES);
-                        for (int c = par; c < n_chunks; c += 2)
-                            gen_basis_slab(P.basis, sk, st, ni * P.nt_slabs + c, x, y, t, xrow,
-                                           sb + c * WG_CHUNK_BYTES, (uint32_t)row64);
-                        fence_proxy_async_smem();
-                        mbar_arrive(&full[stage]);
                     }
-            }
+                    if (it > 0) mbar_wait(&empty[stage], (it - 1) & 1);
+                    uint32_t sa = smem_u32(stage_base + stage * WG_STAGE_BYTES);
+                    uint32_t sb = sa + WG_A_BYTES;
+                    restage_half_slabs(P.dz_img + (size_t)rt * P.dz_slabs * SLAB_FLOATS, mi * 4, m_chunks, half, sa, tid);
+                    if (BASIS) {
+                        for (int c = par; c < n_chunks; c += 2) {
+                            const int slab = ni * P.nt_slabs + c;
+#pragma unroll 1
+                            for (int c16 = 0; c16 < 8; ++c16) {
+                                int f = slab * SLAB_K + c16 * 4;
+                                float v0 = to_tf32(feature_value(P.basis, sk, st, f + 0, x, y, t, xrow));
+                                float v1 = to_tf32(feature_value(P.basis, sk, st, f + 1, x, y, t, xrow));
+                                float v2 = to_tf32(feature_value(P.basis, sk, st, f + 2, x, y, t, xrow));
+                                float v3 = to_tf32(feature_value(P.basis, sk, st, f + 3, x, y, t, xrow));
+                                st_shared_v4(sb + c * WG_CHUNK_BYTES + swz32_off((uint32_t)row64, (uint32_t)c16), v0, v1,
+                                             v2, v3);
+                            }
+                        }
+                    } else {
+                        restage_half_slabs(P.a_img + (size_t)rt * P.a_slabs * SLAB_FLOATS, ni * P.nt_slabs, n_chunks,
+                                           half, sb, tid);
+                    }
+                    fence_proxy_async_smem();
+                    mbar_arrive(&full[stage]);
+                }
             mbar_wait(accf, 0);
             tc_fence_after();
             const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);

@@ -1,0 +1,129 @@
+"""One-off host-side knot placement for the spatial / temporal bases.
+
+These run once per model on the CPU (they call scikit-learn / scipy exactly as upstream does, with the
+same hyper-parameters and the same numpy global-RNG draws, so a seeded run places the same knots) and
+are not part of the accelerated path.  Upstream: stnf/models/st_interp.py:152-431 and :557-581.
+"""
+from __future__ import annotations
+
+import math
+from typing import Sequence, Tuple
+
+import numpy as np
+import torch
+
+BANDWIDTH_SPACINGS = 2.5          # support radius in units of grid spacing / neighbour distance
+GMM_SIGMA_TO_BANDWIDTH = 4.23 * 2.5
+SUBSAMPLE_CAP = 10000
+
+
+def _lattice_side(k: int) -> int:
+    side = int(math.sqrt(k))
+    assert side * side == k, f"n_centers must be perfect squares, got {k}"
+    return side
+
+
+def _lattice_bandwidth(side: int) -> float:
+    return BANDWIDTH_SPACINGS * (1.0 / (side - 1) if side > 1 else 1.0)
+
+
+def uniform_lattice(n_centers: Sequence[int]) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Regular side x side lattices on [0,1]^2, x-major (knot j -> (j // side, j % side)) (st_interp.py:152-185).
+    Built with the same torch.linspace / meshgrid('ij') calls as upstream so the FP32 coordinates are identical."""
+    cs, bs = [], []
+    for k in n_centers:
+        side = _lattice_side(k)
+        axis = torch.linspace(0, 1, side)
+        gx, gy = torch.meshgrid(axis, axis, indexing="ij")
+        cs.append(torch.stack([gx.reshape(-1), gy.reshape(-1)], dim=-1))
+        bs.append(torch.full((k,), _lattice_bandwidth(side)))
+    return torch.cat(cs, dim=0), torch.cat(bs, dim=0)
+
+
+def temporal_knots(n_centers: Sequence[int]) -> Tuple[torch.Tensor, torch.Tensor]:
+    """linspace(0,1,n) per level with bandwidth 2.5/(n-1) (st_interp.py:557-581)."""
+    cs = [torch.linspace(0.0, 1.0, n) for n in n_centers]
+    bs = [torch.full((n,), BANDWIDTH_SPACINGS * (1.0 / (n - 1) if n > 1 else 1.0)) for n in n_centers]
+    return torch.cat(cs), torch.cat(bs)
+
+
+def _maybe_subsample(coords: np.ndarray, label: str) -> np.ndarray:
+    if len(coords) > SUBSAMPLE_CAP:
+        print(f"  {label}: Subsampling {SUBSAMPLE_CAP}/{len(coords)} training samples")
+        pick = np.random.choice(len(coords), SUBSAMPLE_CAP, replace=False)
+        return coords[pick]
+    print(f"  {label}: {len(coords)} training samples (with temporal duplicates)")
+    return coords
+
+
+def gmm_knots(n_centers: Sequence[int], train_coords: np.ndarray):
+    """Spherical Gaussian mixture per level: means -> centres, 4.23*2.5*sigma -> bandwidth, floored at a
+    quarter of the same level's lattice bandwidth (st_interp.py:187-266)."""
+    from sklearn.mixture import GaussianMixture
+    sub = _maybe_subsample(train_coords, "GMM initialization").astype(np.float64)
+    cs, bs = [], []
+    for k in n_centers:
+        floor = 0.25 * _lattice_bandwidth(int(math.sqrt(k)))
+        gm = GaussianMixture(n_components=k, covariance_type="spherical", random_state=42, max_iter=100, n_init=3,
+                             init_params="k-means++", reg_covar=1e-6, tol=1e-3, verbose=0).fit(sub)
+        bw = np.clip(GMM_SIGMA_TO_BANDWIDTH * np.sqrt(gm.covariances_), floor, float("inf"))
+        cs.append(torch.from_numpy(gm.means_).float())
+        bs.append(torch.from_numpy(bw).float())
+    return torch.cat(cs, dim=0), torch.cat(bs, dim=0)
+
+
+def _neighbour_bandwidth(centers: np.ndarray, fallback_side_of: int) -> np.ndarray:
+    """2.5 x mean distance to the (up to) four nearest other centres."""
+    from scipy.spatial.distance import cdist
+    k = len(centers)
+    if k == 1:
+        return np.array([_lattice_bandwidth(int(math.sqrt(fallback_side_of)))])
+    d = cdist(centers, centers)
+    np.fill_diagonal(d, np.inf)
+    nearest = np.sort(d, axis=1)[:, :min(4, k - 1)]
+    return BANDWIDTH_SPACINGS * nearest.mean(axis=1)
+
+
+def random_site_knots(n_centers: Sequence[int], train_coords: np.ndarray):
+    """k observation sites drawn at random (with temporal duplicates, so dense regions get more knots)
+    (st_interp.py:268-338)."""
+    print(f"  Random site initialization: {len(train_coords)} training samples (with temporal duplicates)")
+    cs, bs = [], []
+    for k in n_centers:
+        replace = k > len(train_coords)
+        if replace:
+            print(f"  Warning: k={k} exceeds training samples ({len(train_coords)}), sampling with replacement")
+        pick = np.random.choice(len(train_coords), k, replace=replace)
+        c = train_coords[pick]
+        cs.append(torch.from_numpy(c).float())
+        bs.append(torch.from_numpy(_neighbour_bandwidth(c, n_centers[0])).float())
+    return torch.cat(cs, dim=0), torch.cat(bs, dim=0)
+
+
+def kmeans_balanced_knots(n_centers: Sequence[int], train_coords: np.ndarray):
+    """Size-constrained k-means (equal-population clusters) (st_interp.py:340-431).  Needs the optional
+    `k_means_constrained` package, exactly as upstream."""
+    try:
+        from k_means_constrained import KMeansConstrained
+    except ImportError as e:  # same failure mode as upstream's import inside the method
+        raise ImportError("spatial_init_method='kmeans_balanced' needs the k_means_constrained package") from e
+    sub = _maybe_subsample(train_coords, "Balanced K-means initialization")
+    cs, bs = [], []
+    for k in n_centers:
+        per = len(sub) // k
+        km = KMeansConstrained(n_clusters=k, size_min=max(1, per - 1), size_max=per + (len(sub) % k), random_state=42,
+                               n_init=3, max_iter=100).fit(sub)
+        c = km.cluster_centers_
+        cs.append(torch.from_numpy(c).float())
+        bs.append(torch.from_numpy(_neighbour_bandwidth(c, n_centers[0])).float())
+    return torch.cat(cs, dim=0), torch.cat(bs, dim=0)
+
+
+def place_knots(method: str, n_centers: Sequence[int], train_coords=None):
+    if method == "uniform":
+        return uniform_lattice(n_centers)
+    if method not in ("gmm", "random_site", "kmeans_balanced"):
+        raise ValueError(f"Unknown init_method: {method}")
+    assert train_coords is not None, f"train_coords required for {method} initialization"
+    fn = {"gmm": gmm_knots, "random_site": random_site_knots, "kmeans_balanced": kmeans_balanced_knots}[method]
+    return fn(n_centers, np.asarray(train_coords))

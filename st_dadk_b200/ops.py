@@ -87,19 +87,37 @@ def make_basis(knots4: torch.Tensor, tknots2: torch.Tensor, k_s: int, k_t: int, 
     return L.Basis(_ptr(knots4), _ptr(tknots2), k_s, k_t, p_cov, L.BASIS_CODE[basis_fn])
 
 
+class PointsRef(L.Points):
+    """stdadk_points plus references that keep the addressed tensors alive as long as the struct is."""
+    _keep = None
+
+
 def make_points(coords: Optional[torch.Tensor] = None, t: Optional[torch.Tensor] = None,
                 xcov: Optional[torch.Tensor] = None, grid: Optional[Sequence[int]] = None, row_begin: int = 0,
-                n_rows: Optional[int] = None) -> L.Points:
-    """Array point source (coords (N,2), t (N,1|N)) or the dense grid (nx, ny, nt)."""
+                n_rows: Optional[int] = None, index: Optional[torch.Tensor] = None) -> L.Points:
+    """Array point source (coords (N,2), t (N,1|N)), optionally gathered through `index` (int64 sample ids;
+    rows are positions in `index`), or the dense grid (nx, ny, nt)."""
     if grid is not None:
         nx, ny, nt = grid
         if n_rows is None:
             n_rows = nx * ny * nt - row_begin
-        return L.Points(None, None, None, nx, ny, nt, 0, row_begin, n_rows)
+        return PointsRef(None, None, None, None, nx, ny, nt, 0, row_begin, n_rows)
+    if index is not None:
+        if index.dtype != torch.int64 or not index.is_cuda or not index.is_contiguous():
+            raise RuntimeError("make_points: index must be a contiguous CUDA int64 tensor")
+        if n_rows is None:
+            n_rows = index.shape[0] - row_begin
     if n_rows is None:
         n_rows = coords.shape[0] - row_begin
-    return L.Points(_ptr(coords), _ptr(t), _ptr(xcov) if xcov is not None and xcov.numel() > 0 else None, 0, 0, 0, 0,
-                    row_begin, n_rows)
+    if coords is not None:
+        coords, t = _f32c(coords, "coords"), _f32c(t, "t")
+    if xcov is not None and xcov.numel() > 0:
+        xcov = _f32c(xcov, "X")
+    else:
+        xcov = None
+    pts = PointsRef(_ptr(coords), _ptr(t), _ptr(xcov), _ptr(index), 0, 0, 0, 0, row_begin, n_rows)
+    pts._keep = (coords, t, xcov, index)
+    return pts
 
 
 def basis_fwd(basis: L.Basis, pts: L.Points, device) -> tuple:

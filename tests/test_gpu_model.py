@@ -1,0 +1,157 @@
+"""GPU: the drop-in `stnf` module (autograd bridge) and the training engine against the reference's golden outputs.
+Tolerances as in test_gpu_kernels.py; loss curves: 1e-3 relative (see test)."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import golden, orc
+from test_gpu_kernels import rel_err, rel_l2, T
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+DEFAULT = dict(k_spatial_centers=[25, 81, 121], k_temporal_centers=[10, 15, 45], hidden_dims=[256, 256, 128],
+               dropout=0.0, layernorm=True)
+
+
+def _perturb_ln(model, seed):
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for mod in model.modules():
+            if isinstance(mod, torch.nn.LayerNorm):
+                mod.weight.add_(0.2 * torch.randn(mod.weight.shape, generator=g))
+                mod.bias.add_(0.1 * torch.randn(mod.bias.shape, generator=g))
+
+
+@pytest.mark.parametrize("name,q,seed,taus", [("default_mse", 1, 0, None),
+                                              ("default_mq5", 5, 1, [0.05, 0.25, 0.5, 0.75, 0.95])])
+def test_module_forward_backward_matches_reference(name, q, seed, taus):
+    """Same seed => same initial weights as upstream (same torch init calls in the same order); forward and
+    autograd through the C ABI vs the reference module's FP64 outputs / gradients (default architecture)."""
+    from stnf.models import STInterpMLP
+    g = golden(name)
+    torch.manual_seed(seed)
+    model = STInterpMLP(**DEFAULT, output_dim=q)
+    _perturb_ln(model, seed)
+    for k, v in model.state_dict().items():
+        st = g["stat." + k]
+        assert abs(float(v.double().sum()) - st[0]) <= 1e-6 * max(1.0, abs(st[0])), k
+    model = model.to(DEV).eval()
+    coords, t, y = T(g["coords"]), T(g["t"]), T(g["y"])
+    X = torch.zeros(coords.shape[0], 0, device=DEV)
+    with torch.no_grad():
+        y0 = model(X, coords, t)
+    assert y0.shape == (coords.shape[0], q)
+    assert rel_l2(y0.cpu().numpy(), g["yhat64"]) < 1e-3 and rel_err(y0.cpu().numpy(), g["yhat32"]) < 3e-3
+    yp = model(X, coords, t)
+    if taus is None:
+        loss = torch.nn.functional.mse_loss(yp, y)
+    else:
+        losses = []
+        for qi, tau in enumerate(taus):
+            e = y - yp[:, qi:qi + 1]
+            losses.append(torch.mean(torch.max((tau - 1) * e, tau * e)))
+        loss = torch.mean(torch.stack(losses))
+    assert abs(loss.item() - float(g["loss64"])) < 1e-3 * abs(float(g["loss64"]))
+    loss.backward()
+    for k, p in model.named_parameters():
+        gs = g["gsample." + k]
+        got = p.grad.detach().cpu().numpy().reshape(-1)[::97]
+        assert rel_err(got, gs) < (6e-2 if taus else 4e-2), k
+
+
+def test_reference_api_surface():
+    """The structural assertions of the reference's own unit tests (tests/stnf/models/
+    test_st_interp_delta_reparameterization.py), run on the GPU module."""
+    from stnf.models import STInterpMLP, create_model
+    cfg = dict(p=0, k_spatial_centers=[9], k_temporal_centers=[5], hidden_dims=[32, 16], dropout=0.0, layernorm=False,
+               spatial_learnable=False, spatial_init_method="uniform", spatial_basis_function="wendland", output_dim=5)
+    X, coords, t = torch.zeros(4, 0, device=DEV), torch.rand(4, 2, device=DEV), torch.rand(4, 1, device=DEV)
+    m = STInterpMLP(use_delta_reparameterization=False, **cfg).to(DEV).eval()
+    with torch.no_grad():
+        assert m(X, coords, t).shape == (4, 5)
+    assert hasattr(m, "mlp") and m.mlp_trunk is None and m.delta_params is None
+    md = STInterpMLP(use_delta_reparameterization=True, **cfg).to(DEV)
+    assert md.mlp_trunk is not None and len(md.delta_params) == 5
+    assert all(d.shape == (17,) and d.requires_grad and not torch.allclose(d, torch.zeros_like(d)) for d in md.delta_params)
+    # cumulative beta: delta_k == k+1 everywhere => beta_k[0] = (k+1)(k+2)/2
+    with torch.no_grad():
+        for k, d in enumerate(md.delta_params):
+            d.fill_(float(k + 1))
+    w, b = md._effective_head()
+    assert [float(v) for v in b.detach()] == [(k + 1) * (k + 2) / 2 for k in range(5)]
+    md.eval()
+    with torch.no_grad():
+        a, bb = md(X, coords, t), md(X, coords, t)
+    assert torch.equal(a, bb) and torch.isfinite(a).all()
+    md.train()
+    out = md(X, coords, t)
+    out.sum().backward()
+    assert all(d.grad is not None and d.grad.abs().sum() > 0 for d in md.delta_params)
+    pen = md.compute_sparsity_penalty("sparse_group", 0.01, 0.01)
+    assert set(pen) == {"spatial_penalty", "temporal_penalty", "total_penalty"} and pen["total_penalty"] >= 0
+    mc = create_model({"regression_type": "multi-quantile", "quantile_levels": [0.1, 0.5, 0.9],
+                       "use_delta_reparameterization": True})
+    assert mc.output_dim == 3 and mc.use_delta_reparameterization
+    assert sum(p.numel() for p in STInterpMLP().parameters()) == 176385
+    m2 = copy.deepcopy(m)
+    assert torch.equal(m2(X, coords, t), m(X, coords, t))
+    with pytest.raises(RuntimeError):
+        STInterpMLP(**cfg)(torch.zeros(4, 0), torch.rand(4, 2), torch.rand(4, 1))   # CPU tensors: no fallback
+    # standalone embeddings (values)
+    kn = golden("knots")
+    sb = STInterpMLP().to(DEV).spatial_basis
+    phi = sb(T(golden("basis_values")["coords"]))
+    ref = golden("basis_values")["phi64_wendland"]
+    assert np.max(np.abs(phi.cpu().numpy() - ref) / np.maximum(ref, 2e-2)) < 1e-5
+
+
+def test_training_engine_loss_curve_vs_reference():
+    """20 optimisation steps (MSE, AdamW + clip + EMA, warm-up written after the step) on the fixture's data:
+    per-step loss and gradient norm vs the reference's FP32 CPU run.
+
+    Stated tolerance.  At matched weights the loss agrees to <1e-3 (first steps here; 4e-5 in the single-step
+    tests).  Over many steps at lr=2e-2 the two runs follow slightly different trajectories because TF32 operand
+    rounding perturbs each gradient by ~5e-3 (see test_default_size_network...: the same kernels match a
+    TF32-emulating oracle to 3e-3 and the FP64 one to 2e-2); the per-step loss then differs by up to ~1.6e-2 by
+    step 20.  The test pins: steps 0-3 within 1e-3, every step within 3e-2, gradient norms within 3e-2, and the
+    final raw / EMA predictions within 2e-2 (relative L2)."""
+    from stnf.models import STInterpMLP
+    from stnf.dataio import ObservationTable
+    from st_dadk_b200.trainer import Trainer
+    g = golden("train_curve")
+    n, bs, steps, warm = [int(v) for v in g["meta"]]
+    lr, wd, clip = [float(v) for v in g["hyper"]]
+    torch.manual_seed(123)
+    model = STInterpMLP(**DEFAULT)
+    table = ObservationTable(torch.from_numpy(g["coords"]), torch.from_numpy(g["t"].reshape(-1)),
+                             torch.from_numpy(g["y"].reshape(-1))).to(DEV)
+    bpe = n // bs
+    cfg = dict(lr=lr, weight_decay=wd, grad_clip=clip, warmup_epochs=warm // bpe, epochs=100, regression_type="mean")
+    for graph in (False, True):
+        torch.manual_seed(123)
+        model = STInterpMLP(**DEFAULT)
+        tr = Trainer(model, cfg, DEV, batches_per_epoch=bpe, use_cuda_graph=graph)
+        perm = torch.arange(n, device=DEV)
+        losses, norms = [], []
+        for s in range(steps):
+            lo = (s % bpe) * bs
+            tr.train_step(table, perm, lo, bs)
+            losses.append(tr.pop_loss_sum())
+            norms.append(float(tr.sqnorms[0].sqrt().item()))
+        losses, norms = np.array(losses), np.array(norms)
+        rel = np.abs(losses - g["losses"]) / np.abs(g["losses"])
+        nrel = np.abs(norms - g["grad_norms"]) / g["grad_norms"]
+        print("graph", graph, "loss rel", np.array2string(rel, precision=2), "norm rel", np.array2string(nrel, precision=2))
+        assert rel[:4].max() < 1e-3 and rel.max() < 3e-2, (graph, rel)
+        assert nrel.max() < 3e-2, nrel
+        model.eval()
+        X = torch.zeros(256, 0, device=DEV)
+        with torch.no_grad():
+            raw = model(X, table.coords[:256], table.t[:256, None]).cpu().numpy()
+            tr.flat.apply_shadow()
+            ema = model(X, table.coords[:256], table.t[:256, None]).cpu().numpy()
+            tr.flat.restore()
+        print("raw", rel_l2(raw, g["yhat_raw"]), "ema", rel_l2(ema, g["yhat_ema"]))
+        assert rel_l2(raw, g["yhat_raw"]) < 2e-2 and rel_l2(ema, g["yhat_ema"]) < 2e-2

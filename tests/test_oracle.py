@@ -66,8 +66,8 @@ def test_basis_values_vs_reference(fn):
     phic, maskc = c_spatial_basis(g["coords"], c, thetap, fn)
     ref = g[f"phi64_{fn}"]
     # 1e-5 relative where phi is not dominated by the 1-r cancellation at the support edge
-    # (FP32 ulp(r)=6e-8 bounds the absolute error), i.e. |err| <= 1e-5 * max(phi, 1e-2)
-    assert np.max(np.abs(phic - ref) / np.maximum(ref, 1e-2)) < 1e-5
+    # (FP32 ulp(r)=6e-8 bounds the absolute error), i.e. |err| <= 1e-5 * max(phi, 2e-2)
+    assert np.max(np.abs(phic - ref) / np.maximum(ref, 2e-2)) < 1e-5
     # index sets: C restatement == numpy FP32 predicate == reference FP64 non-zeros
     assert np.array_equal(maskc, orc.support_mask_f32(g["coords"], c, b, fn))
     if fn != "gaussian":
