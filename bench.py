@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""Benchmark of the ST-DADK hot path (contract: see the task statement / DESIGN.md section "Measurement").
+
+Workload (BASELINE.json configs[1], the largest single-GPU configuration): the data/2b-shaped problem --
+S=10,000 sites x T=100 time steps, 100k observed, 80k training samples, batch 4096 (20 steps/epoch), default
+basis resolutions [25,81,121] / [10,15,45], MLP 297-256-256-128-1, LayerNorm, dropout 0.1, AdamW + clip + EMA --
+with synthetic targets on synthetic U[0,1]^2 sites (the 2b training blobs are absent upstream and the GPU box has no
+copy of the reference tree).
+
+A "step" is one optimisation step over one batch of 4096 samples per GPU (forward with the basis fused into block 1,
+fused loss, backward with basis recompute, [one NCCL all-reduce of the flat gradient], grad-norm, fused clip+AdamW+EMA).
+`value` = training samples/s over all ranks with the dataset resident in HBM, timed per step with CUDA events on the
+launching stream, L2 flushed between steps, max over ranks.  The same JSON line carries the dense-prediction
+throughput (1M = T x S points, sharded by point), the end-to-end numbers through the host-buffer API, the roofline of
+the dominant kernel and the CPU baseline.
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (torchrun for N > 1)
+  python bench.py --impl reference --gpus N ...            # CPU arm: the oracle port on the host cores (rank 0 only)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+S_SITES, T_STEPS, N_TRAIN, BATCH = 10_000, 100, 80_000, 4096
+HIDDEN = [256, 256, 128]
+K_SPATIAL, K_TEMPORAL = [25, 81, 121], [10, 15, 45]
+CFG = dict(lr=2e-2, weight_decay=5e-4, grad_clip=10.0, regression_type="mean", scheduler="cosine", epochs=500,
+           warmup_epochs=10, dropout=0.1, layernorm=True, hidden_dims=HIDDEN, k_spatial_centers=K_SPATIAL,
+           k_temporal_centers=K_TEMPORAL)
+METRIC, UNIT = "train_samples_per_s", "samples/s"
+WORKLOAD = "data/2b-shaped train+predict: S=10000 x T=100, 80k train samples, batch 4096/GPU, default basis [25,81,121]/[10,15,45], MLP 297-256-256-128-1"
+
+
+def synth_field(coords, t, rng):
+    x, y = coords[:, 0], coords[:, 1]
+    return (np.sin(2 * np.pi * (x + t)) * np.cos(2 * np.pi * y) + 0.5 * np.sin(6 * np.pi * x * y)
+            + 0.1 * rng.standard_normal(len(x))).astype(np.float32)
+
+
+def synth_dataset(seed, n):
+    """n observed (site, time) samples of the S x T problem, sorted by (t, site) like the upstream dataset."""
+    rng = np.random.default_rng(seed)
+    sites = rng.random((S_SITES, 2)).astype(np.float32)
+    flat = np.sort(rng.choice(S_SITES * T_STEPS, size=n, replace=False))
+    ti, si = flat // S_SITES, flat % S_SITES
+    coords = sites[si]
+    t = (ti / (T_STEPS - 1)).astype(np.float32)
+    return sites, coords, t, synth_field(coords, t, rng)
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def oracle_model(seed=0):
+    from oracle import stdadk_oracle as orc
+    rng = np.random.default_rng(seed)
+    c, b = orc.uniform_spatial_knots(K_SPATIAL)
+    tc, tb = orc.temporal_knots(K_TEMPORAL)
+    dims = [c.shape[0] + tc.shape[0], *HIDDEN]
+    ws, bs, gs, be = [], [], [], []
+    for i in range(len(HIDDEN)):
+        bound = 1 / np.sqrt(dims[i])
+        ws.append(rng.uniform(-bound, bound, (dims[i + 1], dims[i])).astype(np.float32))
+        bs.append(rng.uniform(-bound, bound, dims[i + 1]).astype(np.float32))
+        gs.append(np.ones(dims[i + 1], np.float32))
+        be.append(np.zeros(dims[i + 1], np.float32))
+    bound = 1 / np.sqrt(dims[-1])
+    ws.append(rng.uniform(-bound, bound, (1, dims[-1])).astype(np.float32))
+    bs.append(rng.uniform(-bound, bound, 1).astype(np.float32))
+    return orc.OracleModel(centers=c, bandwidths=b, t_centers=tc, t_bandwidths=tb, weights=ws, biases=bs,
+                           ln_gamma=gs, ln_beta=be, dropout=0.1)
+
+
+def oracle_train_step(m, state, coords, t, y, step):
+    """One CPU training step with the oracle port (FP32 numpy on the host BLAS threads): forward with dropout,
+    MSE, backward, global-norm clip, AdamW, EMA -- the work of upstream's loop body (train_st_interp.py:608-712)."""
+    from oracle import stdadk_oracle as orc
+    n = coords.shape[0]
+    rng = np.random.default_rng(step)
+    masks = [rng.random((n, w.shape[0]), dtype=np.float32) >= 0.1 for w in m.weights[:-1]]
+    yh, cache = orc.forward(m, None, coords, t[:, None], dtype=np.float32, train=True, keep_masks=masks,
+                            return_cache=True)
+    loss, dy = orc.loss_and_grad(yh, y, "mse")
+    g = orc.backward(m, cache, dy.astype(np.float32))
+    params = m.weights + m.biases + m.ln_gamma + m.ln_beta
+    grads = g["weights"] + g["biases"] + g["ln_gamma"] + g["ln_beta"]
+    _, coef = orc.clip_coef(grads, 10.0)
+    for i, (p, gr) in enumerate(zip(params, grads)):
+        st = state.setdefault(i, (np.zeros_like(p), np.zeros_like(p), p.copy()))
+        orc.adamw_ema_step(p, gr.astype(np.float32), st[0], st[1], st[2], step, 2e-2, 5e-4, 0.995, clip=coef)
+    return loss
+
+
+def cpu_baseline(seconds=12.0, max_steps=8):
+    """Bounded sample of the same workload on the host cores: a few B=4096 oracle training steps."""
+    m = oracle_model()
+    _, coords, t, y = synth_dataset(2025, N_TRAIN)
+    state = {}
+    oracle_train_step(m, state, coords[:BATCH], t[:BATCH], y[:BATCH], 1)  # warm-up (BLAS threads, page faults)
+    times = []
+    t_end = time.perf_counter() + seconds
+    s = 1
+    while s <= max_steps and (time.perf_counter() < t_end or len(times) < 2):
+        lo = (s * BATCH) % (N_TRAIN - BATCH)
+        t0 = time.perf_counter()
+        oracle_train_step(m, state, coords[lo:lo + BATCH], t[lo:lo + BATCH], y[lo:lo + BATCH], s + 1)
+        times.append(time.perf_counter() - t0)
+        s += 1
+    per = float(np.median(times))
+    # prediction sample: forward-only over 32768 points
+    n_p = 32768
+    pc = np.random.default_rng(1).random((n_p, 2)).astype(np.float32)
+    pt = np.random.default_rng(2).random((n_p, 1)).astype(np.float32)
+    from oracle import stdadk_oracle as orc
+    t0 = time.perf_counter()
+    orc.forward(m, None, pc, pt, dtype=np.float32)
+    tp = time.perf_counter() - t0
+    return {"value": BATCH / per, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{len(times)} oracle (numpy FP32, host BLAS threads) training steps of batch {BATCH}, median; "
+                      f"predict sample {n_p} points", "ms_per_step": per * 1e3, "predict_points_per_s": n_p / tp}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 100))     # each step is ~0.1-0.2 s of host BLAS: the arm stays within minutes
+    m = oracle_model()
+    _, coords, t, y = synth_dataset(2025, N_TRAIN)
+    state = {}
+    for w in range(max(1, min(args.warmup, 2))):
+        oracle_train_step(m, state, coords[:BATCH], t[:BATCH], y[:BATCH], w + 1)
+    t0 = time.perf_counter()
+    for s in range(steps):
+        lo = (s * BATCH) % (N_TRAIN - BATCH)
+        oracle_train_step(m, state, coords[lo:lo + BATCH], t[lo:lo + BATCH], y[lo:lo + BATCH], s + 3)
+    dt = time.perf_counter() - t0
+    val = steps * BATCH / dt
+    cb = {"value": val, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+          "sample": f"{steps} oracle-port (numpy FP32, host BLAS threads) training steps of batch {BATCH}"}
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+                      "steps": steps, "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
+                      "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": WORKLOAD, "note": "reference CPU path = oracle port on host cores; one "
+                                 "rank only (the reference has no multi-device path)"},
+                      "cpu_baseline": cb,
+                      "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+class ClockSampler:
+    FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown," \
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown," \
+             "clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if rank == 0:
+        ge.build()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()
+    from stnf.models import STInterpMLP
+    from stnf.dataio import ObservationTable
+    from st_dadk_b200 import ops
+    from st_dadk_b200.trainer import Trainer
+    from st_dadk_b200.predict import Predictor
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    tc_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
+    peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+
+    torch.manual_seed(2025)                    # same initial weights on every rank
+    model = STInterpMLP(k_spatial_centers=K_SPATIAL, k_temporal_centers=K_TEMPORAL, hidden_dims=HIDDEN, dropout=0.1,
+                        layernorm=True, output_dim=1)
+    sites, coords, t, y = synth_dataset(2025 + rank, N_TRAIN)     # weak scaling: each rank owns 80k samples
+    host = ObservationTable(torch.from_numpy(coords), torch.from_numpy(t), torch.from_numpy(y)).pin()
+    table = host.to(dev)
+    bpe = (N_TRAIN + BATCH - 1) // BATCH
+    tr = Trainer(model, CFG, dev, batches_per_epoch=bpe, use_cuda_graph=True)
+    perm = torch.randperm(N_TRAIN, generator=torch.Generator().manual_seed(7 + rank)).to(dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # 256 MB > 126 MB L2
+    global_rows = BATCH * world
+    n_off = (N_TRAIN - BATCH) // BATCH
+
+    def one_step(i):
+        tr.train_step(table, perm, (i % n_off) * BATCH, BATCH, global_rows)
+
+    for i in range(max(args.warmup, 3)):
+        one_step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.fill_(1.0)                        # L2 flush between timed iterations (outside the event pair)
+        ev[i][0].record()
+        one_step(args.warmup + i)
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - wall0
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    tms = torch.tensor([dev_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    dev_ms = float(tms.item())
+    value = args.steps * BATCH * world / (dev_ms * 1e-3)
+    final_loss = tr.pop_loss_sum()
+
+    # ---- end-to-end through the host-buffer API: per step H2D of the batch from pinned memory + D2H of the loss
+    hb = 3 * 4 * BATCH + 4 * BATCH                 # coords (8 B) + t (4 B) + y (4 B) per sample
+    for i in range(3):
+        tr.train_step_host(host, (i % n_off) * BATCH, BATCH, global_rows)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        tr.train_step_host(host, ((i + 5) % n_off) * BATCH, BATCH, global_rows)
+    torch.cuda.synchronize()
+    e2e_t = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_val = args.steps * BATCH * world / float(e2e_t.item())
+
+    # ---- dense prediction: T x S = 1M points (space-time field), sharded by point, no collective
+    model.eval()
+    pr = Predictor(model)
+    sites_d = torch.from_numpy(sites).to(dev)
+    n_pred = S_SITES * T_STEPS
+    for _ in range(2):
+        pr.space_time_field(sites_d, T_STEPS, rank, world)
+    torch.cuda.synchronize()
+    reps = 5
+    pe = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for i in range(reps):
+        flush.fill_(1.0)
+        pe[i][0].record()
+        out, _ = pr.space_time_field(sites_d, T_STEPS, rank, world)
+        pe[i][1].record()
+    torch.cuda.synchronize()
+    pms = torch.tensor([sum(a.elapsed_time(b) for a, b in pe) / reps], device=dev)
+    if world > 1:
+        dist.all_reduce(pms, op=dist.ReduceOp.MAX)
+    pred_pps = n_pred / (float(pms.item()) * 1e-3)
+    # 10M-point dense grid (BASELINE configs[2]) generated on the device, sharded by point
+    g10 = (1000, 1000, 10)
+    pr.grid(*g10, rank, world)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    flush.fill_(1.0)
+    a.record()
+    pr.grid(*g10, rank, world)
+    b.record()
+    torch.cuda.synchronize()
+    gms = torch.tensor([a.elapsed_time(b)], device=dev)
+    if world > 1:
+        dist.all_reduce(gms, op=dist.ReduceOp.MAX)
+    grid_pps = 10_000_000 / (float(gms.item()) * 1e-3)
+    # e2e prediction: result copied back to pinned host memory
+    hout = torch.empty(out.shape, dtype=torch.float32).pin_memory()
+    t0 = time.perf_counter()
+    out, _ = pr.space_time_field(sites_d, T_STEPS, rank, world)
+    hout.copy_(out, non_blocking=True)
+    torch.cuda.synchronize()
+    pred_e2e = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(pred_e2e, op=dist.ReduceOp.MAX)
+    pred_e2e_pps = n_pred / float(pred_e2e.item())
+
+    # ---- per-kernel timing (eager, CUDA events around every libstdadk launch) -> roofline of the dominant kernel
+    roof = None
+    kt = {}
+    if rank == 0:
+        kt = tr.profile_step(table, perm, BATCH, global_rows, repeats=10)
+        name, info = max(kt["kernels"].items(), key=lambda kv: kv[1]["ms"] * kv[1]["count"])
+        flops = info["flops"]
+        achieved = flops / (info["ms"] * 1e-3) / 1e12
+        roof = {"kernel": name, "bound": "tensor", "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s",
+                "frac": achieved / tc_peak, "traffic": None, "peak_source": peak_src + ", dense bf16 sustained; the "
+                "kernel runs TF32 (nominal half rate)", "launch_ms": kt["kernels"][name]["ms"],
+                "share_of_step": kt["kernels"][name]["ms"] * kt["kernels"][name]["count"] / max(kt["step_ms"], 1e-9),
+                "algorithmic_flops_per_launch": flops}
+    if rank == 0:
+        cb = cpu_baseline() if world == 1 else None
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "tf32 (fp32 accumulate, fp32 master weights)",
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD, "global_batch": global_rows, "l2": "flushed between timed steps "
+                           "(256 MB write)", "cuda_graph": True, "parallelism": f"dp{world}" if world > 1 else "single"},
+                "clocks": clocks, "gpu_launches": tr.launches_per_step * args.steps,
+                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": hb, "d2h_bytes_per_step": 4},
+                "predict": {"metric": "predict_points_per_s", "value": pred_pps, "unit": "points/s",
+                            "workload": f"T x S = {n_pred} space-time points, sharded by point over {world} GPU(s)",
+                            "e2e_value": pred_e2e_pps, "d2h_bytes": int(out.numel() * 4),
+                            "grid10M_points_per_s": grid_pps},
+                "roofline": roof, "kernel_times_ms": {k: v["ms"] for k, v in kt.get("kernels", {}).items()},
+                "cpu_baseline": cb, "final_loss": final_loss, "wall_s_timed_region": wall}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

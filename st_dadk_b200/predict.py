@@ -1,0 +1,94 @@
+"""Dense-grid / point-set kriging prediction, sharded by point across the GPUs of one box.
+
+Upstream runs T sequential forwards of S points each with a D2H copy per time step (plot_spatial_mse,
+scripts/train_st_interp.py:1233-1248) or one forward over T*S points (plot_temporal_series, :1380-1394).  Points
+are independent (LayerNorm is per row), so rank r of R owns the contiguous block
+[floor(r N / R), floor((r+1) N / R)) and there is no data-path collective; the grid itself is generated on the
+device from the linear index, so a grid prediction reads 0 bytes of input per point.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+from .executor import Executor
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    return (rank * n) // world, ((rank + 1) * n) // world
+
+
+class Predictor:
+    """Forward-only executor bound to a model; weight images are packed once and reused across chunks."""
+
+    def __init__(self, model, chunk_rows: int = 1 << 20):
+        self.model = model
+        self.chunk = int(chunk_rows)
+        self.ex: Optional[Executor] = None
+        self.launches = 0
+
+    def _prepare(self):
+        m = self.model
+        if not next(m.buffers()).is_cuda:
+            raise RuntimeError("Predictor: the model must live on a CUDA device (no CPU path)")
+        with torch.no_grad():
+            spec = m.net_spec()
+        if self.ex is None:
+            self.ex = Executor(spec)
+        else:
+            self.ex.rebind(spec)
+        self.ex.prepare(force=True, for_backward=False)
+        self.launches += 2 + len(spec.weights)
+
+    @torch.no_grad()
+    def _run(self, make_pts, begin: int, end: int, out: torch.Tensor):
+        n_layers = self.ex.spec.n_hidden
+        for b in range(begin, end, self.chunk):
+            r = min(self.chunk, end - b)
+            self.ex.forward(make_pts(b, r), train=False, out=out[b - begin:b - begin + r], prepared=True)
+            self.launches += n_layers
+        return out
+
+    @torch.no_grad()
+    def grid(self, nx: int, ny: int, nt: int, rank: int = 0, world: int = 1, out: Optional[torch.Tensor] = None):
+        """This rank's block of the (nt, nx, ny) grid prediction: returns (yhat (n_local, Q), (begin, end))."""
+        self._prepare()
+        n = nx * ny * nt
+        begin, end = shard_range(n, rank, world)
+        dev = self.ex.device
+        if out is None:
+            out = torch.empty(end - begin, self.model.output_dim, device=dev)
+        self._run(lambda b, r: ops.make_points(grid=(nx, ny, nt), row_begin=b, n_rows=r), begin, end, out)
+        return out, (begin, end)
+
+    @torch.no_grad()
+    def points(self, coords: torch.Tensor, t: torch.Tensor, X: Optional[torch.Tensor] = None, rank: int = 0,
+               world: int = 1, out: Optional[torch.Tensor] = None):
+        """This rank's block of an explicit point set (coords (N,2), t (N,) or (N,1)) resident on the device."""
+        self._prepare()
+        n = coords.shape[0]
+        begin, end = shard_range(n, rank, world)
+        coords, t = coords.float().contiguous(), t.reshape(-1).float().contiguous()
+        if out is None:
+            out = torch.empty(end - begin, self.model.output_dim, device=coords.device)
+        self._run(lambda b, r: ops.make_points(coords, t, X, row_begin=b, n_rows=r), begin, end, out)
+        return out, (begin, end)
+
+    @torch.no_grad()
+    def space_time_field(self, coords: torch.Tensor, T: int, rank: int = 0, world: int = 1):
+        """All T time steps at S sites (the predictions.npz field of upstream, T x S row-major: point n = (t, s)),
+        without materialising repeated coordinates: rows gather site n % S through an index."""
+        self._prepare()
+        S = coords.shape[0]
+        n = S * T
+        begin, end = shard_range(n, rank, world)
+        dev = coords.device
+        idx = torch.arange(begin, end, device=dev, dtype=torch.int64)
+        site = idx % S
+        tt = ((idx // S).float() / float(T - 1)) if T > 1 else torch.zeros(end - begin, device=dev)
+        cc = coords.float().index_select(0, site).contiguous()
+        out = torch.empty(end - begin, self.model.output_dim, device=dev)
+        self._run(lambda b, r: ops.make_points(cc, tt, None, row_begin=b - begin, n_rows=r), begin, end, out)
+        return out, (begin, end)

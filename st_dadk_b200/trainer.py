@@ -154,6 +154,8 @@ class Trainer:
         self.use_cuda_graph = use_cuda_graph
         self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
         self._stage_idx = None
+        self._host_stage = None
+        self._host_perm = None
         self.world = dist.get_world_size() if _dist_on() else 1
         self.rank = dist.get_rank() if _dist_on() else 0
         self.kernel_launches = 0
@@ -366,6 +368,96 @@ class Trainer:
             for gq in self.opt.param_groups:
                 gq["lr"] = gq["initial_lr"] * f
         self.global_step += 1
+
+    def train_step_host(self, host_table, row_begin: int, n_rows: int, global_rows: Optional[int] = None) -> float:
+        """End-to-end step from HOST buffers: the batch host_table[row_begin : row_begin + n_rows] (pinned memory) is
+        copied to a device staging table, the step runs, and the step's loss is read back (the shape of upstream's
+        loop body: .to(device) per batch and loss.item(), train_st_interp.py:609-612, :721)."""
+        if self._host_stage is None or len(self._host_stage) < n_rows:
+            from stnf.dataio import ObservationTable
+            z = lambda *sh: torch.zeros(*sh, dtype=torch.float32, device=self.device)
+            self._host_stage = ObservationTable(z(n_rows, 2), z(n_rows), z(n_rows),
+                                                z(n_rows, self.model.p) if self.model.p > 0 else None)
+            self._host_perm = torch.arange(n_rows, dtype=torch.int64, device=self.device)
+        st = self._host_stage
+        sl = slice(row_begin, row_begin + n_rows)
+        st.coords[:n_rows].copy_(host_table.coords[sl], non_blocking=True)
+        st.t[:n_rows].copy_(host_table.t[sl], non_blocking=True)
+        st.y[:n_rows].copy_(host_table.y[sl], non_blocking=True)
+        if st.X is not None:
+            st.X[:n_rows].copy_(host_table.X[sl], non_blocking=True)
+        self.train_step(st, self._host_perm, 0, n_rows, global_rows)
+        return float(self.ex.loss_acc.item())
+
+    @property
+    def launches_per_step(self) -> int:
+        """libstdadk kernel launches in one optimisation step (counted from the launch sequence)."""
+        nh = self.ex.spec.n_hidden
+        n = 2 + nh + (nh - 1)               # knot tables, forward weight images, dgrad (W^T) images
+        n += nh + nh + nh                   # layer_fwd, layer_bwd, wgrad per block
+        if self.learnable:
+            n += 2                          # W1s image + knot_grad
+        n += (1 if self.clip > 0 else 0) + 2   # grad_sqnorm, step counter, adamw_ema
+        return n
+
+    def profile_step(self, table, perm, n_rows: int, global_rows: int, repeats: int = 10) -> dict:
+        """Eager steps with a CUDA-event pair around every libstdadk launch (on the launching stream): average
+        duration, launch count and algorithmic FLOPs per kernel, plus the summed step time."""
+        rec: List[tuple] = []
+        saved = {}
+
+        def wrap(name, fn, flops_of):
+            def inner(*a, **k):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                r = fn(*a, **k)
+                e1.record()
+                rec.append((name(*a, **k) if callable(name) else name, e0, e1, flops_of(*a, **k)))
+                return r
+            return inner
+
+        rows = float(n_rows)
+        f_fwd = lambda a: 2.0 * rows * a.layer.n_in * a.layer.n_out
+        f_bwd = lambda a: 2.0 * rows * a.layer.n_out * (a.layer.n_in + (a.n_next if not a.head else 0))
+        f_wg = lambda a: 2.0 * rows * a.n_in * a.n_out
+        patches = {
+            "layer_fwd": (lambda a: f"layer_fwd[{a.layer.layer_id}]", f_fwd),
+            "layer_bwd": (lambda a: f"layer_bwd[{a.layer.layer_id}]", f_bwd),
+            "wgrad": (lambda a: f"wgrad[{a.n_in}x{a.n_out}]", f_wg),
+            "knot_grad": ("knot_grad", lambda a: 2.0 * rows * a.n_out * self.model.k_spatial),
+            "pack_image": ("pack_image", lambda *a, **k: 0.0),
+            "knots_prepare": ("knots_prepare", lambda *a, **k: 0.0),
+            "tknots_prepare": ("knots_prepare", lambda *a, **k: 0.0),
+            "grad_sqnorm": ("grad_sqnorm", lambda *a, **k: 0.0),
+            "adamw_ema_step": ("adamw_ema_step", lambda *a, **k: 0.0),
+        }
+        use_graph, self.use_cuda_graph = self.use_cuda_graph, False
+        try:
+            for fname, (nm, fl) in patches.items():
+                saved[fname] = getattr(ops, fname)
+                setattr(ops, fname, wrap(nm, saved[fname], fl))
+            self.train_step(table, perm, 0, n_rows, global_rows)        # warm
+            rec.clear()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for i in range(repeats):
+                self.train_step(table, perm, (i + 1) * n_rows, n_rows, global_rows)
+            s1.record()
+            torch.cuda.synchronize()
+        finally:
+            for fname, fn in saved.items():
+                setattr(ops, fname, fn)
+            self.use_cuda_graph = use_graph
+        agg: Dict[str, dict] = {}
+        for name, e0, e1, fl in rec:
+            d = agg.setdefault(name, {"ms": 0.0, "count": 0, "flops": fl})
+            d["ms"] += e0.elapsed_time(e1)
+            d["count"] += 1
+        for d in agg.values():
+            d["count"] = d["count"] / repeats        # launches per step
+            d["ms"] = d["ms"] / (d["count"] * repeats)  # average per launch
+        return {"kernels": agg, "step_ms": sum(d["ms"] * d["count"] for d in agg.values()),
+                "eager_step_ms_wall": s0.elapsed_time(s1) / repeats}
 
     def pop_loss_sum(self) -> float:
         v = float(self.loss_sum.item())
