@@ -230,7 +230,7 @@ def run_ours(args):
     host = ObservationTable(torch.from_numpy(coords), torch.from_numpy(t), torch.from_numpy(y)).pin()
     table = host.to(dev)
     bpe = (N_TRAIN + BATCH - 1) // BATCH
-    tr = Trainer(model, CFG, dev, batches_per_epoch=bpe, use_cuda_graph=True)
+    tr = Trainer(model, CFG, dev, batches_per_epoch=bpe, use_cuda_graph=not args.no_graph)
     perm = torch.randperm(N_TRAIN, generator=torch.Generator().manual_seed(7 + rank)).to(dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # 256 MB > 126 MB L2
     global_rows = BATCH * world
@@ -349,7 +349,7 @@ def run_ours(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": "tf32 (fp32 accumulate, fp32 master weights)",
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "global_batch": global_rows, "l2": "flushed between timed steps "
-                           "(256 MB write)", "cuda_graph": True, "parallelism": f"dp{world}" if world > 1 else "single"},
+                           "(256 MB write)", "cuda_graph": not args.no_graph, "parallelism": f"dp{world}" if world > 1 else "single"},
                 "clocks": clocks, "gpu_launches": tr.launches_per_step * args.steps,
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": hb, "d2h_bytes_per_step": 4},
                 "predict": {"metric": "predict_points_per_s", "value": pred_pps, "unit": "points/s",
@@ -357,7 +357,7 @@ def run_ours(args):
                             "e2e_value": pred_e2e_pps, "d2h_bytes": int(out.numel() * 4),
                             "grid10M_points_per_s": grid_pps},
                 "roofline": roof, "kernel_times_ms": {k: v["ms"] for k, v in kt.get("kernels", {}).items()},
-                "cpu_baseline": cb, "final_loss": final_loss, "wall_s_timed_region": wall}
+                "cpu_baseline": cb, "mean_train_loss": final_loss / max(1, args.steps + max(args.warmup, 3)), "wall_s_timed_region": wall}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -370,6 +370,8 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-graph", action="store_true",
+                    help="launch every kernel eagerly (for ncu: kernel replay cannot run inside stream capture)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

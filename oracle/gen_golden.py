@@ -208,3 +208,52 @@ if __name__ == "__main__":
     print("golden fixtures written to", OUT)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+def masks_fixture():
+    """Observation / split masks and loss known-answers from the reference's scripts/train_st_interp.py
+    (matplotlib is absent in the container: a two-attribute stub satisfies its module-level imports)."""
+    import types
+    for name in ("matplotlib", "matplotlib.pyplot"):
+        if name not in sys.modules:
+            mod = types.ModuleType(name)
+            mod.use = lambda *a, **k: None
+            sys.modules[name] = mod
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_train", os.path.join(REF, "scripts", "train_st_interp.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    rng = np.random.default_rng(5)
+    T, S = 7, 60
+    coords = rng.random((S, 2)).astype(np.float32)
+    z = rng.standard_normal((T, S)).astype(np.float32)
+    z[2, 5] = np.nan
+    out = {"coords": coords, "z": z}
+    for tag, (om, pat, sm) in {"a": ("site-wise", "corner", "random"), "b": ("random", "uniform", "site-wise"),
+                               "c": ("site-wise", "uniform", "site-wise"), "d": ("random", "corner", "random")}.items():
+        fn = ref.create_spatial_obs_prob_fn(pat, 10.0)
+        obs, sites = ref.sample_observations(z, coords, om, 0.3, fn, seed=2025)
+        tr, va = ref.split_train_valid(obs, sites, sm, 0.8, seed=12025)
+        ds = ref.create_dataset_from_mask(z, coords, tr, 0)
+        out[f"{tag}_obs"], out[f"{tag}_sites"], out[f"{tag}_train"], out[f"{tag}_valid"] = obs, np.asarray(sites), tr, va
+        out[f"{tag}_ds_y"] = np.array([float(s["y"]) for s in ds], dtype=np.float32)
+        out[f"{tag}_ds_t"] = np.array([float(s["t"]) for s in ds], dtype=np.float32)
+        out[f"{tag}_ds_c"] = np.stack([s["coords"].numpy() for s in ds]) if ds else np.zeros((0, 2), np.float32)
+    yp = torch.tensor(rng.standard_normal((11, 3)))
+    yt = torch.tensor(rng.standard_normal((11, 1)))
+    out["loss_yp"], out["loss_yt"] = yp.numpy(), yt.numpy()
+    out["pinball_03"] = ref.quantile_loss(yp[:, :1], yt, 0.3).item()
+    out["nc_p1"] = ref.non_crossing_penalty(yp, "mean", 1).item()
+    out["nc_p2"] = ref.non_crossing_penalty(yp, "sum", 2).item()
+    deltas = [torch.tensor(rng.standard_normal(6)) for _ in range(4)]
+    out["deltas"] = np.stack([d.numpy() for d in deltas])
+    out["pnc"] = ref.compute_p_nc_delta_penalty(deltas).item()
+    out["crps"] = ref.compute_crps_multi_quantile(yp.numpy(), yt.numpy(), [0.1, 0.5, 0.9])
+    out["auto_bs"] = np.array([4096, 8000, 512, 4096, 80000, 4096])   # (config bs, n_train, expected) pairs
+    np.savez_compressed(os.path.join(OUT, "masks_losses.npz"), **out)
+
+
+if __name__ == "__main__":
+    masks_fixture()
+    print("masks_losses.npz", os.path.getsize(os.path.join(OUT, "masks_losses.npz")))

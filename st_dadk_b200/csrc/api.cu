@@ -259,17 +259,25 @@ int stdadk_layer_fwd(const stdadk_fwd_args* a, void* stream) {
     K.thresh16 = dropout_thresh16(a->drop.p);
     K.drop_scale = a->drop.p > 0.0f ? 1.0f / (1.0f - a->drop.p) : 1.0f;
     const bool basis = a->basis != nullptr;
-    SmemPlan sp = plan_smem(K.n_pad, K.has_head ? K.head.q : 0, basis ? K.basis.k_s : 0, basis ? K.basis.k_t : 0, false);
+    int tiles = (int)ceil_div64(a->pts.n_rows, TILE_M);
+    // few tiles (a training batch): 16 worker warps per CTA hide the latency of the serial phases; many tiles
+    // (dense prediction): 8 worker warps and two CTAs per SM so one tile's epilogue overlaps the other's MMAs
+    const int sms = g_sm_count > 0 ? g_sm_count : 148;
+    const int cg = tiles >= 2 * sms ? 2 : 4;
+    SmemPlan sp = plan_smem(K.n_pad, K.has_head ? K.head.q : 0, basis ? K.basis.k_s : 0, basis ? K.basis.k_t : 0, false, cg);
     REQUIRE(sp.total <= 227 * 1024, "layer_fwd: needs %u B of shared memory (> 227 KB): too many knots for the dense path",
             sp.total);
-    int tiles = (int)ceil_div64(a->pts.n_rows, TILE_M);
+#define LAUNCH_FWD(B, C)                                                                   \
+    do {                                                                                   \
+        if (int r = set_smem(layer_fwd_kernel<B, C>, sp.total)) return r;                  \
+        layer_fwd_kernel<B, C><<<tiles, n_threads(C), sp.total, (cudaStream_t)stream>>>(K); \
+    } while (0)
     if (basis) {
-        if (int r = set_smem(layer_fwd_kernel<true>, sp.total)) return r;
-        layer_fwd_kernel<true><<<tiles, NTHREADS, sp.total, (cudaStream_t)stream>>>(K);
+        if (cg == 2) LAUNCH_FWD(true, 2); else LAUNCH_FWD(true, 4);
     } else {
-        if (int r = set_smem(layer_fwd_kernel<false>, sp.total)) return r;
-        layer_fwd_kernel<false><<<tiles, NTHREADS, sp.total, (cudaStream_t)stream>>>(K);
+        if (cg == 2) LAUNCH_FWD(false, 2); else LAUNCH_FWD(false, 4);
     }
+#undef LAUNCH_FWD
     return check_launch("layer_fwd");
 }
 
@@ -314,15 +322,16 @@ int stdadk_layer_bwd(const stdadk_bwd_args* a, void* stream) {
     K.thresh16 = dropout_thresh16(a->drop.p);
     K.drop_scale = a->drop.p > 0.0f ? 1.0f / (1.0f - a->drop.p) : 1.0f;
     const bool basis = a->basis != nullptr;
-    SmemPlan sp = plan_smem(K.n_pad, K.has_head ? K.head.q : 0, basis ? K.basis.k_s : 0, basis ? K.basis.k_t : 0, true);
+    constexpr int BCG = 2;
+    SmemPlan sp = plan_smem(K.n_pad, K.has_head ? K.head.q : 0, basis ? K.basis.k_s : 0, basis ? K.basis.k_t : 0, true, BCG);
     REQUIRE(sp.total <= 227 * 1024, "layer_bwd: needs %u B of shared memory (> 227 KB)", sp.total);
     int tiles = (int)ceil_div64(a->pts.n_rows, TILE_M);
     if (basis) {
-        if (int r = set_smem(layer_bwd_kernel<true>, sp.total)) return r;
-        layer_bwd_kernel<true><<<tiles, NTHREADS, sp.total, (cudaStream_t)stream>>>(K);
+        if (int r = set_smem(layer_bwd_kernel<true, BCG>, sp.total)) return r;
+        layer_bwd_kernel<true, BCG><<<tiles, n_threads(BCG), sp.total, (cudaStream_t)stream>>>(K);
     } else {
-        if (int r = set_smem(layer_bwd_kernel<false>, sp.total)) return r;
-        layer_bwd_kernel<false><<<tiles, NTHREADS, sp.total, (cudaStream_t)stream>>>(K);
+        if (int r = set_smem(layer_bwd_kernel<false, BCG>, sp.total)) return r;
+        layer_bwd_kernel<false, BCG><<<tiles, n_threads(BCG), sp.total, (cudaStream_t)stream>>>(K);
     }
     return check_launch("layer_bwd");
 }
@@ -362,12 +371,13 @@ int stdadk_wgrad(const stdadk_wgrad_args* a, void* stream) {
     uint32_t smem = wgrad_smem_bytes(basis ? K.basis.k_s : 0, basis ? K.basis.k_t : 0);
     REQUIRE(smem <= 227 * 1024, "wgrad: needs %u B of shared memory (> 227 KB)", smem);
     dim3 grid(splits, m_tiles, n_tiles_n);
+    constexpr int WCG = 2;
     if (basis) {
-        if (int r = set_smem(wgrad_kernel<true>, smem)) return r;
-        wgrad_kernel<true><<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(K);
+        if (int r = set_smem(wgrad_kernel<true, WCG>, smem)) return r;
+        wgrad_kernel<true, WCG><<<grid, n_threads(WCG), smem, (cudaStream_t)stream>>>(K);
     } else {
-        if (int r = set_smem(wgrad_kernel<false>, smem)) return r;
-        wgrad_kernel<false><<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(K);
+        if (int r = set_smem(wgrad_kernel<false, WCG>, smem)) return r;
+        wgrad_kernel<false, WCG><<<grid, n_threads(WCG), smem, (cudaStream_t)stream>>>(K);
     }
     return check_launch("wgrad");
 }
@@ -388,9 +398,9 @@ int stdadk_knot_grad(const stdadk_knotgrad_args* a, void* stream) {
     K.n_out = a->n_out;
     K.k_slabs = pad32(a->n_out) / SLAB_K;
     SmemPlan sp = plan_smem(TILE_M, 0, 0, 0, false);
-    if (int r = set_smem(knotgrad_kernel, sp.total)) return r;
+    if (int r = set_smem(knotgrad_kernel<2>, sp.total)) return r;
     dim3 grid((unsigned)ceil_div64(a->pts.n_rows, TILE_M), (unsigned)((a->basis->k_s + TILE_M - 1) / TILE_M));
-    knotgrad_kernel<<<grid, NTHREADS, sp.total, (cudaStream_t)stream>>>(K);
+    knotgrad_kernel<2><<<grid, n_threads(2), sp.total, (cudaStream_t)stream>>>(K);
     return check_launch("knot_grad");
 }
 

@@ -10,22 +10,26 @@
 //                      LayerNorm backward and writes the dz image + bias/LN/head gradients.
 //   wgrad_kernel     : dW += dz^T A, reduction over rows, both operands MN-major from the same images.
 //
-// One CTA = one 128-row tile (128 TMEM lanes).  Warps 0-3: workers (operand generation, epilogue; thread
-// = row), warp 4: producer (bulk copies), warp 5: MMA issuer (one elected thread).
+// One CTA = one 128-row tile (128 TMEM lanes).  Worker warps 0 .. 4*CG-1 (operand generation and epilogue):
+// warp w owns TMEM lane quarter q = w & 3 (the hardware ties a warp to lanes 32*(w%4)..) and column group
+// cg = w >> 2, i.e. thread = (row, 1/CG of the columns); then one producer warp (bulk copies) and one MMA
+// issuer warp (one elected thread).  CG = 4 for latency (few tiles), CG = 2 with two CTAs per SM for throughput.
 #pragma once
 #include "common.cuh"
 
 namespace stdadk {
 
 constexpr int NSTAGE = 2;
-constexpr int NWORK = 128;
-constexpr int NTHREADS = 192;
+constexpr int RED_STRIDE = 2 + STDADK_MAX_Q;   // per (cg, row) scratch: two LayerNorm partials + Q head partials
+__host__ __device__ constexpr int n_work(int cg) { return 128 * cg; }
+__host__ __device__ constexpr int n_threads(int cg) { return 128 * cg + 64; }
+__device__ __forceinline__ void worker_barrier(int nw) { asm volatile("bar.sync 1, %0;" ::"r"(nw) : "memory"); }
 
 // ---------------------------------------------------------------- shared-memory carve-up
 struct SmemPlan {
-    uint32_t a_off, b_off, bar_off, tmem_off, vec_off, headw_off, knots_off, tknots_off, colsum_off, total;
+    uint32_t a_off, b_off, bar_off, tmem_off, vec_off, headw_off, knots_off, tknots_off, colsum_off, red_off, total;
 };
-__host__ __device__ inline SmemPlan plan_smem(int n_pad, int q, int k_s, int k_t, bool bwd) {
+__host__ __device__ inline SmemPlan plan_smem(int n_pad, int q, int k_s, int k_t, bool bwd, int cg = 1) {
     SmemPlan s;
     uint32_t o = 0;
     s.a_off = o; o += NSTAGE * SLAB_BYTES;
@@ -39,6 +43,8 @@ __host__ __device__ inline SmemPlan plan_smem(int n_pad, int q, int k_s, int k_t
     s.tknots_off = o; o += (uint32_t)k_t * 8u;
     o = (o + 15u) & ~15u;
     s.colsum_off = o; o += bwd ? (uint32_t)((3 + q) * n_pad + STDADK_MAX_Q) * 4u : 0u;
+    o = (o + 15u) & ~15u;
+    s.red_off = o; o += (uint32_t)(cg * TILE_M * RED_STRIDE) * 4u;
     s.total = o + 1024;                                   // slack for manual 1024-byte alignment
     return s;
 }
@@ -79,9 +85,9 @@ struct BwdK {
 // Generate one 128-row x 32-feature operand slab (this thread = row r) into swizzled SMEM.
 __device__ __forceinline__ void gen_basis_slab(const BasisP& B, const float4* sk, const float2* st, int slab,
                                                float x, float y, float t, const float* xrow, uint32_t slab_saddr,
-                                               uint32_t r) {
+                                               uint32_t r, int c_begin = 0, int c_end = 8) {
 #pragma unroll 1
-    for (int c = 0; c < 8; ++c) {
+    for (int c = c_begin; c < c_end; ++c) {
         int f = slab * SLAB_K + c * 4;
         float v0 = to_tf32(feature_value(B, sk, st, f + 0, x, y, t, xrow));
         float v1 = to_tf32(feature_value(B, sk, st, f + 1, x, y, t, xrow));
@@ -165,12 +171,13 @@ __device__ __forceinline__ float row_loss(const HeadP& H, const float* yh, float
 // =============================================================================================
 // Forward
 // =============================================================================================
-template <bool BASIS>
-__global__ void __launch_bounds__(NTHREADS) layer_fwd_kernel(const __grid_constant__ FwdK P) {
+template <bool BASIS, int CG>
+__global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kernel(const __grid_constant__ FwdK P) {
+    constexpr int NW = n_work(CG), NT = n_threads(CG);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = align_smem(smem_raw);
     const SmemPlan sp = plan_smem(P.n_pad, P.has_head ? P.head.q : 0, BASIS ? P.basis.k_s : 0,
-                                  BASIS ? P.basis.k_t : 0, false);
+                                  BASIS ? P.basis.k_t : 0, false, CG);
     float* sA = reinterpret_cast<float*>(smem + sp.a_off);
     float* sB = reinterpret_cast<float*>(smem + sp.b_off);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + sp.bar_off);
@@ -184,6 +191,7 @@ __global__ void __launch_bounds__(NTHREADS) layer_fwd_kernel(const __grid_consta
     float* shb = shw + (P.has_head ? P.head.q * P.n_pad : 0);
     float4* sk = reinterpret_cast<float4*>(smem + sp.knots_off);
     float2* st = reinterpret_cast<float2*>(smem + sp.tknots_off);
+    float* red = reinterpret_cast<float*>(smem + sp.red_off);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tile = blockIdx.x;
@@ -191,41 +199,41 @@ __global__ void __launch_bounds__(NTHREADS) layer_fwd_kernel(const __grid_consta
     const bool has_ln = P.L.gamma != nullptr;
     const size_t b_stage_floats = (size_t)n_pad * SLAB_K;
 
-    if (tid == NWORK) {
+    if (tid == NW) {
         for (int s = 0; s < NSTAGE; ++s) {
-            mbar_init(&full[s], BASIS ? 1 + NWORK : 1);
+            mbar_init(&full[s], BASIS ? 1 + NW : 1);
             mbar_init(&empty[s], 1);
         }
         mbar_init(accf, 1);
         mbar_fence_init();
     }
-    if (warp == 4) {
+    if (warp == 4 * CG) {
         __syncwarp();
         tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
     }
-    for (int i = tid; i < n_pad; i += NTHREADS) {
+    for (int i = tid; i < n_pad; i += NT) {
         bool ok = i < n_out;
         sbias[i] = ok ? P.L.bias[i] : 0.0f;
         sgam[i] = (ok && has_ln) ? P.L.gamma[i] : 1.0f;
         sbet[i] = (ok && has_ln) ? P.L.beta[i] : 0.0f;
     }
     if (P.has_head) {
-        for (int i = tid; i < P.head.q * n_pad; i += NTHREADS) {
+        for (int i = tid; i < P.head.q * n_pad; i += NT) {
             int k = i / n_pad, c = i - k * n_pad;
             shw[i] = c < n_out ? P.head.w[(size_t)k * n_out + c] : 0.0f;
         }
         if (tid < P.head.q) shb[tid] = P.head.b[tid];
     }
     if (BASIS) {
-        for (int i = tid; i < P.basis.k_s; i += NTHREADS) sk[i] = P.basis.knots[i];
-        for (int i = tid; i < P.basis.k_t; i += NTHREADS) st[i] = P.basis.tknots[i];
+        for (int i = tid; i < P.basis.k_s; i += NT) sk[i] = P.basis.knots[i];
+        for (int i = tid; i < P.basis.k_t; i += NT) st[i] = P.basis.tknots[i];
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 4) {
+    if (warp == 4 * CG) {
         // ---------------- producer
         if (lane == 0) {
             const float* a_tile = BASIS ? nullptr : P.a_img + (size_t)tile * P.k_slabs * SLAB_FLOATS;
@@ -237,7 +245,7 @@ __global__ void __launch_bounds__(NTHREADS) layer_fwd_kernel(const __grid_consta
             }
         }
         __syncwarp();
-    } else if (warp == 5) {
+    } else if (warp == 4 * CG + 1) {
         // ---------------- MMA issuer
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_tf32((uint32_t)n_pad, 0, 0);
@@ -253,8 +261,10 @@ __global__ void __launch_bounds__(NTHREADS) layer_fwd_kernel(const __grid_consta
         }
         __syncwarp();
     } else {
-        // ---------------- workers: thread = row
-        const long long lrow = (long long)tile * TILE_M + tid;
+        // ---------------- workers: thread = (row, column group)
+        const int q4 = warp & 3, cg = warp >> 2;
+        const int row = q4 * 32 + lane;
+        const long long lrow = (long long)tile * TILE_M + row;
         const bool rvalid = lrow < P.pts.n_rows;
         const long long grow = P.pts.row_begin + lrow;
         if (BASIS) {
@@ -268,7 +278,7 @@ __global__ void __launch_bounds__(NTHREADS) layer_fwd_kernel(const __grid_consta
                 int stage = s % NSTAGE, it = s / NSTAGE;
                 if (it > 0) mbar_wait(&empty[stage], (it - 1) & 1);
                 gen_basis_slab(P.basis, sk, st, s, x, y, t, xrow, smem_u32(sA + (size_t)stage * SLAB_FLOATS),
-                               (uint32_t)tid);
+                               (uint32_t)row, cg * (8 / CG), (cg + 1) * (8 / CG));
                 fence_proxy_async_smem();
                 mbar_arrive(&full[stage]);
             }
@@ -276,29 +286,47 @@ __global__ void __launch_bounds__(NTHREADS) layer_fwd_kernel(const __grid_consta
         // ---------------- epilogue
         mbar_wait(accf, 0);
         tc_fence_after();
-        const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16);
+        float* myred = red + ((size_t)cg * TILE_M + row) * RED_STRIDE;
         float v[32];
         float mean = 0.0f, rstd = 1.0f;
         if (has_ln) {
-            float shift = 0.0f, s1 = 0.0f, s2 = 0.0f;
-            for (int c0 = 0; c0 < n_pad; c0 += 32) {
+            // two-pass statistics; the CG column groups of a row combine their partial sums through SMEM
+            const float inv_n = 1.0f / (float)n_out;
+            float s1 = 0.0f;
+            for (int c0 = 32 * cg; c0 < n_pad; c0 += 32 * CG) {
                 tmem_ld32(trow + c0, v);
-                if (c0 == 0) shift = v[0] + sbias[0];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
+                for (int i = 0; i < 32; ++i)
+                    if (c0 + i < n_out) s1 += v[i] + sbias[c0 + i];
+            }
+            if (CG > 1) {
+                myred[0] = s1;
+                worker_barrier(NW);
+                s1 = 0.0f;
+#pragma unroll
+                for (int g = 0; g < CG; ++g) s1 += red[((size_t)g * TILE_M + row) * RED_STRIDE];
+            }
+            mean = s1 * inv_n;
+            float s2 = 0.0f;
+            for (int c0 = 32 * cg; c0 < n_pad; c0 += 32 * CG) {
+                tmem_ld32(trow + c0, v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
                     if (c0 + i < n_out) {
-                        float d = v[i] + sbias[c0 + i] - shift;
-                        s1 += d;
+                        float d = v[i] + sbias[c0 + i] - mean;
                         s2 = fmaf(d, d, s2);
                     }
-                }
             }
-            float inv_n = 1.0f / (float)n_out;
-            float m1 = s1 * inv_n;
-            mean = shift + m1;
-            float var = fmaxf(s2 * inv_n - m1 * m1, 0.0f);
-            rstd = 1.0f / sqrtf(var + P.L.eps);
-            if (P.stats && rvalid) {
+            if (CG > 1) {
+                myred[1] = s2;
+                worker_barrier(NW);
+                s2 = 0.0f;
+#pragma unroll
+                for (int g = 0; g < CG; ++g) s2 += red[((size_t)g * TILE_M + row) * RED_STRIDE + 1];
+            }
+            rstd = 1.0f / sqrtf(s2 * inv_n + P.L.eps);
+            if (P.stats && rvalid && cg == 0) {
                 P.stats[2 * lrow] = mean;
                 P.stats[2 * lrow + 1] = rstd;
             }
@@ -308,7 +336,7 @@ __global__ void __launch_bounds__(NTHREADS) layer_fwd_kernel(const __grid_consta
         for (int k = 0; k < STDADK_MAX_Q; ++k) yh[k] = 0.0f;
         const bool drop = P.L.drop_p > 0.0f;
         const unsigned int drop_step = drop ? dropout_step(P.L) : 0u;
-        for (int c0 = 0; c0 < n_pad; c0 += 32) {
+        for (int c0 = 32 * cg; c0 < n_pad; c0 += 32 * CG) {
             tmem_ld32(trow + c0, v);
             uint32_t keep = 0xFFFFFFFFu;
             if (drop) {
@@ -346,49 +374,65 @@ __global__ void __launch_bounds__(NTHREADS) layer_fwd_kernel(const __grid_consta
                 for (int c = 0; c < 8; ++c) {
                     float4 o = make_float4(to_tf32(v[4 * c]), to_tf32(v[4 * c + 1]), to_tf32(v[4 * c + 2]),
                                            to_tf32(v[4 * c + 3]));
-                    *reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(dst) + swz_off((uint32_t)tid, c)) = o;
+                    *reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(dst) + swz_off((uint32_t)row, c)) = o;
                 }
             }
         }
         if (P.has_head) {
-            float loss = 0.0f;
-            if (rvalid) {
-                float dy[STDADK_MAX_Q];
+            if (CG > 1) {
 #pragma unroll
                 for (int k = 0; k < STDADK_MAX_Q; ++k)
-                    if (k < P.head.q) {
-                        yh[k] += shb[k];
-                        P.head.yhat[lrow * P.head.q + k] = yh[k];
-                    }
-                if (P.head.loss_type != STDADK_LOSS_NONE) {
-                    loss = row_loss(P.head, yh, P.head.y[sample_of(P.pts, grow)], dy);
-                    if (P.head.dyhat) {
+                    if (k < P.head.q) myred[2 + k] = yh[k];
+                worker_barrier(NW);
+            }
+            if (cg == 0) {
+                float loss = 0.0f;
+                if (rvalid) {
+                    float dy[STDADK_MAX_Q];
 #pragma unroll
-                        for (int k = 0; k < STDADK_MAX_Q; ++k)
-                            if (k < P.head.q) P.head.dyhat[lrow * P.head.q + k] = dy[k];
+                    for (int k = 0; k < STDADK_MAX_Q; ++k)
+                        if (k < P.head.q) {
+                            if (CG > 1) {
+                                float acc = 0.0f;
+#pragma unroll
+                                for (int g = 0; g < CG; ++g) acc += red[((size_t)g * TILE_M + row) * RED_STRIDE + 2 + k];
+                                yh[k] = acc;
+                            }
+                            yh[k] += shb[k];
+                            P.head.yhat[lrow * P.head.q + k] = yh[k];
+                        }
+                    if (P.head.loss_type != STDADK_LOSS_NONE) {
+                        loss = row_loss(P.head, yh, P.head.y[sample_of(P.pts, grow)], dy);
+                        if (P.head.dyhat) {
+#pragma unroll
+                            for (int k = 0; k < STDADK_MAX_Q; ++k)
+                                if (k < P.head.q) P.head.dyhat[lrow * P.head.q + k] = dy[k];
+                        }
                     }
                 }
-            }
-            if (P.head.loss_type != STDADK_LOSS_NONE) {
-                loss = warp_sum(loss);
-                if (lane == 0) atomicAdd(P.head.loss_acc, loss);
+                if (P.head.loss_type != STDADK_LOSS_NONE) {
+                    loss = warp_sum(loss);
+                    if (lane == 0) atomicAdd(P.head.loss_acc, loss);
+                }
             }
         }
         tc_fence_before();
     }
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+    if (warp == 4 * CG) tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
 }
 
 // =============================================================================================
 // Backward
 // =============================================================================================
-template <bool BASIS>
-__global__ void __launch_bounds__(NTHREADS, 1) layer_bwd_kernel(const __grid_constant__ BwdK P) {
+template <bool BASIS, int CG>
+__global__ void __launch_bounds__(n_threads(CG), 1) layer_bwd_kernel(const __grid_constant__ BwdK P) {
+    constexpr int NW = n_work(CG), NT = n_threads(CG);
+    constexpr int MAXCH = MAX_N / 32 / CG;          // column chunks per thread
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = align_smem(smem_raw);
     const int q = P.has_head ? P.head.q : 0;
-    const SmemPlan sp = plan_smem(P.n_pad, q, BASIS ? P.basis.k_s : 0, BASIS ? P.basis.k_t : 0, true);
+    const SmemPlan sp = plan_smem(P.n_pad, q, BASIS ? P.basis.k_s : 0, BASIS ? P.basis.k_t : 0, true, CG);
     float* sA = reinterpret_cast<float*>(smem + sp.a_off);
     float* sB = reinterpret_cast<float*>(smem + sp.b_off);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + sp.bar_off);
@@ -406,6 +450,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) layer_bwd_kernel(const __grid_con
     float* cs_bet = cs_gam + P.n_pad;
     float* cs_hw = cs_bet + P.n_pad;
     float* cs_hb = cs_hw + q * P.n_pad;
+    float* red = reinterpret_cast<float*>(smem + sp.red_off);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tile = blockIdx.x;
@@ -415,41 +460,41 @@ __global__ void __launch_bounds__(NTHREADS, 1) layer_bwd_kernel(const __grid_con
     const int total_slabs = P.k_slabs + P.k_slabs2;
     const uint32_t acc1_off = (uint32_t)(P.tmem_cols / 2);
 
-    if (tid == NWORK) {
+    if (tid == NW) {
         for (int s = 0; s < NSTAGE; ++s) {
-            mbar_init(&full[s], BASIS ? 1 + NWORK : 1);
+            mbar_init(&full[s], BASIS ? 1 + NW : 1);
             mbar_init(&empty[s], 1);
         }
         mbar_init(accf, 1);
         mbar_fence_init();
     }
-    if (warp == 4) {
+    if (warp == 4 * CG) {
         __syncwarp();
         tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
     }
-    for (int i = tid; i < n_pad; i += NTHREADS) {
+    for (int i = tid; i < n_pad; i += NT) {
         bool ok = i < n_out;
         sbias[i] = ok ? P.L.bias[i] : 0.0f;
         sgam[i] = (ok && has_ln) ? P.L.gamma[i] : 1.0f;
         sbet[i] = (ok && has_ln) ? P.L.beta[i] : 0.0f;
     }
-    for (int i = tid; i < (3 + q) * n_pad + STDADK_MAX_Q; i += NTHREADS) cs_bias[i] = 0.0f;
+    for (int i = tid; i < (3 + q) * n_pad + STDADK_MAX_Q; i += NT) cs_bias[i] = 0.0f;
     if (P.has_head) {
-        for (int i = tid; i < q * n_pad; i += NTHREADS) {
+        for (int i = tid; i < q * n_pad; i += NT) {
             int k = i / n_pad, c = i - k * n_pad;
             shw[i] = c < n_out ? P.head.w[(size_t)k * n_out + c] : 0.0f;
         }
     }
     if (BASIS) {
-        for (int i = tid; i < P.basis.k_s; i += NTHREADS) sk[i] = P.basis.knots[i];
-        for (int i = tid; i < P.basis.k_t; i += NTHREADS) st[i] = P.basis.tknots[i];
+        for (int i = tid; i < P.basis.k_s; i += NT) sk[i] = P.basis.knots[i];
+        for (int i = tid; i < P.basis.k_t; i += NT) st[i] = P.basis.tknots[i];
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 4) {
+    if (warp == 4 * CG) {
         if (lane == 0) {
             const float* a_tile = BASIS ? nullptr : P.a_img + (size_t)tile * P.k_slabs * SLAB_FLOATS;
             const float* dzn_tile = P.k_slabs2 ? P.dz_next_img + (size_t)tile * P.k_slabs2 * SLAB_FLOATS : nullptr;
@@ -466,7 +511,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) layer_bwd_kernel(const __grid_con
             }
         }
         __syncwarp();
-    } else if (warp == 5) {
+    } else if (warp == 4 * CG + 1) {
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_tf32((uint32_t)n_pad, 0, 0);
             for (int s = 0; s < total_slabs; ++s) {
@@ -482,7 +527,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) layer_bwd_kernel(const __grid_con
         }
         __syncwarp();
     } else {
-        const long long lrow = (long long)tile * TILE_M + tid;
+        const int q4 = warp & 3, cg = warp >> 2;
+        const int row = q4 * 32 + lane;
+        const long long lrow = (long long)tile * TILE_M + row;
         const bool rvalid = lrow < P.pts.n_rows;
         const long long grow = P.pts.row_begin + lrow;
         if (BASIS) {
@@ -497,7 +544,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) layer_bwd_kernel(const __grid_con
                 if (it > 0) mbar_wait(&empty[stage], (it - 1) & 1);
                 if (s < P.k_slabs) {
                     gen_basis_slab(P.basis, sk, st, s, x, y, t, xrow, smem_u32(sA + (size_t)stage * SLAB_FLOATS),
-                                   (uint32_t)tid);
+                                   (uint32_t)row, cg * (8 / CG), (cg + 1) * (8 / CG));
                     fence_proxy_async_smem();
                 }
                 mbar_arrive(&full[stage]);
@@ -505,7 +552,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) layer_bwd_kernel(const __grid_con
         }
         mbar_wait(accf, 0);
         tc_fence_after();
-        const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16);
+        float* myred = red + ((size_t)cg * TILE_M + row) * RED_STRIDE;
         float mean = 0.0f, rstd = 1.0f;
         if (has_ln && rvalid) {
             mean = P.stats[2 * lrow];
@@ -518,12 +566,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) layer_bwd_kernel(const __grid_con
         const bool drop = P.L.drop_p > 0.0f;
         const unsigned int drop_step = drop ? dropout_step(P.L) : 0u;
         const float inv_n = 1.0f / (float)n_out;
-        uint32_t actbits[MAX_N / 32];
+        uint32_t actbits[MAXCH];
         float Sa = 0.0f, Sb = 0.0f;
         float z[32], g[32], tmp[32];
 
         // pass A: g = dL/dy (after dropout+ReLU backward); LN row sums; dgamma/dbeta/head column sums
-        for (int c0 = 0; c0 < n_pad; c0 += 32) {
+        int ch = 0;
+        for (int c0 = 32 * cg; c0 < n_pad; c0 += 32 * CG, ++ch) {
             tmem_ld32(trow + c0, z);
             if (!P.has_head) tmem_ld32(trow + acc1_off + c0, g);
             uint32_t keep = 0xFFFFFFFFu;
@@ -558,7 +607,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) layer_bwd_kernel(const __grid_con
                 z[i] = xh;
                 tmp[i] = h;
             }
-            actbits[c0 / 32] = act;
+#pragma unroll
+            for (int k = 0; k < MAXCH; ++k)
+                if (k == ch) actbits[k] = act;
             if (P.has_head) {
                 for (int k = 0; k < q; ++k) {
                     float hv[32];
@@ -589,13 +640,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) layer_bwd_kernel(const __grid_con
                 for (int c = 0; c < 8; ++c) {
                     float4 o = make_float4(to_tf32(g[4 * c]), to_tf32(g[4 * c + 1]), to_tf32(g[4 * c + 2]),
                                            to_tf32(g[4 * c + 3]));
-                    *reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(dst) + swz_off((uint32_t)tid, c)) = o;
+                    *reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(dst) + swz_off((uint32_t)row, c)) = o;
                 }
                 float s = warp_transpose_sum(g, lane);
                 atomicAdd(&cs_bias[c0 + lane], s);
             }
         }
-        if (P.has_head) {
+        if (P.has_head && cg == 0) {
             for (int k = 0; k < q; ++k) {
                 float s = warp_sum(dyh[k]);
                 if (lane == 0) atomicAdd(&cs_hb[k], s);
@@ -603,11 +654,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) layer_bwd_kernel(const __grid_con
         }
         // pass B (LayerNorm): dz = rstd * (gy - mean(gy) - xh * mean(gy * xh))
         if (has_ln) {
+            if (CG > 1) {
+                myred[0] = Sa;
+                myred[1] = Sb;
+                worker_barrier(NW);
+                Sa = Sb = 0.0f;
+#pragma unroll
+                for (int gq = 0; gq < CG; ++gq) {
+                    Sa += red[((size_t)gq * TILE_M + row) * RED_STRIDE];
+                    Sb += red[((size_t)gq * TILE_M + row) * RED_STRIDE + 1];
+                }
+            }
             const float ma = Sa * inv_n, mb = Sb * inv_n;
-            for (int c0 = 0; c0 < n_pad; c0 += 32) {
+            ch = 0;
+            for (int c0 = 32 * cg; c0 < n_pad; c0 += 32 * CG, ++ch) {
                 tmem_ld32(trow + c0, z);
                 if (!P.has_head) tmem_ld32(trow + acc1_off + c0, g);
-                const uint32_t act = actbits[c0 / 32];
+                uint32_t act = 0;
+#pragma unroll
+                for (int k = 0; k < MAXCH; ++k)
+                    if (k == ch) act = actbits[k];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     const int col = c0 + i;
@@ -630,7 +696,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) layer_bwd_kernel(const __grid_con
                 for (int c = 0; c < 8; ++c) {
                     float4 o = make_float4(to_tf32(g[4 * c]), to_tf32(g[4 * c + 1]), to_tf32(g[4 * c + 2]),
                                            to_tf32(g[4 * c + 3]));
-                    *reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(dst) + swz_off((uint32_t)tid, c)) = o;
+                    *reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(dst) + swz_off((uint32_t)row, c)) = o;
                 }
                 float s = warp_transpose_sum(g, lane);
                 atomicAdd(&cs_bias[c0 + lane], s);
@@ -638,8 +704,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) layer_bwd_kernel(const __grid_con
         }
         tc_fence_before();
         // flush the CTA's column sums
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int c = tid; c < n_out; c += NWORK) {
+        worker_barrier(NW);
+        for (int c = tid; c < n_out; c += NW) {
             atomicAdd(&P.d_bias[c], cs_bias[c]);
             if (has_ln) {
                 atomicAdd(&P.d_gamma[c], cs_gam[c]);
@@ -650,7 +716,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) layer_bwd_kernel(const __grid_con
         if (tid < q) atomicAdd(&P.d_head_b[tid], cs_hb[tid]);
     }
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+    if (warp == 4 * CG) tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
 }
 
 // =============================================================================================
@@ -690,14 +756,15 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_32b(uint32_t saddr, uint32_t
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (1ull << 61);
 }
 // Restage `n_chunks` half-slabs (64 rows x 128 B each, image swizzle) into the MN-major SMEM form.
+template <int NW>
 __device__ __forceinline__ void restage_half_slabs(const float* img_tile, int slab0, int n_chunks, int half,
                                                    uint32_t sdst, int tid) {
     const int units = n_chunks * 512;  // 16-byte units
-    for (int u0 = tid; u0 < units; u0 += NWORK * 4) {
+    for (int u0 = tid; u0 < units; u0 += NW * 4) {
         float4 v[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            int u = u0 + j * NWORK;
+            int u = u0 + j * NW;
             if (u < units) {
                 int c = u >> 9, w = u & 511;
                 v[j] = __ldg(reinterpret_cast<const float4*>(img_tile + (size_t)(slab0 + c) * SLAB_FLOATS +
@@ -706,7 +773,7 @@ __device__ __forceinline__ void restage_half_slabs(const float* img_tile, int sl
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            int u = u0 + j * NWORK;
+            int u = u0 + j * NW;
             if (u < units) {
                 int c = u >> 9, w = u & 511;
                 uint32_t r = (uint32_t)(w >> 3), pc = (uint32_t)(w & 7);
@@ -717,8 +784,9 @@ __device__ __forceinline__ void restage_half_slabs(const float* img_tile, int sl
     }
 }
 
-template <bool BASIS>
-__global__ void __launch_bounds__(NTHREADS, 1) wgrad_kernel(const __grid_constant__ WgradK P) {
+template <bool BASIS, int CG>
+__global__ void __launch_bounds__(n_threads(CG), 1) wgrad_kernel(const __grid_constant__ WgradK P) {
+    constexpr int NW = n_work(CG), NT = n_threads(CG);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = align_smem(smem_raw);
     uint8_t* stage_base = smem;
@@ -738,15 +806,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_kernel(const __grid_constan
     for (int rt = split; rt < P.n_row_tiles; rt += n_split) ++my_tiles;
     const int n_iter = my_tiles * 2;
 
-    if (tid == NWORK) {
+    if (tid == NW) {
         for (int s = 0; s < NSTAGE; ++s) {
-            mbar_init(&full[s], NWORK);
+            mbar_init(&full[s], NW);
             mbar_init(&empty[s], 1);
         }
         mbar_init(accf, 1);
         mbar_fence_init();
     }
-    if (warp == 4) {
+    if (warp == 4 * CG) {
         __syncwarp();
         tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
     }
@@ -755,13 +823,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_kernel(const __grid_constan
         for (int s = 0; s < NSTAGE; ++s) {
             float4* zp = reinterpret_cast<float4*>(stage_base + s * WG_STAGE_BYTES + m_chunks * WG_CHUNK_BYTES);
             int n16 = (4 - m_chunks) * WG_CHUNK_BYTES / 16;
-            for (int i = tid; i < n16; i += NTHREADS) zp[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = tid; i < n16; i += NT) zp[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         fence_proxy_async_smem();
     }
     if (BASIS) {
-        for (int i = tid; i < P.basis.k_s; i += NTHREADS) sk[i] = P.basis.knots[i];
-        for (int i = tid; i < P.basis.k_t; i += NTHREADS) st[i] = P.basis.tknots[i];
+        for (int i = tid; i < P.basis.k_s; i += NT) sk[i] = P.basis.knots[i];
+        for (int i = tid; i < P.basis.k_t; i += NT) st[i] = P.basis.tknots[i];
     }
     tc_fence_before();
     __syncthreads();
@@ -769,7 +837,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_kernel(const __grid_constan
     const uint32_t tmem_base = *tmem_slot;
 
     if (n_iter > 0) {
-        if (warp == 5) {
+        if (warp == 4 * CG + 1) {
             if (lane == 0) {
                 const uint32_t idesc = umma_idesc_tf32((uint32_t)n_mma, 1, 1);
                 for (int itn = 0; itn < n_iter; ++itn) {
@@ -789,7 +857,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_kernel(const __grid_constan
                 umma_commit(accf);
             }
             __syncwarp();
-        } else if (warp < 4) {
+        } else if (warp < 4 * CG) {
             const int row64 = tid & 63, par = tid >> 6;
             int itn = 0;
             for (int rt = split; rt < P.n_row_tiles; rt += n_split)
@@ -808,9 +876,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_kernel(const __grid_constan
                     if (it > 0) mbar_wait(&empty[stage], (it - 1) & 1);
                     uint32_t sa = smem_u32(stage_base + stage * WG_STAGE_BYTES);
                     uint32_t sb = sa + WG_A_BYTES;
-                    restage_half_slabs(P.dz_img + (size_t)rt * P.dz_slabs * SLAB_FLOATS, mi * 4, m_chunks, half, sa, tid);
+                    restage_half_slabs<NW>(P.dz_img + (size_t)rt * P.dz_slabs * SLAB_FLOATS, mi * 4, m_chunks, half, sa, tid);
                     if (BASIS) {
-                        for (int c = par; c < n_chunks; c += 2) {
+                        for (int c = par; c < n_chunks; c += NW / 64) {
                             const int slab = ni * P.nt_slabs + c;
 #pragma unroll 1
                             for (int c16 = 0; c16 < 8; ++c16) {
@@ -824,7 +892,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_kernel(const __grid_constan
                             }
                         }
                     } else {
-                        restage_half_slabs(P.a_img + (size_t)rt * P.a_slabs * SLAB_FLOATS, ni * P.nt_slabs, n_chunks,
+                        restage_half_slabs<NW>(P.a_img + (size_t)rt * P.a_slabs * SLAB_FLOATS, ni * P.nt_slabs, n_chunks,
                                            half, sb, tid);
                     }
                     fence_proxy_async_smem();
@@ -832,10 +900,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_kernel(const __grid_constan
                 }
             mbar_wait(accf, 0);
             tc_fence_after();
-            const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
-            const int o = mi * TILE_M + tid;
+            const int q4 = warp & 3, cg = warp >> 2;
+            const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16);
+            const int o = mi * TILE_M + q4 * 32 + lane;
             float v[32];
-            for (int c0 = 0; c0 < n_mma; c0 += 32) {
+            for (int c0 = 32 * cg; c0 < n_mma; c0 += 32 * CG) {
                 tmem_ld32(trow + c0, v);
                 if (o < P.n_out) {
                     float* dst = P.dw + (long long)o * P.stride_o;
@@ -850,7 +919,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_kernel(const __grid_constan
         }
     }
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+    if (warp == 4 * CG) tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
 }
 
 }  // namespace stdadk
@@ -871,7 +940,9 @@ struct KnotGradK {
     int n_out, k_slabs, _p0, _p1;
 };
 
-__global__ void __launch_bounds__(NTHREADS) knotgrad_kernel(const __grid_constant__ KnotGradK P) {
+template <int CG>
+__global__ void __launch_bounds__(n_threads(CG)) knotgrad_kernel(const __grid_constant__ KnotGradK P) {
+    constexpr int NW = n_work(CG);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = align_smem(smem_raw);
     const SmemPlan sp = plan_smem(TILE_M, 0, 0, 0, false);
@@ -885,7 +956,7 @@ __global__ void __launch_bounds__(NTHREADS) knotgrad_kernel(const __grid_constan
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ptile = blockIdx.x, ktile = blockIdx.y;
-    if (tid == NWORK) {
+    if (tid == NW) {
         for (int s = 0; s < NSTAGE; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
@@ -893,7 +964,7 @@ __global__ void __launch_bounds__(NTHREADS) knotgrad_kernel(const __grid_constan
         mbar_init(accf, 1);
         mbar_fence_init();
     }
-    if (warp == 4) {
+    if (warp == 4 * CG) {
         __syncwarp();
         tmem_alloc(tmem_slot, TILE_M);
     }
@@ -908,7 +979,7 @@ __global__ void __launch_bounds__(NTHREADS) knotgrad_kernel(const __grid_constan
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 4) {
+    if (warp == 4 * CG) {
         if (lane == 0) {
             const float* a_tile = P.w1s_img + (size_t)ktile * P.k_slabs * SLAB_FLOATS;
             for (int s = 0; s < P.k_slabs; ++s) {
@@ -921,7 +992,7 @@ __global__ void __launch_bounds__(NTHREADS) knotgrad_kernel(const __grid_constan
             }
         }
         __syncwarp();
-    } else if (warp == 5) {
+    } else if (warp == 4 * CG + 1) {
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_tf32(TILE_M, 0, 0);
             for (int s = 0; s < P.k_slabs; ++s) {
@@ -938,14 +1009,15 @@ __global__ void __launch_bounds__(NTHREADS) knotgrad_kernel(const __grid_constan
     } else {
         mbar_wait(accf, 0);
         tc_fence_after();
-        const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
-        const int j = ktile * TILE_M + tid;
+        const int q4 = warp & 3, cg = warp >> 2;
+        const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16);
+        const int j = ktile * TILE_M + q4 * 32 + lane;
         const bool kvalid = j < P.basis.k_s;
         float4 kn = kvalid ? P.basis.knots[j] : make_float4(0.f, 0.f, 1.f, 1.f);
         const long long rows_left = P.pts.n_rows - (long long)ptile * TILE_M;
         float gcx = 0.f, gcy = 0.f, glb = 0.f;
         float v[32];
-        for (int c0 = 0; c0 < TILE_M; c0 += 32) {
+        for (int c0 = 32 * cg; c0 < TILE_M; c0 += 32 * CG) {
             tmem_ld32(trow + c0, v);
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
@@ -974,7 +1046,7 @@ __global__ void __launch_bounds__(NTHREADS) knotgrad_kernel(const __grid_constan
         tc_fence_before();
     }
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem_base, TILE_M);
+    if (warp == 4 * CG) tmem_dealloc(tmem_base, TILE_M);
 }
 
 }  // namespace stdadk
