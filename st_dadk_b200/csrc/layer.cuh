@@ -43,8 +43,8 @@ __host__ __device__ inline SmemPlan plan_smem(int n_pad, int q, int k_s, int k_t
     s.tknots_off = o; o += (uint32_t)k_t * 8u;
     o = (o + 15u) & ~15u;
     s.colsum_off = o; o += bwd ? (uint32_t)((3 + q) * n_pad + STDADK_MAX_Q) * 4u : 0u;
-    o = (o + 15u) & ~15u;
-    s.red_off = o; o += (uint32_t)(cg * TILE_M * RED_STRIDE) * 4u;
+    s.red_off = s.a_off;   // epilogue scratch reuses the operand stages, which are dead once the last MMA committed
+    (void)cg;
     s.total = o + 1024;                                   // slack for manual 1024-byte alignment
     return s;
 }
@@ -82,18 +82,53 @@ struct BwdK {
     float drop_scale;
 };
 
-// Generate one 128-row x 32-feature operand slab (this thread = row r) into swizzled SMEM.
+// Four consecutive features [f, f+4) of the first Linear layer's input row -> one TF32 16-byte chunk.
+// Fast paths: the chunk lies entirely in the spatial block (one LDS.128 per knot, support test, value only where
+// d2 < theta'^2) or entirely in the temporal block; the generic per-feature path handles block boundaries.
+template <int FN>
+__device__ __forceinline__ float4 spatial_chunk(const float4* kp, float x, float y) {
+    float o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        float4 kn = kp[e];
+        o[e] = to_tf32(phi_eval(FN, x - kn.x, y - kn.y, kn.z, kn.w));
+    }
+    return make_float4(o[0], o[1], o[2], o[3]);
+}
+__device__ __forceinline__ float4 feature_chunk(const BasisP& B, const float4* sk, const float2* st, int f, float x,
+                                                float y, float t, const float* xrow) {
+    const int s0 = B.p_cov, s1 = B.p_cov + B.k_s, t1 = s1 + B.k_t;
+    if (f >= s0 && f + 4 <= s1) {
+        const float4* kp = sk + (f - s0);
+        if (B.fn == STDADK_WENDLAND) return spatial_chunk<STDADK_WENDLAND>(kp, x, y);
+        if (B.fn == STDADK_TRIANGULAR) return spatial_chunk<STDADK_TRIANGULAR>(kp, x, y);
+        return spatial_chunk<STDADK_GAUSSIAN>(kp, x, y);
+    }
+    if (f >= s1 && f + 4 <= t1) {
+        const float2* tp = st + (f - s1);
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float2 tk = tp[e];
+            o[e] = to_tf32(psi_eval(t, tk.x, tk.y));
+        }
+        return make_float4(o[0], o[1], o[2], o[3]);
+    }
+    if (f >= t1) return make_float4(0.f, 0.f, 0.f, 0.f);
+    return make_float4(to_tf32(feature_value(B, sk, st, f + 0, x, y, t, xrow)),
+                       to_tf32(feature_value(B, sk, st, f + 1, x, y, t, xrow)),
+                       to_tf32(feature_value(B, sk, st, f + 2, x, y, t, xrow)),
+                       to_tf32(feature_value(B, sk, st, f + 3, x, y, t, xrow)));
+}
+
+// Generate chunks [c_begin, c_end) of one 128-row x 32-feature operand slab (this thread = row r) into swizzled SMEM.
 __device__ __forceinline__ void gen_basis_slab(const BasisP& B, const float4* sk, const float2* st, int slab,
                                                float x, float y, float t, const float* xrow, uint32_t slab_saddr,
                                                uint32_t r, int c_begin = 0, int c_end = 8) {
 #pragma unroll 1
     for (int c = c_begin; c < c_end; ++c) {
-        int f = slab * SLAB_K + c * 4;
-        float v0 = to_tf32(feature_value(B, sk, st, f + 0, x, y, t, xrow));
-        float v1 = to_tf32(feature_value(B, sk, st, f + 1, x, y, t, xrow));
-        float v2 = to_tf32(feature_value(B, sk, st, f + 2, x, y, t, xrow));
-        float v3 = to_tf32(feature_value(B, sk, st, f + 3, x, y, t, xrow));
-        st_shared_v4(slab_saddr + swz_off(r, c), v0, v1, v2, v3);
+        float4 v = feature_chunk(B, sk, st, slab * SLAB_K + c * 4, x, y, t, xrow);
+        st_shared_v4(slab_saddr + swz_off(r, c), v.x, v.y, v.z, v.w);
     }
 }
 
@@ -120,8 +155,10 @@ __device__ __forceinline__ void issue_slab_mma(uint32_t tmem_acc, const float* s
                                           (first && k == 0) ? 0u : 1u);
 }
 
+// 1024-byte alignment of the dynamic shared-memory base, computed as an OFFSET from the extern array so the
+// compiler keeps the pointer in the shared address space (LDS/STS instead of generic LD/ST).
 __device__ __forceinline__ uint8_t* align_smem(uint8_t* p) {
-    return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023));
+    return p + ((1024u - (smem_u32(p) & 1023u)) & 1023u);
 }
 
 // Pinball / MSE loss on one row: fills dy[q] (already scaled) and returns the row's loss contribution.
@@ -882,13 +919,9 @@ __global__ void __launch_bounds__(n_threads(CG), 1) wgrad_kernel(const __grid_co
                             const int slab = ni * P.nt_slabs + c;
 #pragma unroll 1
                             for (int c16 = 0; c16 < 8; ++c16) {
-                                int f = slab * SLAB_K + c16 * 4;
-                                float v0 = to_tf32(feature_value(P.basis, sk, st, f + 0, x, y, t, xrow));
-                                float v1 = to_tf32(feature_value(P.basis, sk, st, f + 1, x, y, t, xrow));
-                                float v2 = to_tf32(feature_value(P.basis, sk, st, f + 2, x, y, t, xrow));
-                                float v3 = to_tf32(feature_value(P.basis, sk, st, f + 3, x, y, t, xrow));
-                                st_shared_v4(sb + c * WG_CHUNK_BYTES + swz32_off((uint32_t)row64, (uint32_t)c16), v0, v1,
-                                             v2, v3);
+                                float4 v = feature_chunk(P.basis, sk, st, slab * SLAB_K + c16 * 4, x, y, t, xrow);
+                                st_shared_v4(sb + c * WG_CHUNK_BYTES + swz32_off((uint32_t)row64, (uint32_t)c16), v.x, v.y,
+                                             v.z, v.w);
                             }
                         }
                     } else {

@@ -145,7 +145,9 @@ class Executor:
         s = self.spec
         n = int(pts.n_rows)
         if not prepared:
-            self.prepare(force=train or save, for_backward=save)
+            # always rebuild the operand images: parameter storage can be rewritten in place by kernels or by
+            # an EMA swap without any version counter the executor could observe (5 tiny launches)
+            self.prepare(force=True, for_backward=save)
         ws = self._workspace(n)
         yhat = out if out is not None else ws.yhat
         basis = self._basis()

@@ -1,0 +1,68 @@
+"""CPU: host-side pieces of the training driver against fixtures produced by the reference's own script
+(oracle/gen_golden.py::masks_fixture) and the known answers of the reference's unit tests."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import golden
+from scripts import train_st_interp as drv
+from scripts.run_grid_search import generate_config_combinations, DEFAULT_GRID
+
+
+@pytest.mark.parametrize("tag,om,pat,sm", [("a", "site-wise", "corner", "random"), ("b", "random", "uniform", "site-wise"),
+                                           ("c", "site-wise", "uniform", "site-wise"), ("d", "random", "corner", "random")])
+def test_masks_and_sample_order_bit_exact(tag, om, pat, sm):
+    g = golden("masks_losses")
+    z, coords = g["z"], g["coords"]
+    fn = drv.create_spatial_obs_prob_fn(pat, 10.0)
+    obs, sites = drv.sample_observations(z, coords, om, 0.3, fn, seed=2025)
+    tr, va = drv.split_train_valid(obs, sites, sm, 0.8, seed=12025)
+    assert np.array_equal(obs, g[f"{tag}_obs"]) and np.array_equal(np.asarray(sites), g[f"{tag}_sites"])
+    assert np.array_equal(tr, g[f"{tag}_train"]) and np.array_equal(va, g[f"{tag}_valid"])
+    tab = drv.create_dataset_from_mask(z, coords, tr, 0)
+    assert np.array_equal(tab.y.numpy(), g[f"{tag}_ds_y"])
+    assert np.array_equal(tab.t.numpy(), g[f"{tag}_ds_t"])
+    assert np.array_equal(tab.coords.numpy(), g[f"{tag}_ds_c"])
+
+
+def test_losses_and_penalties_vs_reference():
+    g = golden("masks_losses")
+    yp, yt = torch.tensor(g["loss_yp"]), torch.tensor(g["loss_yt"])
+    assert drv.quantile_loss(yp[:, :1], yt, 0.3).item() == pytest.approx(float(g["pinball_03"]), rel=1e-12)
+    assert drv.non_crossing_penalty(yp, "mean", 1).item() == pytest.approx(float(g["nc_p1"]), rel=1e-12)
+    assert drv.non_crossing_penalty(yp, "sum", 2).item() == pytest.approx(float(g["nc_p2"]), rel=1e-12)
+    deltas = [torch.tensor(d) for d in g["deltas"]]
+    assert drv.compute_p_nc_delta_penalty(deltas).item() == pytest.approx(float(g["pnc"]), rel=1e-12)
+    assert drv.compute_crps_multi_quantile(g["loss_yp"], g["loss_yt"], [0.1, 0.5, 0.9]) == pytest.approx(float(g["crps"]), rel=1e-12)
+    # known answers pinned by the reference's own tests (tests/stnf/models/test_crps_eq_4_6.py:18-44,
+    # test_p_nc_delta_penalty.py:51-78)
+    one, zero = torch.tensor([[1.0]]), torch.tensor([[0.5]])
+    assert drv.quantile_loss(zero, one, 0.5).item() == pytest.approx(0.25)
+    assert drv.quantile_loss(one, zero, 0.1).item() == pytest.approx(0.45)
+    assert drv.quantile_loss(zero, one, 0.1).item() == pytest.approx(0.05)
+    d = [torch.zeros(6), torch.tensor([2.0, 1.0, -0.5, 0.3, -0.2, 0.0])]
+    assert drv.compute_p_nc_delta_penalty(d).item() == pytest.approx(0.0)
+    assert drv.compute_crps({0.5: np.array([0.5])}, np.array([1.0])) == pytest.approx(0.5)
+    assert drv.auto_batch_size(4096, 8000) == 512 and drv.auto_batch_size(4096, 80000) == 4096
+
+
+def test_grid_of_64_configs():
+    cfgs = generate_config_combinations({"epochs": 50, "n_experiments": 1}, DEFAULT_GRID)
+    assert len(cfgs) == 64 and len({c["tag"] for c in cfgs}) == 64
+    assert {c["config_id"] for c in cfgs} == set(range(1, 65))
+    assert sum(c["spatial_learnable"] for c in cfgs) == 32
+    for r in range(8):                      # 8 configs per GPU on an 8-GPU box
+        assert len(cfgs[r::8]) == 8
+
+
+def test_yaml_schema_accepted():
+    import yaml
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = yaml.safe_load(open(os.path.join(root, "configs", "config_st_interp.yaml")))
+    from stnf.models import create_model
+    rng = np.random.default_rng(0)
+    np.random.seed(0)
+    m = create_model(dict(cfg, k_spatial_centers=[4, 9]), train_coords=rng.random((200, 2)).astype(np.float32))
+    assert m.output_dim == 5 and m.spatial_basis.learnable and m.spatial_basis.k == 13
+    assert m.spatial_basis.centers.shape == (13, 2) and (m.spatial_basis.bandwidths > 0).all()
