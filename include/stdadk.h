@@ -179,7 +179,8 @@ typedef struct {
 int stdadk_version(void);
 const char* stdadk_last_error(void);
 /* sizeof() of the argument structs, for bindings to verify their layout:
- * 0 basis, 1 points, 2 layer, 3 dropout, 4 head, 5 fwd_args, 6 bwd_args, 7 wgrad_args, 8 knotgrad_args, 9 adamw_args */
+ * 0 basis, 1 points, 2 layer, 3 dropout, 4 head, 5 fwd_args, 6 bwd_args, 7 wgrad_args, 8 knotgrad_args, 9 adamw_args,
+ * 10 pack_desc */
 size_t stdadk_sizeof(int which);
 
 size_t stdadk_image_floats(int64_t rows, int64_t cols);
@@ -196,6 +197,14 @@ int stdadk_basis_fwd(const stdadk_basis* basis, const stdadk_points* pts, float*
 int stdadk_pack_image(const float* src, int64_t row_stride, int64_t col_stride, int64_t rows, int64_t cols,
                       float* img, void* stream);
 int stdadk_unpack_image(const float* img, int64_t rows, int64_t cols, float* dst, void* stream);
+/* Several matrices -> images in ONE launch (a training step repacks every weight matrix and its transpose) */
+#define STDADK_MAX_PACK 8
+typedef struct {
+    const float* src;
+    int64_t row_stride, col_stride, rows, cols;
+    float* img;
+} stdadk_pack_desc;
+int stdadk_pack_images(const stdadk_pack_desc* descs, int n, void* stream);
 
 int stdadk_layer_fwd(const stdadk_fwd_args* a, void* stream);
 int stdadk_layer_bwd(const stdadk_bwd_args* a, void* stream);

@@ -71,6 +71,11 @@ class AdamWArgs(C.Structure):
                 ("ema_decay", C.c_float)]
 
 
+class PackDesc(C.Structure):
+    _fields_ = [("src", fp), ("row_stride", C.c_int64), ("col_stride", C.c_int64), ("rows", C.c_int64),
+                ("cols", C.c_int64), ("img", fp)]
+
+
 _lib = None
 
 _PROTOS = {
@@ -83,6 +88,7 @@ _PROTOS = {
     "stdadk_basis_fwd": (C.c_int, [C.POINTER(Basis), C.POINTER(Points), fp, fp, fp]),
     "stdadk_pack_image": (C.c_int, [fp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, fp, fp]),
     "stdadk_unpack_image": (C.c_int, [fp, C.c_int64, C.c_int64, fp, fp]),
+    "stdadk_pack_images": (C.c_int, [C.POINTER(PackDesc), C.c_int, fp]),
     "stdadk_layer_fwd": (C.c_int, [C.POINTER(FwdArgs), fp]),
     "stdadk_layer_bwd": (C.c_int, [C.POINTER(BwdArgs), fp]),
     "stdadk_wgrad": (C.c_int, [C.POINTER(WgradArgs), fp]),
@@ -109,7 +115,7 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        structs = [Basis, Points, Layer, Dropout, Head, FwdArgs, BwdArgs, WgradArgs, KnotGradArgs, AdamWArgs]
+        structs = [Basis, Points, Layer, Dropout, Head, FwdArgs, BwdArgs, WgradArgs, KnotGradArgs, AdamWArgs, PackDesc]
         for i, st in enumerate(structs):
             if L.stdadk_sizeof(i) != C.sizeof(st):
                 raise RuntimeError(f"libstdadk ABI mismatch: {st.__name__} is {C.sizeof(st)} B in the binding, "

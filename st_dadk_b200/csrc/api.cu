@@ -156,6 +156,7 @@ size_t stdadk_sizeof(int which) {
         case 7: return sizeof(stdadk_wgrad_args);
         case 8: return sizeof(stdadk_knotgrad_args);
         case 9: return sizeof(stdadk_adamw_args);
+        case 10: return sizeof(stdadk_pack_desc);
         default: return 0;
     }
 }
@@ -206,6 +207,24 @@ int stdadk_pack_image(const float* src, int64_t row_stride, int64_t col_stride, 
     pack_image_kernel<<<grid_for(chunks, 256), 256, 0, (cudaStream_t)stream>>>(src, row_stride, col_stride, rows, cols,
                                                                                 img, chunks, slabs);
     return check_launch("pack_image");
+}
+
+int stdadk_pack_images(const stdadk_pack_desc* descs, int n, void* stream) {
+    if (int r = check_device()) return r;
+    REQUIRE(descs && n >= 1 && n <= STDADK_MAX_PACK, "pack_images: 1..%d descriptors, got %d", STDADK_MAX_PACK, n);
+    PackBatch B{};
+    B.n = n;
+    long long max_chunks = 0;
+    for (int i = 0; i < n; ++i) {
+        REQUIRE(descs[i].src && descs[i].img && descs[i].rows > 0 && descs[i].cols > 0, "pack_images: bad descriptor %d", i);
+        REQUIRE((reinterpret_cast<uintptr_t>(descs[i].img) & 127) == 0, "pack_images: image %d must be 128-byte aligned", i);
+        B.d[i] = descs[i];
+        long long chunks = ceil_div64(descs[i].rows, TILE_M) * ceil_div64(descs[i].cols, SLAB_K) * (SLAB_FLOATS / 4);
+        if (chunks > max_chunks) max_chunks = chunks;
+    }
+    dim3 grid(grid_for(max_chunks, 256, 2), n);
+    pack_images_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(B);
+    return check_launch("pack_images");
 }
 
 int stdadk_unpack_image(const float* img, int64_t rows, int64_t cols, float* dst, void* stream) {
@@ -264,13 +283,14 @@ int stdadk_layer_fwd(const stdadk_fwd_args* a, void* stream) {
     // (dense prediction): 8 worker warps and two CTAs per SM so one tile's epilogue overlaps the other's MMAs
     const int sms = g_sm_count > 0 ? g_sm_count : 148;
     const int cg = tiles >= 2 * sms ? 2 : 4;
-    SmemPlan sp = plan_smem(K.n_pad, K.has_head ? K.head.q : 0, basis ? K.basis.k_s : 0, basis ? K.basis.k_t : 0, false, cg);
+    const int ns = cg == 2 ? 2 : 4;   // 1 CTA/SM in the latency configuration: spend the shared memory on pipeline depth
+    SmemPlan sp = plan_smem(K.n_pad, K.has_head ? K.head.q : 0, basis ? K.basis.k_s : 0, basis ? K.basis.k_t : 0, false, cg, ns);
     REQUIRE(sp.total <= 227 * 1024, "layer_fwd: needs %u B of shared memory (> 227 KB): too many knots for the dense path",
             sp.total);
 #define LAUNCH_FWD(B, C)                                                                   \
     do {                                                                                   \
-        if (int r = set_smem(layer_fwd_kernel<B, C>, sp.total)) return r;                  \
-        layer_fwd_kernel<B, C><<<tiles, n_threads(C), sp.total, (cudaStream_t)stream>>>(K); \
+        if (int r = set_smem(layer_fwd_kernel<B, C, (C == 2 ? 2 : 4)>, sp.total)) return r;                  \
+        layer_fwd_kernel<B, C, (C == 2 ? 2 : 4)><<<tiles, n_threads(C), sp.total, (cudaStream_t)stream>>>(K); \
     } while (0)
     if (basis) {
         if (cg == 2) LAUNCH_FWD(true, 2); else LAUNCH_FWD(true, 4);
@@ -322,16 +342,16 @@ int stdadk_layer_bwd(const stdadk_bwd_args* a, void* stream) {
     K.thresh16 = dropout_thresh16(a->drop.p);
     K.drop_scale = a->drop.p > 0.0f ? 1.0f / (1.0f - a->drop.p) : 1.0f;
     const bool basis = a->basis != nullptr;
-    constexpr int BCG = 2;
-    SmemPlan sp = plan_smem(K.n_pad, K.has_head ? K.head.q : 0, basis ? K.basis.k_s : 0, basis ? K.basis.k_t : 0, true, BCG);
+    constexpr int BCG = 2, BNS = 4;
+    SmemPlan sp = plan_smem(K.n_pad, K.has_head ? K.head.q : 0, basis ? K.basis.k_s : 0, basis ? K.basis.k_t : 0, true, BCG, BNS);
     REQUIRE(sp.total <= 227 * 1024, "layer_bwd: needs %u B of shared memory (> 227 KB)", sp.total);
     int tiles = (int)ceil_div64(a->pts.n_rows, TILE_M);
     if (basis) {
-        if (int r = set_smem(layer_bwd_kernel<true, BCG>, sp.total)) return r;
-        layer_bwd_kernel<true, BCG><<<tiles, n_threads(BCG), sp.total, (cudaStream_t)stream>>>(K);
+        if (int r = set_smem(layer_bwd_kernel<true, BCG, BNS>, sp.total)) return r;
+        layer_bwd_kernel<true, BCG, BNS><<<tiles, n_threads(BCG), sp.total, (cudaStream_t)stream>>>(K);
     } else {
-        if (int r = set_smem(layer_bwd_kernel<false, BCG>, sp.total)) return r;
-        layer_bwd_kernel<false, BCG><<<tiles, n_threads(BCG), sp.total, (cudaStream_t)stream>>>(K);
+        if (int r = set_smem(layer_bwd_kernel<false, BCG, BNS>, sp.total)) return r;
+        layer_bwd_kernel<false, BCG, BNS><<<tiles, n_threads(BCG), sp.total, (cudaStream_t)stream>>>(K);
     }
     return check_launch("layer_bwd");
 }

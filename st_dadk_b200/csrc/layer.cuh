@@ -19,7 +19,7 @@
 
 namespace stdadk {
 
-constexpr int NSTAGE = 2;
+constexpr int WG_NSTAGE = 2;                  // wgrad: 2 stages of 96 KB
 constexpr int RED_STRIDE = 2 + STDADK_MAX_Q;   // per (cg, row) scratch: two LayerNorm partials + Q head partials
 __host__ __device__ constexpr int n_work(int cg) { return 128 * cg; }
 __host__ __device__ constexpr int n_threads(int cg) { return 128 * cg + 64; }
@@ -29,12 +29,12 @@ __device__ __forceinline__ void worker_barrier(int nw) { asm volatile("bar.sync 
 struct SmemPlan {
     uint32_t a_off, b_off, bar_off, tmem_off, vec_off, headw_off, knots_off, tknots_off, colsum_off, red_off, total;
 };
-__host__ __device__ inline SmemPlan plan_smem(int n_pad, int q, int k_s, int k_t, bool bwd, int cg = 1) {
+__host__ __device__ inline SmemPlan plan_smem(int n_pad, int q, int k_s, int k_t, bool bwd, int cg = 1, int ns = 2) {
     SmemPlan s;
     uint32_t o = 0;
-    s.a_off = o; o += NSTAGE * SLAB_BYTES;
-    s.b_off = o; o += NSTAGE * (uint32_t)n_pad * 128u;
-    s.bar_off = o; o += 64;
+    s.a_off = o; o += ns * SLAB_BYTES;
+    s.b_off = o; o += ns * (uint32_t)n_pad * 128u;
+    s.bar_off = o; o += 128;
     s.tmem_off = o; o += 16;
     s.vec_off = o; o += 3u * n_pad * 4u;                 // bias, gamma, beta
     s.headw_off = o; o += (uint32_t)(q > 0 ? (q * n_pad + STDADK_MAX_Q) * 4 : 0);
@@ -208,13 +208,13 @@ __device__ __forceinline__ float row_loss(const HeadP& H, const float* yh, float
 // =============================================================================================
 // Forward
 // =============================================================================================
-template <bool BASIS, int CG>
+template <bool BASIS, int CG, int NS>
 __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kernel(const __grid_constant__ FwdK P) {
-    constexpr int NW = n_work(CG), NT = n_threads(CG);
+    constexpr int NW = n_work(CG), NT = n_threads(CG), NSTAGE = NS;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = align_smem(smem_raw);
     const SmemPlan sp = plan_smem(P.n_pad, P.has_head ? P.head.q : 0, BASIS ? P.basis.k_s : 0,
-                                  BASIS ? P.basis.k_t : 0, false, CG);
+                                  BASIS ? P.basis.k_t : 0, false, CG, NS);
     float* sA = reinterpret_cast<float*>(smem + sp.a_off);
     float* sB = reinterpret_cast<float*>(smem + sp.b_off);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + sp.bar_off);
@@ -462,14 +462,14 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
 // =============================================================================================
 // Backward
 // =============================================================================================
-template <bool BASIS, int CG>
+template <bool BASIS, int CG, int NS>
 __global__ void __launch_bounds__(n_threads(CG), 1) layer_bwd_kernel(const __grid_constant__ BwdK P) {
-    constexpr int NW = n_work(CG), NT = n_threads(CG);
+    constexpr int NW = n_work(CG), NT = n_threads(CG), NSTAGE = NS;
     constexpr int MAXCH = MAX_N / 32 / CG;          // column chunks per thread
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = align_smem(smem_raw);
     const int q = P.has_head ? P.head.q : 0;
-    const SmemPlan sp = plan_smem(P.n_pad, q, BASIS ? P.basis.k_s : 0, BASIS ? P.basis.k_t : 0, true, CG);
+    const SmemPlan sp = plan_smem(P.n_pad, q, BASIS ? P.basis.k_s : 0, BASIS ? P.basis.k_t : 0, true, CG, NS);
     float* sA = reinterpret_cast<float*>(smem + sp.a_off);
     float* sB = reinterpret_cast<float*>(smem + sp.b_off);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + sp.bar_off);
@@ -782,7 +782,7 @@ constexpr int WG_B_BYTES = 8 * WG_CHUNK_BYTES;               // N <= 256
 constexpr int WG_STAGE_BYTES = WG_A_BYTES + WG_B_BYTES;
 
 __host__ __device__ inline uint32_t wgrad_smem_bytes(int k_s, int k_t) {
-    return NSTAGE * WG_STAGE_BYTES + 64 + 16 + 16 + (uint32_t)k_s * 16u + (uint32_t)k_t * 8u + 16 + 1024;
+    return WG_NSTAGE * WG_STAGE_BYTES + 64 + 16 + 16 + (uint32_t)k_s * 16u + (uint32_t)k_t * 8u + 16 + 1024;
 }
 // byte offset of logical 16-byte chunk `c16` of row `row` in the SWIZZLE_128B_BASE32B form
 __device__ __forceinline__ uint32_t swz32_off(uint32_t row, uint32_t c16) {
@@ -827,11 +827,11 @@ __global__ void __launch_bounds__(n_threads(CG), 1) wgrad_kernel(const __grid_co
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = align_smem(smem_raw);
     uint8_t* stage_base = smem;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + NSTAGE * WG_STAGE_BYTES);
-    uint64_t* empty = full + NSTAGE;
-    uint64_t* accf = full + 2 * NSTAGE;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + NSTAGE * WG_STAGE_BYTES + 64);
-    float4* sk = reinterpret_cast<float4*>(smem + NSTAGE * WG_STAGE_BYTES + 96);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + WG_NSTAGE * WG_STAGE_BYTES);
+    uint64_t* empty = full + WG_NSTAGE;
+    uint64_t* accf = full + 2 * WG_NSTAGE;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + WG_NSTAGE * WG_STAGE_BYTES + 64);
+    float4* sk = reinterpret_cast<float4*>(smem + WG_NSTAGE * WG_STAGE_BYTES + 96);
     float2* st = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(sk) + (size_t)(BASIS ? P.basis.k_s : 0) * 16);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -844,7 +844,7 @@ __global__ void __launch_bounds__(n_threads(CG), 1) wgrad_kernel(const __grid_co
     const int n_iter = my_tiles * 2;
 
     if (tid == NW) {
-        for (int s = 0; s < NSTAGE; ++s) {
+        for (int s = 0; s < WG_NSTAGE; ++s) {
             mbar_init(&full[s], NW);
             mbar_init(&empty[s], 1);
         }
@@ -857,7 +857,7 @@ __global__ void __launch_bounds__(n_threads(CG), 1) wgrad_kernel(const __grid_co
     }
     // unused M chunks must read as zeros (they are never overwritten)
     if (m_chunks < 4) {
-        for (int s = 0; s < NSTAGE; ++s) {
+        for (int s = 0; s < WG_NSTAGE; ++s) {
             float4* zp = reinterpret_cast<float4*>(stage_base + s * WG_STAGE_BYTES + m_chunks * WG_CHUNK_BYTES);
             int n16 = (4 - m_chunks) * WG_CHUNK_BYTES / 16;
             for (int i = tid; i < n16; i += NT) zp[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -878,7 +878,7 @@ __global__ void __launch_bounds__(n_threads(CG), 1) wgrad_kernel(const __grid_co
             if (lane == 0) {
                 const uint32_t idesc = umma_idesc_tf32((uint32_t)n_mma, 1, 1);
                 for (int itn = 0; itn < n_iter; ++itn) {
-                    int stage = itn % NSTAGE, it = itn / NSTAGE;
+                    int stage = itn % WG_NSTAGE, it = itn / WG_NSTAGE;
                     mbar_wait(&full[stage], it & 1);
                     tc_fence_after();
                     uint32_t sa = smem_u32(stage_base + stage * WG_STAGE_BYTES);
@@ -899,7 +899,7 @@ __global__ void __launch_bounds__(n_threads(CG), 1) wgrad_kernel(const __grid_co
             int itn = 0;
             for (int rt = split; rt < P.n_row_tiles; rt += n_split)
                 for (int half = 0; half < 2; ++half, ++itn) {
-                    int stage = itn % NSTAGE, it = itn / NSTAGE;
+                    int stage = itn % WG_NSTAGE, it = itn / WG_NSTAGE;
                     float x = 0.f, y = 0.f, t = 0.f;
                     const float* xrow = nullptr;
                     if (BASIS) {
@@ -975,7 +975,7 @@ struct KnotGradK {
 
 template <int CG>
 __global__ void __launch_bounds__(n_threads(CG)) knotgrad_kernel(const __grid_constant__ KnotGradK P) {
-    constexpr int NW = n_work(CG);
+    constexpr int NW = n_work(CG), NSTAGE = 2;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = align_smem(smem_raw);
     const SmemPlan sp = plan_smem(TILE_M, 0, 0, 0, false);

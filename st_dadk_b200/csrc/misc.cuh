@@ -31,6 +31,35 @@ __global__ void pack_image_kernel(const float* __restrict__ src, long long row_s
     }
 }
 
+struct PackBatch {
+    stdadk_pack_desc d[STDADK_MAX_PACK];
+    int n;
+};
+// blockIdx.y selects the matrix; same per-chunk work as pack_image_kernel
+__global__ void pack_images_kernel(PackBatch B) {
+    const stdadk_pack_desc D = B.d[blockIdx.y];
+    const int slabs = (int)((D.cols + SLAB_K - 1) / SLAB_K);
+    const long long n_chunks = ((D.rows + TILE_M - 1) / TILE_M) * slabs * (long long)(SLAB_FLOATS / 4);
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n_chunks;
+         idx += (long long)gridDim.x * blockDim.x) {
+        int chunk = (int)(idx & 7);
+        int row = (int)((idx >> 3) & 127);
+        long long ts = idx >> 10;
+        int slab = (int)(ts % slabs);
+        long long tile = ts / slabs;
+        long long r = tile * TILE_M + row;
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            long long c = (long long)slab * SLAB_K + chunk * 4 + e;
+            v[e] = (r < D.rows && c < D.cols) ? to_tf32(D.src[r * D.row_stride + c * D.col_stride]) : 0.0f;
+        }
+        float* dst = D.img + ts * SLAB_FLOATS;
+        *reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(dst) + swz_off((uint32_t)row, (uint32_t)chunk)) =
+            make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
 __global__ void unpack_image_kernel(const float* __restrict__ img, long long rows, long long cols,
                                     float* __restrict__ dst, int slabs) {
     long long n = rows * cols;

@@ -88,11 +88,13 @@ class Executor:
         self.loss_acc = torch.zeros(1, dtype=torch.float32, device=dev)
         self._grad_flat = None
         self.grads = None
+        self._knots_ready = False
 
     # ------------------------------------------------------------------ operand preparation
     def rebind(self, spec: NetSpec):
         self.spec = spec
         self._pack_key = None
+        self._knots_ready = False
 
     def _key(self):
         s = self.spec
@@ -106,16 +108,26 @@ class Executor:
         key = (self._key(), for_backward)
         if not force and key == self._pack_key:
             return
-        ops.knots_prepare(s.centers, s.bandwidths if s.log_bandwidths is None else None, s.log_bandwidths,
-                          s.basis_fn, out=self.knots4)
-        ops.tknots_prepare(s.t_centers, s.t_bandwidths, out=self.tknots2)
+        if s.learnable_basis or not self._knots_ready:
+            ops.knots_prepare(s.centers, s.bandwidths if s.log_bandwidths is None else None, s.log_bandwidths,
+                              s.basis_fn, out=self.knots4)
+            ops.tknots_prepare(s.t_centers, s.t_bandwidths, out=self.tknots2)   # fixed buffers: only the first time
+            self._knots_ready = True
+        srcs, outs, slots = [], [], []
         for l, w in enumerate(s.weights):
-            self.w_img[l] = ops.pack_image(w, out=self.w_img[l])
+            srcs.append(w); outs.append(self.w_img[l]); slots.append(("w", l))
             if for_backward and l > 0:
-                self.wt_img[l] = ops.pack_image(w.t(), out=self.wt_img[l])
+                srcs.append(w.t()); outs.append(self.wt_img[l]); slots.append(("wt", l))
         if for_backward and s.learnable_basis:
-            w1s = s.weights[0][:, s.p_cov:s.p_cov + s.centers.shape[0]].t()   # (K_s, n_out)
-            self.w1s_img = ops.pack_image(w1s, out=self.w1s_img)
+            srcs.append(s.weights[0][:, s.p_cov:s.p_cov + s.centers.shape[0]].t())   # (K_s, n_out)
+            outs.append(self.w1s_img); slots.append(("w1s", 0))
+        for (kind, l), img in zip(slots, ops.pack_images(srcs, outs)):   # one launch for all images
+            if kind == "w":
+                self.w_img[l] = img
+            elif kind == "wt":
+                self.wt_img[l] = img
+            else:
+                self.w1s_img = img
         self._pack_key = key
 
     def _workspace(self, n_rows: int) -> _Workspace:

@@ -55,6 +55,23 @@ def pack_image(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.T
     return out
 
 
+def pack_images(srcs, outs):
+    """Pack several strided matrices into their images with one launch; `outs[i]` may be None (allocated)."""
+    res = []
+    descs = (L.PackDesc * len(srcs))()
+    for i, (src, out) in enumerate(zip(srcs, outs)):
+        rows, cols = src.shape
+        if out is None:
+            out = new_image(rows, cols, src.device)
+        descs[i] = L.PackDesc(_ptr(src), src.stride(0), src.stride(1), rows, cols, _ptr(out))
+        res.append(out)
+    for lo in range(0, len(srcs), 8):
+        n = min(8, len(srcs) - lo)
+        sub = (L.PackDesc * n)(*descs[lo:lo + n])
+        L.check(L.lib().stdadk_pack_images(sub, n, _stream()), "pack_images")
+    return res
+
+
 def unpack_image(img: torch.Tensor, rows: int, cols: int) -> torch.Tensor:
     out = torch.empty(rows, cols, dtype=torch.float32, device=img.device)
     L.check(L.lib().stdadk_unpack_image(_ptr(img), rows, cols, _ptr(out), _stream()), "unpack_image")

@@ -393,10 +393,10 @@ class Trainer:
     def launches_per_step(self) -> int:
         """libstdadk kernel launches in one optimisation step (counted from the launch sequence)."""
         nh = self.ex.spec.n_hidden
-        n = 2 + nh + (nh - 1)               # knot tables, forward weight images, dgrad (W^T) images
+        n = 1                               # all weight images (W, W^T, W1s) in one pack_images launch
         n += nh + nh + nh                   # layer_fwd, layer_bwd, wgrad per block
         if self.learnable:
-            n += 2                          # W1s image + knot_grad
+            n += 3                          # knot + temporal tables (knots move), knot_grad
         n += (1 if self.clip > 0 else 0) + 2   # grad_sqnorm, step counter, adamw_ema
         return n
 
@@ -426,6 +426,7 @@ class Trainer:
             "wgrad": (lambda a: f"wgrad[{a.n_in}x{a.n_out}]", f_wg),
             "knot_grad": ("knot_grad", lambda a: 2.0 * rows * a.n_out * self.model.k_spatial),
             "pack_image": ("pack_image", lambda *a, **k: 0.0),
+            "pack_images": ("pack_images", lambda *a, **k: 0.0),
             "knots_prepare": ("knots_prepare", lambda *a, **k: 0.0),
             "tknots_prepare": ("knots_prepare", lambda *a, **k: 0.0),
             "grad_sqnorm": ("grad_sqnorm", lambda *a, **k: 0.0),

@@ -17,7 +17,7 @@ def test_header_symbols_exported():
     g.build()
     lib = ctypes.CDLL(os.path.join(ROOT, "st_dadk_b200", "libstdadk.so"))
     names = _declared()
-    assert len(names) >= 14
+    assert len(names) >= 16
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/stdadk.h but not exported"
     lib.stdadk_version.restype = ctypes.c_int

@@ -58,9 +58,11 @@ def test_module_forward_backward_matches_reference(name, q, seed, taus):
     for k, p in model.named_parameters():
         gs = g["gsample." + k]
         got = p.grad.detach().cpu().numpy().reshape(-1)[::97]
-        # 1-in-97 strided SAMPLE of each gradient: relative L2 error over the sample (TF32 operands: ~5e-3;
-        # the check-loss gradient also jumps by 1/N where a residual changes sign)
-        assert rel_l2(got, gs) < 6e-2, (k, rel_l2(got, gs))
+        # 1-in-97 strided SAMPLE of each gradient, compared on the scale of the whole tensor (RMS from the stored
+        # moments): sampled entries can be near-cancelling column sums whose own magnitude is not a meaningful scale
+        scale = max(float(np.abs(gs).max()), float(np.sqrt(g["gstat." + k][1] / p.numel())))
+        err = float(np.abs(got - gs).max()) / scale
+        assert err < (6e-2 if taus else 3e-2), (k, err)
 
 
 def test_reference_api_surface():
