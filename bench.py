@@ -205,9 +205,11 @@ def run_ours(args):
         ge.build()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    log = lambda m: print(f"[bench r{rank}] {m}", file=sys.stderr, flush=True)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        from datetime import timedelta
+        dist.init_process_group("nccl", device_id=dev, timeout=timedelta(seconds=180))   # a hang fails fast
         dist.barrier()
     from stnf.models import STInterpMLP
     from stnf.dataio import ObservationTable
@@ -239,9 +241,11 @@ def run_ours(args):
     def one_step(i):
         tr.train_step(table, perm, (i % n_off) * BATCH, BATCH, global_rows)
 
+    log("trainer built; warm-up")
     for i in range(max(args.warmup, 3)):
         one_step(i)
     torch.cuda.synchronize()
+    log("warm-up done; timing")
     if world > 1:
         dist.barrier()
     sampler = ClockSampler(local)
@@ -268,6 +272,7 @@ def run_ours(args):
     value = args.steps * BATCH * world / (dev_ms * 1e-3)
     final_loss = tr.pop_loss_sum()
 
+    log(f"timed region done: {dev_ms / args.steps:.4f} ms/step")
     # ---- end-to-end through the host-buffer API: per step H2D of the batch from pinned memory + D2H of the loss
     hb = 3 * 4 * BATCH + 4 * BATCH                 # coords (8 B) + t (4 B) + y (4 B) per sample
     for i in range(3):
@@ -284,6 +289,7 @@ def run_ours(args):
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_val = args.steps * BATCH * world / float(e2e_t.item())
 
+    log("e2e done; prediction")
     # ---- dense prediction: T x S = 1M points (space-time field), sharded by point, no collective
     model.eval()
     pr = Predictor(model)
@@ -329,11 +335,11 @@ def run_ours(args):
         dist.all_reduce(pred_e2e, op=dist.ReduceOp.MAX)
     pred_e2e_pps = n_pred / float(pred_e2e.item())
 
+    log("prediction done; per-kernel profile")
     # ---- per-kernel timing (eager, CUDA events around every libstdadk launch) -> roofline of the dominant kernel
     roof = None
-    kt = {}
+    kt = tr.profile_step(table, perm, BATCH, global_rows, repeats=10)   # every rank: the step contains the all-reduce
     if rank == 0:
-        kt = tr.profile_step(table, perm, BATCH, global_rows, repeats=10)
         name, info = max(kt["kernels"].items(), key=lambda kv: kv[1]["ms"] * kv[1]["count"])
         flops = info["flops"]
         achieved = flops / (info["ms"] * 1e-3) / 1e12

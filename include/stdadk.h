@@ -72,9 +72,11 @@ typedef struct {
 
 typedef struct {
     float p;                  /* 0 => off (eval mode) */
-    uint32_t step;            /* stream position; masks are keyed by (seed, step, layer, row_begin + r, column) */
+    uint32_t step;            /* stream position; masks are keyed by (seed, step, layer, key_offset + r, column) */
     uint64_t seed;
     const int32_t* step_ptr;  /* if non-NULL the step is read from this DEVICE counter (graph replay) */
+    uint64_t key_offset;      /* position of this call's row 0 in the GLOBAL batch: a data-parallel rank passes the
+                                 offset of its shard, so masks do not depend on how the batch is split */
 } stdadk_dropout;
 
 /* Output head + loss (st_interp.py:689 / :849-877 through an effective (Q x d) matrix;
@@ -211,9 +213,11 @@ int stdadk_layer_bwd(const stdadk_bwd_args* a, void* stream);
 int stdadk_wgrad(const stdadk_wgrad_args* a, void* stream);
 int stdadk_knot_grad(const stdadk_knotgrad_args* a, void* stream);
 
-/* sqnorms[g] = sum of squares of g over each group (sqnorms zeroed by the call) */
+/* sqnorms[g] = sum of squares of g over each group.  Bitwise deterministic (replicas of a data-parallel run must
+ * compute the same clip coefficient).  workspace: stdadk_sqnorm_ws_floats() floats, zeroed once by the caller. */
+size_t stdadk_sqnorm_ws_floats(void);
 int stdadk_grad_sqnorm(const float* g, int64_t n, int n_groups, const int64_t* group_end, float* sqnorms,
-                       void* stream);
+                       float* workspace, void* stream);
 int stdadk_adamw_ema_step(const stdadk_adamw_args* a, void* stream);
 
 #ifdef __cplusplus

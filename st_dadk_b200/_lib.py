@@ -33,7 +33,8 @@ class Layer(C.Structure):
 
 
 class Dropout(C.Structure):
-    _fields_ = [("p", C.c_float), ("step", C.c_uint32), ("seed", C.c_uint64), ("step_ptr", fp)]
+    _fields_ = [("p", C.c_float), ("step", C.c_uint32), ("seed", C.c_uint64), ("step_ptr", fp),
+                ("key_offset", C.c_uint64)]
 
 
 class Head(C.Structure):
@@ -93,7 +94,8 @@ _PROTOS = {
     "stdadk_layer_bwd": (C.c_int, [C.POINTER(BwdArgs), fp]),
     "stdadk_wgrad": (C.c_int, [C.POINTER(WgradArgs), fp]),
     "stdadk_knot_grad": (C.c_int, [C.POINTER(KnotGradArgs), fp]),
-    "stdadk_grad_sqnorm": (C.c_int, [fp, C.c_int64, C.c_int, C.POINTER(C.c_int64), fp, fp]),
+    "stdadk_sqnorm_ws_floats": (C.c_size_t, []),
+    "stdadk_grad_sqnorm": (C.c_int, [fp, C.c_int64, C.c_int, C.POINTER(C.c_int64), fp, fp, fp]),
     "stdadk_adamw_ema_step": (C.c_int, [C.POINTER(AdamWArgs), fp]),
     "stdadk_sparse_l1_fwd": (C.c_int, [C.c_void_p, fp]),
 }

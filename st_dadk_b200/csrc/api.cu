@@ -102,6 +102,7 @@ static LayerP to_layer(const stdadk_layer& l, const stdadk_dropout& d) {
     L.step = d.step;
     L.seed = d.seed;
     L.step_ptr = d.step_ptr;
+    L.key_offset = d.key_offset;
     return L;
 }
 static HeadP to_head(const stdadk_head* h) {
@@ -436,15 +437,16 @@ static int make_groups(int n_groups, const int64_t* group_end, int64_t n, Groups
     return 0;
 }
 
+size_t stdadk_sqnorm_ws_floats(void) { return (size_t)SQNORM_BLOCKS * 8 + 8; }
+
 int stdadk_grad_sqnorm(const float* g, int64_t n, int n_groups, const int64_t* group_end, float* sqnorms,
-                       void* stream) {
+                       float* workspace, void* stream) {
     if (int r = check_device()) return r;
-    REQUIRE(g && sqnorms && n > 0, "grad_sqnorm: bad arguments");
+    REQUIRE(g && sqnorms && workspace && n > 0, "grad_sqnorm: bad arguments (workspace of stdadk_sqnorm_ws_floats() "
+            "zero-initialised floats is required)");
     GroupsP G{};
     if (int r = make_groups(n_groups, group_end, n, &G)) return r;
-    cudaError_t e = cudaMemsetAsync(sqnorms, 0, sizeof(float) * n_groups, (cudaStream_t)stream);
-    if (e != cudaSuccess) return fail((int)e, "grad_sqnorm memset: %s", cudaGetErrorString(e));
-    sqnorm_kernel<<<grid_for(n, 256, 4), 256, 0, (cudaStream_t)stream>>>(g, n, G, sqnorms);
+    sqnorm_kernel<<<SQNORM_BLOCKS, SQNORM_THREADS, 0, (cudaStream_t)stream>>>(g, n, G, sqnorms, workspace);
     return check_launch("grad_sqnorm");
 }
 

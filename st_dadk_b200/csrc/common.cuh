@@ -52,6 +52,7 @@ struct LayerP {
     unsigned int step, _pad2;
     unsigned long long seed;
     const int* step_ptr;
+    unsigned long long key_offset;
 };
 __device__ __forceinline__ unsigned int dropout_step(const LayerP& L) {
     return L.step_ptr ? (unsigned int)(*L.step_ptr) : L.step;

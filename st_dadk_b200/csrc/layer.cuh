@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
                 keep = 0;
 #pragma unroll
                 for (int b = 0; b < 4; ++b)
-                    keep |= dropout_keep8(P.L.seed, drop_step, (uint32_t)P.L.layer_id, (unsigned long long)grow,
+                    keep |= dropout_keep8(P.L.seed, drop_step, (uint32_t)P.L.layer_id, P.L.key_offset + (unsigned long long)lrow,
                                           (uint32_t)(c0 / 8 + b), P.thresh16)
                             << (8 * b);
             }
@@ -617,7 +617,7 @@ __global__ void __launch_bounds__(n_threads(CG), 1) layer_bwd_kernel(const __gri
                 keep = 0;
 #pragma unroll
                 for (int b = 0; b < 4; ++b)
-                    keep |= dropout_keep8(P.L.seed, drop_step, (uint32_t)P.L.layer_id, (unsigned long long)grow,
+                    keep |= dropout_keep8(P.L.seed, drop_step, (uint32_t)P.L.layer_id, P.L.key_offset + (unsigned long long)lrow,
                                           (uint32_t)(c0 / 8 + b), P.thresh16)
                             << (8 * b);
             }

@@ -128,7 +128,13 @@ __device__ __forceinline__ int group_of(const GroupsP& G, long long i) {
     return g;
 }
 
-__global__ void sqnorm_kernel(const float* __restrict__ g, long long n, GroupsP G, float* __restrict__ out) {
+// Deterministic (bitwise run-to-run and rank-to-rank: data-parallel replicas must derive the same clip coefficient):
+// fixed grid, fixed per-thread stride, ordered in-block reduction, per-block partials written to `ws`, and the last
+// block to finish (atomic ticket) adds the partials in block order.  ws: gridDim.x * 8 floats + 1 counter.
+constexpr int SQNORM_BLOCKS = 296;
+constexpr int SQNORM_THREADS = 256;
+__global__ void sqnorm_kernel(const float* __restrict__ g, long long n, GroupsP G, float* __restrict__ out,
+                              float* __restrict__ ws) {
     float acc[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = 0.0f;
@@ -140,17 +146,35 @@ __global__ void sqnorm_kernel(const float* __restrict__ g, long long n, GroupsP 
         for (int k = 0; k < 8; ++k)
             if (k == gi) acc[k] = fmaf(v, v, acc[k]);
     }
-    __shared__ float red[8];
-    if (threadIdx.x < 8) red[threadIdx.x] = 0.0f;
-    __syncthreads();
+    __shared__ float wsum[SQNORM_THREADS / 32][8];
+    __shared__ bool last;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
-        if (k < G.n) {
-            float s = warp_sum(acc[k]);
-            if ((threadIdx.x & 31) == 0) atomicAdd(&red[k], s);
-        }
+    for (int k = 0; k < 8; ++k) {
+        float s = warp_sum(acc[k]);          // xor-butterfly: same order every run
+        if (lane == 0) wsum[warp][k] = s;
+    }
     __syncthreads();
-    if (threadIdx.x < G.n) atomicAdd(&out[threadIdx.x], red[threadIdx.x]);
+    if (threadIdx.x < 8) {
+        float s = 0.0f;
+        for (int w = 0; w < SQNORM_THREADS / 32; ++w) s += wsum[w][threadIdx.x];
+        ws[blockIdx.x * 8 + threadIdx.x] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int* ticket = reinterpret_cast<unsigned int*>(ws + gridDim.x * 8);
+        unsigned int t = atomicAdd(ticket, 1u);
+        last = (t == gridDim.x - 1);
+        if (last) *ticket = 0u;              // ready for the next call
+    }
+    __syncthreads();
+    if (last && threadIdx.x < G.n) {
+        __threadfence();
+        float s = 0.0f;
+        for (unsigned int b = 0; b < gridDim.x; ++b) s += ws[b * 8 + threadIdx.x];
+        out[threadIdx.x] = s;
+    }
 }
 
 struct AdamK {

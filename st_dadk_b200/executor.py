@@ -151,7 +151,7 @@ class Executor:
     def forward(self, pts: L.Points, train: bool = False, step: int = 0, seed: int = 0,
                 y: Optional[torch.Tensor] = None, loss: Optional[LossSpec] = None, inv_count: float = 0.0,
                 out: Optional[torch.Tensor] = None, save: bool = False, prepared: bool = False,
-                step_ptr: Optional[torch.Tensor] = None):
+                step_ptr: Optional[torch.Tensor] = None, key_offset: int = 0):
         """Returns yhat (n_rows, Q).  With `y`/`loss`, also accumulates the loss into self.loss_acc and
         leaves dLoss/dyhat in the workspace for `backward()`.  `save=True` keeps what backward needs."""
         s = self.spec
@@ -164,7 +164,7 @@ class Executor:
         yhat = out if out is not None else ws.yhat
         basis = self._basis()
         drop = L.Dropout(s.dropout if train else 0.0, step & 0xFFFFFFFF, seed,
-                         step_ptr.data_ptr() if step_ptr is not None else None)
+                         step_ptr.data_ptr() if step_ptr is not None else None, key_offset)
         head = None
         for l in range(s.n_hidden):
             a = L.FwdArgs()

@@ -176,9 +176,19 @@ def knot_grad(args: L.KnotGradArgs):
     L.check(L.lib().stdadk_knot_grad(C.byref(args), _stream()), "knot_grad")
 
 
-def grad_sqnorm(g: torch.Tensor, group_end: Sequence[int], out: torch.Tensor):
+_sqnorm_ws = {}
+
+
+def grad_sqnorm(g: torch.Tensor, group_end: Sequence[int], out: torch.Tensor, workspace: Optional[torch.Tensor] = None):
+    """Squared L2 norm per parameter group, bitwise deterministic.  `workspace` (zero-initialised, reused across
+    calls on one stream) defaults to a per-device buffer."""
+    if workspace is None:
+        workspace = _sqnorm_ws.get(g.device)
+        if workspace is None:
+            workspace = _sqnorm_ws[g.device] = torch.zeros(L.lib().stdadk_sqnorm_ws_floats(), device=g.device)
     arr = (C.c_int64 * len(group_end))(*group_end)
-    L.check(L.lib().stdadk_grad_sqnorm(_ptr(g), g.numel(), len(group_end), arr, _ptr(out), _stream()), "grad_sqnorm")
+    L.check(L.lib().stdadk_grad_sqnorm(_ptr(g), g.numel(), len(group_end), arr, _ptr(out), _ptr(workspace), _stream()),
+            "grad_sqnorm")
 
 
 def adamw_ema_step(p, g, m, v, shadow, group_end: Sequence[int], hyper: torch.Tensor, sqnorms, step_count,

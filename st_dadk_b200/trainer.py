@@ -311,7 +311,8 @@ class Trainer:
             gv.copy_(sb._gradient_damping_hook(gv))
 
     # ------------------------------------------------------------------ one optimisation step
-    def _step_body(self, table, perm, row_begin: int, n_rows: int, global_rows: int):
+    def _step_compute(self, table, perm, row_begin: int, n_rows: int, global_rows: int, key_offset: int = 0):
+        """Local part of a step: forward (fused loss) and backward into the flat gradient."""
         ex, fl = self.ex, self.flat
         fl.g.zero_()
         ex.loss_acc.zero_()
@@ -319,12 +320,19 @@ class Trainer:
         ex.prepare(force=True, for_backward=True)
         pts = ops.make_points(table.coords, table.t, table.X, index=perm, row_begin=row_begin, n_rows=n_rows)
         ex.forward(pts, train=True, seed=self.seed, y=table.y, loss=self.loss, inv_count=1.0 / (global_rows * self.q),
-                   save=True, prepared=True, step_ptr=self.step_count)
+                   save=True, prepared=True, step_ptr=self.step_count, key_offset=key_offset)
         ex.backward(zero=False)
         self._finish_special_grads()
+
+    def _step_exchange(self):
+        """The one data-parallel exchange of a step: sum of the flat gradient (and of the loss) over ranks."""
         if self.world > 1:
-            dist.all_reduce(fl.g[:fl.n])
-            dist.all_reduce(ex.loss_acc)
+            dist.all_reduce(self.flat.g[:self.flat.n])
+            dist.all_reduce(self.ex.loss_acc)
+
+    def _step_update(self):
+        """Replicated tail: parameter-only penalties, damping, gradient norm, fused clip + AdamW + EMA."""
+        ex, fl = self.ex, self.flat
         pen = self._add_penalty_grads()
         self._damp_center_grads()
         if self.clip > 0:
@@ -335,11 +343,19 @@ class Trainer:
         if pen is not None:
             self.loss_sum += pen
 
-    def train_step(self, table, perm: torch.Tensor, row_begin: int, n_rows: int, global_rows: Optional[int] = None):
+    def _step_body(self, table, perm, row_begin: int, n_rows: int, global_rows: int, key_offset: int = 0):
+        self._step_compute(table, perm, row_begin, n_rows, global_rows, key_offset)
+        self._step_exchange()
+        self._step_update()
+
+    def train_step(self, table, perm: torch.Tensor, row_begin: int, n_rows: int, global_rows: Optional[int] = None,
+                   key_offset: Optional[int] = None):
         """One step on samples perm[row_begin : row_begin + n_rows] of `table` (this rank's shard of a global batch
         of `global_rows` samples).  Warm-up is written after the step, as upstream (train_st_interp.py:714-718)."""
         if global_rows is None:
             global_rows = n_rows
+        if key_offset is None:      # position of this rank's shard inside the global batch (dropout key)
+            key_offset = shard_rows(global_rows, self.rank, self.world)[0] if self.world > 1 else 0
         self._push_hyper()
         if self.use_cuda_graph:
             # Kernel arguments (including the gather window) are frozen in a graph, so a replayed step reads its
@@ -348,21 +364,35 @@ class Trainer:
                 self._stage_idx = torch.zeros(max(n_rows, 1), dtype=torch.int64, device=self.device)
                 self._graphs.clear()
             self._stage_idx[:n_rows].copy_(perm[row_begin:row_begin + n_rows])
-            gkey = (n_rows, global_rows, id(table))
+            gkey = (n_rows, global_rows, id(table), key_offset)
             g = self._graphs.get(gkey)
             if g is None:
                 # first use of this shape: run it eagerly once (sets kernel attributes, sizes workspaces) -- that run
-                # IS this step; the capture below records the same launch sequence for later steps without executing.
-                self._step_body(table, self._stage_idx, 0, n_rows, global_rows)
+                # IS this step; the captures below record the same launch sequence for later steps without executing.
+                # Single GPU: one graph for the whole step.  Data parallel: two graphs with the NCCL all-reduce
+                # issued between them on the same stream (the collective stays outside stream capture).
+                self._step_body(table, self._stage_idx, 0, n_rows, global_rows, key_offset)
                 torch.cuda.synchronize()
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self._step_body(table, self._stage_idx, 0, n_rows, global_rows)
+                if self.world == 1:
+                    g1 = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g1):
+                        self._step_body(table, self._stage_idx, 0, n_rows, global_rows, key_offset)
+                    g = (g1, None)
+                else:
+                    g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g1):
+                        self._step_compute(table, self._stage_idx, 0, n_rows, global_rows, key_offset)
+                    with torch.cuda.graph(g2):
+                        self._step_update()
+                    g = (g1, g2)
                 self._graphs[gkey] = g
             else:
-                g.replay()
+                g[0].replay()
+                if g[1] is not None:
+                    self._step_exchange()
+                    g[1].replay()
         else:
-            self._step_body(table, perm, row_begin, n_rows, global_rows)
+            self._step_body(table, perm, row_begin, n_rows, global_rows, key_offset)
         if self.global_step < self.warmup_steps:
             f = (self.global_step + 1) / self.warmup_steps
             for gq in self.opt.param_groups:

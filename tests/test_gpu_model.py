@@ -55,14 +55,29 @@ def test_module_forward_backward_matches_reference(name, q, seed, taus):
         loss = torch.mean(torch.stack(losses))
     assert abs(loss.item() - float(g["loss64"])) < 1e-3 * abs(float(g["loss64"]))
     loss.backward()
+    # (a) tight: every gradient tensor vs the oracle with the kernels' TF32 operand rounding emulated, built from the
+    #     module's own weights (shown above to be the reference's); (b) loose: the reference's FP64 autograd samples.
+    #     The gap between (a) and (b) is TF32 itself: a 1e-3 perturbation of a pre-activation flips the ReLU of the
+    #     few units sitting at zero, and with only 300 rows one flipped row moves a column sum by several per cent.
+    st = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
+    m = orc.OracleModel(
+        centers=st["spatial_basis.centers"], bandwidths=st["spatial_basis._bandwidths"],
+        t_centers=st["temporal_basis.centers"], t_bandwidths=st["temporal_basis.bandwidths"],
+        weights=[st[f"mlp.{i}.weight"] for i in (0, 3, 6, 9)], biases=[st[f"mlp.{i}.bias"] for i in (0, 3, 6, 9)],
+        ln_gamma=[st[f"mlp.{i}.weight"] for i in (1, 4, 7)], ln_beta=[st[f"mlp.{i}.bias"] for i in (1, 4, 7)])
+    yh, cache = orc.forward(m, None, g["coords"], g["t"], return_cache=True, rnd=orc.tf32_round)
+    gr = orc.backward(m, cache, orc.loss_and_grad(yh, g["y"], "mse" if taus is None else "pinball", taus)[1])
+    emu = {"mlp.0.weight": gr["weights"][0], "mlp.3.weight": gr["weights"][1], "mlp.6.weight": gr["weights"][2],
+           "mlp.9.weight": gr["weights"][3], "mlp.1.weight": gr["ln_gamma"][0], "mlp.4.weight": gr["ln_gamma"][1],
+           "mlp.7.weight": gr["ln_gamma"][2], "mlp.1.bias": gr["ln_beta"][0], "mlp.4.bias": gr["ln_beta"][1],
+           "mlp.7.bias": gr["ln_beta"][2], "mlp.0.bias": gr["biases"][0], "mlp.3.bias": gr["biases"][1],
+           "mlp.6.bias": gr["biases"][2], "mlp.9.bias": gr["biases"][3]}
     for k, p in model.named_parameters():
+        got = p.grad.detach().cpu().numpy()
+        assert rel_err(got, emu[k]) < (2e-2 if taus else 2e-3), (k, rel_err(got, emu[k]))
         gs = g["gsample." + k]
-        got = p.grad.detach().cpu().numpy().reshape(-1)[::97]
-        # 1-in-97 strided SAMPLE of each gradient, compared on the scale of the whole tensor (RMS from the stored
-        # moments): sampled entries can be near-cancelling column sums whose own magnitude is not a meaningful scale
         scale = max(float(np.abs(gs).max()), float(np.sqrt(g["gstat." + k][1] / p.numel())))
-        err = float(np.abs(got - gs).max()) / scale
-        assert err < (6e-2 if taus else 3e-2), (k, err)
+        assert float(np.abs(got.reshape(-1)[::97] - gs).max()) / scale < 0.25, k
 
 
 def test_reference_api_surface():
