@@ -145,13 +145,13 @@ def run_reference(args):
     val = steps * BATCH / dt
     cb = {"value": val, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
           "sample": f"{steps} oracle-port (numpy FP32, host BLAS threads) training steps of batch {BATCH}"}
-    print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+    emit({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
                       "steps": steps, "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
                       "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                       "config": {"workload": WORKLOAD, "note": "reference CPU path = oracle port on host cores; one "
                                  "rank only (the reference has no multi-device path)"},
                       "cpu_baseline": cb,
-                      "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+          "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -364,10 +364,31 @@ def run_ours(args):
                             "grid10M_points_per_s": grid_pps},
                 "roofline": roof, "kernel_times_ms": {k: v["ms"] for k, v in kt.get("kernels", {}).items()},
                 "cpu_baseline": cb, "mean_train_loss": final_loss / max(1, args.steps + max(args.warmup, 3)), "wall_s_timed_region": wall}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Everything libraries print to fd 1 (NCCL's version banner, build logs) goes to stderr; the single JSON line is
+    written to the real stdout by emit()."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(obj):
+    data = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -379,6 +400,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true",
                     help="launch every kernel eagerly (for ncu: kernel replay cannot run inside stream capture)")
     args = ap.parse_args()
+    _quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
