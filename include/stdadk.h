@@ -109,6 +109,8 @@ typedef struct {
     float* out_img;          /* image (rows x n_out) of the block output, or NULL */
     float* stats;            /* (rows x 2) LayerNorm mean, rstd for backward, or NULL */
     const stdadk_head* head; /* non-NULL on the last hidden block: fuses head (+ loss) */
+    const float* addend;     /* optional (rows x n_out) FP32 row-major term added to A W^T + b before LayerNorm: the
+                                support-walked spatial part of block 1 in the large-knot regime (stdadk_sparse_l1_fwd) */
 } stdadk_fwd_args;
 
 /* Backward of one hidden block: recomputes z = A W^T (for block 1 this recomputes the basis),
@@ -132,6 +134,7 @@ typedef struct {
     float* d_bias;             /* (n_out) += */
     float* d_gamma;            /* (n_out) += or NULL */
     float* d_beta;             /* (n_out) += or NULL */
+    const float* addend;       /* as in stdadk_fwd_args (the recomputed z needs the same term) */
 } stdadk_bwd_args;
 
 /* Weight gradient dW (n_out x n_in) += dz^T A, reduction over rows on the tensor cores (both
@@ -182,7 +185,7 @@ int stdadk_version(void);
 const char* stdadk_last_error(void);
 /* sizeof() of the argument structs, for bindings to verify their layout:
  * 0 basis, 1 points, 2 layer, 3 dropout, 4 head, 5 fwd_args, 6 bwd_args, 7 wgrad_args, 8 knotgrad_args, 9 adamw_args,
- * 10 pack_desc */
+ * 10 pack_desc, 11 sparse_args */
 size_t stdadk_sizeof(int which);
 
 size_t stdadk_image_floats(int64_t rows, int64_t cols);
@@ -207,6 +210,27 @@ typedef struct {
     float* img;
 } stdadk_pack_desc;
 int stdadk_pack_images(const stdadk_pack_desc* descs, int n, void* stream);
+
+/* Large-knot regime of block 1 (uniform lattices, fixed knots, K_s up to ~1e5+; BASELINE config 4): walk only the knots
+ * in each point's compact support.  knot j of level l sits at lattice node (j / side, j % side) (st_interp.py:152-185).
+ *   fwd  : zs[n,:]  = sum_{j in supp(s_n)} phi_j(s_n) * w1t[p_cov + j, :]
+ *   wgrad: dw1t[p_cov + j, :] += phi_j(s_n) * dz1[n,:]
+ * w1t / dw1t: first Linear layer stored knot-major, (n_in x n_out) contiguous. */
+#define STDADK_MAX_LEVELS 8
+typedef struct {
+    stdadk_points pts;
+    const float* knots4;      /* as in stdadk_basis */
+    int32_t n_levels, basis_fn, n_out, p_cov;
+    int32_t side[STDADK_MAX_LEVELS];
+    int32_t offset[STDADK_MAX_LEVELS];   /* index of the level's first knot */
+    float thetap[STDADK_MAX_LEVELS];     /* bandwidth * calibration of the level */
+    const float* w1t;
+    float* zs;                /* fwd out (rows x n_out) */
+    const float* dz_img;      /* wgrad in: image (rows x n_out) */
+    float* dw1t;              /* wgrad out, += */
+} stdadk_sparse_args;
+int stdadk_sparse_l1_fwd(const stdadk_sparse_args* a, void* stream);
+int stdadk_sparse_l1_wgrad(const stdadk_sparse_args* a, void* stream);
 
 int stdadk_layer_fwd(const stdadk_fwd_args* a, void* stream);
 int stdadk_layer_bwd(const stdadk_bwd_args* a, void* stream);

@@ -45,14 +45,14 @@ class Head(C.Structure):
 
 class FwdArgs(C.Structure):
     _fields_ = [("basis", C.POINTER(Basis)), ("pts", Points), ("a_img", fp), ("layer", Layer), ("drop", Dropout),
-                ("out_img", fp), ("stats", fp), ("head", C.POINTER(Head))]
+                ("out_img", fp), ("stats", fp), ("head", C.POINTER(Head)), ("addend", fp)]
 
 
 class BwdArgs(C.Structure):
     _fields_ = [("basis", C.POINTER(Basis)), ("pts", Points), ("a_img", fp), ("layer", Layer), ("drop", Dropout),
                 ("stats", fp), ("head", C.POINTER(Head)), ("d_head_w", fp), ("d_head_b", fp), ("dz_next_img", fp),
                 ("wt_next_img", fp), ("n_next", C.c_int32), ("_pad", C.c_int32), ("dz_img", fp), ("d_bias", fp),
-                ("d_gamma", fp), ("d_beta", fp)]
+                ("d_gamma", fp), ("d_beta", fp), ("addend", fp)]
 
 
 class WgradArgs(C.Structure):
@@ -70,6 +70,15 @@ class AdamWArgs(C.Structure):
                 ("n_groups", C.c_int32), ("_pad", C.c_int32), ("group_end", C.POINTER(C.c_int64)), ("hyper", fp),
                 ("sqnorms", fp), ("step_count", fp), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
                 ("ema_decay", C.c_float)]
+
+
+MAX_LEVELS = 8
+
+
+class SparseArgs(C.Structure):
+    _fields_ = [("pts", Points), ("knots4", fp), ("n_levels", C.c_int32), ("basis_fn", C.c_int32), ("n_out", C.c_int32),
+                ("p_cov", C.c_int32), ("side", C.c_int32 * MAX_LEVELS), ("offset", C.c_int32 * MAX_LEVELS),
+                ("thetap", C.c_float * MAX_LEVELS), ("w1t", fp), ("zs", fp), ("dz_img", fp), ("dw1t", fp)]
 
 
 class PackDesc(C.Structure):
@@ -97,9 +106,10 @@ _PROTOS = {
     "stdadk_sqnorm_ws_floats": (C.c_size_t, []),
     "stdadk_grad_sqnorm": (C.c_int, [fp, C.c_int64, C.c_int, C.POINTER(C.c_int64), fp, fp, fp]),
     "stdadk_adamw_ema_step": (C.c_int, [C.POINTER(AdamWArgs), fp]),
-    "stdadk_sparse_l1_fwd": (C.c_int, [C.c_void_p, fp]),
+    "stdadk_sparse_l1_fwd": (C.c_int, [C.POINTER(SparseArgs), fp]),
+    "stdadk_sparse_l1_wgrad": (C.c_int, [C.POINTER(SparseArgs), fp]),
 }
-EXPORTED = [k for k in _PROTOS if k != "stdadk_sparse_l1_fwd"]
+EXPORTED = list(_PROTOS)
 
 
 def lib():
@@ -117,7 +127,7 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        structs = [Basis, Points, Layer, Dropout, Head, FwdArgs, BwdArgs, WgradArgs, KnotGradArgs, AdamWArgs, PackDesc]
+        structs = [Basis, Points, Layer, Dropout, Head, FwdArgs, BwdArgs, WgradArgs, KnotGradArgs, AdamWArgs, PackDesc, SparseArgs]
         for i, st in enumerate(structs):
             if L.stdadk_sizeof(i) != C.sizeof(st):
                 raise RuntimeError(f"libstdadk ABI mismatch: {st.__name__} is {C.sizeof(st)} B in the binding, "

@@ -158,6 +158,7 @@ size_t stdadk_sizeof(int which) {
         case 8: return sizeof(stdadk_knotgrad_args);
         case 9: return sizeof(stdadk_adamw_args);
         case 10: return sizeof(stdadk_pack_desc);
+        case 11: return sizeof(stdadk_sparse_args);
         default: return 0;
     }
 }
@@ -254,6 +255,8 @@ int stdadk_layer_fwd(const stdadk_fwd_args* a, void* stream) {
     if (a->basis)
         if (int r = check_basis_points(a->basis, a->pts, a->layer.n_in)) return r;
     REQUIRE(a->drop.p >= 0.0f && a->drop.p < 1.0f, "layer_fwd: dropout p=%f", a->drop.p);
+    REQUIRE(!a->addend || (a->layer.n_out % 4 == 0 && (reinterpret_cast<uintptr_t>(a->addend) & 15) == 0),
+            "layer_fwd: addend needs n_out %% 4 == 0 and 16-byte alignment");
     if (a->head) {
         REQUIRE(a->head->q >= 1 && a->head->q <= STDADK_MAX_Q, "layer_fwd: head q=%d outside [1,%d]", a->head->q,
                 STDADK_MAX_Q);
@@ -270,6 +273,7 @@ int stdadk_layer_fwd(const stdadk_fwd_args* a, void* stream) {
     K.L = to_layer(a->layer, a->drop);
     K.head = to_head(a->head);
     K.a_img = a->a_img;
+    K.addend = a->addend;
     K.out_img = a->out_img;
     K.stats = a->stats;
     K.has_head = a->head ? 1 : 0;
@@ -326,6 +330,7 @@ int stdadk_layer_bwd(const stdadk_bwd_args* a, void* stream) {
     K.L = to_layer(a->layer, a->drop);
     K.head = to_head(a->head);
     K.a_img = a->a_img;
+    K.addend = a->addend;
     K.stats = a->stats;
     K.dz_next_img = a->dz_next_img;
     K.wt_next_img = a->wt_next_img;
@@ -425,6 +430,41 @@ int stdadk_knot_grad(const stdadk_knotgrad_args* a, void* stream) {
     return check_launch("knot_grad");
 }
 
+static int sparse_fill(const stdadk_sparse_args* a, SparseK* K, bool wgrad) {
+    REQUIRE(a, "sparse_l1: NULL args");
+    REQUIRE(a->n_levels >= 1 && a->n_levels <= SP_MAX_LEVELS, "sparse_l1: 1..%d lattice levels, got %d", SP_MAX_LEVELS,
+            a->n_levels);
+    REQUIRE(a->basis_fn == STDADK_WENDLAND || a->basis_fn == STDADK_TRIANGULAR,
+            "sparse_l1: only compactly supported bases can be walked (the gaussian basis is dense)");
+    REQUIRE(a->n_out >= 4 && a->n_out <= MAX_N && a->n_out % 4 == 0, "sparse_l1: n_out=%d must be a multiple of 4 <= %d",
+            a->n_out, MAX_N);
+    REQUIRE(a->knots4 && a->pts.grid_nx > 0 ? true : (a->pts.coords != nullptr), "sparse_l1: no point source");
+    REQUIRE(a->pts.grid_nx > 0 || (reinterpret_cast<uintptr_t>(a->pts.coords) & 7) == 0, "sparse_l1: coords alignment");
+    if (wgrad) {
+        REQUIRE(a->dz_img && a->dw1t && (reinterpret_cast<uintptr_t>(a->dw1t) & 15) == 0, "sparse_l1_wgrad: dz_img / dw1t");
+    } else {
+        REQUIRE(a->w1t && a->zs && (reinterpret_cast<uintptr_t>(a->w1t) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(a->zs) & 15) == 0, "sparse_l1_fwd: w1t / zs NULL or misaligned");
+    }
+    K->pts = to_points(a->pts);
+    K->lat.n_levels = a->n_levels;
+    for (int l = 0; l < a->n_levels; ++l) {
+        REQUIRE(a->side[l] >= 1 && a->thetap[l] > 0.0f, "sparse_l1: level %d side=%d theta'=%f", l, a->side[l], a->thetap[l]);
+        K->lat.side[l] = a->side[l];
+        K->lat.offset[l] = a->offset[l];
+        K->lat.thetap[l] = a->thetap[l];
+    }
+    K->knots = reinterpret_cast<const float4*>(a->knots4);
+    K->w1t = a->w1t;
+    K->zs = a->zs;
+    K->dz_img = a->dz_img;
+    K->dw1t = a->dw1t;
+    K->n_out = a->n_out;
+    K->p_cov = a->p_cov;
+    K->fn = a->basis_fn;
+    return 0;
+}
+
 static int make_groups(int n_groups, const int64_t* group_end, int64_t n, GroupsP* G) {
     REQUIRE(n_groups >= 1 && n_groups <= 8 && group_end, "optimizer: 1..8 parameter groups supported, got %d", n_groups);
     int64_t prev = 0;
@@ -448,6 +488,26 @@ int stdadk_grad_sqnorm(const float* g, int64_t n, int n_groups, const int64_t* g
     if (int r = make_groups(n_groups, group_end, n, &G)) return r;
     sqnorm_kernel<<<SQNORM_BLOCKS, SQNORM_THREADS, 0, (cudaStream_t)stream>>>(g, n, G, sqnorms, workspace);
     return check_launch("grad_sqnorm");
+}
+
+int stdadk_sparse_l1_fwd(const stdadk_sparse_args* a, void* stream) {
+    if (int r = check_device()) return r;
+    SparseK K{};
+    if (int r = sparse_fill(a, &K, false)) return r;
+    if (a->pts.n_rows <= 0) return 0;
+    int blocks = grid_for(a->pts.n_rows, SP_WARPS, 8);
+    sparse_spatial_fwd_kernel<<<blocks, SP_WARPS * 32, 0, (cudaStream_t)stream>>>(K);
+    return check_launch("sparse_l1_fwd");
+}
+
+int stdadk_sparse_l1_wgrad(const stdadk_sparse_args* a, void* stream) {
+    if (int r = check_device()) return r;
+    SparseK K{};
+    if (int r = sparse_fill(a, &K, true)) return r;
+    if (a->pts.n_rows <= 0) return 0;
+    int blocks = grid_for(a->pts.n_rows, SP_WARPS, 8);
+    sparse_spatial_wgrad_kernel<<<blocks, SP_WARPS * 32, 0, (cudaStream_t)stream>>>(K);
+    return check_launch("sparse_l1_wgrad");
 }
 
 __global__ void step_inc_kernel(int* c) { *c += 1; }

@@ -55,6 +55,7 @@ struct FwdK {
     LayerP L;
     HeadP head;
     const float* a_img;
+    const float* addend;
     float* out_img;
     float* stats;
     int has_head, k_slabs, n_pad, tmem_cols;
@@ -68,6 +69,7 @@ struct BwdK {
     LayerP L;
     HeadP head;
     const float* a_img;
+    const float* addend;
     const float* stats;
     const float* dz_next_img;
     const float* wt_next_img;
@@ -159,6 +161,17 @@ __device__ __forceinline__ void issue_slab_mma(uint32_t tmem_acc, const float* s
 // compiler keeps the pointer in the shared address space (LDS/STS instead of generic LD/ST).
 __device__ __forceinline__ uint8_t* align_smem(uint8_t* p) {
     return p + ((1024u - (smem_u32(p) & 1023u)) & 1023u);
+}
+
+// v[i] += addend[row, c0 + i] for the valid columns of a 32-column chunk (rows of n_out floats, n_out % 4 == 0)
+__device__ __forceinline__ void add_addend_chunk(float (&v)[32], const float* addend_row, int c0, int n_out) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        if (c0 + 4 * c < n_out) {
+            float4 a = *reinterpret_cast<const float4*>(addend_row + c0 + 4 * c);
+            v[4 * c] += a.x; v[4 * c + 1] += a.y; v[4 * c + 2] += a.z; v[4 * c + 3] += a.w;
+        }
+    }
 }
 
 // Pinball / MSE loss on one row: fills dy[q] (already scaled) and returns the row's loss contribution.
@@ -325,6 +338,7 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
         tc_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16);
         float* myred = red + ((size_t)cg * TILE_M + row) * RED_STRIDE;
+        const float* arow = (P.addend && rvalid) ? P.addend + (size_t)lrow * n_out : nullptr;
         float v[32];
         float mean = 0.0f, rstd = 1.0f;
         if (has_ln) {
@@ -333,6 +347,7 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
             float s1 = 0.0f;
             for (int c0 = 32 * cg; c0 < n_pad; c0 += 32 * CG) {
                 tmem_ld32(trow + c0, v);
+                if (arow) add_addend_chunk(v, arow, c0, n_out);
 #pragma unroll
                 for (int i = 0; i < 32; ++i)
                     if (c0 + i < n_out) s1 += v[i] + sbias[c0 + i];
@@ -348,6 +363,7 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
             float s2 = 0.0f;
             for (int c0 = 32 * cg; c0 < n_pad; c0 += 32 * CG) {
                 tmem_ld32(trow + c0, v);
+                if (arow) add_addend_chunk(v, arow, c0, n_out);
 #pragma unroll
                 for (int i = 0; i < 32; ++i)
                     if (c0 + i < n_out) {
@@ -375,6 +391,7 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
         const unsigned int drop_step = drop ? dropout_step(P.L) : 0u;
         for (int c0 = 32 * cg; c0 < n_pad; c0 += 32 * CG) {
             tmem_ld32(trow + c0, v);
+            if (arow) add_addend_chunk(v, arow, c0, n_out);
             uint32_t keep = 0xFFFFFFFFu;
             if (drop) {
                 keep = 0;
@@ -591,6 +608,7 @@ __global__ void __launch_bounds__(n_threads(CG), 1) layer_bwd_kernel(const __gri
         tc_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16);
         float* myred = red + ((size_t)cg * TILE_M + row) * RED_STRIDE;
+        const float* arow = (P.addend && rvalid) ? P.addend + (size_t)lrow * n_out : nullptr;
         float mean = 0.0f, rstd = 1.0f;
         if (has_ln && rvalid) {
             mean = P.stats[2 * lrow];
@@ -611,6 +629,7 @@ __global__ void __launch_bounds__(n_threads(CG), 1) layer_bwd_kernel(const __gri
         int ch = 0;
         for (int c0 = 32 * cg; c0 < n_pad; c0 += 32 * CG, ++ch) {
             tmem_ld32(trow + c0, z);
+            if (arow) add_addend_chunk(z, arow, c0, n_out);
             if (!P.has_head) tmem_ld32(trow + acc1_off + c0, g);
             uint32_t keep = 0xFFFFFFFFu;
             if (drop) {
@@ -706,6 +725,7 @@ __global__ void __launch_bounds__(n_threads(CG), 1) layer_bwd_kernel(const __gri
             ch = 0;
             for (int c0 = 32 * cg; c0 < n_pad; c0 += 32 * CG, ++ch) {
                 tmem_ld32(trow + c0, z);
+                if (arow) add_addend_chunk(z, arow, c0, n_out);
                 if (!P.has_head) tmem_ld32(trow + acc1_off + c0, g);
                 uint32_t act = 0;
 #pragma unroll

@@ -39,6 +39,7 @@ class NetSpec:
     dropout: float = 0.0
     ln_eps: float = 1e-5
     learnable_basis: bool = False
+    lattice_sides: Optional[List[int]] = None  # knots per axis of each level when the knots are the fixed uniform lattice
 
     @property
     def n_hidden(self):
@@ -58,8 +59,9 @@ class LossSpec:
 
 
 class _Workspace:
-    def __init__(self, spec: NetSpec, n_rows: int, device):
+    def __init__(self, spec: NetSpec, n_rows: int, device, sparse: bool = False):
         self.n_rows = n_rows
+        self.zs = torch.empty(n_rows, spec.weights[0].shape[0], dtype=torch.float32, device=device) if sparse else None
         self.h = [ops.new_image(n_rows, w.shape[0], device) for w in spec.weights[:-1]]
         self.dz = [ops.new_image(n_rows, w.shape[0], device) for w in spec.weights]
         self.stats = [torch.empty(n_rows, 2, dtype=torch.float32, device=device) if g is not None else None
@@ -70,9 +72,15 @@ class _Workspace:
 
 class Executor:
     MAX_WORKSPACES = 4
+    # Above this many spatial knots block 1 switches from generating every basis column densely in the tensor-core
+    # operand to walking each point's compact support (st_dadk_b200/csrc/sparse.cuh): dense work grows with K_s, the
+    # walk with the ~20 knots per level inside a support disk.
+    DENSE_MAX_KNOTS = 2048
 
-    def __init__(self, spec: NetSpec):
+    def __init__(self, spec: NetSpec, force_sparse: bool = False):
         self.spec = spec
+        self.force_sparse = force_sparse
+        self._setup_regime(spec)
         dev = spec.centers.device
         if dev.type != "cuda":
             raise RuntimeError("st_dadk_b200.Executor needs CUDA tensors: the hot path has no CPU implementation")
@@ -90,9 +98,41 @@ class Executor:
         self.grads = None
         self._knots_ready = False
 
+    def _setup_regime(self, spec: NetSpec):
+        k_s = spec.centers.shape[0]
+        want = self.force_sparse or k_s > self.DENSE_MAX_KNOTS
+        self.sparse = False
+        if not want:
+            return
+        problems = []
+        if spec.lattice_sides is None or spec.learnable_basis:
+            problems.append("the support walk needs the fixed uniform lattice (spatial_init_method='uniform', not learnable)")
+        if spec.basis_fn == "gaussian":
+            problems.append("the gaussian basis is not compactly supported")
+        if spec.p_cov != 0:
+            problems.append("covariates are not supported together with the support walk")
+        if spec.weights[0].shape[0] % 4:
+            problems.append("first hidden width must be a multiple of 4")
+        if problems:
+            if self.force_sparse or k_s * 16 > 96 * 1024:
+                raise RuntimeError(f"{k_s} spatial knots need the support-walking path, but " + "; ".join(problems))
+            return
+        sides = [int(v) for v in spec.lattice_sides]
+        offs, o = [], 0
+        for sd in sides:
+            offs.append(o)
+            o += sd * sd
+        assert o == k_s, "lattice_sides do not add up to the number of knots"
+        bw = spec.bandwidths[torch.tensor(offs, device=spec.bandwidths.device)].float().cpu().numpy()
+        import numpy as _np
+        calib = _np.float32(L.CALIBRATION[spec.basis_fn])
+        self.lat = (sides, offs, [float(_np.float32(b) * calib) for b in bw])
+        self.sparse = True
+
     # ------------------------------------------------------------------ operand preparation
     def rebind(self, spec: NetSpec):
         self.spec = spec
+        self._setup_regime(spec)
         self._pack_key = None
         self._knots_ready = False
 
@@ -115,7 +155,14 @@ class Executor:
             self._knots_ready = True
         srcs, outs, slots = [], [], []
         for l, w in enumerate(s.weights):
-            srcs.append(w); outs.append(self.w_img[l]); slots.append(("w", l))
+            if l == 0 and self.sparse:
+                k_s = s.centers.shape[0]
+                srcs.append(w[:, k_s:])                 # dense (temporal) columns only; spatial rows are gathered
+                wt = w.t()
+                self._w1t = wt if wt.is_contiguous() else wt.contiguous()
+            else:
+                srcs.append(w)
+            outs.append(self.w_img[l]); slots.append(("w", l))
             if for_backward and l > 0:
                 srcs.append(w.t()); outs.append(self.wt_img[l]); slots.append(("wt", l))
         if for_backward and s.learnable_basis:
@@ -135,17 +182,27 @@ class Executor:
         if ws is None:
             if len(self._ws) >= self.MAX_WORKSPACES:
                 self._ws.pop(next(iter(self._ws)))
-            ws = self._ws[n_rows] = _Workspace(self.spec, n_rows, self.device)
+            ws = self._ws[n_rows] = _Workspace(self.spec, n_rows, self.device, self.sparse)
         return ws
 
     def _basis(self) -> L.Basis:
         s = self.spec
-        return ops.make_basis(self.knots4, self.tknots2, s.centers.shape[0], s.t_centers.shape[0], s.p_cov, s.basis_fn)
+        k_s = 0 if self.sparse else s.centers.shape[0]     # sparse regime: the tensor-core operand holds [X | psi] only
+        return ops.make_basis(self.knots4, self.tknots2, k_s, s.t_centers.shape[0], s.p_cov, s.basis_fn)
+
+    def _n_in(self, l: int) -> int:
+        w = self.spec.weights[l]
+        return w.shape[1] - (self.spec.centers.shape[0] if (l == 0 and self.sparse) else 0)
 
     def _layer(self, l: int) -> L.Layer:
         s = self.spec
         w = s.weights[l]
-        return ops.make_layer(self.w_img[l], s.biases[l], s.gammas[l], s.betas[l], w.shape[1], w.shape[0], s.ln_eps, l)
+        return ops.make_layer(self.w_img[l], s.biases[l], s.gammas[l], s.betas[l], self._n_in(l), w.shape[0], s.ln_eps, l)
+
+    def _sparse_args(self, pts, ws, **kw) -> L.SparseArgs:
+        s = self.spec
+        sides, offs, ths = self.lat
+        return ops.make_sparse_args(pts, self.knots4, s.basis_fn, s.weights[0].shape[0], s.p_cov, sides, offs, ths, **kw)
 
     # ------------------------------------------------------------------ forward
     def forward(self, pts: L.Points, train: bool = False, step: int = 0, seed: int = 0,
@@ -166,11 +223,15 @@ class Executor:
         drop = L.Dropout(s.dropout if train else 0.0, step & 0xFFFFFFFF, seed,
                          step_ptr.data_ptr() if step_ptr is not None else None, key_offset)
         head = None
+        if self.sparse:
+            ops.sparse_l1_fwd(self._sparse_args(pts, ws, w1t=self._w1t, zs=ws.zs))
         for l in range(s.n_hidden):
             a = L.FwdArgs()
             a.pts = pts
             if l == 0:
                 a.basis = C.pointer(basis)
+                if self.sparse:
+                    a.addend = ws.zs.data_ptr()
             else:
                 a.a_img = ws.h[l - 1].data_ptr()
             a.layer = self._layer(l)
@@ -252,6 +313,8 @@ class Executor:
             a.pts = pts
             if l == 0:
                 a.basis = C.pointer(basis)
+                if self.sparse:
+                    a.addend = ws.zs.data_ptr()
             else:
                 a.a_img = ws.h[l - 1].data_ptr()
             a.layer = self._layer(l)
@@ -281,7 +344,17 @@ class Executor:
             else:
                 a.a_img = ws.h[l - 1].data_ptr()
             a.dz_img = ws.dz[l].data_ptr()
-            a.n_in, a.n_out = w.shape[1], w.shape[0]
+            a.n_in, a.n_out = self._n_in(l), w.shape[0]
+            if l == 0 and self.sparse:
+                k_s = s.centers.shape[0]
+                gd = gw[:, k_s:]                       # dense (temporal) columns on the tensor cores ...
+                a.dw = gd.data_ptr()
+                a.stride_o, a.stride_i = gd.stride(0), gd.stride(1)
+                ops.wgrad(a)
+                if gw.stride(0) != 1 or gw.stride(1) != w.shape[0]:
+                    raise RuntimeError("support-walk wgrad needs the first-layer gradient stored (in, out)-contiguous")
+                ops.sparse_l1_wgrad(self._sparse_args(pts, ws, dz_img=ws.dz[0], dw1t=gw))   # ... spatial rows scattered
+                continue
             a.dw = gw.data_ptr()
             a.stride_o, a.stride_i = gw.stride(0), gw.stride(1)
             ops.wgrad(a)

@@ -197,3 +197,23 @@ def adamw_ema_step(p, g, m, v, shadow, group_end: Sequence[int], hyper: torch.Te
     a = L.AdamWArgs(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(shadow), p.numel(), len(group_end), 0, arr, _ptr(hyper),
                     _ptr(sqnorms), _ptr(step_count), beta1, beta2, eps, ema_decay)
     L.check(L.lib().stdadk_adamw_ema_step(C.byref(a), _stream()), "adamw_ema_step")
+
+
+def make_sparse_args(pts: L.Points, knots4, basis_fn: str, n_out: int, p_cov: int, sides, offsets, thetaps, w1t=None,
+                     zs=None, dz_img=None, dw1t=None) -> L.SparseArgs:
+    a = L.SparseArgs()
+    a.pts = pts
+    a.knots4 = _ptr(knots4)
+    a.n_levels, a.basis_fn, a.n_out, a.p_cov = len(sides), L.BASIS_CODE[basis_fn], n_out, p_cov
+    for i, (sd, of, th) in enumerate(zip(sides, offsets, thetaps)):
+        a.side[i], a.offset[i], a.thetap[i] = int(sd), int(of), float(th)
+    a.w1t, a.zs, a.dz_img, a.dw1t = _ptr(w1t), _ptr(zs), _ptr(dz_img), _ptr(dw1t)
+    return a
+
+
+def sparse_l1_fwd(args: L.SparseArgs):
+    L.check(L.lib().stdadk_sparse_l1_fwd(C.byref(args), _stream()), "sparse_l1_fwd")
+
+
+def sparse_l1_wgrad(args: L.SparseArgs):
+    L.check(L.lib().stdadk_sparse_l1_wgrad(C.byref(args), _stream()), "sparse_l1_wgrad")

@@ -254,7 +254,9 @@ class STInterpMLP(nn.Module):
             betas=[ln.bias.detach() if ln is not None else None for _, ln in blocks],
             head_w=head_w.detach().contiguous(), head_b=head_b.detach().contiguous(),
             basis_fn=self.spatial_basis_function, p_cov=self.p, dropout=self._dropout_p,
-            ln_eps=blocks[0][1].eps if blocks and blocks[0][1] is not None else 1e-5, learnable_basis=sb.learnable)
+            ln_eps=blocks[0][1].eps if blocks and blocks[0][1] is not None else 1e-5, learnable_basis=sb.learnable,
+            lattice_sides=[int(math.sqrt(k)) for k in sb.n_centers]
+            if (sb.init_method == "uniform" and not sb.learnable) else None)
 
     def _executor(self, head_w=None, head_b=None):
         spec = self.net_spec(head_w, head_b)

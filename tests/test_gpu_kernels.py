@@ -386,3 +386,58 @@ def test_errors_are_loud():
     a = L.FwdArgs()
     with pytest.raises(RuntimeError, match="libstdadk"):
         ops.layer_fwd(a)                            # NULL weights
+
+
+@pytest.mark.parametrize("fn,sides", [("wendland", (10, 50)), ("triangular", (4, 37, 64))])
+def test_large_knot_regime_support_walk_vs_oracle(fn, sides):
+    """Block 1 in the large-K regime: spatial part by walking each point's compact support (gathers of knot-major W1
+    rows), temporal part on the tensor cores, joined before LayerNorm; forward, loss and all gradients vs the dense
+    FP64 oracle and vs the dense GPU path on the same model."""
+    L, ops, Executor, NetSpec, LossSpec = _mods()
+    rng = np.random.default_rng(21)
+    n_centers = [s * s for s in sides]
+    c, b = orc.uniform_spatial_knots(n_centers)
+    tc, tb = orc.temporal_knots([10, 15])
+    dims = [c.shape[0] + 25, 64, 32]
+    ws = [(rng.standard_normal((dims[i + 1], dims[i])) / np.sqrt(40)).astype(np.float32) for i in range(2)]
+    bs = [rng.standard_normal(dims[i + 1]).astype(np.float32) * 0.1 for i in range(2)]
+    gs = [(1 + 0.1 * rng.standard_normal(dims[i + 1])).astype(np.float32) for i in range(2)]
+    be = [(0.1 * rng.standard_normal(dims[i + 1])).astype(np.float32) for i in range(2)]
+    ws.append((rng.standard_normal((1, 32)) / 6).astype(np.float32))
+    bs.append(np.zeros(1, np.float32))
+    m = orc.OracleModel(centers=c, bandwidths=b, t_centers=tc, t_bandwidths=tb, weights=ws, biases=bs, ln_gamma=gs,
+                        ln_beta=be, basis_fn=fn)
+    n = 700
+    coords = rng.random((n, 2)).astype(np.float32)
+    coords[:4] = [[0, 0], [1, 1], [0.5, 0.5], [1, 0]]
+    t = rng.random((n, 1)).astype(np.float32)
+    y = rng.standard_normal(n).astype(np.float32)
+    yref, cache = orc.forward(m, None, coords, t, return_cache=True, rnd=orc.tf32_round)
+    lref, dy = orc.loss_and_grad(yref, y, "mse")
+    gref = orc.backward(m, cache, dy)
+    y64 = orc.forward(m, None, coords, t)
+    spec = spec_from_oracle(m)
+    spec.lattice_sides = list(sides)
+    ex = Executor(spec, force_sparse=True)
+    assert ex.sparse
+    ex.loss_acc.zero_()
+    pts = ops.make_points(T(coords), T(t))
+    yhat = ex.forward(pts, train=True, y=T(y), loss=LossSpec("mse"), inv_count=1.0 / n, save=True)
+    grads = ex.backward()
+    torch.cuda.synchronize()
+    assert rel_l2(yhat.cpu().numpy(), y64) < 1e-3
+    assert abs(ex.loss_acc.item() - lref) < 1e-3 * abs(lref)
+    # the spatial contribution is accumulated in FP32 (not TF32): compare with some slack against the TF32 emulation
+    for l in range(2):
+        assert rel_err(grads["weights"][l].cpu().numpy(), gref["weights"][l]) < 1e-2, f"dW{l}"
+        assert rel_err(grads["biases"][l].cpu().numpy(), gref["biases"][l]) < 1e-2
+    # dense path on the same model gives the same prediction
+    exd = Executor(spec_from_oracle(m))
+    assert not exd.sparse
+    yd = exd.forward(pts, train=False).cpu().numpy()
+    ys = ex.forward(pts, train=False).cpu().numpy()
+    assert rel_l2(ys, yd) < 1e-3
+    # rows of W1 outside every support get exactly zero gradient (index sets)
+    gw = grads["weights"][0].cpu().numpy()[:, :c.shape[0]]
+    mask = orc.support_mask_f32(coords, c, b, fn).any(axis=0)
+    assert np.all(gw[:, ~mask] == 0) and np.all(np.abs(gw[:, mask]).sum(axis=0) > 0)
