@@ -484,6 +484,7 @@ int stdadk_grad_sqnorm(const float* g, int64_t n, int n_groups, const int64_t* g
     if (int r = check_device()) return r;
     REQUIRE(g && sqnorms && workspace && n > 0, "grad_sqnorm: bad arguments (workspace of stdadk_sqnorm_ws_floats() "
             "zero-initialised floats is required)");
+    REQUIRE((reinterpret_cast<uintptr_t>(g) & 15) == 0, "grad_sqnorm: g must be 16-byte aligned");
     GroupsP G{};
     if (int r = make_groups(n_groups, group_end, n, &G)) return r;
     sqnorm_kernel<<<SQNORM_BLOCKS, SQNORM_THREADS, 0, (cudaStream_t)stream>>>(g, n, G, sqnorms, workspace);
@@ -531,7 +532,10 @@ int stdadk_adamw_ema_step(const stdadk_adamw_args* a, void* stream) {
     K.eps = a->eps;
     K.ema_decay = a->ema_decay;
     step_inc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(a->step_count);
-    adamw_ema_kernel<<<grid_for(a->n, 256, 4), 256, 0, (cudaStream_t)stream>>>(K);
+    REQUIRE(((reinterpret_cast<uintptr_t>(a->p) | reinterpret_cast<uintptr_t>(a->g) | reinterpret_cast<uintptr_t>(a->m) |
+              reinterpret_cast<uintptr_t>(a->v) | reinterpret_cast<uintptr_t>(a->shadow)) & 15) == 0,
+            "adamw: buffers must be 16-byte aligned");
+    adamw_ema_kernel<<<grid_for((a->n + 3) / 4, 256, 8), 256, 0, (cudaStream_t)stream>>>(K);
     return check_launch("adamw_ema_step");
 }
 

@@ -20,7 +20,7 @@
 namespace stdadk {
 
 constexpr int WG_NSTAGE = 2;                  // wgrad: 2 stages of 96 KB
-constexpr int RED_STRIDE = 2 + STDADK_MAX_Q;   // per (cg, row) scratch: two LayerNorm partials + Q head partials
+constexpr int RED_STRIDE = 4 + STDADK_MAX_Q;   // per (cg, row) scratch: four LayerNorm partials + Q head partials
 __host__ __device__ constexpr int n_work(int cg) { return 128 * cg; }
 __host__ __device__ constexpr int n_threads(int cg) { return 128 * cg + 64; }
 __device__ __forceinline__ void worker_barrier(int nw) { asm volatile("bar.sync 1, %0;" ::"r"(nw) : "memory"); }
@@ -36,7 +36,7 @@ __host__ __device__ inline SmemPlan plan_smem(int n_pad, int q, int k_s, int k_t
     s.b_off = o; o += ns * (uint32_t)n_pad * 128u;
     s.bar_off = o; o += 128;
     s.tmem_off = o; o += 16;
-    s.vec_off = o; o += 3u * n_pad * 4u;                 // bias, gamma, beta
+    s.vec_off = o; o += 4u * n_pad * 4u;                 // per column (bias, gamma, beta, -)
     s.headw_off = o; o += (uint32_t)(q > 0 ? (q * n_pad + STDADK_MAX_Q) * 4 : 0);
     o = (o + 15u) & ~15u;
     s.knots_off = o; o += (uint32_t)k_s * 16u;
@@ -234,9 +234,7 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
     uint64_t* empty = full + NSTAGE;
     uint64_t* accf = full + 2 * NSTAGE;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + sp.tmem_off);
-    float* sbias = reinterpret_cast<float*>(smem + sp.vec_off);
-    float* sgam = sbias + P.n_pad;
-    float* sbet = sgam + P.n_pad;
+    float4* sprm = reinterpret_cast<float4*>(smem + sp.vec_off);   // per column (bias, gamma, beta, 0): one LDS.128
     float* shw = reinterpret_cast<float*>(smem + sp.headw_off);
     float* shb = shw + (P.has_head ? P.head.q * P.n_pad : 0);
     float4* sk = reinterpret_cast<float4*>(smem + sp.knots_off);
@@ -263,9 +261,8 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
     }
     for (int i = tid; i < n_pad; i += NT) {
         bool ok = i < n_out;
-        sbias[i] = ok ? P.L.bias[i] : 0.0f;
-        sgam[i] = (ok && has_ln) ? P.L.gamma[i] : 1.0f;
-        sbet[i] = (ok && has_ln) ? P.L.beta[i] : 0.0f;
+        sprm[i] = make_float4(ok ? P.L.bias[i] : 0.0f, (ok && has_ln) ? P.L.gamma[i] : 1.0f,
+                              (ok && has_ln) ? P.L.beta[i] : 0.0f, 0.0f);
     }
     if (P.has_head) {
         for (int i = tid; i < P.head.q * n_pad; i += NT) {
@@ -342,43 +339,64 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
         float v[32];
         float mean = 0.0f, rstd = 1.0f;
         if (has_ln) {
-            // two-pass statistics; the CG column groups of a row combine their partial sums through SMEM
-            const float inv_n = 1.0f / (float)n_out;
-            float s1 = 0.0f;
+            // One pass over the accumulator: sums of (x - K) and (x - K)^2 with a per-thread shift K (the thread's
+            // first value), which removes the cancellation of the raw-moment formula; the CG column groups of a row
+            // publish (K, S1, S2, count) and every thread combines them exactly:
+            //   mean = sum_g (n_g K_g + S1_g) / n,   M2 = sum_g [S2_g - 2 (mean - K_g) S1_g + n_g (mean - K_g)^2]
+            float K = 0.0f, S1 = 0.0f, S2 = 0.0f, cntv = 0.0f;
+            bool have = false;
             for (int c0 = 32 * cg; c0 < n_pad; c0 += 32 * CG) {
+                const int nv = n_out - c0;
+                if (nv <= 0) break;
                 tmem_ld32(trow + c0, v);
                 if (arow) add_addend_chunk(v, arow, c0, n_out);
+                if (!have) {
+                    K = v[0] + sprm[c0].x;
+                    have = true;
+                }
+                if (nv >= 32) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (c0 + i < n_out) s1 += v[i] + sbias[c0 + i];
-            }
-            if (CG > 1) {
-                myred[0] = s1;
-                worker_barrier(NW);
-                s1 = 0.0f;
-#pragma unroll
-                for (int g = 0; g < CG; ++g) s1 += red[((size_t)g * TILE_M + row) * RED_STRIDE];
-            }
-            mean = s1 * inv_n;
-            float s2 = 0.0f;
-            for (int c0 = 32 * cg; c0 < n_pad; c0 += 32 * CG) {
-                tmem_ld32(trow + c0, v);
-                if (arow) add_addend_chunk(v, arow, c0, n_out);
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (c0 + i < n_out) {
-                        float d = v[i] + sbias[c0 + i] - mean;
-                        s2 = fmaf(d, d, s2);
+                    for (int i = 0; i < 32; ++i) {
+                        float d = v[i] + sprm[c0 + i].x - K;
+                        S1 += d;
+                        S2 = fmaf(d, d, S2);
                     }
-            }
-            if (CG > 1) {
-                myred[1] = s2;
-                worker_barrier(NW);
-                s2 = 0.0f;
+                    cntv += 32.0f;
+                } else {
 #pragma unroll
-                for (int g = 0; g < CG; ++g) s2 += red[((size_t)g * TILE_M + row) * RED_STRIDE + 1];
+                    for (int i = 0; i < 32; ++i)
+                        if (i < nv) {
+                            float d = v[i] + sprm[c0 + i].x - K;
+                            S1 += d;
+                            S2 = fmaf(d, d, S2);
+                        }
+                    cntv += (float)nv;
+                }
             }
-            rstd = 1.0f / sqrtf(s2 * inv_n + P.L.eps);
+            const float inv_n = 1.0f / (float)n_out;
+            if (CG > 1) {
+                *reinterpret_cast<float4*>(myred) = make_float4(K, S1, S2, cntv);
+                worker_barrier(NW);
+                float4 part[CG];
+                float tot = 0.0f;
+#pragma unroll
+                for (int g = 0; g < CG; ++g) {
+                    part[g] = *reinterpret_cast<const float4*>(red + ((size_t)g * TILE_M + row) * RED_STRIDE);
+                    tot += fmaf(part[g].w, part[g].x, part[g].y);
+                }
+                mean = tot * inv_n;
+                float m2 = 0.0f;
+#pragma unroll
+                for (int g = 0; g < CG; ++g) {
+                    float dk = mean - part[g].x;
+                    m2 += part[g].z - 2.0f * dk * part[g].y + part[g].w * dk * dk;
+                }
+                rstd = 1.0f / sqrtf(fmaxf(m2 * inv_n, 0.0f) + P.L.eps);
+            } else {
+                float m1 = S1 * inv_n;
+                mean = K + m1;
+                rstd = 1.0f / sqrtf(fmaxf(S2 * inv_n - m1 * m1, 0.0f) + P.L.eps);
+            }
             if (P.stats && rvalid && cg == 0) {
                 P.stats[2 * lrow] = mean;
                 P.stats[2 * lrow + 1] = rstd;
@@ -401,14 +419,17 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
                                           (uint32_t)(c0 / 8 + b), P.thresh16)
                             << (8 * b);
             }
+            const bool chunk_ok = rvalid && (c0 + 32 <= n_out);
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
                 const int col = c0 + i;
-                float x = v[i] + sbias[col];
-                float yv = has_ln ? fmaf((x - mean) * rstd, sgam[col], sbet[col]) : x;
-                float a = fmaxf(yv, 0.0f);
+                const float4 q = sprm[col];
+                // y = ((v + b) - mean) * rstd * gamma + beta  as one FFMA on v:  a = rstd*gamma, c = (b - mean)*a + beta
+                const float sc = has_ln ? rstd * q.y : 1.0f;
+                const float sh = has_ln ? fmaf(q.x - mean, sc, q.z) : q.x;
+                float a = fmaxf(fmaf(v[i], sc, sh), 0.0f);
                 if (drop) a = ((keep >> i) & 1u) ? a * P.drop_scale : 0.0f;
-                if (col >= n_out || !rvalid) a = 0.0f;
+                if (!chunk_ok && (col >= n_out || !rvalid)) a = 0.0f;
                 v[i] = a;
             }
             if (P.has_head) {

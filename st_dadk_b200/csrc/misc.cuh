@@ -131,15 +131,39 @@ __device__ __forceinline__ int group_of(const GroupsP& G, long long i) {
 // Deterministic (bitwise run-to-run and rank-to-rank: data-parallel replicas must derive the same clip coefficient):
 // fixed grid, fixed per-thread stride, ordered in-block reduction, per-block partials written to `ws`, and the last
 // block to finish (atomic ticket) adds the partials in block order.  ws: gridDim.x * 8 floats + 1 counter.
-constexpr int SQNORM_BLOCKS = 296;
+constexpr int SQNORM_BLOCKS = 592;      // 4 x 148 SMs
 constexpr int SQNORM_THREADS = 256;
 __global__ void sqnorm_kernel(const float* __restrict__ g, long long n, GroupsP G, float* __restrict__ out,
                               float* __restrict__ ws) {
     float acc[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = 0.0f;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+    // 16-byte loads, four independent chains per thread; the element -> thread map is fixed, so the result is too
+    const long long n4 = n >> 2;
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
          i += (long long)gridDim.x * blockDim.x) {
+        float4 v = __ldg(g4 + i);
+        const long long e = i << 2;
+        const int g0 = group_of(G, e), g3 = group_of(G, e + 3);
+        if (g0 == g3) {
+            float q = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (k == g0) acc[k] += q;
+        } else {
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int gi = group_of(G, e + j);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (k == gi) acc[k] = fmaf(vv[j], vv[j], acc[k]);
+            }
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {          // tail (n not a multiple of 4)
+        long long i = (n4 << 2) + threadIdx.x;
         float v = g[i];
         int gi = group_of(G, i);
 #pragma unroll
@@ -209,23 +233,48 @@ __global__ void adamw_ema_kernel(AdamK A) {
             if (A.sqnorms && mx > 0.0f) clip[k] = fminf(1.0f, mx / (sqrtf(A.sqnorms[k]) + 1e-6f));
         }
     }
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < A.n;
-         i += (long long)gridDim.x * blockDim.x) {
+    auto update = [&](long long i, float g, float& p, float& m, float& v, float& sh) {
         int gi = group_of(A.G, i);
         float l = lr[0], w = wd[0], c = clip[0];
 #pragma unroll
         for (int k = 1; k < 8; ++k)
             if (k == gi) { l = lr[k]; w = wd[k]; c = clip[k]; }
-        float g = A.g[i] * c;
-        float p = A.p[i] * (1.0f - l * w);
-        float m = A.beta1 * A.m[i] + (1.0f - A.beta1) * g;
-        float v = A.beta2 * A.v[i] + (1.0f - A.beta2) * g * g;
+        g *= c;
+        p *= (1.0f - l * w);
+        m = A.beta1 * m + (1.0f - A.beta1) * g;
+        v = A.beta2 * v + (1.0f - A.beta2) * g * g;
         float denom = sqrtf(v) * inv_sqrt_bc2 + A.eps;
         p -= (l / bc1) * (m / denom);
+        sh = A.ema_decay * sh + (1.0f - A.ema_decay) * p;
+    };
+    const long long n4 = A.n >> 2;
+    const float4* g4 = reinterpret_cast<const float4*>(A.g);
+    float4* p4 = reinterpret_cast<float4*>(A.p);
+    float4* m4 = reinterpret_cast<float4*>(A.m);
+    float4* v4 = reinterpret_cast<float4*>(A.v);
+    float4* s4 = reinterpret_cast<float4*>(A.shadow);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+         i += (long long)gridDim.x * blockDim.x) {
+        float4 g = __ldg(g4 + i), p = p4[i], m = m4[i], v = v4[i];
+        float4 sh = s4 ? s4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const long long e = i << 2;
+        update(e, g.x, p.x, m.x, v.x, sh.x);
+        update(e + 1, g.y, p.y, m.y, v.y, sh.y);
+        update(e + 2, g.z, p.z, m.z, v.z, sh.z);
+        update(e + 3, g.w, p.w, m.w, v.w, sh.w);
+        p4[i] = p;
+        m4[i] = m;
+        v4[i] = v;
+        if (s4) s4[i] = sh;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (A.n & 3)) {
+        long long i = (n4 << 2) + threadIdx.x;
+        float p = A.p[i], m = A.m[i], v = A.v[i], sh = A.shadow ? A.shadow[i] : 0.0f;
+        update(i, A.g[i], p, m, v, sh);
         A.p[i] = p;
         A.m[i] = m;
         A.v[i] = v;
-        if (A.shadow) A.shadow[i] = A.ema_decay * A.shadow[i] + (1.0f - A.ema_decay) * p;
+        if (A.shadow) A.shadow[i] = sh;
     }
 }
 

@@ -35,12 +35,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU.  The probe itself suspends the thread
+// for a hardware time slice; between probes the warp backs off with nanosleep so that waiting warps (the epilogue
+// warps during the main loop) do not steal issue slots from the warps that are producing.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
-    long long t0 = clock64();
+    uint32_t spins = 0;
+    long long t0 = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) __trap();
+        __nanosleep(40);
+        if ((++spins & 0xFFFu) == 0) {
+            long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000LL) __trap();
+        }
     }
 }
 

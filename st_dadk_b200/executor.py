@@ -97,6 +97,7 @@ class Executor:
         self._grad_flat = None
         self.grads = None
         self._knots_ready = False
+        self._side = None
 
     def _setup_regime(self, spec: NetSpec):
         k_s = spec.centers.shape[0]
@@ -291,6 +292,33 @@ class Executor:
         g["log_bandwidths"] = flat[o:o + s.centers.shape[0]]
         self._grad_flat, self.grads = flat, g
 
+    def _wgrad_block(self, l: int, pts, ws, basis, g):
+        """dW_l += dz_l^T A_l (tensor cores; block 1 of the large-knot regime: temporal columns + scattered rows)."""
+        s = self.spec
+        w = s.weights[l]
+        gw = g["weights"][l]
+        a = L.WgradArgs()
+        a.pts = pts
+        if l == 0:
+            a.basis = C.pointer(basis)
+        else:
+            a.a_img = ws.h[l - 1].data_ptr()
+        a.dz_img = ws.dz[l].data_ptr()
+        a.n_in, a.n_out = self._n_in(l), w.shape[0]
+        if l == 0 and self.sparse:
+            k_s = s.centers.shape[0]
+            gd = gw[:, k_s:]                       # dense (temporal) columns on the tensor cores ...
+            a.dw = gd.data_ptr()
+            a.stride_o, a.stride_i = gd.stride(0), gd.stride(1)
+            ops.wgrad(a)
+            if gw.stride(0) != 1 or gw.stride(1) != w.shape[0]:
+                raise RuntimeError("support-walk wgrad needs the first-layer gradient stored (in, out)-contiguous")
+            ops.sparse_l1_wgrad(self._sparse_args(pts, ws, dz_img=ws.dz[0], dw1t=gw))   # ... spatial rows scattered
+            return
+        a.dw = gw.data_ptr()
+        a.stride_o, a.stride_i = gw.stride(0), gw.stride(1)
+        ops.wgrad(a)
+
     def backward(self, dyhat: Optional[torch.Tensor] = None, zero: bool = True) -> dict:
         """Gradients of every parameter for the rows of the last `forward(save=True)`.  `dyhat`
         overrides the loss gradient left by the fused loss (used by the autograd bridge)."""
@@ -307,6 +335,10 @@ class Executor:
             ws.dyhat.copy_(dyhat)
         basis = self._basis()
         nh = s.n_hidden
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        side = self._side
         head = ops.make_head(s.head_w, s.head_b, s.q, ws.yhat, dyhat=ws.dyhat)
         for l in reversed(range(nh)):
             a = L.BwdArgs()
@@ -334,30 +366,12 @@ class Executor:
             a.dz_img = ws.dz[l].data_ptr()
             a.d_bias = g["biases"][l].data_ptr()
             ops.layer_bwd(a)
-        for l in range(nh):
-            w = s.weights[l]
-            gw = g["weights"][l]
-            a = L.WgradArgs()
-            a.pts = pts
-            if l == 0:
-                a.basis = C.pointer(basis)
-            else:
-                a.a_img = ws.h[l - 1].data_ptr()
-            a.dz_img = ws.dz[l].data_ptr()
-            a.n_in, a.n_out = self._n_in(l), w.shape[0]
-            if l == 0 and self.sparse:
-                k_s = s.centers.shape[0]
-                gd = gw[:, k_s:]                       # dense (temporal) columns on the tensor cores ...
-                a.dw = gd.data_ptr()
-                a.stride_o, a.stride_i = gd.stride(0), gd.stride(1)
-                ops.wgrad(a)
-                if gw.stride(0) != 1 or gw.stride(1) != w.shape[0]:
-                    raise RuntimeError("support-walk wgrad needs the first-layer gradient stored (in, out)-contiguous")
-                ops.sparse_l1_wgrad(self._sparse_args(pts, ws, dz_img=ws.dz[0], dw1t=gw))   # ... spatial rows scattered
-                continue
-            a.dw = gw.data_ptr()
-            a.stride_o, a.stride_i = gw.stride(0), gw.stride(1)
-            ops.wgrad(a)
+            # dW_l only needs dz_l: it runs on a second stream, concurrently with the rest of the backward chain
+            # (a 4096-row batch is 32 tiles -- one kernel alone leaves most of the 148 SMs idle)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                self._wgrad_block(l, pts, ws, basis, g)
+        main.wait_stream(side)      # join: every weight gradient is complete before the caller continues
         if s.learnable_basis:
             a = L.KnotGradArgs()
             a.basis = C.pointer(basis)

@@ -355,7 +355,7 @@ def test_adamw_ema_and_sqnorm_vs_oracle():
     L, ops, *_ = _mods()
     rng = np.random.default_rng(1)
     n = 100_003
-    ends = [60_000, n]
+    ends = [60_001, n]          # group boundary inside a 16-byte vector, n not a multiple of 4
     p0 = rng.standard_normal(n).astype(np.float32)
     p, m, v, sh = T(p0), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV), T(p0)
     pn, mn, vn, shn = p0.astype(np.float64), np.zeros(n), np.zeros(n), p0.astype(np.float64)
