@@ -352,13 +352,24 @@ int stdadk_layer_bwd(const stdadk_bwd_args* a, void* stream) {
     SmemPlan sp = plan_smem(K.n_pad, K.has_head ? K.head.q : 0, basis ? K.basis.k_s : 0, basis ? K.basis.k_t : 0, true, BCG, BNS);
     REQUIRE(sp.total <= 227 * 1024, "layer_bwd: needs %u B of shared memory (> 227 KB)", sp.total);
     int tiles = (int)ceil_div64(a->pts.n_rows, TILE_M);
+    const bool ln = a->layer.gamma != nullptr, hd = a->head != nullptr;
+#define LAUNCH_BWD(B, LNV, HD)                                                                              \
+    do {                                                                                                    \
+        if (int r = set_smem(layer_bwd_kernel<B, BCG, BNS, LNV, HD>, sp.total)) return r;                   \
+        layer_bwd_kernel<B, BCG, BNS, LNV, HD><<<tiles, n_threads(BCG), sp.total, (cudaStream_t)stream>>>(K); \
+    } while (0)
     if (basis) {
-        if (int r = set_smem(layer_bwd_kernel<true, BCG, BNS>, sp.total)) return r;
-        layer_bwd_kernel<true, BCG, BNS><<<tiles, n_threads(BCG), sp.total, (cudaStream_t)stream>>>(K);
+        if (ln && hd) LAUNCH_BWD(true, true, true);
+        else if (ln) LAUNCH_BWD(true, true, false);
+        else if (hd) LAUNCH_BWD(true, false, true);
+        else LAUNCH_BWD(true, false, false);
     } else {
-        if (int r = set_smem(layer_bwd_kernel<false, BCG, BNS>, sp.total)) return r;
-        layer_bwd_kernel<false, BCG, BNS><<<tiles, n_threads(BCG), sp.total, (cudaStream_t)stream>>>(K);
+        if (ln && hd) LAUNCH_BWD(false, true, true);
+        else if (ln) LAUNCH_BWD(false, true, false);
+        else if (hd) LAUNCH_BWD(false, false, true);
+        else LAUNCH_BWD(false, false, false);
     }
+#undef LAUNCH_BWD
     return check_launch("layer_bwd");
 }
 

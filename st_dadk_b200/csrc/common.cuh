@@ -149,7 +149,9 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 // bit e of the result = keep flag of column (block*8 + e)
-__device__ __forceinline__ uint32_t dropout_keep8(unsigned long long seed, uint32_t step, uint32_t layer,
+// not inlined: one copy of the 10 Philox rounds per kernel keeps the instruction footprint (and the cold I-cache
+// misses of one-wave launches) down
+__device__ __noinline__ uint32_t dropout_keep8(unsigned long long seed, uint32_t step, uint32_t layer,
                                                   unsigned long long row, uint32_t block, uint32_t thresh16) {
     uint32_t o[4];
     philox4x32_10((uint32_t)row, block, layer | ((uint32_t)(row >> 32) << 8), step, (uint32_t)seed,

@@ -413,7 +413,7 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
             uint32_t keep = 0xFFFFFFFFu;
             if (drop) {
                 keep = 0;
-#pragma unroll
+#pragma unroll 1
                 for (int b = 0; b < 4; ++b)
                     keep |= dropout_keep8(P.L.seed, drop_step, (uint32_t)P.L.layer_id, P.L.key_offset + (unsigned long long)lrow,
                                           (uint32_t)(c0 / 8 + b), P.thresh16)
@@ -433,15 +433,16 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
                 v[i] = a;
             }
             if (P.has_head) {
+#pragma unroll 1
+                for (int k = 0; k < P.head.q; ++k) {     // runtime loop: Q is 1 or a handful; keeps the code small
+                    float acc = 0.0f;
+                    const float* wk = shw + k * n_pad + c0;
 #pragma unroll
-                for (int k = 0; k < STDADK_MAX_Q; ++k)
-                    if (k < P.head.q) {
-                        float acc = yh[k];
-                        const float* wk = shw + k * n_pad + c0;
+                    for (int i = 0; i < 32; ++i) acc = fmaf(v[i], wk[i], acc);
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) acc = fmaf(v[i], wk[i], acc);
-                        yh[k] = acc;
-                    }
+                    for (int kk = 0; kk < STDADK_MAX_Q; ++kk)
+                        if (kk == k) yh[kk] += acc;
+                }
             }
             if (P.out_img) {
                 float* dst = P.out_img + ((size_t)tile * (n_pad / SLAB_K) + (c0 / SLAB_K)) * SLAB_FLOATS;
@@ -497,16 +498,36 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
     if (warp == 4 * CG) tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
 }
 
+// g[i] = sum_k dyh[k] * head_w[k, c0 + i]: the gradient entering the last hidden block, formed per row from the
+// head (runtime loop over the Q outputs so the code stays small)
+__device__ __forceinline__ void head_dh_chunk(float (&g)[32], const float (&dyh)[STDADK_MAX_Q], const float* shw, int n_pad,
+                                              int c0, int q) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) g[i] = 0.0f;
+#pragma unroll 1
+    for (int k = 0; k < q; ++k) {
+        float dk = 0.0f;
+#pragma unroll
+        for (int kk = 0; kk < STDADK_MAX_Q; ++kk)
+            if (kk == k) dk = dyh[kk];
+        const float* wk = shw + k * n_pad + c0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) g[i] = fmaf(dk, wk[i], g[i]);
+    }
+}
+
 // =============================================================================================
 // Backward
 // =============================================================================================
-template <bool BASIS, int CG, int NS>
+// LN / HEAD are compile-time so that each instantiation carries only its own epilogue: the generic kernel was
+// 150 KB of SASS and a one-wave launch (32 tiles) spent ~30% of its stall samples on instruction fetch.
+template <bool BASIS, int CG, int NS, bool LN, bool HEAD>
 __global__ void __launch_bounds__(n_threads(CG), 1) layer_bwd_kernel(const __grid_constant__ BwdK P) {
     constexpr int NW = n_work(CG), NT = n_threads(CG), NSTAGE = NS;
     constexpr int MAXCH = MAX_N / 32 / CG;          // column chunks per thread
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = align_smem(smem_raw);
-    const int q = P.has_head ? P.head.q : 0;
+    const int q = HEAD ? P.head.q : 0;
     const SmemPlan sp = plan_smem(P.n_pad, q, BASIS ? P.basis.k_s : 0, BASIS ? P.basis.k_t : 0, true, CG, NS);
     float* sA = reinterpret_cast<float*>(smem + sp.a_off);
     float* sB = reinterpret_cast<float*>(smem + sp.b_off);
@@ -530,7 +551,7 @@ __global__ void __launch_bounds__(n_threads(CG), 1) layer_bwd_kernel(const __gri
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tile = blockIdx.x;
     const int n_pad = P.n_pad, n_out = P.L.n_out;
-    const bool has_ln = P.L.gamma != nullptr;
+    constexpr bool has_ln = LN;
     const size_t b_stage_floats = (size_t)n_pad * SLAB_K;
     const int total_slabs = P.k_slabs + P.k_slabs2;
     const uint32_t acc1_off = (uint32_t)(P.tmem_cols / 2);
@@ -554,7 +575,7 @@ __global__ void __launch_bounds__(n_threads(CG), 1) layer_bwd_kernel(const __gri
         sbet[i] = (ok && has_ln) ? P.L.beta[i] : 0.0f;
     }
     for (int i = tid; i < (3 + q) * n_pad + STDADK_MAX_Q; i += NT) cs_bias[i] = 0.0f;
-    if (P.has_head) {
+    if (HEAD) {
         for (int i = tid; i < q * n_pad; i += NT) {
             int k = i / n_pad, c = i - k * n_pad;
             shw[i] = c < n_out ? P.head.w[(size_t)k * n_out + c] : 0.0f;
@@ -638,7 +659,7 @@ __global__ void __launch_bounds__(n_threads(CG), 1) layer_bwd_kernel(const __gri
         float dyh[STDADK_MAX_Q];
 #pragma unroll
         for (int k = 0; k < STDADK_MAX_Q; ++k)
-            dyh[k] = (P.has_head && rvalid && k < q) ? P.head.dyhat[lrow * q + k] : 0.0f;
+            dyh[k] = (HEAD && rvalid && k < q) ? P.head.dyhat[lrow * q + k] : 0.0f;
         const bool drop = P.L.drop_p > 0.0f;
         const unsigned int drop_step = drop ? dropout_step(P.L) : 0u;
         const float inv_n = 1.0f / (float)n_out;
@@ -651,11 +672,12 @@ __global__ void __launch_bounds__(n_threads(CG), 1) layer_bwd_kernel(const __gri
         for (int c0 = 32 * cg; c0 < n_pad; c0 += 32 * CG, ++ch) {
             tmem_ld32(trow + c0, z);
             if (arow) add_addend_chunk(z, arow, c0, n_out);
-            if (!P.has_head) tmem_ld32(trow + acc1_off + c0, g);
+            if (!HEAD) tmem_ld32(trow + acc1_off + c0, g);
+            else head_dh_chunk(g, dyh, shw, n_pad, c0, q);
             uint32_t keep = 0xFFFFFFFFu;
             if (drop) {
                 keep = 0;
-#pragma unroll
+#pragma unroll 1
                 for (int b = 0; b < 4; ++b)
                     keep |= dropout_keep8(P.L.seed, drop_step, (uint32_t)P.L.layer_id, P.L.key_offset + (unsigned long long)lrow,
                                           (uint32_t)(c0 / 8 + b), P.thresh16)
@@ -670,15 +692,7 @@ __global__ void __launch_bounds__(n_threads(CG), 1) layer_bwd_kernel(const __gri
                 float yv = has_ln ? fmaf(xh, sgam[col], sbet[col]) : x;
                 bool on = (yv > 0.0f) && ((keep >> i) & 1u) && (col < n_out) && rvalid;
                 act |= (on ? 1u : 0u) << i;
-                float dh;
-                if (P.has_head) {
-                    dh = 0.0f;
-#pragma unroll
-                    for (int k = 0; k < STDADK_MAX_Q; ++k)
-                        if (k < q) dh = fmaf(dyh[k], shw[k * n_pad + col], dh);
-                } else {
-                    dh = g[i];
-                }
+                const float dh = g[i];
                 float h = on ? yv * P.drop_scale : 0.0f;  // forward activation (for the head gradient)
                 g[i] = on ? dh * P.drop_scale : 0.0f;
                 z[i] = xh;
@@ -687,7 +701,7 @@ __global__ void __launch_bounds__(n_threads(CG), 1) layer_bwd_kernel(const __gri
 #pragma unroll
             for (int k = 0; k < MAXCH; ++k)
                 if (k == ch) actbits[k] = act;
-            if (P.has_head) {
+            if (HEAD) {
                 for (int k = 0; k < q; ++k) {
                     float hv[32];
                     const float dk = dyh[k];
@@ -723,7 +737,7 @@ __global__ void __launch_bounds__(n_threads(CG), 1) layer_bwd_kernel(const __gri
                 atomicAdd(&cs_bias[c0 + lane], s);
             }
         }
-        if (P.has_head && cg == 0) {
+        if (HEAD && cg == 0) {
             for (int k = 0; k < q; ++k) {
                 float s = warp_sum(dyh[k]);
                 if (lane == 0) atomicAdd(&cs_hb[k], s);
@@ -747,7 +761,8 @@ __global__ void __launch_bounds__(n_threads(CG), 1) layer_bwd_kernel(const __gri
             for (int c0 = 32 * cg; c0 < n_pad; c0 += 32 * CG, ++ch) {
                 tmem_ld32(trow + c0, z);
                 if (arow) add_addend_chunk(z, arow, c0, n_out);
-                if (!P.has_head) tmem_ld32(trow + acc1_off + c0, g);
+                if (!HEAD) tmem_ld32(trow + acc1_off + c0, g);
+                else head_dh_chunk(g, dyh, shw, n_pad, c0, q);
                 uint32_t act = 0;
 #pragma unroll
                 for (int k = 0; k < MAXCH; ++k)
@@ -756,15 +771,7 @@ __global__ void __launch_bounds__(n_threads(CG), 1) layer_bwd_kernel(const __gri
                 for (int i = 0; i < 32; ++i) {
                     const int col = c0 + i;
                     float xh = (z[i] + sbias[col] - mean) * rstd;
-                    float dh;
-                    if (P.has_head) {
-                        dh = 0.0f;
-#pragma unroll
-                        for (int k = 0; k < STDADK_MAX_Q; ++k)
-                            if (k < q) dh = fmaf(dyh[k], shw[k * n_pad + col], dh);
-                    } else {
-                        dh = g[i];
-                    }
+                    const float dh = g[i];
                     float gy = ((act >> i) & 1u) ? dh * P.drop_scale * sgam[col] : 0.0f;
                     float dz = rstd * (gy - ma - xh * mb);
                     g[i] = (col < n_out && rvalid) ? dz : 0.0f;
