@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 #include "layer.cuh"
 #include "misc.cuh"
@@ -292,17 +293,47 @@ int stdadk_layer_fwd(const stdadk_fwd_args* a, void* stream) {
     SmemPlan sp = plan_smem(K.n_pad, K.has_head ? K.head.q : 0, basis ? K.basis.k_s : 0, basis ? K.basis.k_t : 0, false, cg, ns);
     REQUIRE(sp.total <= 227 * 1024, "layer_fwd: needs %u B of shared memory (> 227 KB): too many knots for the dense path",
             sp.total);
-#define LAUNCH_FWD(B, C)                                                                   \
-    do {                                                                                   \
-        if (int r = set_smem(layer_fwd_kernel<B, C, (C == 2 ? 2 : 4)>, sp.total)) return r;                  \
-        layer_fwd_kernel<B, C, (C == 2 ? 2 : 4)><<<tiles, n_threads(C), sp.total, (cudaStream_t)stream>>>(K); \
+    K.n_tiles = tiles;
+    // Optional (STDADK_CLUSTER=1): clusters of 4 CTAs share every weight slab by multicast (L2 -> SM weight traffic / 4).
+    // Bit-identical output, but measured SLOWER on B200 (1M-point prediction 2.25 ms vs 2.03 ms): the kernels are
+    // issue/latency-bound, not L2-bound, and the cluster couples four tiles' pipelines.  Kept for L2-bound shapes.
+    constexpr int FCL = 4;
+#define LAUNCH_FWD(B, C)                                                                                     \
+    do {                                                                                                     \
+        if (int r = set_smem(layer_fwd_kernel<B, C, (C == 2 ? 2 : 4), 1>, sp.total)) return r;               \
+        layer_fwd_kernel<B, C, (C == 2 ? 2 : 4), 1><<<tiles, n_threads(C), sp.total, (cudaStream_t)stream>>>(K); \
     } while (0)
+#define LAUNCH_FWD_CLUSTER(B)                                                                                \
+    do {                                                                                                     \
+        if (int r = set_smem(layer_fwd_kernel<B, 2, 2, FCL>, sp.total)) return r;                            \
+        cudaLaunchConfig_t cfg{};                                                                            \
+        cfg.gridDim = dim3((unsigned)((tiles + FCL - 1) / FCL * FCL));                                       \
+        cfg.blockDim = dim3(n_threads(2));                                                                   \
+        cfg.dynamicSmemBytes = sp.total;                                                                     \
+        cfg.stream = (cudaStream_t)stream;                                                                   \
+        cudaLaunchAttribute at[1];                                                                           \
+        at[0].id = cudaLaunchAttributeClusterDimension;                                                      \
+        at[0].val.clusterDim.x = FCL;                                                                        \
+        at[0].val.clusterDim.y = 1;                                                                          \
+        at[0].val.clusterDim.z = 1;                                                                          \
+        cfg.attrs = at;                                                                                      \
+        cfg.numAttrs = 1;                                                                                    \
+        cudaError_t e = cudaLaunchKernelEx(&cfg, layer_fwd_kernel<B, 2, 2, FCL>, K);                         \
+        if (e != cudaSuccess) return fail((int)e, "layer_fwd (cluster launch): %s", cudaGetErrorString(e));  \
+    } while (0)
+    const char* cl_env = getenv("STDADK_CLUSTER");
+    const bool use_cluster = cg == 2 && cl_env != nullptr && cl_env[0] == '1';
     if (basis) {
-        if (cg == 2) LAUNCH_FWD(true, 2); else LAUNCH_FWD(true, 4);
+        if (use_cluster) LAUNCH_FWD_CLUSTER(true);
+        else if (cg == 2) LAUNCH_FWD(true, 2);
+        else LAUNCH_FWD(true, 4);
     } else {
-        if (cg == 2) LAUNCH_FWD(false, 2); else LAUNCH_FWD(false, 4);
+        if (use_cluster) LAUNCH_FWD_CLUSTER(false);
+        else if (cg == 2) LAUNCH_FWD(false, 2);
+        else LAUNCH_FWD(false, 4);
     }
 #undef LAUNCH_FWD
+#undef LAUNCH_FWD_CLUSTER
     return check_launch("layer_fwd");
 }
 

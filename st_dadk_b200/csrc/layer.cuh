@@ -61,6 +61,7 @@ struct FwdK {
     int has_head, k_slabs, n_pad, tmem_cols;
     unsigned int thresh16;
     float drop_scale;
+    int n_tiles, _padk;
 };
 
 struct BwdK {
@@ -147,6 +148,27 @@ __device__ __forceinline__ void issue_slab_copies(const float* w_img, int w_slab
     if (a_tile_img) bulk_g2s(sA, a_tile_img + (size_t)slab * SLAB_FLOATS, SLAB_BYTES, bar);
 }
 
+// Cluster variant: the CL CTAs of a cluster work on different row tiles but need the same weight slab; CTA `rank`
+// fetches 1/CL of its rows and multicasts them to all, so the slab crosses L2 -> SM once per cluster instead of once
+// per CTA.  Every CTA's barrier still expects the whole slab (+ its own A slab).
+template <int CL>
+__device__ __forceinline__ void issue_slab_copies_cluster(const float* w_img, int w_slabs, int slab, int n_pad,
+                                                          const float* a_tile_img, float* sA, float* sB, uint64_t* bar,
+                                                          uint32_t rank) {
+    uint32_t bytes = (uint32_t)n_pad * 128u + (a_tile_img ? (uint32_t)SLAB_BYTES : 0u);
+    mbar_arrive_expect_tx(bar, bytes);
+    const int per = n_pad / CL;                    // n_pad is a multiple of 32, CL of {2, 4}
+    int r0 = (int)rank * per;
+    const int r_end = r0 + per;
+    while (r0 < r_end) {                           // split at 128-row image tiles
+        int rows = min(r_end - r0, TILE_M - (r0 % TILE_M));
+        const float* src = w_img + ((size_t)(r0 / TILE_M) * w_slabs + slab) * SLAB_FLOATS + (size_t)(r0 % TILE_M) * SLAB_K;
+        bulk_g2s_mcast(sB + (size_t)r0 * SLAB_K, src, (uint32_t)rows * 128u, bar, (uint16_t)((1u << CL) - 1u));
+        r0 += rows;
+    }
+    if (a_tile_img) bulk_g2s(sA, a_tile_img + (size_t)slab * SLAB_FLOATS, SLAB_BYTES, bar);
+}
+
 // MMA issuer: one 128-byte K slab = 4 MMAs of K=8 (TF32), advancing 32 bytes inside the swizzle atom.
 __device__ __forceinline__ void issue_slab_mma(uint32_t tmem_acc, const float* sA, const float* sB, uint32_t idesc,
                                                bool first) {
@@ -221,9 +243,10 @@ __device__ __forceinline__ float row_loss(const HeadP& H, const float* yh, float
 // =============================================================================================
 // Forward
 // =============================================================================================
-template <bool BASIS, int CG, int NS>
+template <bool BASIS, int CG, int NS, int CL>
 __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kernel(const __grid_constant__ FwdK P) {
     constexpr int NW = n_work(CG), NT = n_threads(CG), NSTAGE = NS;
+    constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1u);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = align_smem(smem_raw);
     const SmemPlan sp = plan_smem(P.n_pad, P.has_head ? P.head.q : 0, BASIS ? P.basis.k_s : 0,
@@ -242,7 +265,9 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
     float* red = reinterpret_cast<float*>(smem + sp.red_off);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int tile = blockIdx.x;
+    const bool tile_valid = (int)blockIdx.x < P.n_tiles;       // a cluster may be padded with a tile-less CTA
+    const int tile = tile_valid ? (int)blockIdx.x : P.n_tiles - 1;
+    const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
     const int n_pad = P.n_pad, n_out = P.L.n_out;
     const bool has_ln = P.L.gamma != nullptr;
     const size_t b_stage_floats = (size_t)n_pad * SLAB_K;
@@ -250,7 +275,7 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
     if (tid == NW) {
         for (int s = 0; s < NSTAGE; ++s) {
             mbar_init(&full[s], BASIS ? 1 + NW : 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], CL);        // every CTA of the cluster must have consumed the stage
         }
         mbar_init(accf, 1);
         mbar_fence_init();
@@ -277,6 +302,7 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();                // peers' barriers are initialised before anything remote arrives
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -287,8 +313,12 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
             for (int s = 0; s < P.k_slabs; ++s) {
                 int stage = s % NSTAGE, it = s / NSTAGE;
                 if (it > 0) mbar_wait(&empty[stage], (it - 1) & 1);
-                issue_slab_copies(P.L.w_img, P.k_slabs, s, n_pad, a_tile, sA + (size_t)stage * SLAB_FLOATS,
-                                  sB + stage * b_stage_floats, &full[stage]);
+                if (CL > 1)
+                    issue_slab_copies_cluster<CL>(P.L.w_img, P.k_slabs, s, n_pad, a_tile, sA + (size_t)stage * SLAB_FLOATS,
+                                                  sB + stage * b_stage_floats, &full[stage], crank);
+                else
+                    issue_slab_copies(P.L.w_img, P.k_slabs, s, n_pad, a_tile, sA + (size_t)stage * SLAB_FLOATS,
+                                      sB + stage * b_stage_floats, &full[stage]);
             }
         }
         __syncwarp();
@@ -302,7 +332,8 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
                 tc_fence_after();
                 issue_slab_mma(tmem_base, sA + (size_t)stage * SLAB_FLOATS, sB + stage * b_stage_floats, idesc,
                                s == 0);
-                umma_commit(&empty[stage]);
+                if (CL > 1) umma_commit_mcast(&empty[stage], CMASK);
+                else umma_commit(&empty[stage]);
             }
             umma_commit(accf);
         }
@@ -312,7 +343,7 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
         const int q4 = warp & 3, cg = warp >> 2;
         const int row = q4 * 32 + lane;
         const long long lrow = (long long)tile * TILE_M + row;
-        const bool rvalid = lrow < P.pts.n_rows;
+        const bool rvalid = tile_valid && lrow < P.pts.n_rows;
         const long long grow = P.pts.row_begin + lrow;
         if (BASIS) {
             float x = 0.f, y = 0.f, t = 0.f;
@@ -444,7 +475,7 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
                         if (kk == k) yh[kk] += acc;
                 }
             }
-            if (P.out_img) {
+            if (P.out_img && tile_valid) {
                 float* dst = P.out_img + ((size_t)tile * (n_pad / SLAB_K) + (c0 / SLAB_K)) * SLAB_FLOATS;
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
@@ -495,6 +526,7 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
         tc_fence_before();
     }
     __syncthreads();
+    if (CL > 1) cluster_sync_all();                // no peer may still multicast into / arrive on this CTA's memory
     if (warp == 4 * CG) tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
 }
 

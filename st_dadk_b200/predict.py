@@ -92,3 +92,45 @@ class Predictor:
         out = torch.empty(end - begin, self.model.output_dim, device=dev)
         self._run(lambda b, r: ops.make_points(cc, tt, None, row_begin=b - begin, n_rows=r), begin, end, out)
         return out, (begin, end)
+
+    @torch.no_grad()
+    def profile_layers(self, nx: int, ny: int, nt: int, repeats: int = 3):
+        """Per-block kernel time of a grid prediction (CUDA events around each launch on the launching stream) with
+        the algorithmic HBM bytes per launch: block 1 reads nothing per point (grid generated on device) and writes
+        the h1 image; later blocks read and write images; the last writes y_hat."""
+        from . import ops as _ops
+        self._prepare()
+        n = min(nx * ny * nt, self.chunk)
+        rec = []
+        orig = _ops.layer_fwd
+
+        def timed(a):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            orig(a)
+            e1.record()
+            rec.append((a.layer.layer_id, a.layer.n_in, a.layer.n_out, bool(a.head), e0, e1))
+
+        out = torch.empty(n, self.model.output_dim, device=self.ex.device)
+        _ops.layer_fwd = timed
+        try:
+            for _ in range(repeats + 1):
+                self.ex.forward(_ops.make_points(grid=(nx, ny, nt), row_begin=0, n_rows=n), train=False, out=out,
+                                prepared=True)
+            torch.cuda.synchronize()
+        finally:
+            _ops.layer_fwd = orig
+        res = {}
+        nl = self.ex.spec.n_hidden
+        for lid, n_in, n_out, has_head, e0, e1 in rec[nl:]:          # first pass = warm-up
+            d = res.setdefault(lid, {"ms": 0.0, "n": 0})
+            d["ms"] += e0.elapsed_time(e1)
+            d["n"] += 1
+            pad = lambda c: (c + 31) // 32 * 32
+            rd = 0 if lid == 0 else 4 * pad(n_in)
+            wr = 4 * self.model.output_dim if has_head else 4 * pad(n_out)
+            d["bytes"] = float(n) * (rd + wr)
+            d["flops"] = 2.0 * n * n_in * n_out
+        for d in res.values():
+            d["ms"] /= d["n"]
+        return n, res

@@ -441,3 +441,25 @@ def test_large_knot_regime_support_walk_vs_oracle(fn, sides):
     gw = grads["weights"][0].cpu().numpy()[:, :c.shape[0]]
     mask = orc.support_mask_f32(coords, c, b, fn).any(axis=0)
     assert np.all(gw[:, ~mask] == 0) and np.all(np.abs(gw[:, mask]).sum(axis=0) > 0)
+
+
+def test_cluster_multicast_prediction_matches_plain_path():
+    """Optional throughput variant (STDADK_CLUSTER=1): clusters of 4 CTAs multicast every weight slab.  Its output
+    must be bit-identical to the plain launch (same arithmetic, only the slab delivery differs), for a tile count
+    that is not a multiple of the cluster size, and match the oracle."""
+    import os
+    L, ops, Executor, NetSpec, LossSpec = _mods()
+    m = _default_oracle_model(3, q=5)
+    ex = Executor(spec_from_oracle(m))
+    nx, ny, nt = 211, 181, 1            # 38191 points = 299 tiles (not a multiple of 4), last tile ragged
+    n = nx * ny * nt
+    plain = ex.forward(ops.make_points(grid=(nx, ny, nt)), train=False).clone()
+    os.environ["STDADK_CLUSTER"] = "1"
+    try:
+        got = ex.forward(ops.make_points(grid=(nx, ny, nt)), train=False).clone()
+    finally:
+        del os.environ["STDADK_CLUSTER"]
+    assert torch.equal(got, plain)
+    idx = np.r_[0:300, n - 300:n]
+    coords, t = orc.grid_points(nx, ny, nt, 0, n)
+    assert rel_l2(got.cpu().numpy()[idx], orc.forward(m, None, coords[idx], t[idx])) < 1e-3
