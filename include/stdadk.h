@@ -111,6 +111,9 @@ typedef struct {
     const stdadk_head* head; /* non-NULL on the last hidden block: fuses head (+ loss) */
     const float* addend;     /* optional (rows x n_out) FP32 row-major term added to A W^T + b before LayerNorm: the
                                 support-walked spatial part of block 1 in the large-knot regime (stdadk_sparse_l1_fwd) */
+    float* x_img;            /* optional out: image (rows x n_out) of the pre-LayerNorm value x = A W^T + b (+ addend),
+                                FP32.  A backward that receives it skips the recomputation GEMM -- worth its 1 KB/row
+                                when the batch is a single wave of tiles and latency, not bandwidth, is the limit. */
 } stdadk_fwd_args;
 
 /* Backward of one hidden block: recomputes z = A W^T (for block 1 this recomputes the basis),
@@ -135,6 +138,7 @@ typedef struct {
     float* d_gamma;            /* (n_out) += or NULL */
     float* d_beta;             /* (n_out) += or NULL */
     const float* addend;       /* as in stdadk_fwd_args (the recomputed z needs the same term) */
+    const float* x_img;        /* optional: x saved by the forward; then a_img / basis / addend are not read */
 } stdadk_bwd_args;
 
 /* Weight gradient dW (n_out x n_in) += dz^T A, reduction over rows on the tensor cores (both

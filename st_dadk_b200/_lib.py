@@ -45,14 +45,14 @@ class Head(C.Structure):
 
 class FwdArgs(C.Structure):
     _fields_ = [("basis", C.POINTER(Basis)), ("pts", Points), ("a_img", fp), ("layer", Layer), ("drop", Dropout),
-                ("out_img", fp), ("stats", fp), ("head", C.POINTER(Head)), ("addend", fp)]
+                ("out_img", fp), ("stats", fp), ("head", C.POINTER(Head)), ("addend", fp), ("x_img", fp)]
 
 
 class BwdArgs(C.Structure):
     _fields_ = [("basis", C.POINTER(Basis)), ("pts", Points), ("a_img", fp), ("layer", Layer), ("drop", Dropout),
                 ("stats", fp), ("head", C.POINTER(Head)), ("d_head_w", fp), ("d_head_b", fp), ("dz_next_img", fp),
                 ("wt_next_img", fp), ("n_next", C.c_int32), ("_pad", C.c_int32), ("dz_img", fp), ("d_bias", fp),
-                ("d_gamma", fp), ("d_beta", fp), ("addend", fp)]
+                ("d_gamma", fp), ("d_beta", fp), ("addend", fp), ("x_img", fp)]
 
 
 class WgradArgs(C.Structure):

@@ -275,6 +275,7 @@ int stdadk_layer_fwd(const stdadk_fwd_args* a, void* stream) {
     K.head = to_head(a->head);
     K.a_img = a->a_img;
     K.addend = a->addend;
+    K.x_img = a->x_img;
     K.out_img = a->out_img;
     K.stats = a->stats;
     K.has_head = a->head ? 1 : 0;
@@ -341,8 +342,8 @@ int stdadk_layer_bwd(const stdadk_bwd_args* a, void* stream) {
     if (int r = check_device()) return r;
     REQUIRE(a, "layer_bwd: NULL args");
     if (int r = check_layer(a->layer, "layer_bwd")) return r;
-    REQUIRE((a->basis != nullptr) != (a->a_img != nullptr), "layer_bwd: give exactly one of basis / a_img");
-    if (a->basis)
+    REQUIRE(a->x_img || ((a->basis != nullptr) != (a->a_img != nullptr)), "layer_bwd: give exactly one of basis / a_img");
+    if (a->basis && !a->x_img)
         if (int r = check_basis_points(a->basis, a->pts, a->layer.n_in)) return r;
     REQUIRE((a->head != nullptr) != (a->dz_next_img != nullptr), "layer_bwd: give exactly one of head / dz_next_img");
     REQUIRE(a->dz_img && a->d_bias, "layer_bwd: dz_img / d_bias NULL");
@@ -362,6 +363,7 @@ int stdadk_layer_bwd(const stdadk_bwd_args* a, void* stream) {
     K.head = to_head(a->head);
     K.a_img = a->a_img;
     K.addend = a->addend;
+    K.x_img = a->x_img;
     K.stats = a->stats;
     K.dz_next_img = a->dz_next_img;
     K.wt_next_img = a->wt_next_img;
@@ -372,13 +374,13 @@ int stdadk_layer_bwd(const stdadk_bwd_args* a, void* stream) {
     K.d_head_w = a->d_head_w;
     K.d_head_b = a->d_head_b;
     K.has_head = a->head ? 1 : 0;
-    K.k_slabs = pad32(a->layer.n_in) / SLAB_K;
+    K.k_slabs = a->x_img ? 0 : pad32(a->layer.n_in) / SLAB_K;      // x saved by the forward: no recomputation GEMM
     K.k_slabs2 = a->head ? 0 : pad32(a->n_next) / SLAB_K;
     K.n_pad = pad32(a->layer.n_out);
     K.tmem_cols = 2 * pow2_cols(K.n_pad);
     K.thresh16 = dropout_thresh16(a->drop.p);
     K.drop_scale = a->drop.p > 0.0f ? 1.0f / (1.0f - a->drop.p) : 1.0f;
-    const bool basis = a->basis != nullptr;
+    const bool basis = a->basis != nullptr && a->x_img == nullptr;
     constexpr int BCG = 2, BNS = 4;
     SmemPlan sp = plan_smem(K.n_pad, K.has_head ? K.head.q : 0, basis ? K.basis.k_s : 0, basis ? K.basis.k_t : 0, true, BCG, BNS);
     REQUIRE(sp.total <= 227 * 1024, "layer_bwd: needs %u B of shared memory (> 227 KB)", sp.total);

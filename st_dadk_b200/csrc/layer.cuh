@@ -57,6 +57,7 @@ struct FwdK {
     const float* a_img;
     const float* addend;
     float* out_img;
+    float* x_img;
     float* stats;
     int has_head, k_slabs, n_pad, tmem_cols;
     unsigned int thresh16;
@@ -71,6 +72,7 @@ struct BwdK {
     HeadP head;
     const float* a_img;
     const float* addend;
+    const float* x_img;
     const float* stats;
     const float* dz_next_img;
     const float* wt_next_img;
@@ -193,6 +195,23 @@ __device__ __forceinline__ void add_addend_chunk(float (&v)[32], const float* ad
             float4 a = *reinterpret_cast<const float4*>(addend_row + c0 + 4 * c);
             v[4 * c] += a.x; v[4 * c + 1] += a.y; v[4 * c + 2] += a.z; v[4 * c + 3] += a.w;
         }
+    }
+}
+
+// one thread's 32-column chunk of a row of an FP32 image (16-byte chunks, swizzled like every operand image)
+__device__ __forceinline__ void image_store_chunk(float* img, int tile, int slabs, int c0, uint32_t row, const float (&v)[32]) {
+    float* dst = img + ((size_t)tile * slabs + (c0 / SLAB_K)) * SLAB_FLOATS;
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(dst) + swz_off(row, c)) =
+            make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+}
+__device__ __forceinline__ void image_load_chunk(const float* img, int tile, int slabs, int c0, uint32_t row, float (&v)[32]) {
+    const float* src = img + ((size_t)tile * slabs + (c0 / SLAB_K)) * SLAB_FLOATS;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        float4 q = *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(src) + swz_off(row, c));
+        v[4 * c] = q.x; v[4 * c + 1] = q.y; v[4 * c + 2] = q.z; v[4 * c + 3] = q.w;
     }
 }
 
@@ -450,6 +469,12 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
                                           (uint32_t)(c0 / 8 + b), P.thresh16)
                             << (8 * b);
             }
+            if (P.x_img && tile_valid) {          // training with a single wave of tiles: keep x for the backward
+                float xs[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) xs[i] = v[i] + sprm[c0 + i].x;
+                image_store_chunk(P.x_img, tile, n_pad / SLAB_K, c0, (uint32_t)row, xs);
+            }
             const bool chunk_ok = rvalid && (c0 + 32 <= n_out);
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
@@ -702,8 +727,14 @@ __global__ void __launch_bounds__(n_threads(CG), 1) layer_bwd_kernel(const __gri
         // pass A: g = dL/dy (after dropout+ReLU backward); LN row sums; dgamma/dbeta/head column sums
         int ch = 0;
         for (int c0 = 32 * cg; c0 < n_pad; c0 += 32 * CG, ++ch) {
-            tmem_ld32(trow + c0, z);
-            if (arow) add_addend_chunk(z, arow, c0, n_out);
+            if (P.x_img) {
+                image_load_chunk(P.x_img, tile, n_pad / SLAB_K, c0, (uint32_t)row, z);    // x saved by the forward
+            } else {
+                tmem_ld32(trow + c0, z);
+                if (arow) add_addend_chunk(z, arow, c0, n_out);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) z[i] += sbias[c0 + i];
+            }
             if (!HEAD) tmem_ld32(trow + acc1_off + c0, g);
             else head_dh_chunk(g, dyh, shw, n_pad, c0, q);
             uint32_t keep = 0xFFFFFFFFu;
@@ -719,7 +750,7 @@ __global__ void __launch_bounds__(n_threads(CG), 1) layer_bwd_kernel(const __gri
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
                 const int col = c0 + i;
-                float x = z[i] + sbias[col];
+                float x = z[i];
                 float xh = has_ln ? (x - mean) * rstd : x;
                 float yv = has_ln ? fmaf(xh, sgam[col], sbet[col]) : x;
                 bool on = (yv > 0.0f) && ((keep >> i) & 1u) && (col < n_out) && rvalid;
@@ -791,8 +822,14 @@ __global__ void __launch_bounds__(n_threads(CG), 1) layer_bwd_kernel(const __gri
             const float ma = Sa * inv_n, mb = Sb * inv_n;
             ch = 0;
             for (int c0 = 32 * cg; c0 < n_pad; c0 += 32 * CG, ++ch) {
-                tmem_ld32(trow + c0, z);
-                if (arow) add_addend_chunk(z, arow, c0, n_out);
+                if (P.x_img) {
+                    image_load_chunk(P.x_img, tile, n_pad / SLAB_K, c0, (uint32_t)row, z);
+                } else {
+                    tmem_ld32(trow + c0, z);
+                    if (arow) add_addend_chunk(z, arow, c0, n_out);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) z[i] += sbias[c0 + i];
+                }
                 if (!HEAD) tmem_ld32(trow + acc1_off + c0, g);
                 else head_dh_chunk(g, dyh, shw, n_pad, c0, q);
                 uint32_t act = 0;
@@ -802,7 +839,7 @@ __global__ void __launch_bounds__(n_threads(CG), 1) layer_bwd_kernel(const __gri
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     const int col = c0 + i;
-                    float xh = (z[i] + sbias[col] - mean) * rstd;
+                    float xh = (z[i] - mean) * rstd;
                     const float dh = g[i];
                     float gy = ((act >> i) & 1u) ? dh * P.drop_scale * sgam[col] : 0.0f;
                     float dz = rstd * (gy - ma - xh * mb);

@@ -59,13 +59,15 @@ class LossSpec:
 
 
 class _Workspace:
-    def __init__(self, spec: NetSpec, n_rows: int, device, sparse: bool = False):
+    def __init__(self, spec: NetSpec, n_rows: int, device, sparse: bool = False, save_x: bool = False):
         self.n_rows = n_rows
         self.zs = torch.empty(n_rows, spec.weights[0].shape[0], dtype=torch.float32, device=device) if sparse else None
         self.h = [ops.new_image(n_rows, w.shape[0], device) for w in spec.weights[:-1]]
         self.dz = [ops.new_image(n_rows, w.shape[0], device) for w in spec.weights]
         self.stats = [torch.empty(n_rows, 2, dtype=torch.float32, device=device) if g is not None else None
                       for g in spec.gammas]
+        # pre-LayerNorm x of every block, kept only for single-wave batches (see Executor.SAVE_X_MAX_ROWS)
+        self.x = [ops.new_image(n_rows, w.shape[0], device) for w in spec.weights] if save_x else None
         self.yhat = torch.empty(n_rows, spec.q, dtype=torch.float32, device=device)
         self.dyhat = torch.empty(n_rows, spec.q, dtype=torch.float32, device=device)
 
@@ -76,6 +78,11 @@ class Executor:
     # operand to walking each point's compact support (st_dadk_b200/csrc/sparse.cuh): dense work grows with K_s, the
     # walk with the ~20 knots per level inside a support disk.
     DENSE_MAX_KNOTS = 2048
+    # Up to this many rows a training forward also stores x = A W^T + b of every block (1 KB/row/block) so that the
+    # backward skips its recomputation GEMM (and, for block 1, regenerating the basis for it): a batch this small is a
+    # single wave of 128-row tiles, bound by per-kernel latency, not by HBM.  Larger batches recompute instead.
+    # (The N x K basis matrix is never stored either way; wgrad regenerates it.)
+    SAVE_X_MAX_ROWS = 148 * 2 * 128
 
     def __init__(self, spec: NetSpec, force_sparse: bool = False):
         self.spec = spec
@@ -183,7 +190,8 @@ class Executor:
         if ws is None:
             if len(self._ws) >= self.MAX_WORKSPACES:
                 self._ws.pop(next(iter(self._ws)))
-            ws = self._ws[n_rows] = _Workspace(self.spec, n_rows, self.device, self.sparse)
+            ws = self._ws[n_rows] = _Workspace(self.spec, n_rows, self.device, self.sparse,
+                                               save_x=n_rows <= self.SAVE_X_MAX_ROWS)
         return ws
 
     def _basis(self) -> L.Basis:
@@ -239,6 +247,8 @@ class Executor:
             a.drop = drop
             if save and ws.stats[l] is not None:
                 a.stats = ws.stats[l].data_ptr()
+            if save and ws.x is not None:
+                a.x_img = ws.x[l].data_ptr()
             if l < s.n_hidden - 1:
                 a.out_img = ws.h[l].data_ptr()
             else:
@@ -351,6 +361,8 @@ class Executor:
                 a.a_img = ws.h[l - 1].data_ptr()
             a.layer = self._layer(l)
             a.drop = drop
+            if ws.x is not None:
+                a.x_img = ws.x[l].data_ptr()
             if ws.stats[l] is not None:
                 a.stats = ws.stats[l].data_ptr()
                 a.d_gamma = g["gammas"][l].data_ptr()
