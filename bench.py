@@ -339,13 +339,20 @@ def run_ours(args):
     log("prediction done; per-kernel profile")
     # ---- per-kernel timing (eager, CUDA events around every libstdadk launch) -> roofline of the dominant kernel
     roof = None
+    traffic = {}
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")) as fh:
+            traffic = json.load(fh)      # DRAM bytes per launch from the committed ncu captures (not measured live)
+    except OSError:
+        pass
     kt = tr.profile_step(table, perm, BATCH, global_rows, repeats=10)   # every rank: the step contains the all-reduce
     if rank == 0:
         name, info = max(kt["kernels"].items(), key=lambda kv: kv[1]["ms"] * kv[1]["count"])
         flops = info["flops"]
         achieved = flops / (info["ms"] * 1e-3) / 1e12
         roof = {"kernel": name, "bound": "tensor", "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s",
-                "frac": achieved / tc_peak, "traffic": None, "peak_source": peak_src + ", dense bf16 sustained; the "
+                "frac": achieved / tc_peak, "traffic": traffic.get("train", {}).get(name),
+                "traffic_source": traffic.get("source"), "peak_source": peak_src + ", dense bf16 sustained; the "
                 "kernel runs TF32 (nominal half rate)", "note": "a 4096-row batch is ONE wave of 32 CTAs on 148 SMs: "
                 "this kernel is latency-bound, not roofline-bound; the throughput regime is in roofline_predict",
                 "launch_ms": kt["kernels"][name]["ms"],
@@ -356,7 +363,8 @@ def run_ours(args):
         lid, d = max(lay.items(), key=lambda kv: kv[1]["ms"])
         ach = d["bytes"] / (d["ms"] * 1e-3) / 1e9
         roof_pred = {"kernel": f"layer_fwd[{lid}] (dense prediction, {n_prof} points per launch)", "bound": "hbm",
-                     "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                     "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                     "traffic": traffic.get("predict", {}).get(f"layer_fwd[{lid}]"), "algorithmic_bytes_per_launch": d["bytes"],
                      "peak_source": peak_src, "launch_ms": d["ms"],
                      "all_blocks": {f"layer_fwd[{k}]": {"ms": v["ms"], "GB/s": v["bytes"] / (v["ms"] * 1e-3) / 1e9,
                                                         "TFLOP/s": v["flops"] / (v["ms"] * 1e-3) / 1e12}
