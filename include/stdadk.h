@@ -189,7 +189,7 @@ int stdadk_version(void);
 const char* stdadk_last_error(void);
 /* sizeof() of the argument structs, for bindings to verify their layout:
  * 0 basis, 1 points, 2 layer, 3 dropout, 4 head, 5 fwd_args, 6 bwd_args, 7 wgrad_args, 8 knotgrad_args, 9 adamw_args,
- * 10 pack_desc, 11 sparse_args */
+ * 10 pack_desc, 11 sparse_args, 12 predict_args */
 size_t stdadk_sizeof(int which);
 
 size_t stdadk_image_floats(int64_t rows, int64_t cols);
@@ -235,6 +235,23 @@ typedef struct {
 } stdadk_sparse_args;
 int stdadk_sparse_l1_fwd(const stdadk_sparse_args* a, void* stream);
 int stdadk_sparse_l1_wgrad(const stdadk_sparse_args* a, void* stream);
+
+/* Whole-network forward for prediction (evaluate_model / plot_spatial_mse / plot_temporal_series,
+ * train_st_interp.py:884-961, :1233-1248, :1380-1394; STInterpMLP.forward in eval mode, st_interp.py:827-882):
+ * basis -> hidden blocks -> head in ONE persistent kernel; activations stay in shared / tensor memory, the only
+ * per-point HBM traffic is the point (12 B, or 0 for a generated grid) and y_hat (4Q B).  Dropout is the identity.
+ * Limits: 1..STDADK_MAX_HIDDEN hidden blocks of width <= 256, dense basis (all knots resident in shared memory);
+ * stdadk_predict_supported() tells whether a shape fits, otherwise chain stdadk_layer_fwd calls. */
+#define STDADK_MAX_HIDDEN 4
+typedef struct {
+    const stdadk_basis* basis;
+    stdadk_points pts;
+    int32_t n_layers, _pad;
+    stdadk_layer layers[STDADK_MAX_HIDDEN];   /* layers[l].w_img = image of W_l; layers[0].n_in = p + k_s + k_t */
+    const stdadk_head* head;                  /* w, b, q, yhat are used */
+} stdadk_predict_args;
+int stdadk_predict_supported(const stdadk_predict_args* a);   /* 1 yes, 0 no (reason in stdadk_last_error) */
+int stdadk_predict(const stdadk_predict_args* a, void* stream);
 
 int stdadk_layer_fwd(const stdadk_fwd_args* a, void* stream);
 int stdadk_layer_bwd(const stdadk_bwd_args* a, void* stream);

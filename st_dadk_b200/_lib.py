@@ -86,6 +86,14 @@ class PackDesc(C.Structure):
                 ("cols", C.c_int64), ("img", fp)]
 
 
+MAX_HIDDEN = 4
+
+
+class PredictArgs(C.Structure):
+    _fields_ = [("basis", C.POINTER(Basis)), ("pts", Points), ("n_layers", C.c_int32), ("_pad", C.c_int32),
+                ("layers", Layer * MAX_HIDDEN), ("head", C.POINTER(Head))]
+
+
 _lib = None
 
 _PROTOS = {
@@ -99,6 +107,8 @@ _PROTOS = {
     "stdadk_pack_image": (C.c_int, [fp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, fp, fp]),
     "stdadk_unpack_image": (C.c_int, [fp, C.c_int64, C.c_int64, fp, fp]),
     "stdadk_pack_images": (C.c_int, [C.POINTER(PackDesc), C.c_int, fp]),
+    "stdadk_predict_supported": (C.c_int, [C.POINTER(PredictArgs)]),
+    "stdadk_predict": (C.c_int, [C.POINTER(PredictArgs), fp]),
     "stdadk_layer_fwd": (C.c_int, [C.POINTER(FwdArgs), fp]),
     "stdadk_layer_bwd": (C.c_int, [C.POINTER(BwdArgs), fp]),
     "stdadk_wgrad": (C.c_int, [C.POINTER(WgradArgs), fp]),
@@ -127,7 +137,8 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        structs = [Basis, Points, Layer, Dropout, Head, FwdArgs, BwdArgs, WgradArgs, KnotGradArgs, AdamWArgs, PackDesc, SparseArgs]
+        structs = [Basis, Points, Layer, Dropout, Head, FwdArgs, BwdArgs, WgradArgs, KnotGradArgs, AdamWArgs, PackDesc, SparseArgs,
+                   PredictArgs]
         for i, st in enumerate(structs):
             if L.stdadk_sizeof(i) != C.sizeof(st):
                 raise RuntimeError(f"libstdadk ABI mismatch: {st.__name__} is {C.sizeof(st)} B in the binding, "

@@ -8,6 +8,7 @@
 #include "layer.cuh"
 #include "misc.cuh"
 #include "sparse.cuh"
+#include "predict.cuh"
 
 using namespace stdadk;
 
@@ -160,6 +161,7 @@ size_t stdadk_sizeof(int which) {
         case 9: return sizeof(stdadk_adamw_args);
         case 10: return sizeof(stdadk_pack_desc);
         case 11: return sizeof(stdadk_sparse_args);
+        case 12: return sizeof(stdadk_predict_args);
         default: return 0;
     }
 }
@@ -336,6 +338,60 @@ int stdadk_layer_fwd(const stdadk_fwd_args* a, void* stream) {
 #undef LAUNCH_FWD
 #undef LAUNCH_FWD_CLUSTER
     return check_launch("layer_fwd");
+}
+
+static int predict_fill(const stdadk_predict_args* a, PredK* K) {
+    REQUIRE(a && a->basis && a->head, "predict: NULL args / basis / head");
+    REQUIRE(a->n_layers >= 1 && a->n_layers <= PF_MAX_LAYERS, "predict: %d hidden blocks outside [1,%d]", a->n_layers,
+            PF_MAX_LAYERS);
+    if (int r = check_basis_points(a->basis, a->pts, a->layers[0].n_in)) return r;
+    REQUIRE(a->head->q >= 1 && a->head->q <= STDADK_MAX_Q, "predict: head q=%d outside [1,%d]", a->head->q, STDADK_MAX_Q);
+    REQUIRE(a->head->w && a->head->b && a->head->yhat, "predict: head w/b/yhat NULL");
+    *K = PredK{};
+    K->basis = to_basis(a->basis);
+    K->pts = to_points(a->pts);
+    K->n_layers = a->n_layers;
+    K->q = a->head->q;
+    K->head_w = a->head->w;
+    K->head_b = a->head->b;
+    K->yhat = a->head->yhat;
+    for (int l = 0; l < a->n_layers; ++l) {
+        const stdadk_layer& y = a->layers[l];
+        if (int r = check_layer(y, "predict")) return r;
+        REQUIRE(l == 0 || y.n_in == a->layers[l - 1].n_out, "predict: block %d n_in=%d != previous n_out=%d", l, y.n_in,
+                a->layers[l - 1].n_out);
+        PredLayerP& L = K->L[l];
+        L.w_img = y.w_img;
+        L.bias = y.bias;
+        L.gamma = y.gamma;
+        L.beta = y.beta;
+        L.n_out = y.n_out;
+        L.n_pad = pad32(y.n_out);
+        L.k_slabs = pad32(y.n_in) / SLAB_K;
+        L.has_ln = y.gamma != nullptr;
+        L.eps = y.ln_eps;
+    }
+    uint32_t bytes = plan_predict(*K);
+    REQUIRE(bytes <= 227 * 1024, "predict: the fused kernel needs %u B of shared memory (> 227 KB) for this shape", bytes);
+    K->n_tiles = (int)ceil_div64(a->pts.n_rows, TILE_M);
+    return 0;
+}
+
+int stdadk_predict_supported(const stdadk_predict_args* a) {
+    PredK K;
+    return predict_fill(a, &K) == 0 ? 1 : 0;
+}
+
+int stdadk_predict(const stdadk_predict_args* a, void* stream) {
+    if (int r = check_device()) return r;
+    PredK Kl;
+    if (int r = predict_fill(a, &Kl)) return r;
+    if (a->pts.n_rows <= 0) return 0;
+    if (int r = set_smem(predict_fused_kernel, Kl.sm.total)) return r;
+    const int sms = g_sm_count > 0 ? g_sm_count : 148;
+    const int grid = Kl.n_tiles < sms ? Kl.n_tiles : sms;
+    predict_fused_kernel<<<grid, PF_NT, Kl.sm.total, (cudaStream_t)stream>>>(Kl);
+    return check_launch("predict");
 }
 
 int stdadk_layer_bwd(const stdadk_bwd_args* a, void* stream) {

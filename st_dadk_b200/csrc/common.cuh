@@ -64,20 +64,40 @@ __device__ __forceinline__ long long sample_of(const PointsP& P, long long g) { 
 // Spatial basis value from the coordinate difference; the support predicate d2 < th2 is evaluated
 // with explicitly rounded products (no FMA contraction) so that index sets match oracle/basis_ref.c
 // bit for bit.  Reference: stnf/models/st_interp.py:462-491.
-__device__ __forceinline__ float phi_eval(int fn, float dx, float dy, float th2, float inv_th) {
-    float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
-    if (fn == STDADK_GAUSSIAN) {
-        float r = sqrtf(d2) * inv_th;
-        return exp2f(-0.72134752044448170f * r * r);  // exp(-r^2/2)
+// MUFU-only helpers (no denormal / special-case wrappers): rsqrt and exp2 to ~2^-22 relative error.
+__device__ __forceinline__ float rsqrt_approx(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// phi from the squared distance.  The support test d2 < th2 is exact; inside the support the value uses
+// sqrt(d2) = d2 * rsqrt(d2) (two instructions instead of the IEEE square root's ten: relative error ~2e-7 in r,
+// far inside the 1e-5 parity tolerance) and the polynomial with 1/3 folded into its coefficients.
+template <int FN>
+__device__ __forceinline__ float phi_from_d2(float d2, float th2, float inv_th) {
+    if (FN == STDADK_GAUSSIAN) return ex2_approx(-0.72134752044448170f * (d2 * inv_th * inv_th));  // exp(-r^2/2)
+    const float r = d2 * rsqrt_approx(fmaxf(d2, 1e-30f)) * inv_th;
+    const float u = fmaxf(1.0f - r, 0.0f);
+    float v;
+    if (FN == STDADK_TRIANGULAR) {
+        v = u;
+    } else {
+        const float u2 = u * u;
+        v = (u2 * u2) * u2 * fmaf(fmaf(35.0f / 3.0f, r, 6.0f), r, 1.0f);
     }
+    return d2 < th2 ? v : 0.0f;
+}
+__device__ __forceinline__ float phi_eval(int fn, float dx, float dy, float th2, float inv_th) {
+    const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+    if (fn == STDADK_GAUSSIAN) return phi_from_d2<STDADK_GAUSSIAN>(d2, th2, inv_th);
     if (!(d2 < th2)) return 0.0f;
-    float r = sqrtf(d2) * inv_th;
-    float u = 1.0f - r;
-    if (u <= 0.0f) return 0.0f;
-    if (fn == STDADK_TRIANGULAR) return u;
-    float u2 = u * u;
-    float u6 = u2 * u2 * u2;
-    return u6 * fmaf(fmaf(35.0f, r, 18.0f), r, 3.0f) * (1.0f / 3.0f);
+    if (fn == STDADK_TRIANGULAR) return phi_from_d2<STDADK_TRIANGULAR>(d2, th2, inv_th);
+    return phi_from_d2<STDADK_WENDLAND>(d2, th2, inv_th);
 }
 // d phi / d r: wendland -(56/3) r (5r+1) (1-r)^5; gaussian -r exp(-r^2/2); triangular -1.
 __device__ __forceinline__ float phi_dr(int fn, float r) {
@@ -91,7 +111,7 @@ __device__ __forceinline__ float phi_dr(int fn, float r) {
 // Temporal Gaussian basis (st_interp.py:583-596).
 __device__ __forceinline__ float psi_eval(float t, float c, float inv_bw) {
     float s = (t - c) * inv_bw;
-    return exp2f(-0.72134752044448170f * s * s);
+    return ex2_approx(-0.72134752044448170f * s * s);
 }
 
 // Coordinates of global row g: from the arrays, or from the dense grid n = (k*nx + i)*ny + j.

@@ -92,12 +92,23 @@ struct BwdK {
 // d2 < theta'^2) or entirely in the temporal block; the generic per-feature path handles block boundaries.
 template <int FN>
 __device__ __forceinline__ float4 spatial_chunk(const float4* kp, float x, float y) {
-    float o[4];
+    float d2[4], th2[4], ith[4];
+    bool in = false;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-        float4 kn = kp[e];
-        o[e] = to_tf32(phi_eval(FN, x - kn.x, y - kn.y, kn.z, kn.w));
+        const float4 kn = kp[e];
+        const float dx = x - kn.x, dy = y - kn.y;
+        d2[e] = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+        th2[e] = kn.z;
+        ith[e] = kn.w;
+        in |= d2[e] < th2[e];
     }
+    // the 32 rows of a warp are neighbours when the points are ordered (grids, sorted sites): most chunks are then
+    // outside every row's support and cost one vote instead of four evaluations
+    if (FN != STDADK_GAUSSIAN && !__any_sync(__activemask(), in)) return make_float4(0.f, 0.f, 0.f, 0.f);
+    float o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[e] = to_tf32(phi_from_d2<FN>(d2[e], th2[e], ith[e]));
     return make_float4(o[0], o[1], o[2], o[3]);
 }
 __device__ __forceinline__ float4 feature_chunk(const BasisP& B, const float4* sk, const float2* st, int f, float x,

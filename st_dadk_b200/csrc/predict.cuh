@@ -1,0 +1,417 @@
+// Whole-network forward for prediction (evaluate_model / plot_spatial_mse / plot_temporal_series of upstream,
+// scripts/train_st_interp.py:884-961, :1233-1248, :1380-1394): one persistent kernel per call, one CTA per SM.
+//
+// A CTA takes 128-row tiles in turn.  Per tile the activations never leave the SM:
+//   block 1 : workers generate [X|phi|psi] slab by slab into a ring that lives in the (still unused) H buffer,
+//             W1 slabs stream L2 -> SMEM through a bulk-copy ring, tcgen05.mma accumulates in TMEM;
+//   epilogue: every worker thread pulls its 64 accumulator columns into registers ONCE, the LayerNorm statistics are
+//             combined across the four column groups through a small scratch, and the normalised ReLU output is
+//             written TF32-rounded into H (128 x 256 fp32 in the SWIZZLE_128B operand form) - slab by slab, each slab
+//             with its own mbarrier, so the MMAs of the next block start while the rest is still being normalised;
+//   block l : A = H, W_l slabs through the same ring, accumulator in the other half of TMEM;
+//   last    : head dot products from registers (FP32), y_hat (rows x Q) is the only HBM write: 4Q bytes per point
+//             against 12 (or 0 for a generated grid) in.
+// HBM traffic per point is therefore ~16 bytes instead of the 4 KB of the layer-by-layer path; what remains is
+// instruction issue in the worker warps and L2 -> SM weight streaming (720 KB per tile at 297-256-256-128).
+#pragma once
+#include "layer.cuh"
+
+namespace stdadk {
+
+constexpr int PF_MAX_LAYERS = 4;
+constexpr int PF_CG = 4;
+constexpr int PF_NW = 128 * PF_CG;          // 512 worker threads (16 warps)
+constexpr int PF_NT = PF_NW + 64;           // + producer warp + MMA warp
+constexpr int PF_WST = 2;                   // weight ring: 2 x (256 rows x 128 B)
+constexpr int PF_AST = 6;                   // block-1 operand ring = H slabs 0..5; slabs 6,7 hold the head scratch
+constexpr int PF_HSLABS = MAX_N / SLAB_K;   // 8
+
+struct PredLayerP {
+    const float* w_img;
+    const float* bias;
+    const float* gamma;
+    const float* beta;
+    int n_out, n_pad, k_slabs, has_ln;
+    float eps;
+    uint32_t prm_off;                       // byte offset of this layer's (bias | gamma | beta), n_pad floats each
+};
+struct PredSmem {
+    uint32_t h_off, w_off, bar_off, tmem_off, headw_off, knots_off, tknots_off, red_off, total;
+};
+struct PredK {
+    BasisP basis;
+    PointsP pts;
+    PredLayerP L[PF_MAX_LAYERS];
+    PredSmem sm;
+    const float* head_w;
+    const float* head_b;
+    float* yhat;
+    int n_layers, q, n_tiles, _pad;
+};
+
+// Fills the per-layer offsets and the carve-up; returns the dynamic shared-memory bytes needed.
+__host__ inline uint32_t plan_predict(PredK& K) {
+    uint32_t o = 0;
+    K.sm.h_off = o; o += PF_HSLABS * SLAB_BYTES;                       // 128 KB
+    K.sm.w_off = o; o += PF_WST * MAX_N * 128u;                        // 64 KB
+    K.sm.bar_off = o; o += 256;
+    K.sm.tmem_off = o; o += 16;
+    for (int l = 0; l < K.n_layers; ++l) {
+        K.L[l].prm_off = o;
+        o += 3u * (uint32_t)K.L[l].n_pad * 4u;
+    }
+    K.sm.headw_off = o; o += (uint32_t)(K.q * K.L[K.n_layers - 1].n_pad + STDADK_MAX_Q) * 4u;
+    o = (o + 15u) & ~15u;
+    K.sm.knots_off = o; o += (uint32_t)K.basis.k_s * 16u;
+    K.sm.tknots_off = o; o += (uint32_t)K.basis.k_t * 8u;
+    o = (o + 15u) & ~15u;
+    K.sm.red_off = o; o += 2u * PF_CG * TILE_M * 16u;                  // LayerNorm partials, double-buffered
+    K.sm.total = o + 1024;
+    return K.sm.total;
+}
+
+// Thread (row, cg) generates chunks 2cg, 2cg+1 of a 32-feature slab.
+__device__ __forceinline__ void pf_gen_slab(const BasisP& B, const float4* sk, const float2* st, int slab, float x, float y,
+                                            float t, const float* xrow, uint32_t slab_saddr, uint32_t rowoff, uint32_t rx,
+                                            int cg) {
+#pragma unroll
+    for (int cc = 0; cc < 8 / PF_CG; ++cc) {
+        const int c = cg * (8 / PF_CG) + cc;
+        float4 v = feature_chunk(B, sk, st, slab * SLAB_K + c * 4, x, y, t, xrow);
+        st_shared_v4(slab_saddr + rowoff + (((uint32_t)c ^ rx) << 4), v.x, v.y, v.z, v.w);
+    }
+}
+
+// bias add + shifted moments of one 32-column chunk held in registers (nv valid columns)
+__device__ __forceinline__ void pf_bias_stats(float (&v)[32], const float* sb, int nv, bool& have, float& K, float& S1,
+                                              float& S2) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float4 b = *reinterpret_cast<const float4*>(sb + 4 * c);
+        v[4 * c] += b.x; v[4 * c + 1] += b.y; v[4 * c + 2] += b.z; v[4 * c + 3] += b.w;
+    }
+    if (!have) {
+        K = v[0];
+        have = true;
+    }
+    if (nv >= 32) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const float d = v[i] - K;
+            S1 += d;
+            S2 = fmaf(d, d, S2);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (i < nv) {
+                const float d = v[i] - K;
+                S1 += d;
+                S2 = fmaf(d, d, S2);
+            }
+    }
+}
+
+// v <- relu(LayerNorm(v)) (or relu(v)); columns >= nv forced to zero
+__device__ __forceinline__ void pf_normalize(float (&v)[32], const float* sg, const float* sbt, bool has_ln, float rstd,
+                                             float nmr, int nv) {
+    if (has_ln) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float4 g = *reinterpret_cast<const float4*>(sg + 4 * c);
+            const float4 b = *reinterpret_cast<const float4*>(sbt + 4 * c);
+            v[4 * c] = fmaxf(fmaf(fmaf(v[4 * c], rstd, nmr), g.x, b.x), 0.0f);
+            v[4 * c + 1] = fmaxf(fmaf(fmaf(v[4 * c + 1], rstd, nmr), g.y, b.y), 0.0f);
+            v[4 * c + 2] = fmaxf(fmaf(fmaf(v[4 * c + 2], rstd, nmr), g.z, b.z), 0.0f);
+            v[4 * c + 3] = fmaxf(fmaf(fmaf(v[4 * c + 3], rstd, nmr), g.w, b.w), 0.0f);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+    }
+    if (nv < 32) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (i >= nv) v[i] = 0.0f;
+    }
+}
+
+__device__ __forceinline__ void pf_store_slab(const float (&v)[32], uint32_t slab_saddr, uint32_t rowoff, uint32_t rx) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        st_shared_v4(slab_saddr + rowoff + (((uint32_t)c ^ rx) << 4), to_tf32(v[4 * c]), to_tf32(v[4 * c + 1]),
+                     to_tf32(v[4 * c + 2]), to_tf32(v[4 * c + 3]));
+}
+
+__device__ __forceinline__ void pf_head_partial(const float (&v)[32], const float* shw, int n_pad, int c0, int q,
+                                                float (&yh)[STDADK_MAX_Q]) {
+#pragma unroll 1
+    for (int k = 0; k < q; ++k) {
+        const float* wk = shw + k * n_pad + c0;
+        float acc = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float4 w = *reinterpret_cast<const float4*>(wk + 4 * c);
+            acc = fmaf(v[4 * c], w.x, acc);
+            acc = fmaf(v[4 * c + 1], w.y, acc);
+            acc = fmaf(v[4 * c + 2], w.z, acc);
+            acc = fmaf(v[4 * c + 3], w.w, acc);
+        }
+#pragma unroll
+        for (int kk = 0; kk < STDADK_MAX_Q; ++kk)
+            if (kk == k) yh[kk] += acc;
+    }
+}
+
+__global__ void __launch_bounds__(PF_NT, 1) predict_fused_kernel(const __grid_constant__ PredK P) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = align_smem(smem_raw);
+    float* sH = reinterpret_cast<float*>(smem + P.sm.h_off);
+    float* sW = reinterpret_cast<float*>(smem + P.sm.w_off);
+    uint64_t* wfull = reinterpret_cast<uint64_t*>(smem + P.sm.bar_off);
+    uint64_t* wempty = wfull + PF_WST;
+    uint64_t* afull = wempty + PF_WST;
+    uint64_t* aempty = afull + PF_AST;
+    uint64_t* hfull = aempty + PF_AST;
+    uint64_t* accf = hfull + PF_HSLABS;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + P.sm.tmem_off);
+    float* shw = reinterpret_cast<float*>(smem + P.sm.headw_off);
+    float4* sk = reinterpret_cast<float4*>(smem + P.sm.knots_off);
+    float2* st = reinterpret_cast<float2*>(smem + P.sm.tknots_off);
+    float4* red = reinterpret_cast<float4*>(smem + P.sm.red_off);
+    float* hscr = sH + (size_t)PF_AST * SLAB_FLOATS;          // head partials [cg][row][MAX_Q] in H slabs 6,7
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nl = P.n_layers;
+    const int last_pad = P.L[nl - 1].n_pad, last_out = P.L[nl - 1].n_out;
+    float* shb = shw + P.q * last_pad;
+
+    if (tid == PF_NW) {
+        for (int s = 0; s < PF_WST; ++s) {
+            mbar_init(&wfull[s], 1);
+            mbar_init(&wempty[s], 1);
+        }
+        for (int s = 0; s < PF_AST; ++s) {
+            mbar_init(&afull[s], PF_NW);
+            mbar_init(&aempty[s], 1);
+        }
+        for (int s = 0; s < PF_HSLABS; ++s) mbar_init(&hfull[s], TILE_M);
+        mbar_init(accf, 1);
+        mbar_fence_init();
+    }
+    if (warp == 4 * PF_CG) {
+        __syncwarp();
+        tmem_alloc(tmem_slot, 512u);
+    }
+    for (int l = 0; l < nl; ++l) {
+        const PredLayerP& Ly = P.L[l];
+        float* prm = reinterpret_cast<float*>(smem + Ly.prm_off);
+        for (int i = tid; i < Ly.n_pad; i += PF_NT) {
+            const bool ok = i < Ly.n_out;
+            prm[i] = ok ? Ly.bias[i] : 0.0f;
+            prm[Ly.n_pad + i] = (ok && Ly.has_ln) ? Ly.gamma[i] : 1.0f;
+            prm[2 * Ly.n_pad + i] = (ok && Ly.has_ln) ? Ly.beta[i] : 0.0f;
+        }
+    }
+    for (int i = tid; i < P.q * last_pad; i += PF_NT) {
+        const int k = i / last_pad, c = i - k * last_pad;
+        shw[i] = c < last_out ? P.head_w[(size_t)k * last_out + c] : 0.0f;
+    }
+    if (tid < P.q) shb[tid] = P.head_b[tid];
+    for (int i = tid; i < P.basis.k_s; i += PF_NT) sk[i] = P.basis.knots[i];
+    for (int i = tid; i < P.basis.k_t; i += PF_NT) st[i] = P.basis.tknots[i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4 * PF_CG) {
+        // ---------------- producer: weight slabs of every block of every tile, in consumption order
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+                for (int l = 0; l < nl; ++l) {
+                    const PredLayerP& Ly = P.L[l];
+                    for (int s = 0; s < Ly.k_slabs; ++s) {
+                        mbar_wait(&wempty[stage], phase ^ 1u);
+                        issue_slab_copies(Ly.w_img, Ly.k_slabs, s, Ly.n_pad, nullptr, nullptr,
+                                          sW + (size_t)stage * MAX_N * SLAB_K, &wfull[stage]);
+                        if (++stage == PF_WST) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 4 * PF_CG + 1) {
+        // ---------------- MMA issuer
+        if (lane == 0) {
+            uint32_t wstage = 0, wphase = 0, astage = 0, aphase = 0, hph = 0;
+            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+                for (int l = 0; l < nl; ++l) {
+                    const PredLayerP& Ly = P.L[l];
+                    const uint32_t idesc = umma_idesc_tf32((uint32_t)Ly.n_pad, 0, 0);
+                    const uint32_t acc = tmem_base + (uint32_t)(l & 1) * MAX_N;
+                    for (int s = 0; s < Ly.k_slabs; ++s) {
+                        const float* a;
+                        if (l == 0) {
+                            mbar_wait(&afull[astage], aphase);
+                            a = sH + (size_t)astage * SLAB_FLOATS;
+                        } else {
+                            mbar_wait(&hfull[s], (hph >> s) & 1u);
+                            hph ^= 1u << s;
+                            a = sH + (size_t)s * SLAB_FLOATS;
+                        }
+                        mbar_wait(&wfull[wstage], wphase);
+                        tc_fence_after();
+                        issue_slab_mma(acc, a, sW + (size_t)wstage * MAX_N * SLAB_K, idesc, s == 0);
+                        umma_commit(&wempty[wstage]);
+                        if (l == 0) {
+                            umma_commit(&aempty[astage]);
+                            if (++astage == PF_AST) {
+                                astage = 0;
+                                aphase ^= 1u;
+                            }
+                        }
+                        if (++wstage == PF_WST) {
+                            wstage = 0;
+                            wphase ^= 1u;
+                        }
+                    }
+                    umma_commit(accf);
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---------------- workers: thread = (row, column group)
+        const int q4 = warp & 3, cg = warp >> 2;
+        const int row = q4 * 32 + lane;
+        const uint32_t rowoff = (uint32_t)row * 128u, rx = (uint32_t)row & 7u;
+        const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16);
+        const uint32_t sH_addr = smem_u32(sH);
+        uint32_t astage = 0, aphase = 0, accn = 0;
+        for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+            const long long lrow = (long long)tile * TILE_M + row;
+            const bool rvalid = lrow < P.pts.n_rows;
+            const long long grow = P.pts.row_begin + lrow;
+            float x = 0.f, y = 0.f, t = 0.f;
+            const float* xrow = nullptr;
+            if (rvalid) {
+                load_point(P.pts, grow, x, y, t);
+                if (P.basis.p_cov > 0 && P.pts.xcov) xrow = P.pts.xcov + sample_of(P.pts, grow) * P.basis.p_cov;
+            }
+            // block-1 operand: generated into the ring (the H buffer is dead until this tile's first epilogue)
+            for (int s = 0; s < P.L[0].k_slabs; ++s) {
+                mbar_wait(&aempty[astage], aphase ^ 1u);
+                pf_gen_slab(P.basis, sk, st, s, x, y, t, xrow, sH_addr + astage * (uint32_t)SLAB_BYTES, rowoff, rx, cg);
+                fence_proxy_async_smem();
+                tc_fence_before();        // orders this thread's earlier TMEM reads before the MMAs this arrival releases
+                mbar_arrive(&afull[astage]);
+                if (++astage == PF_AST) {
+                    astage = 0;
+                    aphase ^= 1u;
+                }
+            }
+            for (int l = 0; l < nl; ++l) {
+                const PredLayerP& Ly = P.L[l];
+                const float* sb = reinterpret_cast<const float*>(smem + Ly.prm_off);
+                const float* sg = sb + Ly.n_pad;
+                const float* sbt = sg + Ly.n_pad;
+                const int c0a = 32 * cg, c0b = 32 * cg + 128;
+                const bool ha = c0a < Ly.n_pad, hb = c0b < Ly.n_pad;
+                const int nva = min(32, Ly.n_out - c0a), nvb = min(32, Ly.n_out - c0b);
+                float4* redl = red + (size_t)(accn & 1u) * (PF_CG * TILE_M);
+                mbar_wait(accf, accn & 1u);
+                ++accn;
+                tc_fence_after();
+                const uint32_t acc = trow + (uint32_t)(l & 1) * MAX_N;
+                float va[32], vb[32];
+                if (ha) tmem_ld32_issue(acc + (uint32_t)c0a, va);
+                if (hb) tmem_ld32_issue(acc + (uint32_t)c0b, vb);
+                if (ha) tmem_ld_wait(va);
+                if (hb) tmem_ld_wait(vb);
+                bool have = false;
+                float K = 0.0f, S1 = 0.0f, S2 = 0.0f;
+                if (ha) pf_bias_stats(va, sb + c0a, nva, have, K, S1, S2);
+                if (hb) pf_bias_stats(vb, sb + c0b, nvb, have, K, S1, S2);
+                float rstd = 1.0f, nmr = 0.0f;
+                if (Ly.has_ln) {
+                    const float cntv = (float)((ha ? max(nva, 0) : 0) + (hb ? max(nvb, 0) : 0));
+                    redl[cg * TILE_M + row] = make_float4(K, S1, S2, cntv);
+                    worker_barrier(PF_NW);
+                    if (ha) {
+                        const float inv_n = 1.0f / (float)Ly.n_out;
+                        float4 part[PF_CG];
+                        float tot = 0.0f;
+#pragma unroll
+                        for (int g = 0; g < PF_CG; ++g) {
+                            part[g] = redl[g * TILE_M + row];
+                            tot += fmaf(part[g].w, part[g].x, part[g].y);
+                        }
+                        const float mean = tot * inv_n;
+                        float m2 = 0.0f;
+#pragma unroll
+                        for (int g = 0; g < PF_CG; ++g) {
+                            const float dk = mean - part[g].x;
+                            m2 += part[g].z - 2.0f * dk * part[g].y + part[g].w * dk * dk;
+                        }
+                        rstd = 1.0f / sqrtf(fmaxf(m2 * inv_n, 0.0f) + Ly.eps);
+                        nmr = -mean * rstd;
+                    }
+                } else {
+                    worker_barrier(PF_NW);   // every thread has seen this accumulator phase before the next can complete
+                }
+                if (l + 1 < nl) {
+                    if (ha) {
+                        pf_normalize(va, sg + c0a, sbt + c0a, Ly.has_ln != 0, rstd, nmr, nva);
+                        pf_store_slab(va, sH_addr + (uint32_t)cg * SLAB_BYTES, rowoff, rx);
+                        fence_proxy_async_smem();
+                        tc_fence_before();
+                        mbar_arrive(&hfull[cg]);
+                    }
+                    if (hb) {
+                        pf_normalize(vb, sg + c0b, sbt + c0b, Ly.has_ln != 0, rstd, nmr, nvb);
+                        pf_store_slab(vb, sH_addr + (uint32_t)(cg + 4) * SLAB_BYTES, rowoff, rx);
+                        fence_proxy_async_smem();
+                        tc_fence_before();
+                        mbar_arrive(&hfull[cg + 4]);
+                    }
+                } else {
+                    float yh[STDADK_MAX_Q];
+#pragma unroll
+                    for (int k = 0; k < STDADK_MAX_Q; ++k) yh[k] = 0.0f;
+                    if (ha) {
+                        pf_normalize(va, sg + c0a, sbt + c0a, Ly.has_ln != 0, rstd, nmr, nva);
+                        pf_head_partial(va, shw, Ly.n_pad, c0a, P.q, yh);
+                    }
+                    if (hb) {
+                        pf_normalize(vb, sg + c0b, sbt + c0b, Ly.has_ln != 0, rstd, nmr, nvb);
+                        pf_head_partial(vb, shw, Ly.n_pad, c0b, P.q, yh);
+                    }
+                    float* mine = hscr + ((size_t)cg * TILE_M + row) * STDADK_MAX_Q;
+                    *reinterpret_cast<float4*>(mine) = make_float4(yh[0], yh[1], yh[2], yh[3]);
+                    *reinterpret_cast<float4*>(mine + 4) = make_float4(yh[4], yh[5], yh[6], yh[7]);
+                    worker_barrier(PF_NW);
+                    if (cg == 0 && rvalid) {
+#pragma unroll
+                        for (int k = 0; k < STDADK_MAX_Q; ++k)
+                            if (k < P.q) {
+                                float acc_k = shb[k];
+#pragma unroll
+                                for (int g = 0; g < PF_CG; ++g) acc_k += hscr[((size_t)g * TILE_M + row) * STDADK_MAX_Q + k];
+                                P.yhat[lrow * P.q + k] = acc_k;
+                            }
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 4 * PF_CG) tmem_dealloc(tmem_base, 512u);
+}
+
+}  // namespace stdadk

@@ -105,6 +105,8 @@ class Executor:
         self.grads = None
         self._knots_ready = False
         self._side = None
+        self.fused_predict = True      # forward-only calls use the whole-network kernel when the shape fits
+        self._fused_ok = None
 
     def _setup_regime(self, spec: NetSpec):
         k_s = spec.centers.shape[0]
@@ -143,6 +145,7 @@ class Executor:
         self._setup_regime(spec)
         self._pack_key = None
         self._knots_ready = False
+        self._fused_ok = None
 
     def _key(self):
         s = self.spec
@@ -226,6 +229,10 @@ class Executor:
             # always rebuild the operand images: parameter storage can be rewritten in place by kernels or by
             # an EMA swap without any version counter the executor could observe (5 tiny launches)
             self.prepare(force=True, for_backward=save)
+        if not train and not save and loss is None and self.fused_predict and not self.sparse:
+            yhat = out if out is not None else torch.empty(n, s.q, dtype=torch.float32, device=self.device)
+            if self._predict_fused(pts, yhat):
+                return yhat
         ws = self._workspace(n)
         yhat = out if out is not None else ws.yhat
         basis = self._basis()
@@ -263,6 +270,28 @@ class Executor:
         if save:
             self._ctx = (pts, drop, ws)
         return yhat
+
+    def _predict_fused(self, pts: L.Points, yhat: torch.Tensor) -> bool:
+        """Forward-only path: the whole network in one persistent kernel (stdadk_predict), no activation images.
+        Returns False when the shape does not fit the fused kernel; the caller then chains layer_fwd."""
+        s = self.spec
+        if s.n_hidden > L.MAX_HIDDEN:
+            return False
+        basis = self._basis()
+        head = ops.make_head(s.head_w, s.head_b, s.q, yhat)
+        a = L.PredictArgs()
+        a.basis = C.pointer(basis)
+        a.pts = pts
+        a.n_layers = s.n_hidden
+        for l in range(s.n_hidden):
+            a.layers[l] = self._layer(l)
+        a.head = C.pointer(head)
+        if self._fused_ok is None:
+            self._fused_ok = ops.predict_supported(a)
+        if not self._fused_ok:
+            return False
+        ops.predict(a)
+        return True
 
     # ------------------------------------------------------------------ backward
     def alloc_grads(self, flat: Optional[torch.Tensor] = None, views: Optional[dict] = None):

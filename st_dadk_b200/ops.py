@@ -164,6 +164,15 @@ def layer_fwd(args: L.FwdArgs):
     L.check(L.lib().stdadk_layer_fwd(C.byref(args), _stream()), "layer_fwd")
 
 
+def predict_supported(args: L.PredictArgs) -> bool:
+    return bool(L.lib().stdadk_predict_supported(C.byref(args)))
+
+
+def predict(args: L.PredictArgs):
+    """Whole-network forward (basis -> hidden blocks -> head) in one persistent kernel."""
+    L.check(L.lib().stdadk_predict(C.byref(args), _stream()), "predict")
+
+
 def layer_bwd(args: L.BwdArgs):
     L.check(L.lib().stdadk_layer_bwd(C.byref(args), _stream()), "layer_bwd")
 

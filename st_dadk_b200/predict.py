@@ -42,13 +42,18 @@ class Predictor:
         self.ex.prepare(force=True, for_backward=False)
         self.launches += 2 + len(spec.weights)
 
+    @property
+    def fused(self) -> bool:
+        """True when forward-only calls run the whole-network kernel (stdadk_predict)."""
+        return bool(self.ex is not None and self.ex.fused_predict and self.ex._fused_ok)
+
     @torch.no_grad()
     def _run(self, make_pts, begin: int, end: int, out: torch.Tensor):
         n_layers = self.ex.spec.n_hidden
         for b in range(begin, end, self.chunk):
             r = min(self.chunk, end - b)
             self.ex.forward(make_pts(b, r), train=False, out=out[b - begin:b - begin + r], prepared=True)
-            self.launches += n_layers
+            self.launches += 1 if self.fused else n_layers
         return out
 
     @torch.no_grad()
@@ -103,6 +108,7 @@ class Predictor:
         n = min(nx * ny * nt, self.chunk)
         rec = []
         orig = _ops.layer_fwd
+        fused, self.ex.fused_predict = self.ex.fused_predict, False     # profile the layer-by-layer kernels
 
         def timed(a):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -120,6 +126,7 @@ class Predictor:
             torch.cuda.synchronize()
         finally:
             _ops.layer_fwd = orig
+            self.ex.fused_predict = fused
         res = {}
         nl = self.ex.spec.n_hidden
         for lid, n_in, n_out, has_head, e0, e1 in rec[nl:]:          # first pass = warm-up
@@ -134,3 +141,27 @@ class Predictor:
         for d in res.values():
             d["ms"] /= d["n"]
         return n, res
+
+    @torch.no_grad()
+    def profile_fused(self, nx: int, ny: int, nt: int, repeats: int = 5):
+        """Average duration of the whole-network kernel over a grid prediction of min(nx*ny*nt, chunk) points, with
+        its algorithmic work: 4Q bytes written per point (nothing read for a generated grid) and the dense FLOPs of
+        every block and the head.  Returns (points, {"ms", "bytes", "flops"}) or (points, None) if the fused kernel
+        does not take this shape."""
+        from . import ops as _ops
+        self._prepare()
+        n = min(nx * ny * nt, self.chunk)
+        out = torch.empty(n, self.model.output_dim, device=self.ex.device)
+        pts = _ops.make_points(grid=(nx, ny, nt), row_begin=0, n_rows=n)
+        self.ex.forward(pts, train=False, out=out, prepared=True)
+        if not self.fused:
+            return n, None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(repeats):
+            self.ex.forward(pts, train=False, out=out, prepared=True)
+        e1.record()
+        torch.cuda.synchronize()
+        s = self.ex.spec
+        flops = sum(2.0 * w.shape[0] * w.shape[1] for w in s.weights) + 2.0 * s.head_w.shape[0] * s.head_w.shape[1]
+        return n, {"ms": e0.elapsed_time(e1) / repeats, "bytes": 4.0 * n * self.model.output_dim, "flops": flops * n}

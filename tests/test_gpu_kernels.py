@@ -453,6 +453,7 @@ def test_cluster_multicast_prediction_matches_plain_path():
     ex = Executor(spec_from_oracle(m))
     nx, ny, nt = 211, 181, 1            # 38191 points = 299 tiles (not a multiple of 4), last tile ragged
     n = nx * ny * nt
+    ex.fused_predict = False            # the layer-by-layer kernels are the ones with a cluster variant
     plain = ex.forward(ops.make_points(grid=(nx, ny, nt)), train=False).clone()
     os.environ["STDADK_CLUSTER"] = "1"
     try:
@@ -463,3 +464,41 @@ def test_cluster_multicast_prediction_matches_plain_path():
     idx = np.r_[0:300, n - 300:n]
     coords, t = orc.grid_points(nx, ny, nt, 0, n)
     assert rel_l2(got.cpu().numpy()[idx], orc.forward(m, None, coords[idx], t[idx])) < 1e-3
+
+
+@pytest.mark.parametrize("hidden,q,fn,ln,n", [((256, 256, 128), 5, "wendland", True, 38191),
+                                              ((256, 256, 128), 1, "wendland", True, 1000),
+                                              ((128, 128), 3, "triangular", True, 20000),
+                                              ((64,), 1, "gaussian", False, 777),
+                                              ((100, 40), 2, "wendland", True, 5000),
+                                              ((256, 192, 96, 32), 8, "wendland", False, 3000)])
+def test_fused_prediction_kernel_vs_layered_path_and_oracle(hidden, q, fn, ln, n):
+    """stdadk_predict (whole network in one persistent kernel, activations in SMEM/TMEM) against the chained
+    layer_fwd path (same TF32 operands, FP32 epilogues: equal up to the rounding of differently ordered FP32 sums and
+    the occasional TF32 tie that flips with them) and against the oracle: 1e-3 relative, like every prediction.
+    Shapes: more tiles than SMs (the persistent loop wraps), ragged last tile, widths that are not multiples of 32,
+    one to four hidden blocks, with and without LayerNorm."""
+    L, ops, Executor, NetSpec, LossSpec = _mods()
+    m = _default_oracle_model(11, q=q, fn=fn, hidden=hidden)
+    if not ln:
+        m.ln_gamma = [None] * len(hidden)
+        m.ln_beta = [None] * len(hidden)
+    ex = Executor(spec_from_oracle(m))
+    rng = np.random.default_rng(5)
+    coords = rng.random((n, 2), dtype=np.float32)
+    t = rng.random(n, dtype=np.float32)
+    pts = ops.make_points(T(coords), T(t))
+    assert ex.fused_predict
+    fused = ex.forward(pts, train=False).clone()
+    assert ex._fused_ok is True, "the fused kernel must accept this shape"
+    ex.fused_predict = False
+    layered = ex.forward(pts, train=False).clone()
+    torch.cuda.synchronize()
+    f, l = fused.cpu().numpy(), layered.cpu().numpy()
+    assert np.isfinite(f).all()
+    assert rel_l2(f, l) < 2e-4, rel_l2(f, l)
+    idx = np.r_[0:min(n, 400), max(0, n - 400):n]
+    ref = orc.forward(m, None, coords[idx], t[idx])
+    assert rel_l2(f[idx], ref) < 1e-3 and rel_err(f[idx], ref) < 3e-3
+    emu = orc.forward(m, None, coords[idx], t[idx], rnd=orc.tf32_round)
+    assert rel_l2(f[idx], emu) < 1e-4, rel_l2(f[idx], emu)
