@@ -177,12 +177,16 @@ typedef struct {
     float* v;
     float* shadow;            /* EMA or NULL */
     int64_t n;
-    int32_t n_groups, _pad;
+    int32_t n_groups;
+    int32_t zero_grad;        /* != 0: g is overwritten with zeros once consumed (optimizer.zero_grad() of the next step,
+                                 train_st_interp.py:612, without a separate fill launch) */
     const int64_t* group_end; /* host array (n_groups): exclusive end offset of each group */
     const float* hyper;       /* device (n_groups x 4) */
     const float* sqnorms;     /* device (n_groups) or NULL (no clipping) */
     int32_t* step_count;      /* device */
     float beta1, beta2, eps, ema_decay;
+    float* loss_acc;          /* optional pair (device scalars): *loss_sum += *loss_acc; *loss_acc = 0 -- the running */
+    float* loss_sum;          /* epoch loss of train_st_interp.py:721 kept on the device                              */
 } stdadk_adamw_args;
 
 int stdadk_version(void);

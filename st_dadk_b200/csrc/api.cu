@@ -340,6 +340,11 @@ int stdadk_layer_fwd(const stdadk_fwd_args* a, void* stream) {
     return check_launch("layer_fwd");
 }
 
+static unsigned long long* g_predict_dbg = nullptr;
+// Development aid (not part of include/stdadk.h): 16 device counters of cycles the fused prediction kernel's roles spend
+// waiting; see tests/prof_predict.py.
+extern "C" void stdadk_debug_counters(void* dev_u64x16) { g_predict_dbg = static_cast<unsigned long long*>(dev_u64x16); }
+
 static int predict_fill(const stdadk_predict_args* a, PredK* K) {
     REQUIRE(a && a->basis && a->head, "predict: NULL args / basis / head");
     REQUIRE(a->n_layers >= 1 && a->n_layers <= PF_MAX_LAYERS, "predict: %d hidden blocks outside [1,%d]", a->n_layers,
@@ -374,6 +379,7 @@ static int predict_fill(const stdadk_predict_args* a, PredK* K) {
     uint32_t bytes = plan_predict(*K);
     REQUIRE(bytes <= 227 * 1024, "predict: the fused kernel needs %u B of shared memory (> 227 KB) for this shape", bytes);
     K->n_tiles = (int)ceil_div64(a->pts.n_rows, TILE_M);
+    K->dbg = g_predict_dbg;
     return 0;
 }
 
@@ -587,7 +593,12 @@ int stdadk_grad_sqnorm(const float* g, int64_t n, int n_groups, const int64_t* g
     REQUIRE((reinterpret_cast<uintptr_t>(g) & 15) == 0, "grad_sqnorm: g must be 16-byte aligned");
     GroupsP G{};
     if (int r = make_groups(n_groups, group_end, n, &G)) return r;
-    sqnorm_kernel<<<SQNORM_BLOCKS, SQNORM_THREADS, 0, (cudaStream_t)stream>>>(g, n, G, sqnorms, workspace);
+    // grid sized by n alone (four 16-byte loads per thread), so the summation order is a function of n: the result is
+    // the same on every run and on every data-parallel rank; a 177k-float gradient takes 44 blocks, not 592
+    long long blocks = ((n >> 2) + SQNORM_THREADS * 4 - 1) / (SQNORM_THREADS * 4);
+    if (blocks < 1) blocks = 1;
+    if (blocks > SQNORM_BLOCKS) blocks = SQNORM_BLOCKS;
+    sqnorm_kernel<<<(int)blocks, SQNORM_THREADS, 0, (cudaStream_t)stream>>>(g, n, G, sqnorms, workspace);
     return check_launch("grad_sqnorm");
 }
 
@@ -631,6 +642,9 @@ int stdadk_adamw_ema_step(const stdadk_adamw_args* a, void* stream) {
     K.beta2 = a->beta2;
     K.eps = a->eps;
     K.ema_decay = a->ema_decay;
+    K.g_zero = a->zero_grad ? const_cast<float*>(a->g) : nullptr;
+    K.loss_acc = a->loss_acc;
+    K.loss_sum = a->loss_sum;
     step_inc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(a->step_count);
     REQUIRE(((reinterpret_cast<uintptr_t>(a->p) | reinterpret_cast<uintptr_t>(a->g) | reinterpret_cast<uintptr_t>(a->m) |
               reinterpret_cast<uintptr_t>(a->v) | reinterpret_cast<uintptr_t>(a->shadow)) & 15) == 0,

@@ -213,6 +213,9 @@ struct AdamK {
     const float* sqnorms;  // (n_groups) or null
     const int* step_count; // device; holds the 1-based step index of THIS update
     float beta1, beta2, eps, ema_decay;
+    float* g_zero;         // == g when the kernel should leave the gradient buffer zeroed for the next step, else null
+    float* loss_acc;       // optional: *loss_sum += *loss_acc; *loss_acc = 0 (one thread), saves two tiny launches
+    float* loss_sum;
 };
 // torch.optim.AdamW (decoupled decay, bias correction) + clip_grad_norm_ coefficient + ModelEMA.update
 // in one pass: 20 B read + 16 B written per parameter (28 B without EMA).
@@ -266,6 +269,11 @@ __global__ void adamw_ema_kernel(AdamK A) {
         m4[i] = m;
         v4[i] = v;
         if (s4) s4[i] = sh;
+        if (A.g_zero) reinterpret_cast<float4*>(A.g_zero)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && A.loss_acc && A.loss_sum) {
+        *A.loss_sum += *A.loss_acc;
+        *A.loss_acc = 0.0f;
     }
     if (blockIdx.x == 0 && threadIdx.x < (A.n & 3)) {
         long long i = (n4 << 2) + threadIdx.x;
@@ -275,6 +283,7 @@ __global__ void adamw_ema_kernel(AdamK A) {
         A.m[i] = m;
         A.v[i] = v;
         if (A.shadow) A.shadow[i] = sh;
+        if (A.g_zero) A.g_zero[i] = 0.0f;
     }
 }
 

@@ -47,7 +47,30 @@ struct PredK {
     const float* head_b;
     float* yhat;
     int n_layers, q, n_tiles, _pad;
+    unsigned long long* dbg;                // optional cycle counters (stdadk_debug_counters), NULL in production
 };
+
+// Development aid, compiled in with -DSTDADK_PF_DEBUG: cycles each role spends waiting / per phase, accumulated
+// into P.dbg (stdadk_debug_counters, tests/prof_predict.py).  Production builds carry none of it.
+#ifdef STDADK_PF_DEBUG
+#define PF_DBG(...) __VA_ARGS__
+#define PF_TIMED_WAIT(acc, ...)                   \
+    do {                                          \
+        if (P.dbg) {                              \
+            long long t_ = clock64();             \
+            __VA_ARGS__;                          \
+            acc += (unsigned long long)(clock64() - t_); \
+        } else {                                  \
+            __VA_ARGS__;                          \
+        }                                         \
+    } while (0)
+#else
+#define PF_DBG(...)
+#define PF_TIMED_WAIT(acc, ...) \
+    do {                        \
+        __VA_ARGS__;            \
+    } while (0)
+#endif
 
 // Fills the per-layer offsets and the carve-up; returns the dynamic shared-memory bytes needed.
 __host__ inline uint32_t plan_predict(PredK& K) {
@@ -70,15 +93,16 @@ __host__ inline uint32_t plan_predict(PredK& K) {
     return K.sm.total;
 }
 
-// Thread (row, cg) generates chunks 2cg, 2cg+1 of a 32-feature slab.
+// One thread generates its row of a whole 32-feature slab (eight 16-byte chunks): column group cg owns slabs
+// cg, cg + 4, ... so a slab costs one barrier arrival per thread of that group and 32 independent evaluations.
 __device__ __forceinline__ void pf_gen_slab(const BasisP& B, const float4* sk, const float2* st, int slab, float x, float y,
-                                            float t, const float* xrow, uint32_t slab_saddr, uint32_t rowoff, uint32_t rx,
-                                            int cg) {
-#pragma unroll
-    for (int cc = 0; cc < 8 / PF_CG; ++cc) {
-        const int c = cg * (8 / PF_CG) + cc;
-        float4 v = feature_chunk(B, sk, st, slab * SLAB_K + c * 4, x, y, t, xrow);
-        st_shared_v4(slab_saddr + rowoff + (((uint32_t)c ^ rx) << 4), v.x, v.y, v.z, v.w);
+                                         float t, const float* xrow, uint32_t row_saddr, uint32_t rx) {
+#pragma unroll 1
+    for (int c2 = 0; c2 < 8; c2 += 2) {        // two chunks (8 evaluations) in flight
+        const float4 v0 = feature_chunk(B, sk, st, slab * SLAB_K + c2 * 4, x, y, t, xrow);
+        const float4 v1 = feature_chunk(B, sk, st, slab * SLAB_K + c2 * 4 + 4, x, y, t, xrow);
+        st_shared_v4(row_saddr + (((uint32_t)c2 ^ rx) << 4), v0.x, v0.y, v0.z, v0.w);
+        st_shared_v4(row_saddr + (((uint32_t)(c2 + 1) ^ rx) << 4), v1.x, v1.y, v1.z, v1.w);
     }
 }
 
@@ -95,12 +119,16 @@ __device__ __forceinline__ void pf_bias_stats(float (&v)[32], const float* sb, i
         have = true;
     }
     if (nv >= 32) {
+        // four independent accumulator pairs: with four warps per scheduler a single 32-long FADD chain would stall
+        float a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
             const float d = v[i] - K;
-            S1 += d;
-            S2 = fmaf(d, d, S2);
+            a1[i & 3] += d;
+            a2[i & 3] = fmaf(d, d, a2[i & 3]);
         }
+        S1 += (a1[0] + a1[1]) + (a1[2] + a1[3]);
+        S2 += (a2[0] + a2[1]) + (a2[2] + a2[3]);
     } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i)
@@ -148,15 +176,16 @@ __device__ __forceinline__ void pf_head_partial(const float (&v)[32], const floa
 #pragma unroll 1
     for (int k = 0; k < q; ++k) {
         const float* wk = shw + k * n_pad + c0;
-        float acc = 0.0f;
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             const float4 w = *reinterpret_cast<const float4*>(wk + 4 * c);
-            acc = fmaf(v[4 * c], w.x, acc);
-            acc = fmaf(v[4 * c + 1], w.y, acc);
-            acc = fmaf(v[4 * c + 2], w.z, acc);
-            acc = fmaf(v[4 * c + 3], w.w, acc);
+            a0 = fmaf(v[4 * c], w.x, a0);
+            a1 = fmaf(v[4 * c + 1], w.y, a1);
+            a2 = fmaf(v[4 * c + 2], w.z, a2);
+            a3 = fmaf(v[4 * c + 3], w.w, a3);
         }
+        const float acc = (a0 + a1) + (a2 + a3);
 #pragma unroll
         for (int kk = 0; kk < STDADK_MAX_Q; ++kk)
             if (kk == k) yh[kk] += acc;
@@ -173,7 +202,8 @@ __global__ void __launch_bounds__(PF_NT, 1) predict_fused_kernel(const __grid_co
     uint64_t* afull = wempty + PF_WST;
     uint64_t* aempty = afull + PF_AST;
     uint64_t* hfull = aempty + PF_AST;
-    uint64_t* accf = hfull + PF_HSLABS;
+    uint64_t* hfree = hfull + PF_HSLABS;   // H slab j (j < PF_AST) no longer read by the last block of the current tile
+    uint64_t* accf = hfree + PF_AST;       // [2]: accumulator-ready of even / odd tiles
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + P.sm.tmem_off);
     float* shw = reinterpret_cast<float*>(smem + P.sm.headw_off);
     float4* sk = reinterpret_cast<float4*>(smem + P.sm.knots_off);
@@ -192,11 +222,13 @@ __global__ void __launch_bounds__(PF_NT, 1) predict_fused_kernel(const __grid_co
             mbar_init(&wempty[s], 1);
         }
         for (int s = 0; s < PF_AST; ++s) {
-            mbar_init(&afull[s], PF_NW);
+            mbar_init(&afull[s], TILE_M);
             mbar_init(&aempty[s], 1);
         }
         for (int s = 0; s < PF_HSLABS; ++s) mbar_init(&hfull[s], TILE_M);
-        mbar_init(accf, 1);
+        for (int s = 0; s < PF_AST; ++s) mbar_init(&hfree[s], 1);
+        mbar_init(&accf[0], 1);
+        mbar_init(&accf[1], 1);
         mbar_fence_init();
     }
     if (warp == 4 * PF_CG) {
@@ -229,11 +261,12 @@ __global__ void __launch_bounds__(PF_NT, 1) predict_fused_kernel(const __grid_co
         // ---------------- producer: weight slabs of every block of every tile, in consumption order
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
+            PF_DBG(unsigned long long w_empty = 0;)
             for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
                 for (int l = 0; l < nl; ++l) {
                     const PredLayerP& Ly = P.L[l];
                     for (int s = 0; s < Ly.k_slabs; ++s) {
-                        mbar_wait(&wempty[stage], phase ^ 1u);
+                        PF_TIMED_WAIT(w_empty, mbar_wait(&wempty[stage], phase ^ 1u));
                         issue_slab_copies(Ly.w_img, Ly.k_slabs, s, Ly.n_pad, nullptr, nullptr,
                                           sW + (size_t)stage * MAX_N * SLAB_K, &wfull[stage]);
                         if (++stage == PF_WST) {
@@ -243,28 +276,34 @@ __global__ void __launch_bounds__(PF_NT, 1) predict_fused_kernel(const __grid_co
                     }
                 }
             }
+            PF_DBG(if (P.dbg) atomicAdd(&P.dbg[7], w_empty);)
         }
         __syncwarp();
     } else if (warp == 4 * PF_CG + 1) {
         // ---------------- MMA issuer
         if (lane == 0) {
-            uint32_t wstage = 0, wphase = 0, astage = 0, aphase = 0, hph = 0;
-            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+            uint32_t wstage = 0, wphase = 0, astage = 0, aphase = 0, hph = 0, it = 0;
+            PF_DBG(unsigned long long w_a = 0, w_w = 0; const long long t_begin = clock64();)
+            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
+                // every block of a tile accumulates into the same half of TMEM (the epilogue has drained it into
+                // registers before it releases the next block's first operand slab); tiles alternate halves so that
+                // block 1 of the next tile runs under the last epilogue of this one
+                const uint32_t acc = tmem_base + (it & 1u) * MAX_N;
                 for (int l = 0; l < nl; ++l) {
                     const PredLayerP& Ly = P.L[l];
                     const uint32_t idesc = umma_idesc_tf32((uint32_t)Ly.n_pad, 0, 0);
-                    const uint32_t acc = tmem_base + (uint32_t)(l & 1) * MAX_N;
+                    const bool last = l == nl - 1;
                     for (int s = 0; s < Ly.k_slabs; ++s) {
                         const float* a;
                         if (l == 0) {
-                            mbar_wait(&afull[astage], aphase);
+                            PF_TIMED_WAIT(w_a, mbar_wait(&afull[astage], aphase));
                             a = sH + (size_t)astage * SLAB_FLOATS;
                         } else {
-                            mbar_wait(&hfull[s], (hph >> s) & 1u);
+                            PF_TIMED_WAIT(w_a, mbar_wait(&hfull[s], (hph >> s) & 1u));
                             hph ^= 1u << s;
                             a = sH + (size_t)s * SLAB_FLOATS;
                         }
-                        mbar_wait(&wfull[wstage], wphase);
+                        PF_TIMED_WAIT(w_w, mbar_wait(&wfull[wstage], wphase));
                         tc_fence_after();
                         issue_slab_mma(acc, a, sW + (size_t)wstage * MAX_N * SLAB_K, idesc, s == 0);
                         umma_commit(&wempty[wstage]);
@@ -274,15 +313,22 @@ __global__ void __launch_bounds__(PF_NT, 1) predict_fused_kernel(const __grid_co
                                 astage = 0;
                                 aphase ^= 1u;
                             }
+                        } else if (last && s < PF_AST) {
+                            umma_commit(&hfree[s]);      // the next tile's block-1 operand may overwrite this H slab
                         }
                         if (++wstage == PF_WST) {
                             wstage = 0;
                             wphase ^= 1u;
                         }
                     }
-                    umma_commit(accf);
+                    umma_commit(&accf[it & 1u]);
                 }
             }
+            PF_DBG(if (P.dbg) {
+                atomicAdd(&P.dbg[0], w_a);
+                atomicAdd(&P.dbg[1], w_w);
+                atomicAdd(&P.dbg[2], (unsigned long long)(clock64() - t_begin));
+            })
         }
         __syncwarp();
     } else {
@@ -293,29 +339,83 @@ __global__ void __launch_bounds__(PF_NT, 1) predict_fused_kernel(const __grid_co
         const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16);
         const uint32_t sH_addr = smem_u32(sH);
         uint32_t astage = 0, aphase = 0, accn = 0;
-        for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-            const long long lrow = (long long)tile * TILE_M + row;
-            const bool rvalid = lrow < P.pts.n_rows;
-            const long long grow = P.pts.row_begin + lrow;
-            float x = 0.f, y = 0.f, t = 0.f;
-            const float* xrow = nullptr;
-            if (rvalid) {
-                load_point(P.pts, grow, x, y, t);
-                if (P.basis.p_cov > 0 && P.pts.xcov) xrow = P.pts.xcov + sample_of(P.pts, grow) * P.basis.p_cov;
-            }
-            // block-1 operand: generated into the ring (the H buffer is dead until this tile's first epilogue)
-            for (int s = 0; s < P.L[0].k_slabs; ++s) {
-                mbar_wait(&aempty[astage], aphase ^ 1u);
-                pf_gen_slab(P.basis, sk, st, s, x, y, t, xrow, sH_addr + astage * (uint32_t)SLAB_BYTES, rowoff, rx, cg);
-                fence_proxy_async_smem();
-                tc_fence_before();        // orders this thread's earlier TMEM reads before the MMAs this arrival releases
-                mbar_arrive(&afull[astage]);
-                if (++astage == PF_AST) {
-                    astage = 0;
-                    aphase ^= 1u;
+#ifdef STDADK_PF_DEBUG
+        unsigned long long w_acc = 0, w_ae = 0, w_bar = 0, ph_gen = 0, ph_ld = 0, ph_norm = 0, ph_head = 0;
+        const long long t_begin = clock64();
+        long long t_last = t_begin;
+#define PF_PHASE(var)                                    \
+    do {                                                 \
+        if (P.dbg) {                                     \
+            const long long n_ = clock64();              \
+            var += (unsigned long long)(n_ - t_last);    \
+            t_last = n_;                                 \
+        }                                                \
+    } while (0)
+#else
+#define PF_PHASE(var)
+#endif
+        // generated grid: this thread's row index decomposed once ((k*nx + i)*ny + j, 64-bit), then advanced by the
+        // tile stride with 32-bit divisions (the 64-bit div/mod triple costs ~500 instructions per row otherwise)
+        const bool is_grid = P.pts.nx > 0;
+        uint32_t gk = 0, gi = 0, gj = 0;
+        const uint32_t gstep = (uint32_t)TILE_M * gridDim.x;
+        if (is_grid) {
+            const long long g0 = P.pts.row_begin + (long long)blockIdx.x * TILE_M + row;
+            const long long r0 = g0 / P.pts.ny;
+            gj = (uint32_t)(g0 - r0 * P.pts.ny);
+            gk = (uint32_t)(r0 / P.pts.nx);
+            gi = (uint32_t)(r0 - (long long)gk * P.pts.nx);
+        }
+        // Software pipeline over this CTA's tiles: the operand of block 1 of the NEXT tile is generated just before the
+        // last epilogue of the current one (into H slabs the last block has already consumed), so those MMAs run
+        // under the epilogue + head instead of leaving the workers waiting for them.
+        const int k_last = nl >= 2 ? P.L[nl - 1].k_slabs : 0;
+        long long lrow = 0, nxt_lrow = 0;
+        bool rvalid = false, nxt_valid = false, have_cur = false;
+        uint32_t it = 0;                                   // iteration index of the current tile
+        for (int next = blockIdx.x; have_cur || next < P.n_tiles; next += gridDim.x) {
+            const bool have_next = next < P.n_tiles;
+            for (int l = have_cur ? 0 : nl - 1; l < nl; ++l) {
+                if (l == nl - 1) {
+                    if (have_next) {
+                        nxt_lrow = (long long)next * TILE_M + row;
+                        nxt_valid = nxt_lrow < P.pts.n_rows;
+                        const long long grow = P.pts.row_begin + nxt_lrow;
+                        float x = 0.f, y = 0.f, t = 0.f;
+                        const float* xrow = nullptr;
+                        if (is_grid) {
+                            x = P.pts.nx > 1 ? __fdiv_rn((float)gi, (float)(P.pts.nx - 1)) : 0.0f;     // as load_point()
+                            y = P.pts.ny > 1 ? __fdiv_rn((float)gj, (float)(P.pts.ny - 1)) : 0.0f;
+                            t = P.pts.nt > 1 ? __fdiv_rn((float)gk, (float)(P.pts.nt - 1)) : 0.0f;
+                            const uint32_t jj = gj + gstep, qj = jj / (uint32_t)P.pts.ny;
+                            gj = jj - qj * (uint32_t)P.pts.ny;
+                            const uint32_t ii = gi + qj, qi = ii / (uint32_t)P.pts.nx;
+                            gi = ii - qi * (uint32_t)P.pts.nx;
+                            gk += qi;
+                        } else if (nxt_valid) {
+                            load_point(P.pts, grow, x, y, t);
+                        }
+                        if (nxt_valid && P.basis.p_cov > 0 && P.pts.xcov)
+                            xrow = P.pts.xcov + sample_of(P.pts, grow) * P.basis.p_cov;
+                        for (int s = 0; s < P.L[0].k_slabs; ++s) {
+                            if ((s & (PF_CG - 1)) == cg) {
+                                PF_TIMED_WAIT(w_ae, mbar_wait(&aempty[astage], aphase ^ 1u));
+                                if (have_cur && s < PF_AST && (int)astage < k_last)   // H slab still feeds the last block?
+                                    PF_TIMED_WAIT(w_ae, mbar_wait(&hfree[astage], it & 1u));
+                                pf_gen_slab(P.basis, sk, st, s, x, y, t, xrow,
+                                            sH_addr + astage * (uint32_t)SLAB_BYTES + rowoff, rx);
+                                fence_proxy_async_smem();
+                                mbar_arrive(&afull[astage]);
+                            }
+                            if (++astage == PF_AST) {
+                                astage = 0;
+                                aphase ^= 1u;
+                            }
+                        }
+                    }
+                    PF_PHASE(ph_gen);
+                    if (!have_cur) break;
                 }
-            }
-            for (int l = 0; l < nl; ++l) {
                 const PredLayerP& Ly = P.L[l];
                 const float* sb = reinterpret_cast<const float*>(smem + Ly.prm_off);
                 const float* sg = sb + Ly.n_pad;
@@ -324,15 +424,29 @@ __global__ void __launch_bounds__(PF_NT, 1) predict_fused_kernel(const __grid_co
                 const bool ha = c0a < Ly.n_pad, hb = c0b < Ly.n_pad;
                 const int nva = min(32, Ly.n_out - c0a), nvb = min(32, Ly.n_out - c0b);
                 float4* redl = red + (size_t)(accn & 1u) * (PF_CG * TILE_M);
-                mbar_wait(accf, accn & 1u);
+                PF_TIMED_WAIT(w_acc, mbar_wait(&accf[it & 1u], ((it >> 1) * (uint32_t)nl + (uint32_t)l) & 1u));
+                PF_DBG(if (P.dbg) t_last = clock64();)
                 ++accn;
                 tc_fence_after();
-                const uint32_t acc = trow + (uint32_t)(l & 1) * MAX_N;
+                const uint32_t acc = trow + (it & 1u) * MAX_N;
+                // both arrays are DEFINED on every path right here: a register written only under `if (ha)` and read
+                // under a later `if (ha)` looks live from the top of the tile loop to the register allocator, which then
+                // keeps 64 registers away from the basis generation
                 float va[32], vb[32];
-                if (ha) tmem_ld32_issue(acc + (uint32_t)c0a, va);
-                if (hb) tmem_ld32_issue(acc + (uint32_t)c0b, vb);
-                if (ha) tmem_ld_wait(va);
-                if (hb) tmem_ld_wait(vb);
+                if (ha) {
+                    tmem_ld32_issue(acc + (uint32_t)c0a, va);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) va[i] = 0.0f;
+                }
+                if (hb) {
+                    tmem_ld32_issue(acc + (uint32_t)c0b, vb);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) vb[i] = 0.0f;
+                }
+                tmem_ld_wait(va);
+                tmem_ld_wait(vb);
                 bool have = false;
                 float K = 0.0f, S1 = 0.0f, S2 = 0.0f;
                 if (ha) pf_bias_stats(va, sb + c0a, nva, have, K, S1, S2);
@@ -341,7 +455,9 @@ __global__ void __launch_bounds__(PF_NT, 1) predict_fused_kernel(const __grid_co
                 if (Ly.has_ln) {
                     const float cntv = (float)((ha ? max(nva, 0) : 0) + (hb ? max(nvb, 0) : 0));
                     redl[cg * TILE_M + row] = make_float4(K, S1, S2, cntv);
-                    worker_barrier(PF_NW);
+                    PF_PHASE(ph_ld);
+                    PF_TIMED_WAIT(w_bar, worker_barrier(PF_NW));
+                    PF_DBG(if (P.dbg) t_last = clock64();)
                     if (ha) {
                         const float inv_n = 1.0f / (float)Ly.n_out;
                         float4 part[PF_CG];
@@ -379,6 +495,7 @@ __global__ void __launch_bounds__(PF_NT, 1) predict_fused_kernel(const __grid_co
                         tc_fence_before();
                         mbar_arrive(&hfull[cg + 4]);
                     }
+                    PF_PHASE(ph_norm);
                 } else {
                     float yh[STDADK_MAX_Q];
 #pragma unroll
@@ -405,9 +522,24 @@ __global__ void __launch_bounds__(PF_NT, 1) predict_fused_kernel(const __grid_co
                                 P.yhat[lrow * P.q + k] = acc_k;
                             }
                     }
+                    PF_PHASE(ph_head);
                 }
             }
+            if (have_cur) ++it;
+            have_cur = have_next;
+            lrow = nxt_lrow;
+            rvalid = nxt_valid;
         }
+        PF_DBG(if (P.dbg && tid == 0) {
+            atomicAdd(&P.dbg[3], w_acc);
+            atomicAdd(&P.dbg[4], w_ae);
+            atomicAdd(&P.dbg[5], (unsigned long long)(clock64() - t_begin));
+            atomicAdd(&P.dbg[6], w_bar);
+            atomicAdd(&P.dbg[8], ph_gen);
+            atomicAdd(&P.dbg[9], ph_ld);
+            atomicAdd(&P.dbg[10], ph_norm);
+            atomicAdd(&P.dbg[11], ph_head);
+        })
         tc_fence_before();
     }
     __syncthreads();

@@ -24,31 +24,25 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+// try_wait suspends the thread in hardware until the phase completes or `hint_ns` elapses: a waiting warp issues
+// one instruction per time slice instead of spinning, so it does not take issue slots from the warps doing the work.
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity, uint32_t hint_ns = 20000u) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.b32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU.  The probe itself suspends the thread
-// for a hardware time slice; between probes the warp backs off with nanosleep so that waiting warps (the epilogue
-// warps during the main loop) do not steal issue slots from the warps that are producing.
+// Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
-    uint32_t spins = 0;
-    long long t0 = 0;
+    long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        __nanosleep(40);
-        if ((++spins & 0xFFFu) == 0) {
-            long long now = clock64();
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > 4000000000LL) __trap();
-        }
+        if (clock64() - t0 > 4000000000LL) __trap();
     }
 }
 

@@ -151,6 +151,7 @@ class Trainer:
         self.sqnorms = torch.zeros(len(self.flat.group_end), device=self.device)
         self.seed = int(torch.initial_seed() & (2 ** 63 - 1))
         self.loss_sum = torch.zeros(1, device=self.device)      # running sum of per-step losses (one sync / epoch)
+        self._g_clean = False     # True while the flat gradient and loss_acc are known to be zero (left so by AdamW)
         self.use_cuda_graph = use_cuda_graph
         self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
         self._stage_idx = None
@@ -314,8 +315,10 @@ class Trainer:
     def _step_compute(self, table, perm, row_begin: int, n_rows: int, global_rows: int, key_offset: int = 0):
         """Local part of a step: forward (fused loss) and backward into the flat gradient."""
         ex, fl = self.ex, self.flat
-        fl.g.zero_()
-        ex.loss_acc.zero_()
+        if not self._g_clean:          # steady state: the previous step's AdamW kernel left g and loss_acc zeroed
+            fl.g.zero_()
+            ex.loss_acc.zero_()
+        self._g_clean = False
         self._refresh_head()
         ex.prepare(force=True, for_backward=True)
         pts = ops.make_points(table.coords, table.t, table.X, index=perm, row_begin=row_begin, n_rows=n_rows)
@@ -337,9 +340,13 @@ class Trainer:
         self._damp_center_grads()
         if self.clip > 0:
             ops.grad_sqnorm(fl.g[:fl.n], fl.group_end, self.sqnorms)
+        scratch_tail = fl.g.numel() > fl.n       # scratch gradients behind the parameters are not seen by the kernel
         ops.adamw_ema_step(fl.p, fl.g[:fl.n], fl.m, fl.v, fl.shadow, fl.group_end, self.hyper,
-                           self.sqnorms if self.clip > 0 else None, self.step_count, ema_decay=self.ema_decay)
-        self.loss_sum += ex.loss_acc
+                           self.sqnorms if self.clip > 0 else None, self.step_count, ema_decay=self.ema_decay,
+                           zero_grad=True, loss_acc=ex.loss_acc, loss_sum=self.loss_sum)
+        if scratch_tail:
+            fl.g[fl.n:].zero_()
+        self._g_clean = True
         if pen is not None:
             self.loss_sum += pen
 

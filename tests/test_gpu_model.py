@@ -188,3 +188,30 @@ def test_training_engine_loss_curve_vs_reference():
             weights=[st[f"mlp.{i}.weight"] for i in (0, 3, 6, 9)], biases=[st[f"mlp.{i}.bias"] for i in (0, 3, 6, 9)],
             ln_gamma=[st[f"mlp.{i}.weight"] for i in (1, 4, 7)], ln_beta=[st[f"mlp.{i}.bias"] for i in (1, 4, 7)])
         assert rel_l2(ema, orc.forward(m, None, g["coords"][:256], g["t"][:256])) < 1e-3
+
+
+def test_space_time_field_equals_explicit_points_any_sharding():
+    """Predictor.space_time_field (T x S field of upstream's predictions.npz; sites visited in a space-filling order
+    and scattered back) must equal the same points passed explicitly, bit for bit, for whole-step and ragged shards;
+    shards concatenated = the single-rank field."""
+    from stnf.models import STInterpMLP
+    from st_dadk_b200.predict import Predictor
+    torch.manual_seed(3)
+    model = STInterpMLP(**DEFAULT, output_dim=3)
+    _perturb_ln(model, 3)
+    model = model.to(DEV).eval()
+    S, Tn = 700, 6
+    g = torch.Generator().manual_seed(0)
+    sites = torch.rand(S, 2, generator=g).to(DEV)
+    pr = Predictor(model)
+    field, (b, e) = pr.space_time_field(sites, Tn)
+    assert (b, e) == (0, S * Tn) and field.shape == (S * Tn, 3)
+    coords = sites.repeat(Tn, 1)
+    t = torch.arange(Tn, device=DEV).repeat_interleave(S).float() / (Tn - 1)
+    explicit, _ = pr.points(coords, t)
+    assert torch.equal(field, explicit)
+    for world in (2, 3, 4):          # 2, 3: whole time steps per rank (ordered path); 4: ragged shards (plain path)
+        parts = [pr.space_time_field(sites, Tn, r, world)[0] for r in range(world)]
+        assert torch.equal(torch.cat(parts), field)
+    again, _ = pr.space_time_field(sites, Tn)      # cached expansion
+    assert torch.equal(again, field)
