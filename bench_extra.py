@@ -51,5 +51,81 @@ def config4(batches=(4096, 65536), steps=20):
                           "kernel_ms": {k: round(v["ms"], 4) for k, v in kt["kernels"].items()}}), flush=True)
 
 
+def _write_kaust_csv(path, sites, T, seed=2025, with_t=True):
+    """Synthetic stand-in for the upstream CSVs (not shipped): z = sin(2pi(x+t)) cos(2pi y) + 0.5 sin(6pi x y) + 0.1 N(0,1)
+    (SURVEY.md section 8d, config 2), KAUST long format x,y,t,z."""
+    rng = np.random.default_rng(seed)
+    S = sites.shape[0]
+    with open(path, "w") as f:
+        f.write("x,y,t,z\n")
+        for k in range(1, T + 1):
+            tt = (k - 1) / max(T - 1, 1)
+            z = (np.sin(2 * np.pi * (sites[:, 0] + tt)) * np.cos(2 * np.pi * sites[:, 1])
+                 + 0.5 * np.sin(6 * np.pi * sites[:, 0] * sites[:, 1]) + 0.1 * rng.standard_normal(S))
+            f.write("\n".join(f"{a:.6f},{b:.6f},{k},{c:.6f}" for (a, b), c in zip(sites, z)) + "\n")
+
+
+def config1(epochs=30, out_root="/tmp/stdadk_cfg1"):
+    """BASELINE config 1 shape: configs/config_st_interp.yaml as shipped (gmm knots, learnable, multi-quantile Q=5)
+    and the uniform/fixed/mean variant on a 1a-shaped file (90,000 points, one time step; obs 0.1 / train 0.8 =>
+    7,200 training samples, batch auto-halved to 512), whole driver: CSV load, knot init, training, evaluation,
+    dense prediction, artefact files.  Wall-clock per run."""
+    import yaml
+    from scripts.train_st_interp import run_single_experiment
+    os.makedirs(out_root, exist_ok=True)
+    rng = np.random.default_rng(7)
+    csv = os.path.join(out_root, "1a_like.csv")
+    _write_kaust_csv(csv, np.round(rng.random((90000, 2)), 6), 1)
+    base = yaml.safe_load(open(os.path.join(ROOT, "configs", "config_st_interp.yaml")))
+    base.update(data_file=csv, epochs=epochs, patience=epochs, n_experiments=1, obs_method="random")
+    variants = {"shipped (gmm, learnable, Q=5)": {},
+                "uniform / fixed / mean": dict(spatial_init_method="uniform", spatial_learnable=False,
+                                               regression_type="mean")}
+    for name, upd in variants.items():
+        cfg = dict(base, **upd)
+        d = os.path.join(out_root, name.split()[0])
+        import contextlib
+        import io
+        t0 = time.time()
+        with contextlib.redirect_stdout(io.StringIO()):
+            r = run_single_experiment(cfg, 1, d, "cuda:0", verbose=False)
+        torch.cuda.synchronize()
+        wall = time.time() - t0
+        print(json.dumps({"workload": f"config1: 1a-shaped, {name}", "epochs": epochs, "wall_s": wall,
+                          "train_time_s": r.get("training_time_seconds", r.get("total_time_seconds")),
+                          "test_rmse": r.get("test_rmse"), "train_samples": 7200, "batch": 512}), flush=True)
+
+
+def config5(epochs=50, configs_per_gpu=(1, 4), out_root="/tmp/stdadk_cfg5"):
+    """BASELINE config 5: the 64-configuration sweep (lr x dropout x hidden x basis function x knot mode) on a
+    2a-shaped data set (S=1000 sites x T=100), n_experiments=1, fixed epochs, through scripts/run_grid_search.py on
+    ONE GPU: sequentially and with several configurations in flight on separate streams."""
+    import subprocess
+    import yaml
+    os.makedirs(out_root, exist_ok=True)
+    rng = np.random.default_rng(11)
+    csv = os.path.join(out_root, "2a_like.csv")
+    _write_kaust_csv(csv, np.round(rng.random((1000, 2)), 6), 100)
+    base = yaml.safe_load(open(os.path.join(ROOT, "configs", "config_st_interp.yaml")))
+    base.update(data_file=csv, epochs=epochs, patience=epochs, n_experiments=1, obs_method="random",
+                regression_type="mean")
+    ypath = os.path.join(out_root, "base.yaml")
+    yaml.safe_dump(base, open(ypath, "w"))
+    for c in configs_per_gpu:
+        out = os.path.join(out_root, f"sweep_c{c}")
+        t0 = time.time()
+        pr = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "run_grid_search.py"), "--config", ypath,
+                             "--output_dir", out, "--configs_per_gpu", str(c)], capture_output=True, text=True)
+        wall = time.time() - t0
+        last = [ln for ln in pr.stdout.strip().splitlines() if ln.startswith("{")]
+        errs = sum(1 for r, _, fs in os.walk(out) for f in fs if f == "error.txt")
+        print(json.dumps({"workload": "config5: 64-config sweep, 2a-shaped (S=1000, T=100), 1 GPU", "epochs": epochs,
+                          "configs_per_gpu": c, "wall_s": wall, "rc": pr.returncode, "failed_configs": errs,
+                          "rank_line": json.loads(last[-1]) if last else None,
+                          "stderr_tail": pr.stderr[-300:] if pr.returncode else ""}), flush=True)
+
+
 if __name__ == "__main__":
-    config4()
+    which = sys.argv[1:] or ["config4"]
+    for w in which:
+        {"config4": config4, "config1": config1, "config5": config5}[w]()

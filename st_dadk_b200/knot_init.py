@@ -6,7 +6,9 @@ are not part of the accelerated path.  Upstream: stnf/models/st_interp.py:152-43
 """
 from __future__ import annotations
 
+import hashlib
 import math
+import threading
 from typing import Sequence, Tuple
 
 import numpy as np
@@ -56,18 +58,42 @@ def _maybe_subsample(coords: np.ndarray, label: str) -> np.ndarray:
     return coords
 
 
+# The mixture fit is a pure function of (sample, k) -- upstream fixes random_state=42 -- and costs seconds on the host,
+# more than a whole 50-epoch training run on the GPU.  A sweep refits the same sample for every configuration that
+# shares data and seed (half of BASELINE config 5), so fits are memoised per process; concurrent callers of the same
+# key wait for the first one instead of refitting.
+_GMM_CACHE: dict = {}
+_GMM_LOCK = threading.Lock()
+_GMM_CACHE_MAX = 32
+
+
+def _gmm_fit(sub: np.ndarray, k: int):
+    from sklearn.mixture import GaussianMixture
+    key = (hashlib.sha1(np.ascontiguousarray(sub).tobytes()).hexdigest(), int(k))
+    with _GMM_LOCK:
+        slot = _GMM_CACHE.get(key)
+        if slot is None:
+            if len(_GMM_CACHE) >= _GMM_CACHE_MAX:
+                _GMM_CACHE.pop(next(iter(_GMM_CACHE)))
+            slot = _GMM_CACHE[key] = {"lock": threading.Lock(), "value": None}
+    with slot["lock"]:
+        if slot["value"] is None:
+            gm = GaussianMixture(n_components=k, covariance_type="spherical", random_state=42, max_iter=100, n_init=3,
+                                 init_params="k-means++", reg_covar=1e-6, tol=1e-3, verbose=0).fit(sub)
+            slot["value"] = (gm.means_.copy(), gm.covariances_.copy())
+    return slot["value"]
+
+
 def gmm_knots(n_centers: Sequence[int], train_coords: np.ndarray):
     """Spherical Gaussian mixture per level: means -> centres, 4.23*2.5*sigma -> bandwidth, floored at a
     quarter of the same level's lattice bandwidth (st_interp.py:187-266)."""
-    from sklearn.mixture import GaussianMixture
     sub = _maybe_subsample(train_coords, "GMM initialization").astype(np.float64)
     cs, bs = [], []
     for k in n_centers:
         floor = 0.25 * _lattice_bandwidth(int(math.sqrt(k)))
-        gm = GaussianMixture(n_components=k, covariance_type="spherical", random_state=42, max_iter=100, n_init=3,
-                             init_params="k-means++", reg_covar=1e-6, tol=1e-3, verbose=0).fit(sub)
-        bw = np.clip(GMM_SIGMA_TO_BANDWIDTH * np.sqrt(gm.covariances_), floor, float("inf"))
-        cs.append(torch.from_numpy(gm.means_).float())
+        means, cov = _gmm_fit(sub, k)
+        bw = np.clip(GMM_SIGMA_TO_BANDWIDTH * np.sqrt(cov), floor, float("inf"))
+        cs.append(torch.from_numpy(means.copy()).float())
         bs.append(torch.from_numpy(bw).float())
     return torch.cat(cs, dim=0), torch.cat(bs, dim=0)
 

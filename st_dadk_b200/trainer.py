@@ -23,6 +23,8 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+import threading
+
 from . import _lib as L
 from . import ops
 from .executor import Executor, LossSpec, NetSpec
@@ -33,6 +35,9 @@ def _dist_on() -> bool:
 
 
 # ------------------------------------------------------------------------------------------------
+_CAPTURE_LOCK = threading.Lock()
+
+
 class FlatState:
     """Flat parameter / gradient / moment / EMA buffers with the model's Parameters re-pointed into them.
 
@@ -149,6 +154,9 @@ class Trainer:
         self._init_optimizer(batches_per_epoch)
         self.step_count = torch.zeros(1, dtype=torch.int32, device=self.device)   # AdamW step == dropout stream
         self.sqnorms = torch.zeros(len(self.flat.group_end), device=self.device)
+        # own reduction workspace (partials + ticket): trainers of different configurations run concurrently on
+        # separate streams of one GPU and must not share it
+        self._sqnorm_ws = torch.zeros(L.lib().stdadk_sqnorm_ws_floats(), device=self.device)
         self.seed = int(torch.initial_seed() & (2 ** 63 - 1))
         self.loss_sum = torch.zeros(1, device=self.device)      # running sum of per-step losses (one sync / epoch)
         self._g_clean = False     # True while the flat gradient and loss_acc are known to be zero (left so by AdamW)
@@ -339,7 +347,7 @@ class Trainer:
         pen = self._add_penalty_grads()
         self._damp_center_grads()
         if self.clip > 0:
-            ops.grad_sqnorm(fl.g[:fl.n], fl.group_end, self.sqnorms)
+            ops.grad_sqnorm(fl.g[:fl.n], fl.group_end, self.sqnorms, self._sqnorm_ws)
         scratch_tail = fl.g.numel() > fl.n       # scratch gradients behind the parameters are not seen by the kernel
         ops.adamw_ema_step(fl.p, fl.g[:fl.n], fl.m, fl.v, fl.shadow, fl.group_end, self.hyper,
                            self.sqnorms if self.clip > 0 else None, self.step_count, ema_decay=self.ema_decay,
@@ -378,20 +386,25 @@ class Trainer:
                 # IS this step; the captures below record the same launch sequence for later steps without executing.
                 # Single GPU: one graph for the whole step.  Data parallel: two graphs with the NCCL all-reduce
                 # issued between them on the same stream (the collective stays outside stream capture).
-                self._step_body(table, self._stage_idx, 0, n_rows, global_rows, key_offset)
-                torch.cuda.synchronize()
-                if self.world == 1:
-                    g1 = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g1):
-                        self._step_body(table, self._stage_idx, 0, n_rows, global_rows, key_offset)
-                    g = (g1, None)
-                else:
-                    g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g1):
-                        self._step_compute(table, self._stage_idx, 0, n_rows, global_rows, key_offset)
-                    with torch.cuda.graph(g2):
-                        self._step_update()
-                    g = (g1, g2)
+                # Captures are serialised across the threads of a process (several configurations train concurrently on
+                # separate streams of one GPU, scripts/run_grid_search.py) and use thread-local capture mode, so what
+                # the other threads enqueue meanwhile neither enters nor invalidates this capture.
+                with _CAPTURE_LOCK:
+                    self._step_body(table, self._stage_idx, 0, n_rows, global_rows, key_offset)
+                    torch.cuda.current_stream().synchronize()
+                    mode = dict(capture_error_mode="thread_local")
+                    if self.world == 1:
+                        g1 = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g1, **mode):
+                            self._step_body(table, self._stage_idx, 0, n_rows, global_rows, key_offset)
+                        g = (g1, None)
+                    else:
+                        g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g1, **mode):
+                            self._step_compute(table, self._stage_idx, 0, n_rows, global_rows, key_offset)
+                        with torch.cuda.graph(g2, **mode):
+                            self._step_update()
+                        g = (g1, g2)
                 self._graphs[gkey] = g
             else:
                 g[0].replay()
