@@ -94,6 +94,11 @@ class PredictArgs(C.Structure):
                 ("layers", Layer * MAX_HIDDEN), ("head", C.POINTER(Head))]
 
 
+class TrainFwdArgs(C.Structure):
+    _fields_ = [("net", PredictArgs), ("drop", Dropout), ("h_img", fp * MAX_HIDDEN), ("x_img", fp * MAX_HIDDEN),
+                ("stats", fp * MAX_HIDDEN)]
+
+
 _lib = None
 
 _PROTOS = {
@@ -109,6 +114,7 @@ _PROTOS = {
     "stdadk_pack_images": (C.c_int, [C.POINTER(PackDesc), C.c_int, fp]),
     "stdadk_predict_supported": (C.c_int, [C.POINTER(PredictArgs)]),
     "stdadk_predict": (C.c_int, [C.POINTER(PredictArgs), fp]),
+    "stdadk_train_fwd": (C.c_int, [C.POINTER(TrainFwdArgs), fp]),
     "stdadk_layer_fwd": (C.c_int, [C.POINTER(FwdArgs), fp]),
     "stdadk_layer_bwd": (C.c_int, [C.POINTER(BwdArgs), fp]),
     "stdadk_wgrad": (C.c_int, [C.POINTER(WgradArgs), fp]),
@@ -138,7 +144,7 @@ def lib():
             fn.restype = res
             fn.argtypes = args
         structs = [Basis, Points, Layer, Dropout, Head, FwdArgs, BwdArgs, WgradArgs, KnotGradArgs, AdamWArgs, PackDesc, SparseArgs,
-                   PredictArgs]
+                   PredictArgs, TrainFwdArgs]
         for i, st in enumerate(structs):
             if L.stdadk_sizeof(i) != C.sizeof(st):
                 raise RuntimeError(f"libstdadk ABI mismatch: {st.__name__} is {C.sizeof(st)} B in the binding, "

@@ -162,6 +162,7 @@ size_t stdadk_sizeof(int which) {
         case 10: return sizeof(stdadk_pack_desc);
         case 11: return sizeof(stdadk_sparse_args);
         case 12: return sizeof(stdadk_predict_args);
+        case 13: return sizeof(stdadk_train_fwd_args);
         default: return 0;
     }
 }
@@ -342,7 +343,7 @@ int stdadk_layer_fwd(const stdadk_fwd_args* a, void* stream) {
 
 static unsigned long long* g_predict_dbg = nullptr;
 // Development aid (not part of include/stdadk.h): 16 device counters of cycles the fused prediction kernel's roles spend
-// waiting; see tests/prof_predict.py.
+// waiting; see tools/prof_predict.py.
 extern "C" void stdadk_debug_counters(void* dev_u64x16) { g_predict_dbg = static_cast<unsigned long long*>(dev_u64x16); }
 
 static int predict_fill(const stdadk_predict_args* a, PredK* K) {
@@ -393,11 +394,44 @@ int stdadk_predict(const stdadk_predict_args* a, void* stream) {
     PredK Kl;
     if (int r = predict_fill(a, &Kl)) return r;
     if (a->pts.n_rows <= 0) return 0;
-    if (int r = set_smem(predict_fused_kernel, Kl.sm.total)) return r;
+    if (int r = set_smem(predict_fused_kernel<false>, Kl.sm.total)) return r;
     const int sms = g_sm_count > 0 ? g_sm_count : 148;
     const int grid = Kl.n_tiles < sms ? Kl.n_tiles : sms;
-    predict_fused_kernel<<<grid, PF_NT, Kl.sm.total, (cudaStream_t)stream>>>(Kl);
+    predict_fused_kernel<false><<<grid, PF_NT, Kl.sm.total, (cudaStream_t)stream>>>(Kl);
     return check_launch("predict");
+}
+
+int stdadk_train_fwd(const stdadk_train_fwd_args* a, void* stream) {
+    if (int r = check_device()) return r;
+    REQUIRE(a, "train_fwd: NULL args");
+    PredK Kl;
+    if (int r = predict_fill(&a->net, &Kl)) return r;
+    const stdadk_head* h = a->net.head;
+    REQUIRE(h->loss_type == STDADK_LOSS_NONE || (h->y && h->loss_acc), "train_fwd: loss requested without y / loss_acc");
+    REQUIRE(a->drop.p >= 0.0f && a->drop.p < 1.0f, "train_fwd: dropout p=%f", a->drop.p);
+    for (int l = 0; l < a->net.n_layers; ++l) {
+        REQUIRE(l == a->net.n_layers - 1 || a->h_img[l], "train_fwd: h_img[%d] is NULL (the backward of block %d reads it)", l,
+                l + 1);
+        REQUIRE(((reinterpret_cast<uintptr_t>(a->h_img[l]) | reinterpret_cast<uintptr_t>(a->x_img[l])) & 127) == 0,
+                "train_fwd: images must be 128-byte aligned");
+        Kl.h_img[l] = l < a->net.n_layers - 1 ? a->h_img[l] : nullptr;
+        Kl.x_img[l] = a->x_img[l];
+        Kl.stats[l] = a->stats[l];
+    }
+    if (a->net.pts.n_rows <= 0) return 0;
+    Kl.head = to_head(h);
+    Kl.seed = a->drop.seed;
+    Kl.key_offset = a->drop.key_offset;
+    Kl.step_ptr = a->drop.step_ptr;
+    Kl.step = a->drop.step;
+    Kl.drop_p = a->drop.p;
+    Kl.thresh16 = dropout_thresh16(a->drop.p);
+    Kl.drop_scale = a->drop.p > 0.0f ? 1.0f / (1.0f - a->drop.p) : 1.0f;
+    if (int r = set_smem(predict_fused_kernel<true>, Kl.sm.total)) return r;
+    const int sms = g_sm_count > 0 ? g_sm_count : 148;
+    const int grid = Kl.n_tiles < sms ? Kl.n_tiles : sms;
+    predict_fused_kernel<true><<<grid, PF_NT, Kl.sm.total, (cudaStream_t)stream>>>(Kl);
+    return check_launch("train_fwd");
 }
 
 int stdadk_layer_bwd(const stdadk_bwd_args* a, void* stream) {

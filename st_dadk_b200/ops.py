@@ -173,6 +173,11 @@ def predict(args: L.PredictArgs):
     L.check(L.lib().stdadk_predict(C.byref(args), _stream()), "predict")
 
 
+def train_fwd(args: L.TrainFwdArgs):
+    """Forward of a training step (dropout, loss, saved tensors for the backward) in one launch."""
+    L.check(L.lib().stdadk_train_fwd(C.byref(args), _stream()), "train_fwd")
+
+
 def layer_bwd(args: L.BwdArgs):
     L.check(L.lib().stdadk_layer_bwd(C.byref(args), _stream()), "layer_bwd")
 

@@ -285,8 +285,11 @@ def _default_oracle_model(seed, q=1, fn="wendland", hidden=(256, 256, 128)):
                            basis_fn=fn)
 
 
-@pytest.mark.parametrize("q,loss,taus,p", [(1, "mse", None, 0.0), (5, "pinball", [0.05, 0.25, 0.5, 0.75, 0.95], 0.1)])
-def test_default_size_network_with_dropout_vs_oracle(q, loss, taus, p):
+@pytest.mark.parametrize("q,loss,taus,p,fused_train", [(1, "mse", None, 0.0, False),
+                                                       (5, "pinball", [0.05, 0.25, 0.5, 0.75, 0.95], 0.1, False),
+                                                       (5, "pinball", [0.05, 0.25, 0.5, 0.75, 0.95], 0.1, True),
+                                                       (1, "mse", None, 0.0, True)])
+def test_default_size_network_with_dropout_vs_oracle(q, loss, taus, p, fused_train):
     """Default architecture 297-256-256-128-Q, ragged batch, dropout masks drawn in-kernel (Philox keyed on the
     global row) and replayed by the oracle: outputs, loss and all gradients."""
     L, ops, Executor, NetSpec, LossSpec = _mods()
@@ -308,10 +311,12 @@ def test_default_size_network_with_dropout_vs_oracle(q, loss, taus, p):
     gemu = orc.backward(m, cache_e, orc.loss_and_grad(yemu, y, loss, taus)[1])
     spec = spec_from_oracle(m, dropout=p)
     ex = Executor(spec)
+    ex.fused_train = fused_train      # stdadk_train_fwd (whole forward in one launch) vs one layer_fwd per block
     ex.loss_acc.zero_()
     pts = ops.make_points(T(coords), T(t))
     yhat = ex.forward(pts, train=True, step=step, seed=seed, y=T(y), loss=LossSpec(loss, taus or ()),
                       inv_count=1.0 / (n * q), save=True)
+    assert not fused_train or ex._fused_ok is True
     grads = ex.backward()
     torch.cuda.synchronize()
     assert rel_err(yhat.cpu().numpy(), yref) < 1e-3

@@ -1,4 +1,5 @@
-"""Profiling driver: dense prediction of 1M space-time points (3 layer_fwd launches), eager launches."""
+"""Profiling driver: dense prediction of 1M grid points.  Default: the whole-network kernel (stdadk_predict);
+PRED_LAYERED=1: one layer_fwd launch per block; PRED_DBG=1 (library built with -DSTDADK_PF_DEBUG): wait/phase cycles."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -7,6 +8,9 @@ from st_dadk_b200.predict import Predictor
 torch.manual_seed(0)
 model = STInterpMLP(dropout=0.1).to("cuda").eval()
 pr = Predictor(model)
+pr._prepare()
+if os.environ.get("PRED_LAYERED"):
+    pr.ex.fused_predict = False
 n = int(os.environ.get("PRED_N", "1000"))
 for _ in range(2):
     out, _ = pr.grid(n, 1000, 1)
