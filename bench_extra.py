@@ -81,6 +81,11 @@ def config1(epochs=30, out_root="/tmp/stdadk_cfg1"):
     variants = {"shipped (gmm, learnable, Q=5)": {},
                 "uniform / fixed / mean": dict(spatial_init_method="uniform", spatial_learnable=False,
                                                regression_type="mean")}
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):          # warm-up: CUDA context, library load, kernel attributes
+        run_single_experiment(dict(base, epochs=2, spatial_init_method="uniform", spatial_learnable=False,
+                                   regression_type="mean"), 1, os.path.join(out_root, "warm"), "cuda:0", verbose=False)
     for name, upd in variants.items():
         cfg = dict(base, **upd)
         d = os.path.join(out_root, name.split()[0])

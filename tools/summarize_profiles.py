@@ -77,7 +77,7 @@ def train_names(name, k):
     if name.startswith("layer_bwd_kernel<0") and name.rstrip(">(BwdK)").endswith("1"):
         return "layer_bwd[2]"
     if name.startswith("layer_bwd_kernel<0"):
-        return "layer_bwd[1]"
+        return f"layer_bwd[{1 - k % 2}]"      # per step: block 2 (head), then 1, then 0 (x saved: image variant)
     if name.startswith("adamw"):
         return "adamw_ema_step"
     if name.startswith("sqnorm"):
