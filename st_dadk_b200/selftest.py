@@ -44,9 +44,15 @@ def smoke():
     yref, cache = orc.forward(m, None, coords, t[:, None], train=True, keep_masks=masks, return_cache=True)
     lref, dy = orc.loss_and_grad(yref, y, "mse")
     gref = orc.backward(m, cache, dy)
-    tr.train_step(table, perm, 0, n)
-    loss = tr.pop_loss_sum()
+    # one optimisation step in its three phases, so that the gradient can be read before the fused AdamW kernel
+    # consumes and zeroes it
+    tr._push_hyper()
+    tr._step_compute(table, perm, 0, n, n)
     gw = tr.flat.gviews[id(model.mlp[0].weight)].cpu().numpy()
+    tr._step_exchange()
+    tr._step_update()
+    loss = tr.pop_loss_sum()
+    assert float(tr.flat.g.abs().max()) == 0.0, "smoke: the update must leave the gradient buffer zeroed"
     rel = abs(loss - lref) / abs(lref)
     gerr = np.abs(gw - gref["weights"][0]).max() / np.abs(gref["weights"][0]).max()
     assert rel < 1e-3, f"smoke: training loss {loss} vs oracle {lref}"
