@@ -75,7 +75,11 @@ class FlatState:
         q, d = model.output_dim, model.last_hidden_dim
         self.n_scratch = q * d + q if model.delta_params is not None else 0
         mk = lambda extra=0: torch.zeros(n + extra, dtype=torch.float32, device=device)
-        self.p, self.g, self.m, self.v, self.shadow = mk(), mk(self.n_scratch), mk(), mk(), mk()
+        # g carries, behind the parameter gradients, the scratch head gradient of the delta parameterisation and ONE
+        # more float: the step's loss accumulator, so that a data-parallel step needs a single all-reduce
+        self.p, self.g, self.m, self.v, self.shadow = mk(), mk(self.n_scratch + 1), mk(), mk(), mk()
+        self.n_exchange = n + self.n_scratch + 1
+        self.loss_slot = self.g[n + self.n_scratch:n + self.n_scratch + 1]
         self.views: Dict[int, torch.Tensor] = {}
         self.gviews: Dict[int, torch.Tensor] = {}
         o = 0
@@ -149,6 +153,7 @@ class Trainer:
         self.head_w = torch.empty(self.q, m.last_hidden_dim, device=self.device)
         self.head_b = torch.empty(self.q, device=self.device)
         self.ex = Executor(self._spec())
+        self.ex.loss_acc = self.flat.loss_slot      # the loss accumulator travels with the gradient all-reduce
         self.ex.alloc_grads(self.flat.g, self.flat.grad_views_for(m))
         self._init_loss()
         self._init_optimizer(batches_per_epoch)
@@ -338,8 +343,7 @@ class Trainer:
     def _step_exchange(self):
         """The one data-parallel exchange of a step: sum of the flat gradient (and of the loss) over ranks."""
         if self.world > 1:
-            dist.all_reduce(self.flat.g[:self.flat.n])
-            dist.all_reduce(self.ex.loss_acc)
+            dist.all_reduce(self.flat.g[:self.flat.n_exchange])     # gradients + loss accumulator in one call
 
     def _step_update(self):
         """Replicated tail: parameter-only penalties, damping, gradient norm, fused clip + AdamW + EMA."""
@@ -348,12 +352,12 @@ class Trainer:
         self._damp_center_grads()
         if self.clip > 0:
             ops.grad_sqnorm(fl.g[:fl.n], fl.group_end, self.sqnorms, self._sqnorm_ws)
-        scratch_tail = fl.g.numel() > fl.n       # scratch gradients behind the parameters are not seen by the kernel
+        scratch_tail = fl.n_scratch > 0          # scratch gradients behind the parameters are not seen by the kernel
         ops.adamw_ema_step(fl.p, fl.g[:fl.n], fl.m, fl.v, fl.shadow, fl.group_end, self.hyper,
                            self.sqnorms if self.clip > 0 else None, self.step_count, ema_decay=self.ema_decay,
                            zero_grad=True, loss_acc=ex.loss_acc, loss_sum=self.loss_sum)
         if scratch_tail:
-            fl.g[fl.n:].zero_()
+            fl.g[fl.n:fl.n + fl.n_scratch].zero_()
         self._g_clean = True
         if pen is not None:
             self.loss_sum += pen
@@ -393,7 +397,12 @@ class Trainer:
                     self._step_body(table, self._stage_idx, 0, n_rows, global_rows, key_offset)
                     torch.cuda.current_stream().synchronize()
                     mode = dict(capture_error_mode="thread_local")
-                    if self.world == 1:
+                    # Data parallel: the collective stays between two graphs.  Capturing the NCCL all-reduce as a node
+                    # of one graph (STDADK_DDP_ONE_GRAPH=1) was measured: 0.2412 vs 0.2427 ms per step on 2 GPUs -- no
+                    # gain -- and the process then hung in teardown, so it is not the default.
+                    one_graph = self.world == 1 or (dist.get_backend() == "nccl"
+                                                    and os.environ.get("STDADK_DDP_ONE_GRAPH", "0") == "1")
+                    if one_graph:
                         g1 = torch.cuda.CUDAGraph()
                         with torch.cuda.graph(g1, **mode):
                             self._step_body(table, self._stage_idx, 0, n_rows, global_rows, key_offset)
@@ -541,6 +550,8 @@ class Trainer:
             else:
                 ex.forward(pts, train=False, out=out[b:b + r], prepared=True)
         loss = float(torch.stack(losses).mean().item()) if losses else float("nan")
+        if with_loss:
+            ex.loss_acc.zero_()      # training steps rely on the accumulator being zero between steps
         return out, loss
 
     def state_for_checkpoint(self):

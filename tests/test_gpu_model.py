@@ -215,3 +215,37 @@ def test_space_time_field_equals_explicit_points_any_sharding():
         assert torch.equal(torch.cat(parts), field)
     again, _ = pr.space_time_field(sites, Tn)      # cached expansion
     assert torch.equal(again, field)
+
+
+def test_step_tail_bookkeeping_gradient_zeroing_and_loss_sum():
+    """The fused AdamW kernel leaves the flat gradient (and the loss accumulator that rides at its end) zeroed, and
+    an evaluation between two steps must not leak its loss into the running training loss: per-step losses of a run
+    with interleaved `evaluate` calls equal those of a run without, and equal the eager (graph-free) run."""
+    from stnf.models import STInterpMLP
+    from stnf.dataio import ObservationTable
+    from st_dadk_b200.trainer import Trainer
+    rng = np.random.default_rng(4)
+    n, B = 3000, 1000
+    c, t = rng.random((n, 2)).astype(np.float32), rng.random(n).astype(np.float32)
+    y = (np.sin(5 * c[:, 0]) + t).astype(np.float32)
+    table = ObservationTable(torch.from_numpy(c), torch.from_numpy(t), torch.from_numpy(y)).to(DEV)
+    perm = torch.arange(n, device=DEV)
+    cfg = dict(lr=1e-2, weight_decay=5e-4, grad_clip=5.0, regression_type="mean")
+
+    def run(graph, with_eval):
+        torch.manual_seed(2)
+        tr = Trainer(STInterpMLP(hidden_dims=[64, 32], dropout=0.1), cfg, DEV, batches_per_epoch=3, use_cuda_graph=graph)
+        out = []
+        for s in range(6):
+            tr.train_step(table, perm, (s % 3) * B, B)
+            out.append(tr.pop_loss_sum())
+            assert float(tr.flat.g.abs().max()) == 0.0           # gradients and loss slot zeroed by the update
+            if with_eval:
+                tr.evaluate(table, batch_rows=1024)
+        return out, tr.flat.p.clone()
+
+    (l0, p0), (l1, p1), (l2, p2) = run(True, False), run(True, True), run(False, True)
+    # (loss and weight-gradient accumulation use floating-point atomics: equal to rounding, not bit for bit; a leaked
+    # validation loss would be an O(1) difference)
+    assert np.allclose(l0, l1, rtol=1e-5) and torch.allclose(p0, p1, rtol=0, atol=1e-5)
+    assert np.allclose(l0, l2, rtol=1e-5) and torch.allclose(p0, p2, rtol=0, atol=1e-5)
