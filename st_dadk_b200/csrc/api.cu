@@ -134,11 +134,11 @@ static int check_basis_points(const stdadk_basis* b, const stdadk_points& p, int
             b->p_cov + b->k_s + b->k_t, n_in);
     if (p.grid_nx > 0) {
         REQUIRE(p.grid_ny > 0 && p.grid_nt > 0, "points: grid sizes must all be positive");
-    } else {
+    } else if (p.n_rows > 0) {       // an empty batch (X of shape (0, p), st_interp.py:836-846) has no storage to point at
         REQUIRE(p.coords && p.t, "points: coords/t are NULL and no grid was given");
         REQUIRE((reinterpret_cast<uintptr_t>(p.coords) & 7) == 0, "points: coords must be 8-byte aligned");
     }
-    REQUIRE(b->p_cov == 0 || p.xcov || p.grid_nx > 0, "points: xcov is NULL but p_cov > 0");
+    REQUIRE(b->p_cov == 0 || p.xcov || p.grid_nx > 0 || p.n_rows <= 0, "points: xcov is NULL but p_cov > 0");
     return 0;
 }
 

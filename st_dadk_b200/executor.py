@@ -230,6 +230,9 @@ class Executor:
         leaves dLoss/dyhat in the workspace for `backward()`.  `save=True` keeps what backward needs."""
         s = self.spec
         n = int(pts.n_rows)
+        if n == 0:          # empty batch: nothing to launch (empty tensors have no storage to hand to the library)
+            self._ctx = None
+            return out if out is not None else torch.empty(0, s.q, dtype=torch.float32, device=self.device)
         if not prepared:
             # always rebuild the operand images: parameter storage can be rewritten in place by kernels or by
             # an EMA swap without any version counter the executor could observe (5 tiny launches)

@@ -507,3 +507,54 @@ def test_fused_prediction_kernel_vs_layered_path_and_oracle(hidden, q, fn, ln, n
     assert rel_l2(f[idx], ref) < 1e-3 and rel_err(f[idx], ref) < 3e-3
     emu = orc.forward(m, None, coords[idx], t[idx], rnd=orc.tf32_round)
     assert rel_l2(f[idx], emu) < 1e-4, rel_l2(f[idx], emu)
+
+
+def test_covariates_ragged_single_row_and_empty_inputs():
+    """Edge cases of the reference's forward signature (st_interp.py:827-846): X with p > 0 covariates in front of
+    the basis columns (first-layer width not a multiple of 4 -> chunks straddling the X|phi and phi|psi boundaries),
+    a single row, an empty batch -- through the whole-network kernel, the per-block kernels and a training step."""
+    L, ops, Executor, NetSpec, LossSpec = _mods()
+    kn = golden("knots")
+    rng = np.random.default_rng(21)
+    p, hidden, q = 3, (96, 64), 2
+    dims = [p + kn["centers"].shape[0] + kn["t_centers"].shape[0], *hidden]
+    ws = [rng.uniform(-0.1, 0.1, (dims[i + 1], dims[i])).astype(np.float32) for i in range(len(hidden))]
+    bs = [rng.uniform(-0.1, 0.1, dims[i + 1]).astype(np.float32) for i in range(len(hidden))]
+    ws.append(rng.uniform(-0.1, 0.1, (q, dims[-1])).astype(np.float32))
+    bs.append(rng.uniform(-0.1, 0.1, q).astype(np.float32))
+    m = orc.OracleModel(centers=kn["centers"], bandwidths=kn["bandwidths"], t_centers=kn["t_centers"],
+                        t_bandwidths=kn["t_bandwidths"], weights=ws, biases=bs,
+                        ln_gamma=[(1 + 0.1 * rng.standard_normal(h)).astype(np.float32) for h in hidden],
+                        ln_beta=[(0.1 * rng.standard_normal(h)).astype(np.float32) for h in hidden], p=p)
+    ex = Executor(spec_from_oracle(m))
+    for n in (1, 2, 129, 700):
+        X = rng.standard_normal((n, p)).astype(np.float32)
+        coords, t = rng.random((n, 2), dtype=np.float32), rng.random(n, dtype=np.float32)
+        y = rng.standard_normal(n).astype(np.float32)
+        ref = orc.forward(m, X, coords, t)
+        pts = ops.make_points(T(coords), T(t), T(X))
+        ex.fused_predict = True
+        fused = ex.forward(pts, train=False).clone()
+        assert ex._fused_ok is True
+        ex.fused_predict = False
+        layered = ex.forward(pts, train=False).clone()
+        assert rel_l2(fused.cpu().numpy(), ref) < 1e-3 and rel_l2(layered.cpu().numpy(), ref) < 1e-3
+        # one training forward/backward: gradients of the covariate columns of W1 against the oracle
+        yref, cache = orc.forward(m, X, coords, t, return_cache=True, rnd=orc.tf32_round)
+        gref = orc.backward(m, cache, orc.loss_and_grad(yref, y, "pinball", [0.3, 0.7])[1])
+        ex.loss_acc.zero_()
+        ex.forward(pts, train=True, y=T(y), loss=LossSpec("pinball", (0.3, 0.7)), inv_count=1.0 / (n * q), save=True)
+        gr = ex.backward()
+        torch.cuda.synchronize()
+        gw = gr["weights"][0].cpu().numpy()
+        assert rel_err(gw[:, :p], gref["weights"][0][:, :p]) < 2e-2, n
+        assert rel_err(gw, gref["weights"][0]) < 2e-2, n
+    # empty batch: every entry point accepts n_rows = 0 and launches nothing
+    e2 = torch.empty(0, 2, device="cuda")
+    e1 = torch.empty(0, device="cuda")
+    ex.fused_predict = True
+    out = ex.forward(ops.make_points(e2, e1, torch.empty(0, p, device="cuda"), n_rows=0), train=False)
+    assert out.shape == (0, q)
+    ex.fused_predict = False
+    out = ex.forward(ops.make_points(e2, e1, torch.empty(0, p, device="cuda"), n_rows=0), train=False)
+    assert out.shape[0] == 0
