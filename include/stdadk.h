@@ -187,6 +187,7 @@ typedef struct {
     float beta1, beta2, eps, ema_decay;
     float* loss_acc;          /* optional pair (device scalars): *loss_sum += *loss_acc; *loss_acc = 0 -- the running */
     float* loss_sum;          /* epoch loss of train_st_interp.py:721 kept on the device                              */
+    float* loss_last;         /* optional: receives this step's loss (what loss.item() returns upstream, :721)        */
 } stdadk_adamw_args;
 
 int stdadk_version(void);

@@ -679,6 +679,7 @@ int stdadk_adamw_ema_step(const stdadk_adamw_args* a, void* stream) {
     K.g_zero = a->zero_grad ? const_cast<float*>(a->g) : nullptr;
     K.loss_acc = a->loss_acc;
     K.loss_sum = a->loss_sum;
+    K.loss_last = a->loss_last;
     step_inc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(a->step_count);
     REQUIRE(((reinterpret_cast<uintptr_t>(a->p) | reinterpret_cast<uintptr_t>(a->g) | reinterpret_cast<uintptr_t>(a->m) |
               reinterpret_cast<uintptr_t>(a->v) | reinterpret_cast<uintptr_t>(a->shadow)) & 15) == 0,

@@ -216,6 +216,7 @@ struct AdamK {
     float* g_zero;         // == g when the kernel should leave the gradient buffer zeroed for the next step, else null
     float* loss_acc;       // optional: *loss_sum += *loss_acc; *loss_acc = 0 (one thread), saves two tiny launches
     float* loss_sum;
+    float* loss_last;      // optional: the step's loss before the accumulator is cleared
 };
 // torch.optim.AdamW (decoupled decay, bias correction) + clip_grad_norm_ coefficient + ModelEMA.update
 // in one pass: 20 B read + 16 B written per parameter (28 B without EMA).
@@ -272,7 +273,9 @@ __global__ void adamw_ema_kernel(AdamK A) {
         if (A.g_zero) reinterpret_cast<float4*>(A.g_zero)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0 && A.loss_acc && A.loss_sum) {
-        *A.loss_sum += *A.loss_acc;
+        const float step_loss = *A.loss_acc;
+        *A.loss_sum += step_loss;
+        if (A.loss_last) *A.loss_last = step_loss;
         *A.loss_acc = 0.0f;
     }
     if (blockIdx.x == 0 && threadIdx.x < (A.n & 3)) {

@@ -206,13 +206,14 @@ def grad_sqnorm(g: torch.Tensor, group_end: Sequence[int], out: torch.Tensor, wo
 
 
 def adamw_ema_step(p, g, m, v, shadow, group_end: Sequence[int], hyper: torch.Tensor, sqnorms, step_count,
-                   beta1=0.9, beta2=0.999, eps=1e-8, ema_decay=0.0, zero_grad=False, loss_acc=None, loss_sum=None):
+                   beta1=0.9, beta2=0.999, eps=1e-8, ema_decay=0.0, zero_grad=False, loss_acc=None, loss_sum=None,
+                   loss_last=None):
     """zero_grad: the kernel leaves `g` zeroed (next step's zero_grad); loss_acc/loss_sum: device scalars,
     loss_sum += loss_acc; loss_acc = 0 inside the same launch."""
     arr = (C.c_int64 * len(group_end))(*group_end)
     a = L.AdamWArgs(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(shadow), p.numel(), len(group_end), int(bool(zero_grad)),
                     arr, _ptr(hyper), _ptr(sqnorms), _ptr(step_count), beta1, beta2, eps, ema_decay, _ptr(loss_acc),
-                    _ptr(loss_sum))
+                    _ptr(loss_sum), _ptr(loss_last))
     L.check(L.lib().stdadk_adamw_ema_step(C.byref(a), _stream()), "adamw_ema_step")
 
 

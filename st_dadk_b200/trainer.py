@@ -164,6 +164,7 @@ class Trainer:
         self._sqnorm_ws = torch.zeros(L.lib().stdadk_sqnorm_ws_floats(), device=self.device)
         self.seed = int(torch.initial_seed() & (2 ** 63 - 1))
         self.loss_sum = torch.zeros(1, device=self.device)      # running sum of per-step losses (one sync / epoch)
+        self.loss_last = torch.zeros(1, device=self.device)     # loss of the most recent step (written by AdamW)
         self._g_clean = False     # True while the flat gradient and loss_acc are known to be zero (left so by AdamW)
         self.use_cuda_graph = use_cuda_graph
         self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
@@ -355,7 +356,7 @@ class Trainer:
         scratch_tail = fl.n_scratch > 0          # scratch gradients behind the parameters are not seen by the kernel
         ops.adamw_ema_step(fl.p, fl.g[:fl.n], fl.m, fl.v, fl.shadow, fl.group_end, self.hyper,
                            self.sqnorms if self.clip > 0 else None, self.step_count, ema_decay=self.ema_decay,
-                           zero_grad=True, loss_acc=ex.loss_acc, loss_sum=self.loss_sum)
+                           zero_grad=True, loss_acc=ex.loss_acc, loss_sum=self.loss_sum, loss_last=self.loss_last)
         if scratch_tail:
             fl.g[fl.n:fl.n + fl.n_scratch].zero_()
         self._g_clean = True
@@ -428,25 +429,67 @@ class Trainer:
                 gq["lr"] = gq["initial_lr"] * f
         self.global_step += 1
 
-    def train_step_host(self, host_table, row_begin: int, n_rows: int, global_rows: Optional[int] = None) -> float:
+    def train_step_host(self, host_table, row_begin: int, n_rows: int, global_rows: Optional[int] = None,
+                        lagged: bool = False) -> float:
         """End-to-end step from HOST buffers: the batch host_table[row_begin : row_begin + n_rows] (pinned memory) is
         copied to a device staging table, the step runs, and the step's loss is read back (the shape of upstream's
-        loop body: .to(device) per batch and loss.item(), train_st_interp.py:609-612, :721)."""
-        if self._host_stage is None or len(self._host_stage) < n_rows:
+        loop body: .to(device) per batch and loss.item(), train_st_interp.py:609-612, :721).
+
+        Staging is double-buffered and the H2D copies go through their own stream.  `lagged=False` returns THIS step's
+        loss (one host synchronisation per step, like upstream's loss.item()).  `lagged=True` returns the loss of the
+        PREVIOUS step (NaN on the first call; `flush_host_loss()` returns the last one): the host then runs one step
+        ahead, so the next batch's copy and launch overlap the running step -- every step's inputs are still copied
+        and every step's loss still read back."""
+        if self._host_stage is None or len(self._host_stage[0]) < n_rows:
             from stnf.dataio import ObservationTable
             z = lambda *sh: torch.zeros(*sh, dtype=torch.float32, device=self.device)
-            self._host_stage = ObservationTable(z(n_rows, 2), z(n_rows), z(n_rows),
-                                                z(n_rows, self.model.p) if self.model.p > 0 else None)
+            mk = lambda: ObservationTable(z(n_rows, 2), z(n_rows), z(n_rows),
+                                          z(n_rows, self.model.p) if self.model.p > 0 else None)
+            self._host_stage = [mk(), mk()]
             self._host_perm = torch.arange(n_rows, dtype=torch.int64, device=self.device)
-        st = self._host_stage
+            self._host_copy_stream = torch.cuda.Stream(device=self.device)
+            self._host_ready = [torch.cuda.Event(), torch.cuda.Event()]     # staging buffer k filled
+            self._host_done = [torch.cuda.Event(), torch.cuda.Event()]      # step that read buffer k finished
+            self._host_loss = [torch.full((1,), float("nan")).pin_memory(), torch.full((1,), float("nan")).pin_memory()]
+            self._host_k = 0
+            self._host_pending = None
+            main = torch.cuda.current_stream()
+            for e in self._host_done:
+                e.record(main)
+        k = self._host_k
+        self._host_k ^= 1
+        st = self._host_stage[k]
         sl = slice(row_begin, row_begin + n_rows)
-        st.coords[:n_rows].copy_(host_table.coords[sl], non_blocking=True)
-        st.t[:n_rows].copy_(host_table.t[sl], non_blocking=True)
-        st.y[:n_rows].copy_(host_table.y[sl], non_blocking=True)
-        if st.X is not None:
-            st.X[:n_rows].copy_(host_table.X[sl], non_blocking=True)
+        main = torch.cuda.current_stream()
+        with torch.cuda.stream(self._host_copy_stream):
+            self._host_copy_stream.wait_event(self._host_done[k])       # the step two calls ago has released buffer k
+            st.coords[:n_rows].copy_(host_table.coords[sl], non_blocking=True)
+            st.t[:n_rows].copy_(host_table.t[sl], non_blocking=True)
+            st.y[:n_rows].copy_(host_table.y[sl], non_blocking=True)
+            if st.X is not None:
+                st.X[:n_rows].copy_(host_table.X[sl], non_blocking=True)
+            self._host_ready[k].record(self._host_copy_stream)
+        main.wait_event(self._host_ready[k])
         self.train_step(st, self._host_perm, 0, n_rows, global_rows)
-        return float(self.ex.loss_acc.item())
+        self._host_loss[k].copy_(self.loss_last, non_blocking=True)
+        self._host_done[k].record(main)
+        prev, self._host_pending = self._host_pending, k
+        if not lagged:
+            self._host_done[k].synchronize()
+            self._host_pending = None
+            return float(self._host_loss[k].item())
+        if prev is None:
+            return float("nan")
+        self._host_done[prev].synchronize()
+        return float(self._host_loss[prev].item())
+
+    def flush_host_loss(self) -> float:
+        """Loss of the last `train_step_host(..., lagged=True)` step (waits for it)."""
+        if self._host_pending is None:
+            return float("nan")
+        k, self._host_pending = self._host_pending, None
+        self._host_done[k].synchronize()
+        return float(self._host_loss[k].item())
 
     @property
     def launches_per_step(self) -> int:

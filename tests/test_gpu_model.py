@@ -245,7 +245,51 @@ def test_step_tail_bookkeeping_gradient_zeroing_and_loss_sum():
         return out, tr.flat.p.clone()
 
     (l0, p0), (l1, p1), (l2, p2) = run(True, False), run(True, True), run(False, True)
-    # (loss and weight-gradient accumulation use floating-point atomics: equal to rounding, not bit for bit; a leaked
-    # validation loss would be an O(1) difference)
-    assert np.allclose(l0, l1, rtol=1e-5) and torch.allclose(p0, p1, rtol=0, atol=1e-5)
-    assert np.allclose(l0, l2, rtol=1e-5) and torch.allclose(p0, p2, rtol=0, atol=1e-5)
+    # Loss and weight-gradient accumulation use floating-point atomics, so runs agree to rounding, not bit for bit --
+    # and Adam turns a rounding-level difference of a near-zero gradient entry into an update of order lr, so single
+    # parameters may differ by ~1e-2 while the mean stays tiny.  A leaked validation loss would be an O(1) difference.
+    close = lambda a, b: float((a - b).abs().mean()) < 2e-4
+    assert np.allclose(l0, l1, rtol=2e-3) and close(p0, p1)
+    assert np.allclose(l0, l2, rtol=2e-3) and close(p0, p2)
+
+
+def test_host_buffer_step_sync_and_lagged_match_device_step():
+    """Trainer.train_step_host (pinned host batch -> H2D -> step -> D2H loss, double-buffered staging): the
+    synchronous form returns each step's loss, the lagged form the previous step's (then flush); both equal the
+    device-resident train_step losses and end at the same parameters."""
+    from stnf.models import STInterpMLP
+    from stnf.dataio import ObservationTable
+    from st_dadk_b200.trainer import Trainer
+    rng = np.random.default_rng(8)
+    n, B, steps = 4000, 1000, 7
+    c, t = rng.random((n, 2)).astype(np.float32), rng.random(n).astype(np.float32)
+    y = (np.cos(4 * c[:, 1]) - t).astype(np.float32)
+    host = ObservationTable(torch.from_numpy(c).pin_memory(), torch.from_numpy(t).pin_memory(),
+                            torch.from_numpy(y).pin_memory())
+    dev_table = ObservationTable(torch.from_numpy(c), torch.from_numpy(t), torch.from_numpy(y)).to(DEV)
+    perm = torch.arange(n, device=DEV)
+    cfg = dict(lr=1e-2, weight_decay=5e-4, grad_clip=5.0, regression_type="mean")
+
+    def run(mode):
+        torch.manual_seed(6)
+        tr = Trainer(STInterpMLP(hidden_dims=[64, 32], dropout=0.1), cfg, DEV, batches_per_epoch=4, use_cuda_graph=True)
+        out = []
+        for s in range(steps):
+            b = (s % 4) * B
+            if mode == "device":
+                tr.train_step(dev_table, perm, b, B)
+                out.append(tr.pop_loss_sum())
+            elif mode == "sync":
+                out.append(tr.train_step_host(host, b, B))
+            else:
+                out.append(tr.train_step_host(host, b, B, lagged=True))
+        if mode == "lagged":
+            assert np.isnan(out[0])
+            out = out[1:] + [tr.flush_host_loss()]
+        torch.cuda.synchronize()
+        return out, tr.flat.p.clone()
+
+    (ld, pd_), (ls, ps), (ll, pl) = run("device"), run("sync"), run("lagged")
+    close = lambda a, b: float((a - b).abs().mean()) < 2e-4      # see the note on atomics + Adam above
+    assert np.allclose(ld, ls, rtol=2e-3) and np.allclose(ld, ll, rtol=2e-3), (ld, ls, ll)
+    assert close(pd_, ps) and close(pd_, pl)
