@@ -115,29 +115,33 @@ __device__ __forceinline__ void pf_gen_slab(const BasisP& B, const float4* sk, c
     }
 }
 
-// bias add + shifted moments of one 32-column chunk held in registers (nv valid columns)
+// bias add + shifted moments of one 32-column chunk held in registers (nv valid columns); packed FP32 throughout
 __device__ __forceinline__ void pf_bias_stats(float (&v)[32], const float* sb, int nv, bool& have, float& K, float& S1,
                                               float& S2) {
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
         const float4 b = *reinterpret_cast<const float4*>(sb + 4 * c);
-        v[4 * c] += b.x; v[4 * c + 1] += b.y; v[4 * c + 2] += b.z; v[4 * c + 3] += b.w;
+        const float2 lo = add2(make_float2(v[4 * c], v[4 * c + 1]), make_float2(b.x, b.y));
+        const float2 hi = add2(make_float2(v[4 * c + 2], v[4 * c + 3]), make_float2(b.z, b.w));
+        v[4 * c] = lo.x; v[4 * c + 1] = lo.y; v[4 * c + 2] = hi.x; v[4 * c + 3] = hi.y;
     }
     if (!have) {
         K = v[0];
         have = true;
     }
     if (nv >= 32) {
-        // four independent accumulator pairs: with four warps per scheduler a single 32-long FADD chain would stall
-        float a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
+        // two independent packed accumulator pairs (= four scalar chains): with four warps per scheduler a single
+        // 32-long FADD chain would stall
+        const float2 nk = make_float2(-K, -K);
+        float2 a1[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, a2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            const float d = v[i] - K;
-            a1[i & 3] += d;
-            a2[i & 3] = fmaf(d, d, a2[i & 3]);
+        for (int i = 0; i < 32; i += 2) {
+            const float2 d = add2(make_float2(v[i], v[i + 1]), nk);
+            a1[(i >> 1) & 1] = add2(a1[(i >> 1) & 1], d);
+            a2[(i >> 1) & 1] = fma2(d, d, a2[(i >> 1) & 1]);
         }
-        S1 += (a1[0] + a1[1]) + (a1[2] + a1[3]);
-        S2 += (a2[0] + a2[1]) + (a2[2] + a2[3]);
+        S1 += (a1[0].x + a1[0].y) + (a1[1].x + a1[1].y);
+        S2 += (a2[0].x + a2[0].y) + (a2[1].x + a2[1].y);
     } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i)
@@ -153,14 +157,19 @@ __device__ __forceinline__ void pf_bias_stats(float (&v)[32], const float* sb, i
 __device__ __forceinline__ void pf_normalize(float (&v)[32], const float* sg, const float* sbt, bool has_ln, float rstd,
                                              float nmr, int nv) {
     if (has_ln) {
+        const float2 r2 = make_float2(rstd, rstd), n2 = make_float2(nmr, nmr);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             const float4 g = *reinterpret_cast<const float4*>(sg + 4 * c);
             const float4 b = *reinterpret_cast<const float4*>(sbt + 4 * c);
-            v[4 * c] = fmaxf(fmaf(fmaf(v[4 * c], rstd, nmr), g.x, b.x), 0.0f);
-            v[4 * c + 1] = fmaxf(fmaf(fmaf(v[4 * c + 1], rstd, nmr), g.y, b.y), 0.0f);
-            v[4 * c + 2] = fmaxf(fmaf(fmaf(v[4 * c + 2], rstd, nmr), g.z, b.z), 0.0f);
-            v[4 * c + 3] = fmaxf(fmaf(fmaf(v[4 * c + 3], rstd, nmr), g.w, b.w), 0.0f);
+            const float2 y0 = fma2(fma2(make_float2(v[4 * c], v[4 * c + 1]), r2, n2), make_float2(g.x, g.y),
+                                   make_float2(b.x, b.y));
+            const float2 y1 = fma2(fma2(make_float2(v[4 * c + 2], v[4 * c + 3]), r2, n2), make_float2(g.z, g.w),
+                                   make_float2(b.z, b.w));
+            v[4 * c] = fmaxf(y0.x, 0.0f);
+            v[4 * c + 1] = fmaxf(y0.y, 0.0f);
+            v[4 * c + 2] = fmaxf(y1.x, 0.0f);
+            v[4 * c + 3] = fmaxf(y1.y, 0.0f);
         }
     } else {
 #pragma unroll

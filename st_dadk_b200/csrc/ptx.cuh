@@ -190,6 +190,24 @@ __device__ __forceinline__ uint32_t swz_off(uint32_t row, uint32_t chunk) {
 __device__ __forceinline__ float to_tf32(float x) {
     return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
+// Packed FP32 (two lanes per instruction, FFMA2 / FADD2 on sm_100): same rounding as the scalar forms, half the
+// issue slots.  ptxas pairs the registers without moves when the operands come from adjacent array elements.
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "add.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t saddr, float a, float b, float c, float d) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
