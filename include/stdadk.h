@@ -194,7 +194,7 @@ int stdadk_version(void);
 const char* stdadk_last_error(void);
 /* sizeof() of the argument structs, for bindings to verify their layout:
  * 0 basis, 1 points, 2 layer, 3 dropout, 4 head, 5 fwd_args, 6 bwd_args, 7 wgrad_args, 8 knotgrad_args, 9 adamw_args,
- * 10 pack_desc, 11 sparse_args, 12 predict_args, 13 train_fwd_args */
+ * 10 pack_desc, 11 sparse_args, 12 predict_args, 13 train_fwd_args, 14 peer_allreduce_args */
 size_t stdadk_sizeof(int which);
 
 size_t stdadk_image_floats(int64_t rows, int64_t cols);
@@ -283,6 +283,25 @@ size_t stdadk_sqnorm_ws_floats(void);
 int stdadk_grad_sqnorm(const float* g, int64_t n, int n_groups, const int64_t* group_end, float* sqnorms,
                        float* workspace, void* stream);
 int stdadk_adamw_ema_step(const stdadk_adamw_args* a, void* stream);
+
+/* Data-parallel training (one sum of the flat gradient per step; upstream itself is single
+ * device): one-shot all-reduce over peer memory.  src[r] / flags[r] are rank r's gradient buffer and flag block as
+ * mapped into THIS process (CUDA VMM / symmetric memory, own rank included); flags[r] points at 2*STDADK_MAX_PEERS
+ * zero-initialised uint32.  out[i] = sum_r src[r][i] added in rank order (identical bits on every rank).  n must be
+ * a multiple of 4, all pointers 16-byte aligned.  The kernel returns only after every peer has finished reading
+ * src[rank], so the caller may overwrite it next.  Barrier ids derive from *step_count (equal on all ranks, must
+ * grow by one between calls -- the AdamW step counter).  ticket: one zero-initialised local uint32. */
+#define STDADK_MAX_PEERS 8
+typedef struct {
+    int32_t world, rank;
+    const float* src[STDADK_MAX_PEERS];
+    uint32_t* flags[STDADK_MAX_PEERS];
+    float* out;
+    int64_t n;
+    const int32_t* step_count;
+    uint32_t* ticket;
+} stdadk_peer_allreduce_args;
+int stdadk_peer_allreduce(const stdadk_peer_allreduce_args* a, void* stream);
 
 #ifdef __cplusplus
 }

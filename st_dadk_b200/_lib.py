@@ -94,6 +94,14 @@ class PredictArgs(C.Structure):
                 ("layers", Layer * MAX_HIDDEN), ("head", C.POINTER(Head))]
 
 
+MAX_PEERS = 8
+
+
+class PeerAllreduceArgs(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("src", fp * MAX_PEERS), ("flags", fp * MAX_PEERS),
+                ("out", fp), ("n", C.c_int64), ("step_count", fp), ("ticket", fp)]
+
+
 class TrainFwdArgs(C.Structure):
     _fields_ = [("net", PredictArgs), ("drop", Dropout), ("h_img", fp * MAX_HIDDEN), ("x_img", fp * MAX_HIDDEN),
                 ("stats", fp * MAX_HIDDEN)]
@@ -115,6 +123,7 @@ _PROTOS = {
     "stdadk_predict_supported": (C.c_int, [C.POINTER(PredictArgs)]),
     "stdadk_predict": (C.c_int, [C.POINTER(PredictArgs), fp]),
     "stdadk_train_fwd": (C.c_int, [C.POINTER(TrainFwdArgs), fp]),
+    "stdadk_peer_allreduce": (C.c_int, [C.POINTER(PeerAllreduceArgs), fp]),
     "stdadk_layer_fwd": (C.c_int, [C.POINTER(FwdArgs), fp]),
     "stdadk_layer_bwd": (C.c_int, [C.POINTER(BwdArgs), fp]),
     "stdadk_wgrad": (C.c_int, [C.POINTER(WgradArgs), fp]),
@@ -144,7 +153,7 @@ def lib():
             fn.restype = res
             fn.argtypes = args
         structs = [Basis, Points, Layer, Dropout, Head, FwdArgs, BwdArgs, WgradArgs, KnotGradArgs, AdamWArgs, PackDesc, SparseArgs,
-                   PredictArgs, TrainFwdArgs]
+                   PredictArgs, TrainFwdArgs, PeerAllreduceArgs]
         for i, st in enumerate(structs):
             if L.stdadk_sizeof(i) != C.sizeof(st):
                 raise RuntimeError(f"libstdadk ABI mismatch: {st.__name__} is {C.sizeof(st)} B in the binding, "

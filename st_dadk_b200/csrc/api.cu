@@ -163,6 +163,7 @@ size_t stdadk_sizeof(int which) {
         case 11: return sizeof(stdadk_sparse_args);
         case 12: return sizeof(stdadk_predict_args);
         case 13: return sizeof(stdadk_train_fwd_args);
+        case 14: return sizeof(stdadk_peer_allreduce_args);
         default: return 0;
     }
 }
@@ -657,6 +658,36 @@ int stdadk_sparse_l1_wgrad(const stdadk_sparse_args* a, void* stream) {
 }
 
 __global__ void step_inc_kernel(int* c) { *c += 1; }
+
+int stdadk_peer_allreduce(const stdadk_peer_allreduce_args* a, void* stream) {
+    if (int r = check_device()) return r;
+    REQUIRE(a && a->out && a->step_count && a->ticket, "peer_allreduce: NULL argument");
+    REQUIRE(a->world >= 2 && a->world <= PEER_MAX && a->rank >= 0 && a->rank < a->world,
+            "peer_allreduce: world=%d rank=%d outside [2,%d]", a->world, a->rank, PEER_MAX);
+    REQUIRE(a->n > 0 && a->n % 4 == 0, "peer_allreduce: n=%lld must be a positive multiple of 4", (long long)a->n);
+    static_assert(PEER_MAX == STDADK_MAX_PEERS, "peer limits differ");
+    PeerK K{};
+    for (int r = 0; r < a->world; ++r) {
+        REQUIRE(a->src[r] && a->flags[r], "peer_allreduce: rank %d buffer / flags not mapped", r);
+        REQUIRE((reinterpret_cast<uintptr_t>(a->src[r]) & 15) == 0, "peer_allreduce: buffers must be 16-byte aligned");
+        K.src[r] = a->src[r];
+        K.flags[r] = a->flags[r];
+    }
+    REQUIRE((reinterpret_cast<uintptr_t>(a->out) & 15) == 0, "peer_allreduce: out must be 16-byte aligned");
+    K.out = a->out;
+    K.n4 = a->n / 4;
+    K.step_count = a->step_count;
+    K.ticket = a->ticket;
+    K.rank = a->rank;
+    K.world = a->world;
+    // every block of every rank waits on flags: keep the grid small enough to be co-resident (it always is: <= 148)
+    long long blocks = (K.n4 + PEER_THREADS * 4 - 1) / (PEER_THREADS * 4);
+    const int sms = g_sm_count > 0 ? g_sm_count : 148;
+    if (blocks > sms) blocks = sms;
+    if (blocks < 1) blocks = 1;
+    peer_allreduce_kernel<<<(int)blocks, PEER_THREADS, 0, (cudaStream_t)stream>>>(K);
+    return check_launch("peer_allreduce");
+}
 
 int stdadk_adamw_ema_step(const stdadk_adamw_args* a, void* stream) {
     if (int r = check_device()) return r;

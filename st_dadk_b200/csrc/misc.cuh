@@ -201,6 +201,72 @@ __global__ void sqnorm_kernel(const float* __restrict__ g, long long n, GroupsP 
     }
 }
 
+// ---------------------------------------------------------------- data-parallel gradient exchange over peer memory
+// One-shot all-reduce of the flat gradient between the GPUs of one box (NVLink / NVSwitch), replacing the NCCL call
+// of a data-parallel step: every rank's gradient buffer lives in symmetric memory that all ranks have mapped, so each
+// rank simply reads all W buffers and adds them in RANK ORDER (the result is bitwise identical on every rank) into a
+// local output.  Two flag barriers through the same mappings: "ready" (my gradient is complete, you may read it) and
+// "done" (I have finished reading yours; the kernel does not end before every peer has said so, so the next kernel may
+// overwrite the buffer).  Barrier ids come from the device-side step counter (2s+1, 2s+2: monotonic, graph-replay
+// safe).  Waits are bounded: a missing peer traps after ~2 s instead of hanging the GPU.
+constexpr int PEER_MAX = 8;
+struct PeerK {
+    const float* src[PEER_MAX];       // rank r's gradient buffer as mapped in this process (own buffer at [rank])
+    unsigned int* flags[PEER_MAX];    // rank r's flag block: [0, PEER_MAX) ready, [PEER_MAX, 2 PEER_MAX) done
+    float* out;
+    long long n4;                     // float4 elements
+    const int* step_count;
+    unsigned int* ticket;             // local, zero-initialised
+    int rank, world;
+};
+__device__ __forceinline__ void peer_signal(unsigned int* p, unsigned int v) {
+    __threadfence_system();
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void peer_wait(const unsigned int* p, unsigned int v) {
+    unsigned int cur;
+    unsigned long long t0 = 0, now;
+    for (;;) {
+        asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(cur) : "l"(p) : "memory");
+        if ((int)(cur - v) >= 0) break;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 2000000000ull) __trap();
+        __nanosleep(100);
+    }
+    __threadfence_system();
+}
+constexpr int PEER_THREADS = 256;
+__global__ void __launch_bounds__(PEER_THREADS) peer_allreduce_kernel(const __grid_constant__ PeerK P) {
+    const unsigned int id = 2u * (unsigned int)(*P.step_count) + 1u;
+    __shared__ bool last;
+    if (blockIdx.x == 0 && threadIdx.x < P.world) peer_signal(&P.flags[threadIdx.x][P.rank], id);
+    if (threadIdx.x < P.world) peer_wait(&P.flags[P.rank][threadIdx.x], id);
+    __syncthreads();
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < P.n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < PEER_MAX; ++r)
+            if (r < P.world) {
+                const float4 v = __ldcg(reinterpret_cast<const float4*>(P.src[r]) + i);
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+        reinterpret_cast<float4*>(P.out)[i] = acc;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(P.ticket, 1u);
+        last = (t == gridDim.x - 1);
+        if (last) *P.ticket = 0u;
+    }
+    __syncthreads();
+    if (last && threadIdx.x < P.world) {
+        peer_signal(&P.flags[threadIdx.x][PEER_MAX + P.rank], id + 1u);
+        peer_wait(&P.flags[P.rank][PEER_MAX + threadIdx.x], id + 1u);
+    }
+}
+
 struct AdamK {
     float* p;
     const float* g;

@@ -217,6 +217,11 @@ def adamw_ema_step(p, g, m, v, shadow, group_end: Sequence[int], hyper: torch.Te
     L.check(L.lib().stdadk_adamw_ema_step(C.byref(a), _stream()), "adamw_ema_step")
 
 
+def peer_allreduce(args: L.PeerAllreduceArgs):
+    """One-shot sum of the ranks' gradient buffers over peer memory (see st_dadk_b200/peer.py)."""
+    L.check(L.lib().stdadk_peer_allreduce(C.byref(args), _stream()), "peer_allreduce")
+
+
 def make_sparse_args(pts: L.Points, knots4, basis_fn: str, n_out: int, p_cov: int, sides, offsets, thetaps, w1t=None,
                      zs=None, dz_img=None, dw1t=None) -> L.SparseArgs:
     a = L.SparseArgs()

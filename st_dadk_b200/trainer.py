@@ -47,7 +47,7 @@ class FlatState:
     is coalesced; the Parameter seen by PyTorch is the `.t()` view with the upstream (out, in) shape.
     """
 
-    def __init__(self, model, device):
+    def __init__(self, model, device, alloc_g=None):
         self.model = model
         blocks = model.hidden_blocks()
         entries = []   # (param, stored_shape, transposed)
@@ -77,7 +77,9 @@ class FlatState:
         mk = lambda extra=0: torch.zeros(n + extra, dtype=torch.float32, device=device)
         # g carries, behind the parameter gradients, the scratch head gradient of the delta parameterisation and ONE
         # more float: the step's loss accumulator, so that a data-parallel step needs a single all-reduce
-        self.p, self.g, self.m, self.v, self.shadow = mk(), mk(self.n_scratch + 1), mk(), mk(), mk()
+        self.p, self.m, self.v, self.shadow = mk(), mk(), mk(), mk()
+        # (a data-parallel trainer places g in symmetric memory so that peers can read it: alloc_g)
+        self.g = mk(self.n_scratch + 1) if alloc_g is None else alloc_g(n + self.n_scratch + 1)
         self.n_exchange = n + self.n_scratch + 1
         self.loss_slot = self.g[n + self.n_scratch:n + self.n_scratch + 1]
         self.views: Dict[int, torch.Tensor] = {}
@@ -145,7 +147,27 @@ class Trainer:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("st_dadk_b200.Trainer runs on CUDA (sm_100) only; there is no CPU training path")
-        self.flat = FlatState(self.model, self.device)
+        # Data parallel over NCCL ranks of one box, optional (STDADK_PEER_ALLREDUCE=1): the gradient lives in symmetric
+        # memory and the per-step exchange is one peer-memory kernel inside the step graph (st_dadk_b200/peer.py).
+        # Results equal the NCCL path (replicas bit-identical, |dp| 2e-7), but on 2 GPUs it measured 0.206 ms per step
+        # against 0.193 ms with NCCL's low-latency all-reduce between two graphs, so NCCL stays the default.
+        self._peer = None
+        if _dist_on() and dist.get_backend() == "nccl" and os.environ.get("STDADK_PEER_ALLREDUCE", "0") == "1":
+            ok = torch.ones(1, device=self.device)
+            try:
+                from .peer import PeerExchange
+                peer = PeerExchange(self.device)
+                self.flat = FlatState(self.model, self.device, alloc_g=peer.alloc)
+                self._peer = peer
+            except Exception as e:       # noqa: BLE001 -- any set-up failure falls back to NCCL, loudly
+                warnings.warn(f"peer-memory gradient exchange unavailable ({e!r}); using the NCCL all-reduce")
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)       # all ranks must agree on the exchange path
+            if float(ok.item()) == 0.0:
+                self._peer = None
+                self.flat = FlatState(self.model, self.device)
+        else:
+            self.flat = FlatState(self.model, self.device)
         m = self.model
         self.learnable = bool(m.spatial_basis.learnable)
         self.q = m.output_dim
@@ -344,7 +366,10 @@ class Trainer:
     def _step_exchange(self):
         """The one data-parallel exchange of a step: sum of the flat gradient (and of the loss) over ranks."""
         if self.world > 1:
-            dist.all_reduce(self.flat.g[:self.flat.n_exchange])     # gradients + loss accumulator in one call
+            if self._peer is not None:
+                self._peer.allreduce(self.step_count)                # one kernel over NVLink peer memory
+            else:
+                dist.all_reduce(self.flat.g[:self.flat.n_exchange])  # gradients + loss accumulator in one call
 
     def _step_update(self):
         """Replicated tail: parameter-only penalties, damping, gradient norm, fused clip + AdamW + EMA."""
@@ -398,11 +423,12 @@ class Trainer:
                     self._step_body(table, self._stage_idx, 0, n_rows, global_rows, key_offset)
                     torch.cuda.current_stream().synchronize()
                     mode = dict(capture_error_mode="thread_local")
-                    # Data parallel: the collective stays between two graphs.  Capturing the NCCL all-reduce as a node
+                    # Data parallel over NCCL: the collective stays between two graphs (the peer-memory exchange is a
+                    # plain kernel and is captured with the rest).  Capturing the NCCL all-reduce as a node
                     # of one graph (STDADK_DDP_ONE_GRAPH=1) was measured: 0.2412 vs 0.2427 ms per step on 2 GPUs -- no
                     # gain -- and the process then hung in teardown, so it is not the default.
-                    one_graph = self.world == 1 or (dist.get_backend() == "nccl"
-                                                    and os.environ.get("STDADK_DDP_ONE_GRAPH", "0") == "1")
+                    one_graph = self.world == 1 or self._peer is not None or (
+                        dist.get_backend() == "nccl" and os.environ.get("STDADK_DDP_ONE_GRAPH", "0") == "1")
                     if one_graph:
                         g1 = torch.cuda.CUDAGraph()
                         with torch.cuda.graph(g1, **mode):

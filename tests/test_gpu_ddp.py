@@ -67,3 +67,19 @@ def test_two_rank_step_equals_single_rank(graph):
     assert np.array_equal(p0, p1) and np.array_equal(s0, s1) and l0 == l1        # replicas stay bit-identical
     assert np.max(np.abs(p0 - ps)) < 2e-5 * max(1.0, np.abs(ps).max())           # == single rank on the full batch
     assert np.allclose(l0, ls, rtol=1e-5)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs of one box (NVLink peer memory)")
+def test_peer_memory_exchange_matches_nccl_two_gpus():
+    """tools/check_peer_allreduce.py under torchrun on 2 GPUs: gradient exchange through symmetric memory
+    (stdadk_peer_allreduce, inside the step graph) vs the NCCL all-reduce -- replicas bit-identical, same weights."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port),
+                        os.path.join(root, "tools", "check_peer_allreduce.py")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -1,0 +1,53 @@
+"""torchrun --nproc-per-node N tools/check_peer_allreduce.py: peer-memory gradient exchange vs the NCCL all-reduce on
+the same data -- replicas bit-identical across ranks, both paths agree, per-step time of each."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch, torch.distributed as dist
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+from stnf.models import STInterpMLP
+from stnf.dataio import ObservationTable
+from st_dadk_b200.trainer import Trainer, shard_rows
+rng = np.random.default_rng(0)
+n, B = 48 * 4096 * world, 4096 * world
+c, t = rng.random((n, 2)).astype(np.float32), rng.random(n).astype(np.float32)
+y = (np.sin(5 * c[:, 0]) + t).astype(np.float32)
+table = ObservationTable(torch.from_numpy(c), torch.from_numpy(t), torch.from_numpy(y)).to(dev)
+perm = torch.randperm(n, generator=torch.Generator().manual_seed(1)).to(dev)
+cfg = dict(lr=1e-2, weight_decay=5e-4, grad_clip=5.0, regression_type="mean")
+res = {}
+for mode in ("0", "1"):
+    os.environ["STDADK_PEER_ALLREDUCE"] = mode
+    torch.manual_seed(3)
+    tr = Trainer(STInterpMLP(dropout=0.1), cfg, dev, batches_per_epoch=20, use_cuda_graph=True)
+    assert (tr._peer is not None) == (mode == "1"), "exchange path not as requested"
+    lo, hi = shard_rows(B, rank, world)
+    losses = []
+    for s in range(8):
+        tr.train_step(table, perm, s * B + lo, hi - lo, B)
+        losses.append(tr.pop_loss_sum())
+    torch.cuda.synchronize()
+    p = tr.flat.p.clone()
+    gathered = [torch.empty_like(p) for _ in range(world)]
+    dist.all_gather(gathered, p)
+    same = all(torch.equal(gathered[0], g) for g in gathered)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dist.barrier(); torch.cuda.synchronize()
+    e0.record()
+    for s in range(50):
+        tr.train_step(table, perm, ((s + 8) % 40) * B + lo, hi - lo, B)
+    e1.record(); torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / 50], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    res[mode] = (p, losses, same, float(ms.item()))
+    if rank == 0:
+        print(f"peer={mode}: replicas identical={same}  {float(ms.item()):.4f} ms/step  losses {losses[:3]}", flush=True)
+if rank == 0:
+    d = float((res["0"][0] - res["1"][0]).abs().mean())
+    print("mean |p_nccl - p_peer| =", d, " loss rel diff", max(abs(a - b) / abs(a) for a, b in zip(res["0"][1], res["1"][1])), flush=True)
+    assert res["0"][2] and res["1"][2] and d < 2e-4
+    print("CHECK OK", flush=True)
+dist.barrier()
+dist.destroy_process_group()
