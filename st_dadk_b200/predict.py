@@ -30,6 +30,9 @@ class Predictor:
         self.launches = 0
         self._field_key = None
         self._field_pts = None
+        self.d2h_chunk_rows = 1 << 18      # field predictions delivered to the host: rows per overlapped D2H piece
+        self._copy_stream = None
+        self.host_copy_done = None
 
     def _prepare(self):
         m = self.model
@@ -84,9 +87,14 @@ class Predictor:
         return out, (begin, end)
 
     @torch.no_grad()
-    def space_time_field(self, coords: torch.Tensor, T: int, rank: int = 0, world: int = 1):
+    def space_time_field(self, coords: torch.Tensor, T: int, rank: int = 0, world: int = 1,
+                         host_out: Optional[torch.Tensor] = None):
         """All T time steps at S sites (the predictions.npz field of upstream, T x S row-major: point n = (t, s)),
-        without materialising repeated coordinates: rows gather site n % S through an index."""
+        without materialising repeated coordinates: rows gather site n % S through an index.
+
+        `host_out` (pinned (n_local, Q) float32): the field is produced in a few chunks and each chunk is copied to the
+        host on a second stream while the next one is computed; the caller synchronises (`torch.cuda.synchronize()` or
+        `Predictor.host_copy_done.synchronize()`) before reading it."""
         self._prepare()
         S = coords.shape[0]
         n = S * T
@@ -111,13 +119,37 @@ class Predictor:
             self._field_key, self._field_pts = key, (cc, tt, order)
         cc, tt, order = self._field_pts
         out = torch.empty(end - begin, self.model.output_dim, device=dev)
-        self._run(lambda b, r: ops.make_points(cc, tt, None, row_begin=b - begin, n_rows=r), begin, end, out)
-        if order is not None:
-            q = out.shape[1]
-            res = torch.empty_like(out)
-            res.view(-1, S, q).index_copy_(1, order, out.view(-1, S, q))
-            out = res
-        return out, (begin, end)
+        q = out.shape[1]
+        res = torch.empty_like(out) if order is not None else out
+        n_local = end - begin
+        if host_out is None:
+            pieces = [(0, n_local)]
+        else:
+            if host_out.shape != out.shape or not host_out.is_pinned():
+                raise RuntimeError("space_time_field: host_out must be a pinned float32 tensor of shape (n_local, Q)")
+            step = max(1, self.d2h_chunk_rows)
+            if order is not None:
+                step = max(S, step // S * S)            # whole time steps, so that a chunk can be put in site order
+            pieces = [(b, min(step, n_local - b)) for b in range(0, n_local, step)]
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=dev)
+                self.host_copy_done = torch.cuda.Event()
+        main = torch.cuda.current_stream()
+        for b0, r0 in pieces:
+            self._run(lambda b, r: ops.make_points(cc, tt, None, row_begin=b - begin, n_rows=r), begin + b0,
+                      begin + b0 + r0, out[b0:b0 + r0])
+            if order is not None:
+                res[b0:b0 + r0].view(-1, S, q).index_copy_(1, order, out[b0:b0 + r0].view(-1, S, q))
+            if host_out is not None:
+                ready = torch.cuda.Event()
+                ready.record(main)
+                with torch.cuda.stream(self._copy_stream):
+                    self._copy_stream.wait_event(ready)
+                    host_out[b0:b0 + r0].copy_(res[b0:b0 + r0], non_blocking=True)
+        if host_out is not None:
+            self.host_copy_done.record(self._copy_stream)
+            res.record_stream(self._copy_stream)
+        return res, (begin, end)
 
     @torch.no_grad()
     def profile_layers(self, nx: int, ny: int, nt: int, repeats: int = 3):

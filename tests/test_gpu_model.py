@@ -215,6 +215,12 @@ def test_space_time_field_equals_explicit_points_any_sharding():
         assert torch.equal(torch.cat(parts), field)
     again, _ = pr.space_time_field(sites, Tn)      # cached expansion
     assert torch.equal(again, field)
+    # delivered to pinned host memory in pieces, each copy overlapping the next piece's kernel
+    hout = torch.empty(S * Tn, 3).pin_memory()
+    pr.d2h_chunk_rows = 2 * S + 5                  # -> pieces of two whole time steps
+    piecewise, _ = pr.space_time_field(sites, Tn, host_out=hout)
+    pr.host_copy_done.synchronize()
+    assert torch.equal(piecewise, field) and torch.equal(hout, field.cpu())
 
 
 def test_step_tail_bookkeeping_gradient_zeroing_and_loss_sum():
