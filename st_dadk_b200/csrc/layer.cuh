@@ -920,31 +920,46 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_32b(uint32_t saddr, uint32_t
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (1ull << 61);
 }
-// Restage `n_chunks` half-slabs (64 rows x 128 B each, image swizzle) into the MN-major SMEM form.
+// Restage half-slabs (64 rows x 128 B each, image swizzle) of the dz tile and (optionally) of the A tile into the
+// MN-major SMEM form.  ALL loads of the half tile are issued before the first store (8 + 16 16-byte loads per thread
+// at 256 workers): the restage is bound by global-load latency, and with four loads in flight per thread it ran at
+// ~16 GB/s per SM -- 26 us per row tile, which made wgrad the largest kernel of a large-batch step.
 template <int NW>
-__device__ __forceinline__ void restage_half_slabs(const float* img_tile, int slab0, int n_chunks, int half,
-                                                   uint32_t sdst, int tid) {
-    const int units = n_chunks * 512;  // 16-byte units
-    for (int u0 = tid; u0 < units; u0 += NW * 4) {
-        float4 v[4];
+__device__ __forceinline__ void restage_half_tiles(const float* dz_tile, int mslab0, int m_chunks, const float* a_tile,
+                                                   int nslab0, int n_chunks, int half, uint32_t sa, uint32_t sb, int tid) {
+    constexpr int BD = 2048 / NW, BA = 4096 / NW;      // dz: <= 4 chunks, A: <= 8 chunks of 512 units
+    static_assert(NW * BD == 2048 && NW * BA == 4096, "worker count must divide the half-tile unit counts");
+    const int units_d = m_chunks * 512, units_a = a_tile ? n_chunks * 512 : 0;
+    const size_t hoff = (size_t)half * WG_HALF_ROWS * SLAB_K;
+    float4 vd[BD], va[BA];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            int u = u0 + j * NW;
-            if (u < units) {
-                int c = u >> 9, w = u & 511;
-                v[j] = __ldg(reinterpret_cast<const float4*>(img_tile + (size_t)(slab0 + c) * SLAB_FLOATS +
-                                                             half * WG_HALF_ROWS * SLAB_K) + w);
-            }
+    for (int j = 0; j < BD; ++j) {
+        const int u = tid + j * NW;
+        if (u < units_d)
+            vd[j] = __ldg(reinterpret_cast<const float4*>(dz_tile + (size_t)(mslab0 + (u >> 9)) * SLAB_FLOATS + hoff) + (u & 511));
+    }
+#pragma unroll
+    for (int j = 0; j < BA; ++j) {
+        const int u = tid + j * NW;
+        if (u < units_a)
+            va[j] = __ldg(reinterpret_cast<const float4*>(a_tile + (size_t)(nslab0 + (u >> 9)) * SLAB_FLOATS + hoff) + (u & 511));
+    }
+#pragma unroll
+    for (int j = 0; j < BD; ++j) {
+        const int u = tid + j * NW;
+        if (u < units_d) {
+            const int c = u >> 9, w = u & 511;
+            const uint32_t r = (uint32_t)(w >> 3), lc = (uint32_t)(w & 7) ^ (r & 7u);
+            st_shared_v4(sa + c * WG_CHUNK_BYTES + swz32_off(r, lc), vd[j].x, vd[j].y, vd[j].z, vd[j].w);
         }
+    }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            int u = u0 + j * NW;
-            if (u < units) {
-                int c = u >> 9, w = u & 511;
-                uint32_t r = (uint32_t)(w >> 3), pc = (uint32_t)(w & 7);
-                uint32_t lc = pc ^ (r & 7u);
-                st_shared_v4(sdst + c * WG_CHUNK_BYTES + swz32_off(r, lc), v[j].x, v[j].y, v[j].z, v[j].w);
-            }
+    for (int j = 0; j < BA; ++j) {
+        const int u = tid + j * NW;
+        if (u < units_a) {
+            const int c = u >> 9, w = u & 511;
+            const uint32_t r = (uint32_t)(w >> 3), lc = (uint32_t)(w & 7) ^ (r & 7u);
+            st_shared_v4(sb + c * WG_CHUNK_BYTES + swz32_off(r, lc), va[j].x, va[j].y, va[j].z, va[j].w);
         }
     }
 }
@@ -1041,7 +1056,9 @@ __global__ void __launch_bounds__(n_threads(CG), 1) wgrad_kernel(const __grid_co
                     if (it > 0) mbar_wait(&empty[stage], (it - 1) & 1);
                     uint32_t sa = smem_u32(stage_base + stage * WG_STAGE_BYTES);
                     uint32_t sb = sa + WG_A_BYTES;
-                    restage_half_slabs<NW>(P.dz_img + (size_t)rt * P.dz_slabs * SLAB_FLOATS, mi * 4, m_chunks, half, sa, tid);
+                    restage_half_tiles<NW>(P.dz_img + (size_t)rt * P.dz_slabs * SLAB_FLOATS, mi * 4, m_chunks,
+                                           BASIS ? nullptr : P.a_img + (size_t)rt * P.a_slabs * SLAB_FLOATS,
+                                           ni * P.nt_slabs, n_chunks, half, sa, sb, tid);
                     if (BASIS) {
                         for (int c = par; c < n_chunks; c += NW / 64) {
                             const int slab = ni * P.nt_slabs + c;
@@ -1052,9 +1069,6 @@ __global__ void __launch_bounds__(n_threads(CG), 1) wgrad_kernel(const __grid_co
                                              v.z, v.w);
                             }
                         }
-                    } else {
-                        restage_half_slabs<NW>(P.a_img + (size_t)rt * P.a_slabs * SLAB_FLOATS, ni * P.nt_slabs, n_chunks,
-                                           half, sb, tid);
                     }
                     fence_proxy_async_smem();
                     mbar_arrive(&full[stage]);
