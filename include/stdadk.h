@@ -111,6 +111,10 @@ typedef struct {
     const stdadk_head* head; /* non-NULL on the last hidden block: fuses head (+ loss) */
     const float* addend;     /* optional (rows x n_out) FP32 row-major term added to A W^T + b before LayerNorm: the
                                 support-walked spatial part of block 1 in the large-knot regime (stdadk_sparse_l1_fwd) */
+    float* feat_img;         /* optional out, block 1 only: image (rows x n_in) of the generated operand [X|phi|psi] (TF32).
+                                Large batches pay the basis evaluation three times per step (forward, the backward's
+                                recompute GEMM, wgrad); with this image the other two read it back instead -- pass it as
+                                a_img (and basis = NULL) to stdadk_layer_bwd / stdadk_wgrad of block 1. */
     float* x_img;            /* optional out: image (rows x n_out) of the pre-LayerNorm value x = A W^T + b (+ addend),
                                 FP32.  A backward that receives it skips the recomputation GEMM -- worth its 1 KB/row
                                 when the batch is a single wave of tiles and latency, not bandwidth, is the limit. */

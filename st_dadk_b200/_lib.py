@@ -45,7 +45,7 @@ class Head(C.Structure):
 
 class FwdArgs(C.Structure):
     _fields_ = [("basis", C.POINTER(Basis)), ("pts", Points), ("a_img", fp), ("layer", Layer), ("drop", Dropout),
-                ("out_img", fp), ("stats", fp), ("head", C.POINTER(Head)), ("addend", fp), ("x_img", fp)]
+                ("out_img", fp), ("stats", fp), ("head", C.POINTER(Head)), ("addend", fp), ("feat_img", fp), ("x_img", fp)]
 
 
 class BwdArgs(C.Structure):

@@ -280,6 +280,7 @@ int stdadk_layer_fwd(const stdadk_fwd_args* a, void* stream) {
     K.a_img = a->a_img;
     K.addend = a->addend;
     K.x_img = a->x_img;
+    K.feat_img = a->basis ? a->feat_img : nullptr;
     K.out_img = a->out_img;
     K.stats = a->stats;
     K.has_head = a->head ? 1 : 0;

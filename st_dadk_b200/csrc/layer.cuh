@@ -58,6 +58,7 @@ struct FwdK {
     const float* addend;
     float* out_img;
     float* x_img;
+    float* feat_img;
     float* stats;
     int has_head, k_slabs, n_pad, tmem_cols;
     unsigned int thresh16;
@@ -140,11 +141,13 @@ __device__ __forceinline__ float4 feature_chunk(const BasisP& B, const float4* s
 // Generate chunks [c_begin, c_end) of one 128-row x 32-feature operand slab (this thread = row r) into swizzled SMEM.
 __device__ __forceinline__ void gen_basis_slab(const BasisP& B, const float4* sk, const float2* st, int slab,
                                                float x, float y, float t, const float* xrow, uint32_t slab_saddr,
-                                               uint32_t r, int c_begin = 0, int c_end = 8) {
+                                               uint32_t r, int c_begin = 0, int c_end = 8, float* gslab = nullptr) {
 #pragma unroll 1
     for (int c = c_begin; c < c_end; ++c) {
         float4 v = feature_chunk(B, sk, st, slab * SLAB_K + c * 4, x, y, t, xrow);
         st_shared_v4(slab_saddr + swz_off(r, c), v.x, v.y, v.z, v.w);
+        if (gslab)      // same slab, same swizzle, in the global operand image (read back by the backward / wgrad)
+            *reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(gslab) + swz_off(r, c)) = v;
     }
 }
 
@@ -386,7 +389,8 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
                 int stage = s % NSTAGE, it = s / NSTAGE;
                 if (it > 0) mbar_wait(&empty[stage], (it - 1) & 1);
                 gen_basis_slab(P.basis, sk, st, s, x, y, t, xrow, smem_u32(sA + (size_t)stage * SLAB_FLOATS),
-                               (uint32_t)row, cg * (8 / CG), (cg + 1) * (8 / CG));
+                               (uint32_t)row, cg * (8 / CG), (cg + 1) * (8 / CG),
+                               (P.feat_img && tile_valid) ? P.feat_img + ((size_t)tile * P.k_slabs + s) * SLAB_FLOATS : nullptr);
                 fence_proxy_async_smem();
                 mbar_arrive(&full[stage]);
             }

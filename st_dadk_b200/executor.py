@@ -59,8 +59,11 @@ class LossSpec:
 
 
 class _Workspace:
-    def __init__(self, spec: NetSpec, n_rows: int, device, sparse: bool = False, save_x: bool = False):
+    def __init__(self, spec: NetSpec, n_rows: int, device, sparse: bool = False, save_x: bool = False,
+                 save_feat: bool = False):
         self.n_rows = n_rows
+        # block-1 operand [X|phi|psi] as an image, kept for LARGE batches (see Executor.SAVE_FEAT_MIN_ROWS)
+        self.feat = ops.new_image(n_rows, spec.weights[0].shape[1], device) if save_feat else None
         self.zs = torch.empty(n_rows, spec.weights[0].shape[0], dtype=torch.float32, device=device) if sparse else None
         self.h = [ops.new_image(n_rows, w.shape[0], device) for w in spec.weights[:-1]]
         self.dz = [ops.new_image(n_rows, w.shape[0], device) for w in spec.weights]
@@ -83,6 +86,11 @@ class Executor:
     # single wave of 128-row tiles, bound by per-kernel latency, not by HBM.  Larger batches recompute instead.
     # (The N x K basis matrix is never stored either way; wgrad regenerates it.)
     SAVE_X_MAX_ROWS = 148 * 2 * 128
+    # Beyond that, the step is throughput-bound and evaluating the basis three times (forward, the backward's recompute
+    # GEMM of block 1, wgrad of block 1) is its largest single cost (batch 65,536: backward 147 us and wgrad 139 us
+    # for block 1 against 102 / 47 us for block 2).  The forward then also writes its generated operand (1.25 KB/row)
+    # and the other two read it back through TMA like any activation image.
+    SAVE_FEAT_MIN_ROWS = SAVE_X_MAX_ROWS + 1
 
     def __init__(self, spec: NetSpec, force_sparse: bool = False):
         self.spec = spec
@@ -199,7 +207,8 @@ class Executor:
             if len(self._ws) >= self.MAX_WORKSPACES:
                 self._ws.pop(next(iter(self._ws)))
             ws = self._ws[n_rows] = _Workspace(self.spec, n_rows, self.device, self.sparse,
-                                               save_x=n_rows <= self.SAVE_X_MAX_ROWS)
+                                               save_x=n_rows <= self.SAVE_X_MAX_ROWS,
+                                               save_feat=(not self.sparse and n_rows >= self.SAVE_FEAT_MIN_ROWS))
         return ws
 
     def _basis(self) -> L.Basis:
@@ -260,6 +269,8 @@ class Executor:
                 a.basis = C.pointer(basis)
                 if self.sparse:
                     a.addend = ws.zs.data_ptr()
+                if save and ws.feat is not None:
+                    a.feat_img = ws.feat.data_ptr()
             else:
                 a.a_img = ws.h[l - 1].data_ptr()
             a.layer = self._layer(l)
@@ -387,10 +398,10 @@ class Executor:
         gw = g["weights"][l]
         a = L.WgradArgs()
         a.pts = pts
-        if l == 0:
+        if l == 0 and ws.feat is None:
             a.basis = C.pointer(basis)
         else:
-            a.a_img = ws.h[l - 1].data_ptr()
+            a.a_img = (ws.feat if l == 0 else ws.h[l - 1]).data_ptr()
         a.dz_img = ws.dz[l].data_ptr()
         a.n_in, a.n_out = self._n_in(l), w.shape[0]
         if l == 0 and self.sparse:
@@ -431,12 +442,12 @@ class Executor:
         for l in reversed(range(nh)):
             a = L.BwdArgs()
             a.pts = pts
-            if l == 0:
+            if l == 0 and ws.feat is None:
                 a.basis = C.pointer(basis)
                 if self.sparse:
                     a.addend = ws.zs.data_ptr()
             else:
-                a.a_img = ws.h[l - 1].data_ptr()
+                a.a_img = (ws.feat if l == 0 else ws.h[l - 1]).data_ptr()
             a.layer = self._layer(l)
             a.drop = drop
             if ws.x is not None:

@@ -33,7 +33,7 @@ def test_ctypes_structs_match_header_sizes():
     assert ctypes.sizeof(L.Basis) == 32 and ctypes.sizeof(L.Points) == 64
     assert ctypes.sizeof(L.Layer) == 48 and ctypes.sizeof(L.Dropout) == 32
     assert ctypes.sizeof(L.Head) == 24 + 8 + 32 + 16 + 24
-    assert ctypes.sizeof(L.FwdArgs) == 8 + 64 + 8 + 48 + 32 + 40
+    assert ctypes.sizeof(L.FwdArgs) == 8 + 64 + 8 + 48 + 32 + 48
 
 
 def test_product_never_imports_oracle():

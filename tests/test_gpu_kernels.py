@@ -575,3 +575,34 @@ def test_shapes_the_fused_kernel_does_not_take_fall_back_to_block_kernels():
     # the kernels' operand rounding emulated; the FP64 bound is the TF32 budget of this deeper shape
     assert rel_l2(out.cpu().numpy(), orc.forward(m, None, coords, t, rnd=orc.tf32_round)) < 5e-4    # measured 1.4e-4
     assert rel_l2(out.cpu().numpy(), orc.forward(m, None, coords, t)) < 3e-3
+
+
+def test_large_batch_stored_operand_matches_regenerated_basis():
+    """Throughput regime (more rows than one wave of tiles): the forward stores its generated block-1 operand and the
+    backward / wgrad of block 1 read it back instead of regenerating the basis.  Same TF32 values either way, so the
+    gradients agree to the rounding of differently ordered FP32 atomics; outputs are identical."""
+    L, ops, Executor, NetSpec, LossSpec = _mods()
+    m = _default_oracle_model(13, q=1)
+    rng = np.random.default_rng(4)
+    n = Executor.SAVE_X_MAX_ROWS + 1000          # 38,888 rows: 304 tiles, ragged
+    coords, t = rng.random((n, 2), dtype=np.float32), rng.random(n, dtype=np.float32)
+    y = rng.standard_normal(n).astype(np.float32)
+    res = []
+    for stored in (True, False):
+        ex = Executor(spec_from_oracle(m))
+        if not stored:
+            ex.SAVE_FEAT_MIN_ROWS = 1 << 60
+        ex.loss_acc.zero_()
+        pts = ops.make_points(T(coords), T(t))
+        yh = ex.forward(pts, train=True, y=T(y), loss=LossSpec("mse", ()), inv_count=1.0 / n, save=True).clone()
+        assert (ex._ctx[2].feat is not None) == stored
+        g = ex.backward()
+        torch.cuda.synchronize()
+        res.append((yh, [w.clone() for w in g["weights"]], [b.clone() for b in g["biases"]], ex.loss_acc.item()))
+    (y0, w0, b0, l0), (y1, w1, b1, l1) = res
+    assert torch.equal(y0, y1) and abs(l0 - l1) <= 1e-6 * abs(l1)
+    for a, b in zip(w0 + b0, w1 + b1):
+        assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < 2e-5
+    # and against the oracle on a subset of rows' worth of statistics: the loss
+    yref = orc.forward(m, None, coords[:2000], t[:2000])
+    assert rel_l2(y0[:2000].cpu().numpy(), yref) < 1e-3
