@@ -86,11 +86,14 @@ class Executor:
     # single wave of 128-row tiles, bound by per-kernel latency, not by HBM.  Larger batches recompute instead.
     # (The N x K basis matrix is never stored either way; wgrad regenerates it.)
     SAVE_X_MAX_ROWS = 148 * 2 * 128
-    # Beyond that, the step is throughput-bound and evaluating the basis three times (forward, the backward's recompute
+    # Beyond that the step is throughput-bound and evaluating the basis three times (forward, the backward's recompute
     # GEMM of block 1, wgrad of block 1) is its largest single cost (batch 65,536: backward 147 us and wgrad 139 us
-    # for block 1 against 102 / 47 us for block 2).  The forward then also writes its generated operand (1.25 KB/row)
-    # and the other two read it back through TMA like any activation image.
+    # for block 1 against 102 / 47 us for block 2).  OPTIONAL (`store_basis_operand = True`): the forward also writes
+    # its generated operand (1.25 KB/row) and the other two read it back through TMA like any activation image:
+    # 0.74 -> 0.64 ms per step at 65,536 rows, 2.48 -> 2.12 ms at 262,144.  Off by default: the design point of this
+    # path is that the N x K basis matrix is never materialised in HBM and the backward recomputes it.
     SAVE_FEAT_MIN_ROWS = SAVE_X_MAX_ROWS + 1
+    store_basis_operand = False
 
     def __init__(self, spec: NetSpec, force_sparse: bool = False):
         self.spec = spec
@@ -208,7 +211,8 @@ class Executor:
                 self._ws.pop(next(iter(self._ws)))
             ws = self._ws[n_rows] = _Workspace(self.spec, n_rows, self.device, self.sparse,
                                                save_x=n_rows <= self.SAVE_X_MAX_ROWS,
-                                               save_feat=(not self.sparse and n_rows >= self.SAVE_FEAT_MIN_ROWS))
+                                               save_feat=(self.store_basis_operand and not self.sparse
+                                                          and n_rows >= self.SAVE_FEAT_MIN_ROWS))
         return ws
 
     def _basis(self) -> L.Basis:

@@ -578,8 +578,8 @@ def test_shapes_the_fused_kernel_does_not_take_fall_back_to_block_kernels():
 
 
 def test_large_batch_stored_operand_matches_regenerated_basis():
-    """Throughput regime (more rows than one wave of tiles): the forward stores its generated block-1 operand and the
-    backward / wgrad of block 1 read it back instead of regenerating the basis.  Same TF32 values either way, so the
+    """Throughput regime (more rows than one wave of tiles), optional mode `store_basis_operand`: the forward stores
+    its generated block-1 operand and the backward / wgrad of block 1 read it back instead of regenerating the basis.  Same TF32 values either way, so the
     gradients agree to the rounding of differently ordered FP32 atomics; outputs are identical."""
     L, ops, Executor, NetSpec, LossSpec = _mods()
     m = _default_oracle_model(13, q=1)
@@ -590,8 +590,7 @@ def test_large_batch_stored_operand_matches_regenerated_basis():
     res = []
     for stored in (True, False):
         ex = Executor(spec_from_oracle(m))
-        if not stored:
-            ex.SAVE_FEAT_MIN_ROWS = 1 << 60
+        ex.store_basis_operand = stored
         ex.loss_acc.zero_()
         pts = ops.make_points(T(coords), T(t))
         yh = ex.forward(pts, train=True, y=T(y), loss=LossSpec("mse", ()), inv_count=1.0 / n, save=True).clone()
