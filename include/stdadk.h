@@ -36,7 +36,8 @@ enum { STDADK_LOSS_NONE = 0, STDADK_LOSS_MSE = 1, STDADK_LOSS_PINBALL = 2 };
 
 /* Basis description.  knots4[j] = (cx, cy, theta'^2, 1/theta'), theta' = bandwidth * calibration
  * (st_interp.py:447-448, CALIBRATION_FACTORS :56-60); tknots2[k] = (c, 1/bw) (st_interp.py:583-596).
- * Feature order of the first Linear layer: [X (p_cov) | phi (k_s) | psi (k_t)] (st_interp.py:843-846). */
+ * Feature order of the first Linear layer: [X (p_cov) | phi (k_s) | psi (k_t)] (st_interp.py:843-846).
+ * Both tables must be 16-byte aligned (they are staged into shared memory with bulk async copies). */
 typedef struct {
     const float* knots4;
     const float* tknots2;

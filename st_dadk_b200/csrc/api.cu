@@ -128,6 +128,8 @@ static HeadP to_head(const stdadk_head* h) {
 static int check_basis_points(const stdadk_basis* b, const stdadk_points& p, int n_in) {
     REQUIRE(b->knots4 || b->k_s == 0, "basis: knots4 is NULL");
     REQUIRE(b->tknots2 || b->k_t == 0, "basis: tknots2 is NULL");
+    REQUIRE(((reinterpret_cast<uintptr_t>(b->knots4) | reinterpret_cast<uintptr_t>(b->tknots2)) & 15) == 0,
+            "basis: knots4 / tknots2 must be 16-byte aligned (staged into shared memory with bulk async copies)");
     REQUIRE(b->k_s >= 0 && b->k_t >= 0 && b->p_cov >= 0, "basis: negative sizes");
     REQUIRE(b->basis_fn >= 0 && b->basis_fn <= 2, "basis: unknown basis_fn %d", b->basis_fn);
     REQUIRE(n_in < 0 || b->p_cov + b->k_s + b->k_t == n_in, "basis: p+k_s+k_t=%d != layer n_in=%d",

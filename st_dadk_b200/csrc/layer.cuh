@@ -164,6 +164,18 @@ __device__ __forceinline__ void issue_slab_copies(const float* w_img, int w_slab
     if (a_tile_img) bulk_g2s(sA, a_tile_img + (size_t)slab * SLAB_FLOATS, SLAB_BYTES, bar);
 }
 
+// Knot tables (knots4: cx, cy, theta'^2, 1/theta'; tknots2: c, 1/bw) -> shared memory with bulk async copies (TMA 1-D)
+// completing on `bar` (initialised with count 1; consumers wait for phase 0).  Called by ONE thread after the barrier
+// initialisation.  An odd last temporal knot (8 bytes, below the 16-byte granule) is copied by hand; it becomes
+// visible with the __syncthreads() that follows in every caller.
+__device__ __forceinline__ void stage_knots_async(const BasisP& B, float4* sk, float2* st, uint64_t* bar) {
+    const uint32_t ks_bytes = (uint32_t)B.k_s * 16u, kt_bytes = ((uint32_t)B.k_t >> 1) * 16u;
+    mbar_arrive_expect_tx(bar, ks_bytes + kt_bytes);
+    if (ks_bytes) bulk_g2s(sk, B.knots, ks_bytes, bar);
+    if (kt_bytes) bulk_g2s(st, B.tknots, kt_bytes, bar);
+    if (B.k_t & 1) st[B.k_t - 1] = B.tknots[B.k_t - 1];
+}
+
 // Cluster variant: the CL CTAs of a cluster work on different row tiles but need the same weight slab; CTA `rank`
 // fetches 1/CL of its rows and multicasts them to all, so the slab crosses L2 -> SM once per cluster instead of once
 // per CTA.  Every CTA's barrier still expects the whole slab (+ its own A slab).
@@ -289,6 +301,7 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + sp.bar_off);
     uint64_t* empty = full + NSTAGE;
     uint64_t* accf = full + 2 * NSTAGE;
+    uint64_t* kbar = accf + 1;                                       // knot tables have landed (BASIS)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + sp.tmem_off);
     float4* sprm = reinterpret_cast<float4*>(smem + sp.vec_off);   // per column (bias, gamma, beta, 0): one LDS.128
     float* shw = reinterpret_cast<float*>(smem + sp.headw_off);
@@ -311,7 +324,9 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
             mbar_init(&empty[s], CL);        // every CTA of the cluster must have consumed the stage
         }
         mbar_init(accf, 1);
+        mbar_init(kbar, 1);
         mbar_fence_init();
+        if (BASIS) stage_knots_async(P.basis, sk, st, kbar);
     }
     if (warp == 4 * CG) {
         __syncwarp();
@@ -328,10 +343,6 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
             shw[i] = c < n_out ? P.head.w[(size_t)k * n_out + c] : 0.0f;
         }
         if (tid < P.head.q) shb[tid] = P.head.b[tid];
-    }
-    if (BASIS) {
-        for (int i = tid; i < P.basis.k_s; i += NT) sk[i] = P.basis.knots[i];
-        for (int i = tid; i < P.basis.k_t; i += NT) st[i] = P.basis.tknots[i];
     }
     tc_fence_before();
     __syncthreads();
@@ -385,6 +396,7 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
                 load_point(P.pts, grow, x, y, t);
                 if (P.basis.p_cov > 0 && P.pts.xcov) xrow = P.pts.xcov + sample_of(P.pts, grow) * P.basis.p_cov;
             }
+            mbar_wait(kbar, 0);
             for (int s = 0; s < P.k_slabs; ++s) {
                 int stage = s % NSTAGE, it = s / NSTAGE;
                 if (it > 0) mbar_wait(&empty[stage], (it - 1) & 1);
@@ -606,6 +618,7 @@ __global__ void __launch_bounds__(n_threads(CG), 1) layer_bwd_kernel(const __gri
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + sp.bar_off);
     uint64_t* empty = full + NSTAGE;
     uint64_t* accf = full + 2 * NSTAGE;
+    uint64_t* kbar = accf + 1;                                       // knot tables have landed (BASIS)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + sp.tmem_off);
     float* sbias = reinterpret_cast<float*>(smem + sp.vec_off);
     float* sgam = sbias + P.n_pad;
@@ -634,7 +647,9 @@ __global__ void __launch_bounds__(n_threads(CG), 1) layer_bwd_kernel(const __gri
             mbar_init(&empty[s], 1);
         }
         mbar_init(accf, 1);
+        mbar_init(kbar, 1);
         mbar_fence_init();
+        if (BASIS) stage_knots_async(P.basis, sk, st, kbar);
     }
     if (warp == 4 * CG) {
         __syncwarp();
@@ -652,10 +667,6 @@ __global__ void __launch_bounds__(n_threads(CG), 1) layer_bwd_kernel(const __gri
             int k = i / n_pad, c = i - k * n_pad;
             shw[i] = c < n_out ? P.head.w[(size_t)k * n_out + c] : 0.0f;
         }
-    }
-    if (BASIS) {
-        for (int i = tid; i < P.basis.k_s; i += NT) sk[i] = P.basis.knots[i];
-        for (int i = tid; i < P.basis.k_t; i += NT) st[i] = P.basis.tknots[i];
     }
     tc_fence_before();
     __syncthreads();
@@ -707,6 +718,7 @@ __global__ void __launch_bounds__(n_threads(CG), 1) layer_bwd_kernel(const __gri
                 load_point(P.pts, grow, x, y, t);
                 if (P.basis.p_cov > 0 && P.pts.xcov) xrow = P.pts.xcov + sample_of(P.pts, grow) * P.basis.p_cov;
             }
+            mbar_wait(kbar, 0);
             for (int s = 0; s < total_slabs; ++s) {
                 int stage = s % NSTAGE, it = s / NSTAGE;
                 if (it > 0) mbar_wait(&empty[stage], (it - 1) & 1);
@@ -977,6 +989,7 @@ __global__ void __launch_bounds__(n_threads(CG), 1) wgrad_kernel(const __grid_co
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + WG_NSTAGE * WG_STAGE_BYTES);
     uint64_t* empty = full + WG_NSTAGE;
     uint64_t* accf = full + 2 * WG_NSTAGE;
+    uint64_t* kbar = accf + 1;                                       // knot tables have landed (BASIS)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + WG_NSTAGE * WG_STAGE_BYTES + 64);
     float4* sk = reinterpret_cast<float4*>(smem + WG_NSTAGE * WG_STAGE_BYTES + 96);
     float2* st = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(sk) + (size_t)(BASIS ? P.basis.k_s : 0) * 16);
@@ -996,7 +1009,9 @@ __global__ void __launch_bounds__(n_threads(CG), 1) wgrad_kernel(const __grid_co
             mbar_init(&empty[s], 1);
         }
         mbar_init(accf, 1);
+        mbar_init(kbar, 1);
         mbar_fence_init();
+        if (BASIS) stage_knots_async(P.basis, sk, st, kbar);
     }
     if (warp == 4 * CG) {
         __syncwarp();
@@ -1010,10 +1025,6 @@ __global__ void __launch_bounds__(n_threads(CG), 1) wgrad_kernel(const __grid_co
             for (int i = tid; i < n16; i += NT) zp[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         fence_proxy_async_smem();
-    }
-    if (BASIS) {
-        for (int i = tid; i < P.basis.k_s; i += NT) sk[i] = P.basis.knots[i];
-        for (int i = tid; i < P.basis.k_t; i += NT) st[i] = P.basis.tknots[i];
     }
     tc_fence_before();
     __syncthreads();
@@ -1044,6 +1055,7 @@ __global__ void __launch_bounds__(n_threads(CG), 1) wgrad_kernel(const __grid_co
         } else if (warp < 4 * CG) {
             const int row64 = tid & 63, par = tid >> 6;
             int itn = 0;
+            if (BASIS) mbar_wait(kbar, 0);
             for (int rt = split; rt < P.n_row_tiles; rt += n_split)
                 for (int half = 0; half < 2; ++half, ++itn) {
                     int stage = itn % WG_NSTAGE, it = itn / WG_NSTAGE;

@@ -86,7 +86,7 @@ __host__ inline uint32_t plan_predict(PredK& K) {
     uint32_t o = 0;
     K.sm.h_off = o; o += PF_HSLABS * SLAB_BYTES;                       // 128 KB
     K.sm.w_off = o; o += PF_WST * MAX_N * 128u;                        // 64 KB
-    K.sm.bar_off = o; o += 256;
+    K.sm.bar_off = o; o += 320;
     K.sm.tmem_off = o; o += 16;
     for (int l = 0; l < K.n_layers; ++l) {
         K.L[l].prm_off = o;
@@ -249,6 +249,7 @@ __global__ void __launch_bounds__(PF_NT, 1) predict_fused_kernel(const __grid_co
     uint64_t* hfull = aempty + PF_AST;
     uint64_t* hfree = hfull + PF_HSLABS;   // H slab j (j < PF_AST) no longer read by the last block of the current tile
     uint64_t* accf = hfree + PF_AST;       // [2]: accumulator-ready of even / odd tiles
+    uint64_t* kbar = accf + 2;             // knot tables have landed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + P.sm.tmem_off);
     float* shw = reinterpret_cast<float*>(smem + P.sm.headw_off);
     float4* sk = reinterpret_cast<float4*>(smem + P.sm.knots_off);
@@ -274,7 +275,9 @@ __global__ void __launch_bounds__(PF_NT, 1) predict_fused_kernel(const __grid_co
         for (int s = 0; s < PF_AST; ++s) mbar_init(&hfree[s], 1);
         mbar_init(&accf[0], 1);
         mbar_init(&accf[1], 1);
+        mbar_init(kbar, 1);
         mbar_fence_init();
+        stage_knots_async(P.basis, sk, st, kbar);
     }
     if (warp == 4 * PF_CG) {
         __syncwarp();
@@ -295,8 +298,6 @@ __global__ void __launch_bounds__(PF_NT, 1) predict_fused_kernel(const __grid_co
         shw[i] = c < last_out ? P.head_w[(size_t)k * last_out + c] : 0.0f;
     }
     if (tid < P.q) shb[tid] = P.head_b[tid];
-    for (int i = tid; i < P.basis.k_s; i += PF_NT) sk[i] = P.basis.knots[i];
-    for (int i = tid; i < P.basis.k_t; i += PF_NT) st[i] = P.basis.tknots[i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -415,6 +416,7 @@ __global__ void __launch_bounds__(PF_NT, 1) predict_fused_kernel(const __grid_co
         // last epilogue of the current one (into H slabs the last block has already consumed), so those MMAs run
         // under the epilogue + head instead of leaving the workers waiting for them.
         const int k_last = nl >= 2 ? P.L[nl - 1].k_slabs : 0;
+        mbar_wait(kbar, 0);
         long long lrow = 0, nxt_lrow = 0;
         bool rvalid = false, nxt_valid = false, have_cur = false;
         int cur_tile = 0;
