@@ -335,6 +335,26 @@ class Executor:
         ops.train_fwd(a)
         return True
 
+    def fused_supported(self) -> bool:
+        """Whether forward-only calls on this network run through the whole-network kernel (decided once per binding;
+        needs the operand images, i.e. prepare() first)."""
+        s = self.spec
+        if self.sparse or not self.fused_predict or s.n_hidden > L.MAX_HIDDEN:
+            return False
+        if self._fused_ok is None:
+            probe = torch.empty(1, s.q, dtype=torch.float32, device=self.device)
+            basis = self._basis()
+            head = ops.make_head(s.head_w, s.head_b, s.q, probe)
+            a = L.PredictArgs()
+            a.basis = C.pointer(basis)
+            a.pts = ops.make_points(grid=(1, 1, 1), row_begin=0, n_rows=1)
+            a.n_layers = s.n_hidden
+            for l in range(s.n_hidden):
+                a.layers[l] = self._layer(l)
+            a.head = C.pointer(head)
+            self._fused_ok = ops.predict_supported(a)
+        return bool(self._fused_ok)
+
     def _predict_fused(self, pts: L.Points, yhat: torch.Tensor) -> bool:
         """Forward-only path: the whole network in one persistent kernel (stdadk_predict), no activation images.
         Returns False when the shape does not fit the fused kernel; the caller then chains layer_fwd."""

@@ -22,6 +22,7 @@ def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
 
 class Predictor:
     """Forward-only executor bound to a model; weight images are packed once and reused across chunks."""
+    FUSED_CHUNK = 1 << 26      # rows per launch of the whole-network kernel (67M; tiles are counted in 32 bits)
 
     def __init__(self, model, chunk_rows: int = 1 << 20):
         self.model = model
@@ -55,8 +56,11 @@ class Predictor:
     @torch.no_grad()
     def _run(self, make_pts, begin: int, end: int, out: torch.Tensor):
         n_layers = self.ex.spec.n_hidden
-        for b in range(begin, end, self.chunk):
-            r = min(self.chunk, end - b)
+        # the whole-network kernel keeps nothing in HBM per row, so a shard goes in ONE launch; only the per-block
+        # fallback (2 KB of activation images per row) needs bounded chunks
+        step = self.FUSED_CHUNK if self.ex.fused_supported() else self.chunk
+        for b in range(begin, end, step):
+            r = min(step, end - b)
             self.ex.forward(make_pts(b, r), train=False, out=out[b - begin:b - begin + r], prepared=True)
             self.launches += 1 if self.fused else n_layers
         return out
