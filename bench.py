@@ -297,7 +297,7 @@ def run_ours(args):
     log("e2e done; prediction")
     # ---- dense prediction: T x S = 1M points (space-time field), sharded by point, no collective
     model.eval()
-    pr = Predictor(model)
+    pr = Predictor(model, static_weights=True)      # serving: weights are fixed between prediction calls
     sites_d = torch.from_numpy(sites).to(dev)
     n_pred = S_SITES * T_STEPS
     for _ in range(2):

@@ -24,9 +24,14 @@ class Predictor:
     """Forward-only executor bound to a model; weight images are packed once and reused across chunks."""
     FUSED_CHUNK = 1 << 26      # rows per launch of the whole-network kernel (67M; tiles are counted in 32 bits)
 
-    def __init__(self, model, chunk_rows: int = 1 << 20):
+    def __init__(self, model, chunk_rows: int = 1 << 20, static_weights: bool = False):
+        """static_weights=True (serving): the model's parameters do not change between calls, so the knot tables and
+        weight images are built on the first call only.  The default rebuilds them on every call, because parameter
+        storage can be rewritten in place (optimizer kernel, EMA swap) without any version counter changing."""
         self.model = model
         self.chunk = int(chunk_rows)
+        self.static_weights = bool(static_weights)
+        self._prepared = False
         self.ex: Optional[Executor] = None
         self.launches = 0
         self._field_key = None
@@ -36,6 +41,8 @@ class Predictor:
         self.host_copy_done = None
 
     def _prepare(self):
+        if self.static_weights and self._prepared:
+            return
         m = self.model
         if not next(m.buffers()).is_cuda:
             raise RuntimeError("Predictor: the model must live on a CUDA device (no CPU path)")
@@ -47,6 +54,7 @@ class Predictor:
             self.ex.rebind(spec)
         self.ex.prepare(force=True, for_backward=False)
         self.launches += 2 + len(spec.weights)
+        self._prepared = True
 
     @property
     def fused(self) -> bool:

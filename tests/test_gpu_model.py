@@ -215,6 +215,9 @@ def test_space_time_field_equals_explicit_points_any_sharding():
         assert torch.equal(torch.cat(parts), field)
     again, _ = pr.space_time_field(sites, Tn)      # cached expansion
     assert torch.equal(again, field)
+    served = Predictor(model, static_weights=True)  # serving mode: operand images built once
+    for _ in range(2):
+        assert torch.equal(served.space_time_field(sites, Tn)[0], field)
     # delivered to pinned host memory in pieces, each copy overlapping the next piece's kernel
     hout = torch.empty(S * Tn, 3).pin_memory()
     pr.d2h_chunk_rows = 2 * S + 5                  # -> pieces of two whole time steps
