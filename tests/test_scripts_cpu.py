@@ -66,3 +66,64 @@ def test_yaml_schema_accepted():
     m = create_model(dict(cfg, k_spatial_centers=[4, 9]), train_coords=rng.random((200, 2)).astype(np.float32))
     assert m.output_dim == 5 and m.spatial_basis.learnable and m.spatial_basis.k == 13
     assert m.spatial_basis.centers.shape == (13, 2) and (m.spatial_basis.bandwidths > 0).all()
+
+
+def test_flat_state_layout_on_cpu():
+    """FlatState (host logic, no kernels): parameters re-pointed into one flat buffer with upstream's shapes, Linear
+    weights stored (in, out)-contiguous behind a .t() view, gradient views of the same geometry, and -- behind the
+    gradients -- the delta head's scratch and the one-float loss slot that lets a data-parallel step use ONE
+    all-reduce (n_exchange)."""
+    from stnf.models import STInterpMLP
+    from st_dadk_b200.trainer import FlatState
+    for kw in (dict(output_dim=1), dict(output_dim=3, use_delta_reparameterization=True), dict(spatial_learnable=True)):
+        torch.manual_seed(0)
+        model = STInterpMLP(k_spatial_centers=[9, 25], k_temporal_centers=[4], hidden_dims=[32, 16], **kw)
+        before = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        fl = FlatState(model, "cpu")
+        n_par = sum(p.numel() for p in model.parameters())
+        assert fl.n == n_par and fl.p.numel() == n_par
+        assert fl.n_exchange == fl.n + fl.n_scratch + 1 and fl.g.numel() == fl.n_exchange
+        assert fl.loss_slot.data_ptr() == fl.g[fl.n + fl.n_scratch:].data_ptr() and fl.loss_slot.numel() == 1
+        for k, v in model.state_dict().items():          # same keys, shapes and values as before the re-pointing
+            assert v.shape == before[k].shape and torch.equal(v, before[k]), k
+        w = model.hidden_blocks()[0][0].weight
+        assert w.shape == (32, 34 + 4) and w.t().is_contiguous()           # (in, out)-contiguous storage
+        for p in model.parameters():
+            gv = fl.gviews[id(p)]
+            assert gv.shape == p.shape
+            gv.fill_(1.0)
+        assert float(fl.g[:fl.n].sum()) == n_par and float(fl.g[fl.n:].abs().sum()) == 0.0
+        # allocation hook used by the peer-memory exchange: g lives in caller-provided storage
+        store = torch.zeros(fl.n_exchange + 64)
+        torch.manual_seed(0)
+        m2 = STInterpMLP(k_spatial_centers=[9, 25], k_temporal_centers=[4], hidden_dims=[32, 16], **kw)
+        f2 = FlatState(m2, "cpu", alloc_g=lambda size: store[:size])
+        assert f2.g.data_ptr() == store.data_ptr() and f2.g.numel() == fl.n_exchange
+
+
+def test_gmm_knot_fit_is_memoised_and_thread_safe():
+    """knot_init.gmm_knots: the scikit-learn mixture fit (seconds on the host; upstream fixes random_state=42) is a
+    pure function of (sample, k): a sweep's repeated fits come from the per-process cache, identical to a fresh fit."""
+    import threading
+    import time
+    from st_dadk_b200 import knot_init as K
+    K._GMM_CACHE.clear()
+    rng = np.random.default_rng(5)
+    pts = rng.random((600, 2))
+    t0 = time.perf_counter()
+    c0, b0 = K.gmm_knots([4, 9], pts)
+    t_first = time.perf_counter() - t0
+    out = []
+    ths = [threading.Thread(target=lambda: out.append(K.gmm_knots([4, 9], pts.copy()))) for _ in range(4)]
+    t0 = time.perf_counter()
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    t_cached = time.perf_counter() - t0
+    assert len(K._GMM_CACHE) == 2 and t_cached < max(0.5 * t_first, 0.05)
+    for c, b in out:
+        assert torch.equal(c, c0) and torch.equal(b, b0)
+    c1, b1 = K.gmm_knots([4, 9], pts + 1e-3)                  # another sample: refit, different result
+    assert len(K._GMM_CACHE) == 4 and not torch.equal(c1, c0)
+    assert c0.shape == (13, 2) and b0.shape == (13,) and bool((b0 > 0).all())
