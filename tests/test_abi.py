@@ -48,3 +48,32 @@ def test_product_never_imports_oracle():
                         if not f.endswith("selftest.py"):
                             bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_sass_is_blackwell_native():
+    """The compiled kernels use the sm_100a tensor-core / TMEM / TMA instructions and no legacy tensor path:
+    `tcgen05.mma` -> UTC*MMA, `tcgen05.ld` -> LDTM, bulk async copies -> UBLKCP, mbarrier -> SYNCS, packed FP32 ->
+    FFMA2 (B200_PROFILING.md, "What proves a Blackwell-native kernel").  Skipped when cuobjdump is not installed."""
+    import shutil
+    import subprocess
+    import pytest
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    import __graft_entry__ as g
+    g.build()
+    lib = os.path.join(ROOT, "st_dadk_b200", "libstdadk.so")
+    arch = subprocess.run([exe, "-lelf", lib], capture_output=True, text=True).stdout
+    assert "sm_100a" in arch, arch
+    sass = subprocess.run([exe, "-sass", lib], capture_output=True, text=True).stdout
+    count = lambda pat: len(re.findall(pat, sass))
+    assert count(r"\bUTC[A-Z]*MMA\b") >= 50        # tcgen05.mma in forward, backward, wgrad, knot-grad, fused kernels
+    assert count(r"\bLDTM\b") >= 20                # accumulators read back from tensor memory
+    assert count(r"\bUBLKCP\b") >= 50              # TMA 1-D bulk copies of operand slabs and knot tables
+    assert count(r"\bSYNCS\b") >= 100              # mbarrier pipelines
+    assert count(r"\bFFMA2\b") >= 100              # packed FP32 epilogue math
+    assert count(r"\bHMMA\b") == 0 and count(r"\b[HQI]GMMA\b") == 0      # no mma.sync / wgmma
+    for kernel in ("layer_fwd_kernel", "layer_bwd_kernel", "wgrad_kernel", "knotgrad_kernel", "predict_fused_kernel",
+                   "sparse_spatial_fwd_kernel", "sparse_spatial_wgrad_kernel", "adamw_ema_kernel", "sqnorm_kernel",
+                   "peer_allreduce_kernel", "pack_images_kernel"):
+        assert kernel in sass, kernel
