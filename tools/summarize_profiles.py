@@ -125,6 +125,9 @@ NOTES = """## Reading
   (parameters and knots are warp-broadcast loads, 4 bytes per wavefront); the pipe columns above add up to the
   kernel's real ceiling (DESIGN.md section 4).
 * Layered prediction kernels: block 2 moves exactly the algorithmic bytes (1.02 GB in + 0.98 GB out).
+* SASS evidence of the instruction mix (UTCHMMA = tcgen05.mma, LDTM = tcgen05.ld, UBLKCP = TMA bulk copies, SYNCS =
+  mbarrier, FFMA2/FADD2 = packed FP32; no HMMA): `profiles/r1_sass_mnemonics.txt`, checked by
+  `tests/test_abi.py::test_sass_is_blackwell_native`.
 """
 
 if __name__ == "__main__":
