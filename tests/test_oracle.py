@@ -155,3 +155,84 @@ def test_shard_and_grid():
     assert c[0].tolist() == [np.float32(999 / 999), np.float32(998 / 999)] and t[0, 0] == 0
     assert c[2].tolist() == [0.0, 0.0] and t[2, 0] == np.float32(1 / 9)
     assert orc.shard_range(0, 0, 4) == (0, 0)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Size-independent properties (the ones the GPU tests rely on at full size, where no oracle run is affordable)
+# ---------------------------------------------------------------------------------------------------------------------
+from hypothesis import given, settings, strategies as hs   # noqa: E402
+
+
+@settings(max_examples=60, deadline=None)
+@given(n=hs.integers(0, 10**9), world=hs.integers(1, 64))
+def test_property_shard_ranges_partition_in_order(n, world):
+    """Contiguous block sharding: shards tile [0, n) in rank order and their sizes differ by at most one."""
+    edges = [orc.shard_range(n, r, world) for r in range(world)]
+    assert edges[0][0] == 0 and edges[-1][1] == n
+    sizes = []
+    for (b, e), nxt in zip(edges, edges[1:] + [(n, n)]):
+        assert b <= e == nxt[0]
+        sizes.append(e - b)
+    assert max(sizes) - min(sizes) <= 1
+
+
+@settings(max_examples=25, deadline=None)
+@given(rows=hs.integers(1, 300), cols=hs.integers(1, 70), lo=hs.integers(0, 2**33), step=hs.integers(0, 2**31 - 1),
+       layer=hs.integers(0, 3), seed=hs.integers(0, 2**64 - 1), p=hs.sampled_from([0.05, 0.1, 0.5]))
+def test_property_dropout_mask_is_keyed_by_global_row(rows, cols, lo, step, layer, seed, p):
+    """A shard that starts at global row `lo` draws exactly the rows [lo, lo+rows) of the unsharded mask (rows beyond
+    2^32 included), and a different layer / step gives a different stream."""
+    full = orc.dropout_keep_mask(rows + 7, cols, p, seed, step, layer, row_offset=lo)
+    part = orc.dropout_keep_mask(rows, cols, p, seed, step, layer, row_offset=lo + 7)
+    assert np.array_equal(full[7:], part)
+    if rows * cols >= 256:
+        assert not np.array_equal(part, orc.dropout_keep_mask(rows, cols, p, seed, step + 1, layer, row_offset=lo + 7))
+        assert not np.array_equal(part, orc.dropout_keep_mask(rows, cols, p, seed, step, layer + 1, row_offset=lo + 7))
+
+
+@settings(max_examples=30, deadline=None)
+@given(nx=hs.integers(1, 60), ny=hs.integers(1, 60), nt=hs.integers(1, 12), a=hs.integers(0, 10**4), b=hs.integers(0, 10**4))
+def test_property_grid_generator_is_a_window_of_the_full_grid(nx, ny, nt, a, b):
+    """grid_points(begin, end) is the [begin, end) window of the full grid in x-major order (any sharding of a dense
+    grid concatenates to the whole), coordinates stay in [0, 1] and the end points are exact."""
+    n = nx * ny * nt
+    begin, end = sorted((a % (n + 1), b % (n + 1)))
+    cf, tf = orc.grid_points(nx, ny, nt, 0, n)
+    c, t = orc.grid_points(nx, ny, nt, begin, end)
+    assert np.array_equal(c, cf[begin:end]) and np.array_equal(t, tf[begin:end])
+    assert cf.min() >= 0.0 and cf.max() <= 1.0 and tf.min() >= 0.0 and tf.max() <= 1.0
+    assert tuple(cf[0]) == (0.0, 0.0) and tf[0, 0] == 0.0
+    assert cf[-1, 0] == (1.0 if nx > 1 else 0.0) and cf[-1, 1] == (1.0 if ny > 1 else 0.0)
+    assert tf[-1, 0] == (1.0 if nt > 1 else 0.0)
+
+
+@settings(max_examples=50, deadline=None)
+@given(hs.lists(hs.floats(float(np.float32(-1e30)), float(np.float32(1e30)), allow_nan=False, width=32), min_size=1,
+                max_size=64))
+def test_property_tf32_rounding(xs):
+    """tf32_round: idempotent, monotone, sign-symmetric, within half a TF32 ulp (2^-11 relative) of its argument."""
+    x = np.asarray(xs, dtype=np.float32)
+    r = orc.tf32_round(x)
+    assert np.array_equal(orc.tf32_round(r), r)
+    assert np.array_equal(orc.tf32_round(-x), -r)
+    normal = np.abs(x) > 1e-30
+    assert np.all(np.abs(r[normal].astype(np.float64) - x[normal]) <= np.abs(x[normal].astype(np.float64)) * 2.0 ** -11)
+    order = np.argsort(x, kind="stable")
+    assert np.all(np.diff(r[order]) >= 0)
+    assert np.all((r.view(np.uint32) & np.uint32(0x1FFF)) == 0)
+
+
+@settings(max_examples=20, deadline=None)
+@given(seed=hs.integers(0, 2**32 - 1), fn=hs.sampled_from(["wendland", "triangular"]))
+def test_property_support_sets_and_basis_values_agree(seed, fn):
+    """phi > 0 only inside the FP32 support predicate the kernels use, phi <= 1, phi == 1 exactly at a knot, and the
+    predicate is symmetric under reflection of the lattice (x -> 1 - x)."""
+    rng = np.random.default_rng(seed)
+    c, bw = orc.uniform_spatial_knots([9, 25])
+    pts = rng.random((64, 2)).astype(np.float32)
+    phi = orc.spatial_basis(pts, c, bw, fn, np.float64)
+    mask = orc.support_mask_f32(pts, c, bw, fn)
+    assert np.all(phi[~mask] <= 1e-12) and np.all(phi <= 1.0 + 1e-12) and np.all(phi >= 0.0)
+    at_knots = orc.spatial_basis(c, c, bw, fn, np.float64)
+    assert np.allclose(np.diag(at_knots), 1.0, atol=1e-12)
+    assert orc.support_mask_f32(c, c, bw, fn).diagonal().all()
