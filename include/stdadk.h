@@ -69,6 +69,10 @@ typedef struct {
     int32_t n_in, n_out;
     float ln_eps;
     int32_t layer_id;    /* dropout stream id */
+    const float* w_img_lo; /* precision "tf32x3": image of W - tf32(W) (stdadk_pack_desc.part = 1); NULL = plain TF32.
+                              With it every GEMM of the call runs three tensor-core passes hi*hi + hi*lo + lo*hi into the
+                              same FP32 accumulator (FP32-faithful products; the reference is FP32 throughout,
+                              st_interp.py:656-692), and every operand image of the call needs its *_lo twin. */
 } stdadk_layer;
 
 typedef struct {
@@ -119,6 +123,8 @@ typedef struct {
     float* x_img;            /* optional out: image (rows x n_out) of the pre-LayerNorm value x = A W^T + b (+ addend),
                                 FP32.  A backward that receives it skips the recomputation GEMM -- worth its 1 KB/row
                                 when the batch is a single wave of tiles and latency, not bandwidth, is the limit. */
+    const float* a_img_lo;   /* tf32x3 (layer.w_img_lo != NULL): residual image of a_img */
+    float* out_img_lo;       /* tf32x3: residual image of out_img (written together with it) */
 } stdadk_fwd_args;
 
 /* Backward of one hidden block: recomputes z = A W^T (for block 1 this recomputes the basis),
@@ -144,6 +150,11 @@ typedef struct {
     float* d_beta;             /* (n_out) += or NULL */
     const float* addend;       /* as in stdadk_fwd_args (the recomputed z needs the same term) */
     const float* x_img;        /* optional: x saved by the forward; then a_img / basis / addend are not read */
+    /* tf32x3 (layer.w_img_lo != NULL): residual images of a_img, dz_next_img, wt_next_img and (out) dz_img */
+    const float* a_img_lo;
+    const float* dz_next_img_lo;
+    const float* wt_next_img_lo;
+    float* dz_img_lo;
 } stdadk_bwd_args;
 
 /* Weight gradient dW (n_out x n_in) += dz^T A, reduction over rows on the tensor cores (both
@@ -157,6 +168,8 @@ typedef struct {
     int32_t n_in, n_out;
     float* dw;
     int64_t stride_o, stride_i;
+    const float* a_img_lo;     /* tf32x3: residual images; dz_img_lo != NULL selects the three-pass product */
+    const float* dz_img_lo;
 } stdadk_wgrad_args;
 
 /* Gradient of the learnable knots (st_interp.py:94-108, closed form of SURVEY.md 9.1):
@@ -169,6 +182,8 @@ typedef struct {
     int32_t n_out, _pad;
     float* d_centers;
     float* d_log_bw;
+    const float* dz_img_lo;   /* tf32x3: residual images (both or neither) */
+    const float* w1s_img_lo;
 } stdadk_knotgrad_args;
 
 /* Fused clip + AdamW + EMA over one flat buffer (train_st_interp.py:696-718, torch.optim.AdamW,
@@ -222,6 +237,8 @@ typedef struct {
     const float* src;
     int64_t row_stride, col_stride, rows, cols;
     float* img;
+    int32_t part;             /* 0: tf32(src) (the operand image); 1: tf32(src - tf32(src)), the tf32x3 residual image */
+    int32_t _pad;
 } stdadk_pack_desc;
 int stdadk_pack_images(const stdadk_pack_desc* descs, int n, void* stream);
 

@@ -29,7 +29,7 @@ class Points(C.Structure):
 
 class Layer(C.Structure):
     _fields_ = [("w_img", fp), ("bias", fp), ("gamma", fp), ("beta", fp), ("n_in", C.c_int32), ("n_out", C.c_int32),
-                ("ln_eps", C.c_float), ("layer_id", C.c_int32)]
+                ("ln_eps", C.c_float), ("layer_id", C.c_int32), ("w_img_lo", fp)]
 
 
 class Dropout(C.Structure):
@@ -45,24 +45,27 @@ class Head(C.Structure):
 
 class FwdArgs(C.Structure):
     _fields_ = [("basis", C.POINTER(Basis)), ("pts", Points), ("a_img", fp), ("layer", Layer), ("drop", Dropout),
-                ("out_img", fp), ("stats", fp), ("head", C.POINTER(Head)), ("addend", fp), ("feat_img", fp), ("x_img", fp)]
+                ("out_img", fp), ("stats", fp), ("head", C.POINTER(Head)), ("addend", fp), ("feat_img", fp), ("x_img", fp),
+                ("a_img_lo", fp), ("out_img_lo", fp)]
 
 
 class BwdArgs(C.Structure):
     _fields_ = [("basis", C.POINTER(Basis)), ("pts", Points), ("a_img", fp), ("layer", Layer), ("drop", Dropout),
                 ("stats", fp), ("head", C.POINTER(Head)), ("d_head_w", fp), ("d_head_b", fp), ("dz_next_img", fp),
                 ("wt_next_img", fp), ("n_next", C.c_int32), ("_pad", C.c_int32), ("dz_img", fp), ("d_bias", fp),
-                ("d_gamma", fp), ("d_beta", fp), ("addend", fp), ("x_img", fp)]
+                ("d_gamma", fp), ("d_beta", fp), ("addend", fp), ("x_img", fp), ("a_img_lo", fp), ("dz_next_img_lo", fp),
+                ("wt_next_img_lo", fp), ("dz_img_lo", fp)]
 
 
 class WgradArgs(C.Structure):
     _fields_ = [("basis", C.POINTER(Basis)), ("pts", Points), ("a_img", fp), ("dz_img", fp), ("n_in", C.c_int32),
-                ("n_out", C.c_int32), ("dw", fp), ("stride_o", C.c_int64), ("stride_i", C.c_int64)]
+                ("n_out", C.c_int32), ("dw", fp), ("stride_o", C.c_int64), ("stride_i", C.c_int64), ("a_img_lo", fp),
+                ("dz_img_lo", fp)]
 
 
 class KnotGradArgs(C.Structure):
     _fields_ = [("basis", C.POINTER(Basis)), ("pts", Points), ("dz_img", fp), ("w1s_img", fp), ("n_out", C.c_int32),
-                ("_pad", C.c_int32), ("d_centers", fp), ("d_log_bw", fp)]
+                ("_pad", C.c_int32), ("d_centers", fp), ("d_log_bw", fp), ("dz_img_lo", fp), ("w1s_img_lo", fp)]
 
 
 class AdamWArgs(C.Structure):
@@ -83,7 +86,7 @@ class SparseArgs(C.Structure):
 
 class PackDesc(C.Structure):
     _fields_ = [("src", fp), ("row_stride", C.c_int64), ("col_stride", C.c_int64), ("rows", C.c_int64),
-                ("cols", C.c_int64), ("img", fp)]
+                ("cols", C.c_int64), ("img", fp), ("part", C.c_int32), ("_pad", C.c_int32)]
 
 
 MAX_HIDDEN = 4

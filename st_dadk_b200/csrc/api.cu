@@ -93,6 +93,7 @@ static PointsP to_points(const stdadk_points& p) {
 static LayerP to_layer(const stdadk_layer& l, const stdadk_dropout& d) {
     LayerP L{};
     L.w_img = l.w_img;
+    L.w_img_lo = l.w_img_lo;
     L.bias = l.bias;
     L.gamma = l.gamma;
     L.beta = l.beta;
@@ -250,7 +251,8 @@ static int check_layer(const stdadk_layer& l, const char* who) {
             l.n_out, MAX_N);
     REQUIRE(l.n_in >= 1, "%s: n_in=%d", who, l.n_in);
     REQUIRE((l.gamma == nullptr) == (l.beta == nullptr), "%s: gamma and beta must both be given or both NULL", who);
-    REQUIRE((reinterpret_cast<uintptr_t>(l.w_img) & 127) == 0, "%s: weight image must be 128-byte aligned", who);
+    REQUIRE(((reinterpret_cast<uintptr_t>(l.w_img) | reinterpret_cast<uintptr_t>(l.w_img_lo)) & 127) == 0,
+            "%s: weight images must be 128-byte aligned", who);
     return 0;
 }
 
@@ -273,6 +275,12 @@ int stdadk_layer_fwd(const stdadk_fwd_args* a, void* stream) {
     } else {
         REQUIRE(a->out_img, "layer_fwd: out_img is NULL and there is no head");
     }
+    const bool x3 = a->layer.w_img_lo != nullptr;
+    if (x3) {
+        REQUIRE(!a->a_img || a->a_img_lo, "layer_fwd: tf32x3 needs a_img_lo next to a_img");
+        REQUIRE(!a->out_img || a->out_img_lo, "layer_fwd: tf32x3 needs out_img_lo next to out_img");
+        REQUIRE(!a->feat_img, "layer_fwd: feat_img is not available in tf32x3 mode");
+    }
     if (a->pts.n_rows <= 0) return 0;
     FwdK K{};
     K.basis = to_basis(a->basis);
@@ -280,6 +288,9 @@ int stdadk_layer_fwd(const stdadk_fwd_args* a, void* stream) {
     K.L = to_layer(a->layer, a->drop);
     K.head = to_head(a->head);
     K.a_img = a->a_img;
+    K.a_img_lo = a->a_img_lo;
+    K.out_img_lo = x3 ? a->out_img_lo : nullptr;
+    K.passes = x3 ? 3 : 1;
     K.addend = a->addend;
     K.x_img = a->x_img;
     K.feat_img = a->basis ? a->feat_img : nullptr;
@@ -455,6 +466,12 @@ int stdadk_layer_bwd(const stdadk_bwd_args* a, void* stream) {
     } else {
         REQUIRE(a->wt_next_img && a->n_next >= 1 && a->n_next <= MAX_N, "layer_bwd: wt_next_img / n_next invalid");
     }
+    const bool x3 = a->layer.w_img_lo != nullptr;
+    if (x3) {
+        REQUIRE(a->x_img || !a->a_img || a->a_img_lo, "layer_bwd: tf32x3 needs a_img_lo next to a_img");
+        REQUIRE(a->head || (a->dz_next_img_lo && a->wt_next_img_lo), "layer_bwd: tf32x3 needs dz_next_img_lo / wt_next_img_lo");
+        REQUIRE(a->dz_img_lo, "layer_bwd: tf32x3 needs dz_img_lo");
+    }
     if (a->pts.n_rows <= 0) return 0;
     BwdK K{};
     K.basis = to_basis(a->basis);
@@ -462,6 +479,11 @@ int stdadk_layer_bwd(const stdadk_bwd_args* a, void* stream) {
     K.L = to_layer(a->layer, a->drop);
     K.head = to_head(a->head);
     K.a_img = a->a_img;
+    K.a_img_lo = a->a_img_lo;
+    K.dz_next_img_lo = a->dz_next_img_lo;
+    K.wt_next_img_lo = a->wt_next_img_lo;
+    K.dz_img_lo = x3 ? a->dz_img_lo : nullptr;
+    K.passes = x3 ? 3 : 1;
     K.addend = a->addend;
     K.x_img = a->x_img;
     K.stats = a->stats;
@@ -515,10 +537,15 @@ int stdadk_wgrad(const stdadk_wgrad_args* a, void* stream) {
     if (a->basis)
         if (int r = check_basis_points(a->basis, a->pts, a->n_in)) return r;
     if (a->pts.n_rows <= 0) return 0;
+    const bool x3 = a->dz_img_lo != nullptr;
+    REQUIRE(!x3 || !a->a_img || a->a_img_lo, "wgrad: tf32x3 needs a_img_lo next to a_img");
     WgradK K{};
     K.basis = to_basis(a->basis);
     K.pts = to_points(a->pts);
     K.a_img = a->a_img;
+    K.a_img_lo = a->a_img_lo;
+    K.dz_img_lo = a->dz_img_lo;
+    K.passes = x3 ? 3 : 1;
     K.dz_img = a->dz_img;
     K.dw = a->dw;
     K.stride_o = a->stride_o;
@@ -561,8 +588,12 @@ int stdadk_knot_grad(const stdadk_knotgrad_args* a, void* stream) {
     KnotGradK K{};
     K.basis = to_basis(a->basis);
     K.pts = to_points(a->pts);
+    REQUIRE((a->dz_img_lo != nullptr) == (a->w1s_img_lo != nullptr), "knot_grad: give both residual images or neither");
     K.dz_img = a->dz_img;
     K.w1s_img = a->w1s_img;
+    K.dz_img_lo = a->dz_img_lo;
+    K.w1s_img_lo = a->w1s_img_lo;
+    K.passes = a->dz_img_lo ? 3 : 1;
     K.d_centers = a->d_centers;
     K.d_log_bw = a->d_log_bw;
     K.n_out = a->n_out;
@@ -582,7 +613,8 @@ static int sparse_fill(const stdadk_sparse_args* a, SparseK* K, bool wgrad) {
             "sparse_l1: only compactly supported bases can be walked (the gaussian basis is dense)");
     REQUIRE(a->n_out >= 4 && a->n_out <= MAX_N && a->n_out % 4 == 0, "sparse_l1: n_out=%d must be a multiple of 4 <= %d",
             a->n_out, MAX_N);
-    REQUIRE(a->knots4 && a->pts.grid_nx > 0 ? true : (a->pts.coords != nullptr), "sparse_l1: no point source");
+    REQUIRE(a->knots4, "sparse_l1: knots4 is NULL");
+    REQUIRE(a->pts.grid_nx > 0 || a->pts.coords != nullptr, "sparse_l1: no point source");
     REQUIRE(a->pts.grid_nx > 0 || (reinterpret_cast<uintptr_t>(a->pts.coords) & 7) == 0, "sparse_l1: coords alignment");
     if (wgrad) {
         REQUIRE(a->dz_img && a->dw1t && (reinterpret_cast<uintptr_t>(a->dw1t) & 15) == 0, "sparse_l1_wgrad: dz_img / dw1t");
@@ -714,10 +746,10 @@ int stdadk_adamw_ema_step(const stdadk_adamw_args* a, void* stream) {
     K.loss_acc = a->loss_acc;
     K.loss_sum = a->loss_sum;
     K.loss_last = a->loss_last;
-    step_inc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(a->step_count);
     REQUIRE(((reinterpret_cast<uintptr_t>(a->p) | reinterpret_cast<uintptr_t>(a->g) | reinterpret_cast<uintptr_t>(a->m) |
               reinterpret_cast<uintptr_t>(a->v) | reinterpret_cast<uintptr_t>(a->shadow)) & 15) == 0,
             "adamw: buffers must be 16-byte aligned");
+    step_inc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(a->step_count);     // only once every argument check has passed
     adamw_ema_kernel<<<grid_for((a->n + 3) / 4, 256, 8), 256, 0, (cudaStream_t)stream>>>(K);
     return check_launch("adamw_ema_step");
 }

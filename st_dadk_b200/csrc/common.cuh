@@ -44,6 +44,7 @@ struct HeadP {
 };
 struct LayerP {
     const float* w_img;
+    const float* w_img_lo;      // tf32x3: image of W - tf32(W); NULL = single-pass TF32
     const float* bias;
     const float* gamma;
     const float* beta;

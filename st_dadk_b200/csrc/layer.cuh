@@ -55,15 +55,17 @@ struct FwdK {
     LayerP L;
     HeadP head;
     const float* a_img;
+    const float* a_img_lo;      // tf32x3 residual images (NULL in TF32 mode)
     const float* addend;
     float* out_img;
+    float* out_img_lo;
     float* x_img;
     float* feat_img;
     float* stats;
     int has_head, k_slabs, n_pad, tmem_cols;
     unsigned int thresh16;
     float drop_scale;
-    int n_tiles, _padk;
+    int n_tiles, passes;        // passes: 1 (TF32) or 3 (tf32x3)
 };
 
 struct BwdK {
@@ -72,18 +74,22 @@ struct BwdK {
     LayerP L;
     HeadP head;
     const float* a_img;
+    const float* a_img_lo;
     const float* addend;
     const float* x_img;
     const float* stats;
     const float* dz_next_img;
+    const float* dz_next_img_lo;
     const float* wt_next_img;
+    const float* wt_next_img_lo;
     float* dz_img;
+    float* dz_img_lo;
     float* d_bias;
     float* d_gamma;
     float* d_beta;
     float* d_head_w;
     float* d_head_b;
-    int has_head, k_slabs, k_slabs2, n_pad, tmem_cols, _pad;
+    int has_head, k_slabs, k_slabs2, n_pad, tmem_cols, passes;
     unsigned int thresh16;
     float drop_scale;
 };
@@ -92,7 +98,7 @@ struct BwdK {
 // Fast paths: the chunk lies entirely in the spatial block (one LDS.128 per knot, support test, value only where
 // d2 < theta'^2) or entirely in the temporal block; the generic per-feature path handles block boundaries.
 template <int FN>
-__device__ __forceinline__ float4 spatial_chunk(const float4* kp, float x, float y) {
+__device__ __forceinline__ float4 spatial_chunk(const float4* kp, float x, float y, bool lo) {
     float d2[4], th2[4], ith[4];
     bool in = false;
 #pragma unroll
@@ -109,17 +115,18 @@ __device__ __forceinline__ float4 spatial_chunk(const float4* kp, float x, float
     if (FN != STDADK_GAUSSIAN && !__any_sync(__activemask(), in)) return make_float4(0.f, 0.f, 0.f, 0.f);
     float o[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) o[e] = to_tf32(phi_from_d2<FN>(d2[e], th2[e], ith[e]));
+    for (int e = 0; e < 4; ++e) o[e] = tf32_part(phi_from_d2<FN>(d2[e], th2[e], ith[e]), lo);
     return make_float4(o[0], o[1], o[2], o[3]);
 }
+// `lo` (tf32x3 mode): the chunk of the residual image, tf32(v - tf32(v)), instead of tf32(v).
 __device__ __forceinline__ float4 feature_chunk(const BasisP& B, const float4* sk, const float2* st, int f, float x,
-                                                float y, float t, const float* xrow) {
+                                                float y, float t, const float* xrow, bool lo = false) {
     const int s0 = B.p_cov, s1 = B.p_cov + B.k_s, t1 = s1 + B.k_t;
     if (f >= s0 && f + 4 <= s1) {
         const float4* kp = sk + (f - s0);
-        if (B.fn == STDADK_WENDLAND) return spatial_chunk<STDADK_WENDLAND>(kp, x, y);
-        if (B.fn == STDADK_TRIANGULAR) return spatial_chunk<STDADK_TRIANGULAR>(kp, x, y);
-        return spatial_chunk<STDADK_GAUSSIAN>(kp, x, y);
+        if (B.fn == STDADK_WENDLAND) return spatial_chunk<STDADK_WENDLAND>(kp, x, y, lo);
+        if (B.fn == STDADK_TRIANGULAR) return spatial_chunk<STDADK_TRIANGULAR>(kp, x, y, lo);
+        return spatial_chunk<STDADK_GAUSSIAN>(kp, x, y, lo);
     }
     if (f >= s1 && f + 4 <= t1) {
         const float2* tp = st + (f - s1);
@@ -127,24 +134,25 @@ __device__ __forceinline__ float4 feature_chunk(const BasisP& B, const float4* s
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             float2 tk = tp[e];
-            o[e] = to_tf32(psi_eval(t, tk.x, tk.y));
+            o[e] = tf32_part(psi_eval(t, tk.x, tk.y), lo);
         }
         return make_float4(o[0], o[1], o[2], o[3]);
     }
     if (f >= t1) return make_float4(0.f, 0.f, 0.f, 0.f);
-    return make_float4(to_tf32(feature_value(B, sk, st, f + 0, x, y, t, xrow)),
-                       to_tf32(feature_value(B, sk, st, f + 1, x, y, t, xrow)),
-                       to_tf32(feature_value(B, sk, st, f + 2, x, y, t, xrow)),
-                       to_tf32(feature_value(B, sk, st, f + 3, x, y, t, xrow)));
+    return make_float4(tf32_part(feature_value(B, sk, st, f + 0, x, y, t, xrow), lo),
+                       tf32_part(feature_value(B, sk, st, f + 1, x, y, t, xrow), lo),
+                       tf32_part(feature_value(B, sk, st, f + 2, x, y, t, xrow), lo),
+                       tf32_part(feature_value(B, sk, st, f + 3, x, y, t, xrow), lo));
 }
 
 // Generate chunks [c_begin, c_end) of one 128-row x 32-feature operand slab (this thread = row r) into swizzled SMEM.
 __device__ __forceinline__ void gen_basis_slab(const BasisP& B, const float4* sk, const float2* st, int slab,
                                                float x, float y, float t, const float* xrow, uint32_t slab_saddr,
-                                               uint32_t r, int c_begin = 0, int c_end = 8, float* gslab = nullptr) {
+                                               uint32_t r, int c_begin = 0, int c_end = 8, float* gslab = nullptr,
+                                               bool lo = false) {
 #pragma unroll 1
     for (int c = c_begin; c < c_end; ++c) {
-        float4 v = feature_chunk(B, sk, st, slab * SLAB_K + c * 4, x, y, t, xrow);
+        float4 v = feature_chunk(B, sk, st, slab * SLAB_K + c * 4, x, y, t, xrow, lo);
         st_shared_v4(slab_saddr + swz_off(r, c), v.x, v.y, v.z, v.w);
         if (gslab)      // same slab, same swizzle, in the global operand image (read back by the backward / wgrad)
             *reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(gslab) + swz_off(r, c)) = v;
@@ -205,6 +213,26 @@ __device__ __forceinline__ void issue_slab_mma(uint32_t tmem_acc, const float* s
 #pragma unroll
     for (int k = 0; k < 4; ++k) umma_tf32(tmem_acc, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc,
                                           (first && k == 0) ? 0u : 1u);
+}
+
+// tf32x3 ("virtual slabs"): with passes = 3 every K slab is issued three times into the same accumulator, as
+// (A_hi, B_hi), (A_hi, B_lo), (A_lo, B_hi); the stage ring, barriers and shared-memory footprint are those of the
+// single-pass kernels, only the slab count and the image each copy reads from change.
+__device__ __forceinline__ bool pass_a_lo(int p) { return p == 2; }
+__device__ __forceinline__ bool pass_b_lo(int p) { return p == 1; }
+// hi and residual image of one 32-column chunk of an output row (residual only in tf32x3 mode)
+__device__ __forceinline__ void store_operand_chunk(float* img, float* img_lo, int tile, int slabs, int c0, uint32_t row,
+                                                    const float (&v)[32]) {
+    const size_t off = ((size_t)tile * slabs + (c0 / SLAB_K)) * SLAB_FLOATS;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float4 hi = make_float4(to_tf32(v[4 * c]), to_tf32(v[4 * c + 1]), to_tf32(v[4 * c + 2]), to_tf32(v[4 * c + 3]));
+        *reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(img + off) + swz_off(row, c)) = hi;
+        if (img_lo)
+            *reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(img_lo + off) + swz_off(row, c)) =
+                make_float4(to_tf32(v[4 * c] - hi.x), to_tf32(v[4 * c + 1] - hi.y), to_tf32(v[4 * c + 2] - hi.z),
+                            to_tf32(v[4 * c + 3] - hi.w));
+    }
 }
 
 // 1024-byte alignment of the dynamic shared-memory base, computed as an OFFSET from the extern array so the
@@ -353,15 +381,19 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
     if (warp == 4 * CG) {
         // ---------------- producer
         if (lane == 0) {
-            const float* a_tile = BASIS ? nullptr : P.a_img + (size_t)tile * P.k_slabs * SLAB_FLOATS;
-            for (int s = 0; s < P.k_slabs; ++s) {
-                int stage = s % NSTAGE, it = s / NSTAGE;
+            const size_t a_off = (size_t)tile * P.k_slabs * SLAB_FLOATS;
+            const int n_virt = P.k_slabs * P.passes;
+            for (int v = 0; v < n_virt; ++v) {
+                const int s = v / P.passes, p = v - s * P.passes;
+                int stage = v % NSTAGE, it = v / NSTAGE;
                 if (it > 0) mbar_wait(&empty[stage], (it - 1) & 1);
+                const float* w_src = pass_b_lo(p) ? P.L.w_img_lo : P.L.w_img;
+                const float* a_tile = BASIS ? nullptr : (pass_a_lo(p) ? P.a_img_lo : P.a_img) + a_off;
                 if (CL > 1)
-                    issue_slab_copies_cluster<CL>(P.L.w_img, P.k_slabs, s, n_pad, a_tile, sA + (size_t)stage * SLAB_FLOATS,
+                    issue_slab_copies_cluster<CL>(w_src, P.k_slabs, s, n_pad, a_tile, sA + (size_t)stage * SLAB_FLOATS,
                                                   sB + stage * b_stage_floats, &full[stage], crank);
                 else
-                    issue_slab_copies(P.L.w_img, P.k_slabs, s, n_pad, a_tile, sA + (size_t)stage * SLAB_FLOATS,
+                    issue_slab_copies(w_src, P.k_slabs, s, n_pad, a_tile, sA + (size_t)stage * SLAB_FLOATS,
                                       sB + stage * b_stage_floats, &full[stage]);
             }
         }
@@ -370,7 +402,8 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
         // ---------------- MMA issuer
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_tf32((uint32_t)n_pad, 0, 0);
-            for (int s = 0; s < P.k_slabs; ++s) {
+            const int n_virt = P.k_slabs * P.passes;
+            for (int s = 0; s < n_virt; ++s) {
                 int stage = s % NSTAGE, it = s / NSTAGE;
                 mbar_wait(&full[stage], it & 1);
                 tc_fence_after();
@@ -397,12 +430,15 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
                 if (P.basis.p_cov > 0 && P.pts.xcov) xrow = P.pts.xcov + sample_of(P.pts, grow) * P.basis.p_cov;
             }
             mbar_wait(kbar, 0);
-            for (int s = 0; s < P.k_slabs; ++s) {
-                int stage = s % NSTAGE, it = s / NSTAGE;
+            const int n_virt = P.k_slabs * P.passes;
+            for (int v = 0; v < n_virt; ++v) {
+                const int s = v / P.passes, p = v - s * P.passes;
+                int stage = v % NSTAGE, it = v / NSTAGE;
                 if (it > 0) mbar_wait(&empty[stage], (it - 1) & 1);
                 gen_basis_slab(P.basis, sk, st, s, x, y, t, xrow, smem_u32(sA + (size_t)stage * SLAB_FLOATS),
                                (uint32_t)row, cg * (8 / CG), (cg + 1) * (8 / CG),
-                               (P.feat_img && tile_valid) ? P.feat_img + ((size_t)tile * P.k_slabs + s) * SLAB_FLOATS : nullptr);
+                               (P.feat_img && tile_valid && p == 0) ? P.feat_img + ((size_t)tile * P.k_slabs + s) * SLAB_FLOATS : nullptr,
+                               pass_a_lo(p));
                 fence_proxy_async_smem();
                 mbar_arrive(&full[stage]);
             }
@@ -527,15 +563,8 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
                         if (kk == k) yh[kk] += acc;
                 }
             }
-            if (P.out_img && tile_valid) {
-                float* dst = P.out_img + ((size_t)tile * (n_pad / SLAB_K) + (c0 / SLAB_K)) * SLAB_FLOATS;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    float4 o = make_float4(to_tf32(v[4 * c]), to_tf32(v[4 * c + 1]), to_tf32(v[4 * c + 2]),
-                                           to_tf32(v[4 * c + 3]));
-                    *reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(dst) + swz_off((uint32_t)row, c)) = o;
-                }
-            }
+            if (P.out_img && tile_valid)
+                store_operand_chunk(P.out_img, P.out_img_lo, tile, n_pad / SLAB_K, c0, (uint32_t)row, v);
         }
         if (P.has_head) {
             if (CG > 1) {
@@ -638,7 +667,8 @@ __global__ void __launch_bounds__(n_threads(CG), 1) layer_bwd_kernel(const __gri
     const int n_pad = P.n_pad, n_out = P.L.n_out;
     constexpr bool has_ln = LN;
     const size_t b_stage_floats = (size_t)n_pad * SLAB_K;
-    const int total_slabs = P.k_slabs + P.k_slabs2;
+    const int virt1 = P.k_slabs * P.passes;                 // GEMM 1 (recompute), then GEMM 2 (dgrad): virtual slabs
+    const int total_slabs = virt1 + P.k_slabs2 * P.passes;
     const uint32_t acc1_off = (uint32_t)(P.tmem_cols / 2);
 
     if (tid == NW) {
@@ -675,18 +705,22 @@ __global__ void __launch_bounds__(n_threads(CG), 1) layer_bwd_kernel(const __gri
 
     if (warp == 4 * CG) {
         if (lane == 0) {
-            const float* a_tile = BASIS ? nullptr : P.a_img + (size_t)tile * P.k_slabs * SLAB_FLOATS;
-            const float* dzn_tile = P.k_slabs2 ? P.dz_next_img + (size_t)tile * P.k_slabs2 * SLAB_FLOATS : nullptr;
-            for (int s = 0; s < total_slabs; ++s) {
-                int stage = s % NSTAGE, it = s / NSTAGE;
+            const size_t a_off = (size_t)tile * P.k_slabs * SLAB_FLOATS, dzn_off = (size_t)tile * P.k_slabs2 * SLAB_FLOATS;
+            for (int v = 0; v < total_slabs; ++v) {
+                int stage = v % NSTAGE, it = v / NSTAGE;
                 if (it > 0) mbar_wait(&empty[stage], (it - 1) & 1);
                 float* a_dst = sA + (size_t)stage * SLAB_FLOATS;
                 float* b_dst = sB + stage * b_stage_floats;
-                if (s < P.k_slabs)
-                    issue_slab_copies(P.L.w_img, P.k_slabs, s, n_pad, a_tile, a_dst, b_dst, &full[stage]);
-                else
-                    issue_slab_copies(P.wt_next_img, P.k_slabs2, s - P.k_slabs, n_pad, dzn_tile, a_dst, b_dst,
+                if (v < virt1) {
+                    const int s = v / P.passes, p = v - s * P.passes;
+                    const float* a_tile = BASIS ? nullptr : (pass_a_lo(p) ? P.a_img_lo : P.a_img) + a_off;
+                    issue_slab_copies(pass_b_lo(p) ? P.L.w_img_lo : P.L.w_img, P.k_slabs, s, n_pad, a_tile, a_dst, b_dst,
                                       &full[stage]);
+                } else {
+                    const int s = (v - virt1) / P.passes, p = (v - virt1) - s * P.passes;
+                    issue_slab_copies(pass_b_lo(p) ? P.wt_next_img_lo : P.wt_next_img, P.k_slabs2, s, n_pad,
+                                      (pass_a_lo(p) ? P.dz_next_img_lo : P.dz_next_img) + dzn_off, a_dst, b_dst, &full[stage]);
+                }
             }
         }
         __syncwarp();
@@ -697,9 +731,9 @@ __global__ void __launch_bounds__(n_threads(CG), 1) layer_bwd_kernel(const __gri
                 int stage = s % NSTAGE, it = s / NSTAGE;
                 mbar_wait(&full[stage], it & 1);
                 tc_fence_after();
-                bool second = s >= P.k_slabs;
+                bool second = s >= virt1;
                 issue_slab_mma(tmem_base + (second ? acc1_off : 0u), sA + (size_t)stage * SLAB_FLOATS,
-                               sB + stage * b_stage_floats, idesc, s == 0 || s == P.k_slabs);
+                               sB + stage * b_stage_floats, idesc, s == 0 || s == virt1);
                 umma_commit(&empty[stage]);
             }
             umma_commit(accf);
@@ -719,12 +753,13 @@ __global__ void __launch_bounds__(n_threads(CG), 1) layer_bwd_kernel(const __gri
                 if (P.basis.p_cov > 0 && P.pts.xcov) xrow = P.pts.xcov + sample_of(P.pts, grow) * P.basis.p_cov;
             }
             mbar_wait(kbar, 0);
-            for (int s = 0; s < total_slabs; ++s) {
-                int stage = s % NSTAGE, it = s / NSTAGE;
+            for (int v = 0; v < total_slabs; ++v) {
+                int stage = v % NSTAGE, it = v / NSTAGE;
                 if (it > 0) mbar_wait(&empty[stage], (it - 1) & 1);
-                if (s < P.k_slabs) {
+                if (v < virt1) {
+                    const int s = v / P.passes, p = v - s * P.passes;
                     gen_basis_slab(P.basis, sk, st, s, x, y, t, xrow, smem_u32(sA + (size_t)stage * SLAB_FLOATS),
-                                   (uint32_t)row, cg * (8 / CG), (cg + 1) * (8 / CG));
+                                   (uint32_t)row, cg * (8 / CG), (cg + 1) * (8 / CG), nullptr, pass_a_lo(p));
                     fence_proxy_async_smem();
                 }
                 mbar_arrive(&full[stage]);
@@ -816,13 +851,7 @@ __global__ void __launch_bounds__(n_threads(CG), 1) layer_bwd_kernel(const __gri
                 s = warp_transpose_sum(tmp, lane);
                 atomicAdd(&cs_bet[c0 + lane], s);
             } else {
-                float* dst = P.dz_img + ((size_t)tile * (n_pad / SLAB_K) + (c0 / SLAB_K)) * SLAB_FLOATS;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    float4 o = make_float4(to_tf32(g[4 * c]), to_tf32(g[4 * c + 1]), to_tf32(g[4 * c + 2]),
-                                           to_tf32(g[4 * c + 3]));
-                    *reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(dst) + swz_off((uint32_t)row, c)) = o;
-                }
+                store_operand_chunk(P.dz_img, P.dz_img_lo, tile, n_pad / SLAB_K, c0, (uint32_t)row, g);
                 float s = warp_transpose_sum(g, lane);
                 atomicAdd(&cs_bias[c0 + lane], s);
             }
@@ -872,13 +901,7 @@ __global__ void __launch_bounds__(n_threads(CG), 1) layer_bwd_kernel(const __gri
                     float dz = rstd * (gy - ma - xh * mb);
                     g[i] = (col < n_out && rvalid) ? dz : 0.0f;
                 }
-                float* dst = P.dz_img + ((size_t)tile * (n_pad / SLAB_K) + (c0 / SLAB_K)) * SLAB_FLOATS;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    float4 o = make_float4(to_tf32(g[4 * c]), to_tf32(g[4 * c + 1]), to_tf32(g[4 * c + 2]),
-                                           to_tf32(g[4 * c + 3]));
-                    *reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(dst) + swz_off((uint32_t)row, c)) = o;
-                }
+                store_operand_chunk(P.dz_img, P.dz_img_lo, tile, n_pad / SLAB_K, c0, (uint32_t)row, g);
                 float s = warp_transpose_sum(g, lane);
                 atomicAdd(&cs_bias[c0 + lane], s);
             }
@@ -914,10 +937,12 @@ struct WgradK {
     BasisP basis;
     PointsP pts;
     const float* a_img;
+    const float* a_img_lo;      // tf32x3 residual images (NULL in TF32 mode)
     const float* dz_img;
+    const float* dz_img_lo;
     float* dw;
     long long stride_o, stride_i;
-    int n_in, n_out, a_slabs, dz_slabs, n_row_tiles, nt_slabs, tmem_cols, _pad;
+    int n_in, n_out, a_slabs, dz_slabs, n_row_tiles, nt_slabs, tmem_cols, passes;
 };
 constexpr int WG_HALF_ROWS = 64;
 constexpr int WG_CHUNK_BYTES = WG_HALF_ROWS * 128;           // 8 KB: 64 rows of one slab
@@ -1001,7 +1026,7 @@ __global__ void __launch_bounds__(n_threads(CG), 1) wgrad_kernel(const __grid_co
     const int n_mma = n_chunks * SLAB_K;
     int my_tiles = 0;
     for (int rt = split; rt < P.n_row_tiles; rt += n_split) ++my_tiles;
-    const int n_iter = my_tiles * 2;
+    const int n_iter = my_tiles * 2 * P.passes;     // (row tile, half, tf32x3 pass)
 
     if (tid == NW) {
         for (int s = 0; s < WG_NSTAGE; ++s) {
@@ -1057,7 +1082,8 @@ __global__ void __launch_bounds__(n_threads(CG), 1) wgrad_kernel(const __grid_co
             int itn = 0;
             if (BASIS) mbar_wait(kbar, 0);
             for (int rt = split; rt < P.n_row_tiles; rt += n_split)
-                for (int half = 0; half < 2; ++half, ++itn) {
+                for (int hp = 0; hp < 2 * P.passes; ++hp, ++itn) {
+                    const int half = hp / P.passes, pass = hp - half * P.passes;
                     int stage = itn % WG_NSTAGE, it = itn / WG_NSTAGE;
                     float x = 0.f, y = 0.f, t = 0.f;
                     const float* xrow = nullptr;
@@ -1072,15 +1098,17 @@ __global__ void __launch_bounds__(n_threads(CG), 1) wgrad_kernel(const __grid_co
                     if (it > 0) mbar_wait(&empty[stage], (it - 1) & 1);
                     uint32_t sa = smem_u32(stage_base + stage * WG_STAGE_BYTES);
                     uint32_t sb = sa + WG_A_BYTES;
-                    restage_half_tiles<NW>(P.dz_img + (size_t)rt * P.dz_slabs * SLAB_FLOATS, mi * 4, m_chunks,
-                                           BASIS ? nullptr : P.a_img + (size_t)rt * P.a_slabs * SLAB_FLOATS,
+                    restage_half_tiles<NW>((pass_a_lo(pass) ? P.dz_img_lo : P.dz_img) + (size_t)rt * P.dz_slabs * SLAB_FLOATS,
+                                           mi * 4, m_chunks,
+                                           BASIS ? nullptr
+                                                 : (pass_b_lo(pass) ? P.a_img_lo : P.a_img) + (size_t)rt * P.a_slabs * SLAB_FLOATS,
                                            ni * P.nt_slabs, n_chunks, half, sa, sb, tid);
                     if (BASIS) {
                         for (int c = par; c < n_chunks; c += NW / 64) {
                             const int slab = ni * P.nt_slabs + c;
 #pragma unroll 1
                             for (int c16 = 0; c16 < 8; ++c16) {
-                                float4 v = feature_chunk(P.basis, sk, st, slab * SLAB_K + c16 * 4, x, y, t, xrow);
+                                float4 v = feature_chunk(P.basis, sk, st, slab * SLAB_K + c16 * 4, x, y, t, xrow, pass_b_lo(pass));
                                 st_shared_v4(sb + c * WG_CHUNK_BYTES + swz32_off((uint32_t)row64, (uint32_t)c16), v.x, v.y,
                                              v.z, v.w);
                             }
@@ -1125,10 +1153,12 @@ struct KnotGradK {
     BasisP basis;
     PointsP pts;
     const float* dz_img;
+    const float* dz_img_lo;     // tf32x3 residual images (NULL in TF32 mode)
     const float* w1s_img;
+    const float* w1s_img_lo;
     float* d_centers;
     float* d_log_bw;
-    int n_out, k_slabs, _p0, _p1;
+    int n_out, k_slabs, passes, _p1;
 };
 
 template <int CG>
@@ -1172,21 +1202,24 @@ __global__ void __launch_bounds__(n_threads(CG)) knotgrad_kernel(const __grid_co
 
     if (warp == 4 * CG) {
         if (lane == 0) {
-            const float* a_tile = P.w1s_img + (size_t)ktile * P.k_slabs * SLAB_FLOATS;
-            for (int s = 0; s < P.k_slabs; ++s) {
-                int stage = s % NSTAGE, it = s / NSTAGE;
+            const size_t a_off = (size_t)ktile * P.k_slabs * SLAB_FLOATS;
+            for (int v = 0; v < P.k_slabs * P.passes; ++v) {
+                const int s = v / P.passes, p = v - s * P.passes;
+                int stage = v % NSTAGE, it = v / NSTAGE;
                 if (it > 0) mbar_wait(&empty[stage], (it - 1) & 1);
                 mbar_arrive_expect_tx(&full[stage], 2 * SLAB_BYTES);
-                bulk_g2s(sA + (size_t)stage * SLAB_FLOATS, a_tile + (size_t)s * SLAB_FLOATS, SLAB_BYTES, &full[stage]);
+                bulk_g2s(sA + (size_t)stage * SLAB_FLOATS,
+                         (pass_a_lo(p) ? P.w1s_img_lo : P.w1s_img) + a_off + (size_t)s * SLAB_FLOATS, SLAB_BYTES, &full[stage]);
                 bulk_g2s(sB + (size_t)stage * SLAB_FLOATS,
-                         P.dz_img + ((size_t)ptile * P.k_slabs + s) * SLAB_FLOATS, SLAB_BYTES, &full[stage]);
+                         (pass_b_lo(p) ? P.dz_img_lo : P.dz_img) + ((size_t)ptile * P.k_slabs + s) * SLAB_FLOATS, SLAB_BYTES,
+                         &full[stage]);
             }
         }
         __syncwarp();
     } else if (warp == 4 * CG + 1) {
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_tf32(TILE_M, 0, 0);
-            for (int s = 0; s < P.k_slabs; ++s) {
+            for (int s = 0; s < P.k_slabs * P.passes; ++s) {
                 int stage = s % NSTAGE, it = s / NSTAGE;
                 mbar_wait(&full[stage], it & 1);
                 tc_fence_after();

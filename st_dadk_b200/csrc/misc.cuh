@@ -52,7 +52,7 @@ __global__ void pack_images_kernel(PackBatch B) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             long long c = (long long)slab * SLAB_K + chunk * 4 + e;
-            v[e] = (r < D.rows && c < D.cols) ? to_tf32(D.src[r * D.row_stride + c * D.col_stride]) : 0.0f;
+            v[e] = (r < D.rows && c < D.cols) ? tf32_part(D.src[r * D.row_stride + c * D.col_stride], D.part != 0) : 0.0f;
         }
         float* dst = D.img + ts * SLAB_FLOATS;
         *reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(dst) + swz_off((uint32_t)row, (uint32_t)chunk)) =

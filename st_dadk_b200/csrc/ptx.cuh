@@ -190,6 +190,12 @@ __device__ __forceinline__ uint32_t swz_off(uint32_t row, uint32_t chunk) {
 __device__ __forceinline__ float to_tf32(float x) {
     return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
+// tf32x3 operand split: a value is fed to the tensor cores as hi = tf32(x) and lo = tf32(x - hi) (x - hi is exact in
+// FP32); hi*hi + hi*lo + lo*hi accumulated in FP32 reproduces the FP32 product to ~2^-21.  `lo` selects the part.
+__device__ __forceinline__ float tf32_part(float x, bool lo) {
+    const float hi = to_tf32(x);
+    return lo ? to_tf32(x - hi) : hi;
+}
 // Packed FP32 (two lanes per instruction, FFMA2 / FADD2 on sm_100): same rounding as the scalar forms, half the
 // issue slots.  ptxas pairs the registers without moves when the operands come from adjacent array elements.
 __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {

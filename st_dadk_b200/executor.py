@@ -40,6 +40,10 @@ class NetSpec:
     ln_eps: float = 1e-5
     learnable_basis: bool = False
     lattice_sides: Optional[List[int]] = None  # knots per axis of each level when the knots are the fixed uniform lattice
+    # "tf32": one tensor-core pass on TF32-rounded operands (throughput mode; outputs within 1e-3 of the FP32 reference).
+    # "tf32x3": every operand is split into tf32(x) + tf32(x - tf32(x)) and every GEMM runs hi*hi + hi*lo + lo*hi into
+    # the same FP32 accumulator: FP32-faithful products, for runs that must track the reference's FP32 trajectory.
+    precision: str = "tf32"
 
     @property
     def n_hidden(self):
@@ -67,6 +71,9 @@ class _Workspace:
         self.zs = torch.empty(n_rows, spec.weights[0].shape[0], dtype=torch.float32, device=device) if sparse else None
         self.h = [ops.new_image(n_rows, w.shape[0], device) for w in spec.weights[:-1]]
         self.dz = [ops.new_image(n_rows, w.shape[0], device) for w in spec.weights]
+        x3 = spec.precision == "tf32x3"                 # residual images of every activation / dz image
+        self.h_lo = [ops.new_image(n_rows, w.shape[0], device) for w in spec.weights[:-1]] if x3 else None
+        self.dz_lo = [ops.new_image(n_rows, w.shape[0], device) for w in spec.weights] if x3 else None
         self.stats = [torch.empty(n_rows, 2, dtype=torch.float32, device=device) if g is not None else None
                       for g in spec.gammas]
         # pre-LayerNorm x of every block, kept only for single-wave batches (see Executor.SAVE_X_MAX_ROWS)
@@ -104,11 +111,15 @@ class Executor:
             raise RuntimeError("st_dadk_b200.Executor needs CUDA tensors: the hot path has no CPU implementation")
         self.device = dev
         self._ws: Dict[int, _Workspace] = {}
+        self.on_evict = None
         self._ctx = None
         self._pack_key = None
         self.w_img: List[torch.Tensor] = [None] * spec.n_hidden
         self.wt_img: List[torch.Tensor] = [None] * spec.n_hidden
         self.w1s_img = None
+        self.w_img_lo: List[torch.Tensor] = [None] * spec.n_hidden      # tf32x3 residual images
+        self.wt_img_lo: List[torch.Tensor] = [None] * spec.n_hidden
+        self.w1s_img_lo = None
         self.knots4 = torch.empty(max(spec.centers.shape[0], 1), 4, dtype=torch.float32, device=dev)
         self.tknots2 = torch.empty(max(spec.t_centers.shape[0], 1), 2, dtype=torch.float32, device=dev)
         self.loss_acc = torch.zeros(1, dtype=torch.float32, device=dev)
@@ -124,7 +135,13 @@ class Executor:
         self.fused_train = False
         self._fused_ok = None
 
+    @property
+    def x3(self) -> bool:
+        return self.spec.precision == "tf32x3"
+
     def _setup_regime(self, spec: NetSpec):
+        if spec.precision not in ("tf32", "tf32x3"):
+            raise ValueError(f"precision must be 'tf32' or 'tf32x3', got {spec.precision!r}")
         k_s = spec.centers.shape[0]
         want = self.force_sparse or k_s > self.DENSE_MAX_KNOTS
         self.sparse = False
@@ -157,6 +174,10 @@ class Executor:
 
     # ------------------------------------------------------------------ operand preparation
     def rebind(self, spec: NetSpec):
+        if spec.precision != self.spec.precision:
+            self._ws.clear()                       # workspaces carry (or lack) the residual images
+            if self.on_evict is not None:
+                self.on_evict()
         self.spec = spec
         self._setup_regime(spec)
         self._pack_key = None
@@ -180,26 +201,37 @@ class Executor:
                               s.basis_fn, out=self.knots4)
             ops.tknots_prepare(s.t_centers, s.t_bandwidths, out=self.tknots2)   # fixed buffers: only the first time
             self._knots_ready = True
-        srcs, outs, slots = [], [], []
+        srcs, outs, slots, parts = [], [], [], []
+        x3 = self.x3
+
+        def add(src, kind, l):
+            store = {"w": self.w_img, "wt": self.wt_img, "w1s": None}[kind]
+            srcs.append(src); outs.append(store[l] if store is not None else self.w1s_img)
+            slots.append((kind, l, 0)); parts.append(0)
+            if x3:                                       # residual image of the same matrix
+                store = {"w": self.w_img_lo, "wt": self.wt_img_lo, "w1s": None}[kind]
+                srcs.append(src); outs.append(store[l] if store is not None else self.w1s_img_lo)
+                slots.append((kind, l, 1)); parts.append(1)
+
         for l, w in enumerate(s.weights):
             if l == 0 and self.sparse:
                 k_s = s.centers.shape[0]
-                srcs.append(w[:, k_s:])                 # dense (temporal) columns only; spatial rows are gathered
+                add(w[:, k_s:], "w", l)                  # dense (temporal) columns only; spatial rows are gathered
                 wt = w.t()
                 self._w1t = wt if wt.is_contiguous() else wt.contiguous()
             else:
-                srcs.append(w)
-            outs.append(self.w_img[l]); slots.append(("w", l))
+                add(w, "w", l)
             if for_backward and l > 0:
-                srcs.append(w.t()); outs.append(self.wt_img[l]); slots.append(("wt", l))
+                add(w.t(), "wt", l)
         if for_backward and s.learnable_basis:
-            srcs.append(s.weights[0][:, s.p_cov:s.p_cov + s.centers.shape[0]].t())   # (K_s, n_out)
-            outs.append(self.w1s_img); slots.append(("w1s", 0))
-        for (kind, l), img in zip(slots, ops.pack_images(srcs, outs)):   # one launch for all images
+            add(s.weights[0][:, s.p_cov:s.p_cov + s.centers.shape[0]].t(), "w1s", 0)   # (K_s, n_out)
+        for (kind, l, part), img in zip(slots, ops.pack_images(srcs, outs, parts)):   # one launch per 8 images
             if kind == "w":
-                self.w_img[l] = img
+                (self.w_img_lo if part else self.w_img)[l] = img
             elif kind == "wt":
-                self.wt_img[l] = img
+                (self.wt_img_lo if part else self.wt_img)[l] = img
+            elif part:
+                self.w1s_img_lo = img
             else:
                 self.w1s_img = img
         self._pack_key = key
@@ -209,9 +241,11 @@ class Executor:
         if ws is None:
             if len(self._ws) >= self.MAX_WORKSPACES:
                 self._ws.pop(next(iter(self._ws)))
+                if self.on_evict is not None:      # whoever captured CUDA graphs over the evicted buffers drops them
+                    self.on_evict()
             ws = self._ws[n_rows] = _Workspace(self.spec, n_rows, self.device, self.sparse,
                                                save_x=n_rows <= self.SAVE_X_MAX_ROWS,
-                                               save_feat=(self.store_basis_operand and not self.sparse
+                                               save_feat=(self.store_basis_operand and not self.sparse and not self.x3
                                                           and n_rows >= self.SAVE_FEAT_MIN_ROWS))
         return ws
 
@@ -227,7 +261,8 @@ class Executor:
     def _layer(self, l: int) -> L.Layer:
         s = self.spec
         w = s.weights[l]
-        return ops.make_layer(self.w_img[l], s.biases[l], s.gammas[l], s.betas[l], self._n_in(l), w.shape[0], s.ln_eps, l)
+        return ops.make_layer(self.w_img[l], s.biases[l], s.gammas[l], s.betas[l], self._n_in(l), w.shape[0], s.ln_eps, l,
+                              self.w_img_lo[l] if self.x3 else None)
 
     def _sparse_args(self, pts, ws, **kw) -> L.SparseArgs:
         s = self.spec
@@ -250,7 +285,7 @@ class Executor:
             # always rebuild the operand images: parameter storage can be rewritten in place by kernels or by
             # an EMA swap without any version counter the executor could observe (5 tiny launches)
             self.prepare(force=True, for_backward=save)
-        if not train and not save and loss is None and self.fused_predict and not self.sparse:
+        if not train and not save and loss is None and self.fused_predict and not self.sparse and not self.x3:
             yhat = out if out is not None else torch.empty(n, s.q, dtype=torch.float32, device=self.device)
             if self._predict_fused(pts, yhat):
                 return yhat
@@ -260,7 +295,7 @@ class Executor:
         drop = L.Dropout(s.dropout if train else 0.0, step & 0xFFFFFFFF, seed,
                          step_ptr.data_ptr() if step_ptr is not None else None, key_offset)
         head = None
-        if self.fused_train and not self.sparse and self._train_fwd_fused(pts, ws, yhat, drop, y, loss, inv_count, save):
+        if self.fused_train and not self.sparse and not self.x3 and self._train_fwd_fused(pts, ws, yhat, drop, y, loss, inv_count, save):
             if save:
                 self._ctx = (pts, drop, ws)
             return yhat
@@ -277,6 +312,8 @@ class Executor:
                     a.feat_img = ws.feat.data_ptr()
             else:
                 a.a_img = ws.h[l - 1].data_ptr()
+                if self.x3:
+                    a.a_img_lo = ws.h_lo[l - 1].data_ptr()
             a.layer = self._layer(l)
             a.drop = drop
             if save and ws.stats[l] is not None:
@@ -285,6 +322,8 @@ class Executor:
                 a.x_img = ws.x[l].data_ptr()
             if l < s.n_hidden - 1:
                 a.out_img = ws.h[l].data_ptr()
+                if self.x3:
+                    a.out_img_lo = ws.h_lo[l].data_ptr()
             else:
                 if loss is not None:
                     code = L.LOSS_MSE if loss.kind == "mse" else L.LOSS_PINBALL
@@ -339,7 +378,7 @@ class Executor:
         """Whether forward-only calls on this network run through the whole-network kernel (decided once per binding;
         needs the operand images, i.e. prepare() first)."""
         s = self.spec
-        if self.sparse or not self.fused_predict or s.n_hidden > L.MAX_HIDDEN:
+        if self.sparse or self.x3 or not self.fused_predict or s.n_hidden > L.MAX_HIDDEN:
             return False
         if self._fused_ok is None:
             probe = torch.empty(1, s.q, dtype=torch.float32, device=self.device)
@@ -426,7 +465,11 @@ class Executor:
             a.basis = C.pointer(basis)
         else:
             a.a_img = (ws.feat if l == 0 else ws.h[l - 1]).data_ptr()
+            if self.x3:
+                a.a_img_lo = ws.h_lo[l - 1].data_ptr()
         a.dz_img = ws.dz[l].data_ptr()
+        if self.x3:
+            a.dz_img_lo = ws.dz_lo[l].data_ptr()
         a.n_in, a.n_out = self._n_in(l), w.shape[0]
         if l == 0 and self.sparse:
             k_s = s.centers.shape[0]
@@ -472,6 +515,8 @@ class Executor:
                     a.addend = ws.zs.data_ptr()
             else:
                 a.a_img = (ws.feat if l == 0 else ws.h[l - 1]).data_ptr()
+                if self.x3:
+                    a.a_img_lo = ws.h_lo[l - 1].data_ptr()
             a.layer = self._layer(l)
             a.drop = drop
             if ws.x is not None:
@@ -488,7 +533,12 @@ class Executor:
                 a.dz_next_img = ws.dz[l + 1].data_ptr()
                 a.wt_next_img = self.wt_img[l + 1].data_ptr()
                 a.n_next = s.weights[l + 1].shape[0]
+                if self.x3:
+                    a.dz_next_img_lo = ws.dz_lo[l + 1].data_ptr()
+                    a.wt_next_img_lo = self.wt_img_lo[l + 1].data_ptr()
             a.dz_img = ws.dz[l].data_ptr()
+            if self.x3:
+                a.dz_img_lo = ws.dz_lo[l].data_ptr()
             a.d_bias = g["biases"][l].data_ptr()
             ops.layer_bwd(a)
             # dW_l only needs dz_l: it runs on a second stream, concurrently with the rest of the backward chain
@@ -503,6 +553,9 @@ class Executor:
             a.pts = pts
             a.dz_img = ws.dz[0].data_ptr()
             a.w1s_img = self.w1s_img.data_ptr()
+            if self.x3:
+                a.dz_img_lo = ws.dz_lo[0].data_ptr()
+                a.w1s_img_lo = self.w1s_img_lo.data_ptr()
             a.n_out = s.weights[0].shape[0]
             a.d_centers = g["centers"].data_ptr()
             a.d_log_bw = g["log_bandwidths"].data_ptr()

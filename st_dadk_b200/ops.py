@@ -55,15 +55,17 @@ def pack_image(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.T
     return out
 
 
-def pack_images(srcs, outs):
-    """Pack several strided matrices into their images with one launch; `outs[i]` may be None (allocated)."""
+def pack_images(srcs, outs, parts=None):
+    """Pack several strided matrices into their images with one launch; `outs[i]` may be None (allocated).
+    parts[i] = 1 asks for the tf32x3 residual image tf32(src - tf32(src)) instead of tf32(src)."""
     res = []
     descs = (L.PackDesc * len(srcs))()
     for i, (src, out) in enumerate(zip(srcs, outs)):
         rows, cols = src.shape
         if out is None:
             out = new_image(rows, cols, src.device)
-        descs[i] = L.PackDesc(_ptr(src), src.stride(0), src.stride(1), rows, cols, _ptr(out))
+        descs[i] = L.PackDesc(_ptr(src), src.stride(0), src.stride(1), rows, cols, _ptr(out),
+                              int(parts[i]) if parts is not None else 0, 0)
         res.append(out)
     for lo in range(0, len(srcs), 8):
         n = min(8, len(srcs) - lo)
@@ -145,8 +147,8 @@ def basis_fwd(basis: L.Basis, pts: L.Points, device) -> tuple:
     return phi, psi
 
 
-def make_layer(w_img, bias, gamma, beta, n_in, n_out, eps, layer_id) -> L.Layer:
-    return L.Layer(_ptr(w_img), _ptr(bias), _ptr(gamma), _ptr(beta), n_in, n_out, eps, layer_id)
+def make_layer(w_img, bias, gamma, beta, n_in, n_out, eps, layer_id, w_img_lo=None) -> L.Layer:
+    return L.Layer(_ptr(w_img), _ptr(bias), _ptr(gamma), _ptr(beta), n_in, n_out, eps, layer_id, _ptr(w_img_lo))
 
 
 def make_head(w, b, q, yhat, loss_type=L.LOSS_NONE, y=None, taus=None, inv_count=0.0, dyhat=None, loss_acc=None,

@@ -144,6 +144,8 @@ class Trainer:
     def __init__(self, model, config: dict, device, batches_per_epoch: int = 1, use_cuda_graph: bool = False):
         self.model = model.to(device)
         self.cfg = config
+        if config.get("precision") is not None:
+            self.model.precision = config["precision"]
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("st_dadk_b200.Trainer runs on CUDA (sm_100) only; there is no CPU training path")
@@ -176,6 +178,8 @@ class Trainer:
         self.head_b = torch.empty(self.q, device=self.device)
         self.ex = Executor(self._spec())
         self.ex.loss_acc = self.flat.loss_slot      # the loss accumulator travels with the gradient all-reduce
+        # captured graphs hold raw pointers into the executor's workspaces: drop them when one is evicted
+        self.ex.on_evict = lambda: self._graphs.clear()
         self.ex.alloc_grads(self.flat.g, self.flat.grad_views_for(m))
         self._init_loss()
         self._init_optimizer(batches_per_epoch)
@@ -263,14 +267,40 @@ class Trainer:
         self.ema_decay = 1.0 - 1.0 / (10.0 * self.batches_per_epoch)
         self.global_step = 0
         ng = len(self.opt.param_groups)
-        self.hyper_host = torch.zeros(ng, 4, dtype=torch.float32).pin_memory()
+        # Per-step hyper-parameters travel host -> device through a RING of pinned slots, each guarded by an event:
+        # the host runs many steps ahead of the GPU (graph replay, no per-step sync), so a single pinned buffer would
+        # be overwritten while the copy of an earlier step is still pending and that step would then use a later lr.
+        self._hyper_ring = [torch.zeros(ng, 4, dtype=torch.float32).pin_memory() for _ in range(self.HYPER_SLOTS)]
+        self._hyper_ev = [None] * self.HYPER_SLOTS
+        self._hyper_k = 0
+        self._hyper_last = None
         self.hyper = torch.zeros(ng, 4, dtype=torch.float32, device=self.device)
 
-    def _push_hyper(self):
-        for i, gq in enumerate(self.opt.param_groups):
+    HYPER_SLOTS = 16
+
+    def _hyper_values(self):
+        rows = []
+        for gq in self.opt.param_groups:
             clip = self.clip * (0.1 if (self.learnable and gq.get("name") == "basis") else 1.0)
-            self.hyper_host[i, 0], self.hyper_host[i, 1], self.hyper_host[i, 2] = gq["lr"], self.wd, clip
-        self.hyper.copy_(self.hyper_host, non_blocking=True)
+            rows.append((float(gq["lr"]), float(self.wd), float(clip)))
+        return tuple(rows)
+
+    def _push_hyper(self):
+        vals = self._hyper_values()
+        if vals == self._hyper_last:           # unchanged since the last step (after warm-up: once per epoch)
+            return
+        k = self._hyper_k
+        self._hyper_k = (k + 1) % self.HYPER_SLOTS
+        if self._hyper_ev[k] is not None:
+            self._hyper_ev[k].synchronize()    # the copy that last read this slot has completed
+        slot = self._hyper_ring[k]
+        for i, (lr, wd, clip) in enumerate(vals):
+            slot[i, 0], slot[i, 1], slot[i, 2] = lr, wd, clip
+        self.hyper.copy_(slot, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self._hyper_ev[k] = ev
+        self._hyper_last = vals
 
     def begin_epoch(self, epoch: int):
         """Progressive unfreezing of the basis group (train_st_interp.py:582-602)."""
@@ -327,7 +357,15 @@ class Trainer:
             return None
         total = sum(terms)
         params = [p for p in self.model.parameters() if p.requires_grad]
-        grads = torch.autograd.grad(total, params, allow_unused=True)
+        # Tensor hooks also fire inside torch.autograd.grad: the damping hook on `centers` is switched off here so the
+        # penalty gradient arrives undamped and _damp_center_grads() damps the SUMMED gradient once, as upstream's
+        # loss.backward() does (st_interp.py:111-142, train_st_interp.py:661-693).
+        sb = self.model.spatial_basis
+        sb._hook_enabled = False
+        try:
+            grads = torch.autograd.grad(total, params, allow_unused=True)
+        finally:
+            sb._hook_enabled = True
         for p, gr in zip(params, grads):
             if gr is not None:
                 self.flat.gviews[id(p)].add_(gr)
@@ -345,7 +383,7 @@ class Trainer:
         sb = self.model.spatial_basis
         if self.learnable and sb.gradient_damping:
             gv = self.flat.gviews[id(sb.centers)]
-            gv.copy_(sb._gradient_damping_hook(gv))
+            gv.copy_(sb._damping_factor() * gv)
 
     # ------------------------------------------------------------------ one optimisation step
     def _step_compute(self, table, perm, row_begin: int, n_rows: int, global_rows: int, key_offset: int = 0):
@@ -409,7 +447,8 @@ class Trainer:
                 self._stage_idx = torch.zeros(max(n_rows, 1), dtype=torch.int64, device=self.device)
                 self._graphs.clear()
             self._stage_idx[:n_rows].copy_(perm[row_begin:row_begin + n_rows])
-            gkey = (n_rows, global_rows, id(table), key_offset)
+            gkey = (n_rows, global_rows, table.coords.data_ptr(), table.t.data_ptr(), table.y.data_ptr(),
+                    table.X.data_ptr() if table.X is not None else 0, key_offset)
             g = self._graphs.get(gkey)
             if g is None:
                 # first use of this shape: run it eagerly once (sets kernel attributes, sizes workspaces) -- that run
@@ -472,6 +511,7 @@ class Trainer:
             mk = lambda: ObservationTable(z(n_rows, 2), z(n_rows), z(n_rows),
                                           z(n_rows, self.model.p) if self.model.p > 0 else None)
             self._host_stage = [mk(), mk()]
+            self._graphs.clear()               # graphs captured on the previous staging tables point at freed memory
             self._host_perm = torch.arange(n_rows, dtype=torch.int64, device=self.device)
             self._host_copy_stream = torch.cuda.Stream(device=self.device)
             self._host_ready = [torch.cuda.Event(), torch.cuda.Event()]     # staging buffer k filled
@@ -723,7 +763,7 @@ def fit(model, train_table, val_table, config: dict, device, output_dir=None, ba
             print(msg)
         if tr.learnable and (epoch + 1) % 100 == 0:
             centers_hist.append((epoch + 1, model.spatial_basis.centers.detach().cpu().numpy().copy()))
-        if math.isnan(train_loss) or bad >= patience:
+        if bad >= patience:      # a NaN epoch never improves `best`, so upstream too runs on until patience is spent
             if verbose and bad >= patience:
                 print(f"\nEarly stopping triggered at epoch {epoch + 1}")
             break

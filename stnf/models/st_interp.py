@@ -69,10 +69,17 @@ class SpatialBasisEmbedding(nn.Module):
             self.register_buffer("_bandwidths", bandwidths)
 
     # st_interp.py:111-142 -- gradient of a knot that drifted d beyond the threshold is scaled by exp(-strength*d)
-    def _gradient_damping_hook(self, grad):
+    _hook_enabled = True      # the trainer switches the hook off while it differentiates parameter-only penalties
+
+    def _damping_factor(self):
         with torch.no_grad():
             drift = (self.centers - self.centers_init).norm(dim=1, keepdim=True)
-            return grad * torch.exp(-self.damping_strength * (drift - self.damping_threshold).clamp_min(0.0))
+            return torch.exp(-self.damping_strength * (drift - self.damping_threshold).clamp_min(0.0))
+
+    def _gradient_damping_hook(self, grad):
+        if not self._hook_enabled:
+            return grad
+        return grad * self._damping_factor()
 
     @property
     def bandwidths(self):
@@ -207,6 +214,9 @@ class STInterpMLP(nn.Module):
             self.mlp_trunk = None
             self.delta_params = None
         self._ex: Optional[Executor] = None
+        # tensor-core precision of the kernels under this module: "tf32" (throughput) or "tf32x3" (FP32-faithful
+        # three-pass split, see NetSpec.precision); `create_model` reads it from the config key `precision`
+        self.precision = "tf32"
         self._dropout_step = 0
         self._seed_override: Optional[int] = None
 
@@ -256,7 +266,8 @@ class STInterpMLP(nn.Module):
             basis_fn=self.spatial_basis_function, p_cov=self.p, dropout=self._dropout_p,
             ln_eps=blocks[0][1].eps if blocks and blocks[0][1] is not None else 1e-5, learnable_basis=sb.learnable,
             lattice_sides=[int(math.sqrt(k)) for k in sb.n_centers]
-            if (sb.init_method == "uniform" and not sb.learnable) else None)
+            if (sb.init_method == "uniform" and not sb.learnable) else None,
+            precision=getattr(self, "precision", "tf32"))
 
     def _executor(self, head_w=None, head_b=None):
         spec = self.net_spec(head_w, head_b)
@@ -370,7 +381,7 @@ def create_model(config: dict, train_coords: np.ndarray = None) -> STInterpMLP:
     multi = config.get("regression_type", "mean") == "multi-quantile"
     q = len(config.get("quantile_levels", [0.1, 0.5, 0.9])) if multi else 1
     get = config.get
-    return STInterpMLP(
+    model = STInterpMLP(
         p=get("p_covariates", 0), k_spatial_centers=get("k_spatial_centers", [25, 81, 121]),
         k_temporal_centers=get("k_temporal_centers", [10, 15, 45]), hidden_dims=get("hidden_dims", [256, 256, 128]),
         dropout=get("dropout", 0.1), layernorm=get("layernorm", True), spatial_learnable=get("spatial_learnable", False),
@@ -379,3 +390,5 @@ def create_model(config: dict, train_coords: np.ndarray = None) -> STInterpMLP:
         gradient_damping=get("gradient_damping", False), damping_threshold=get("damping_threshold", 0.3),
         damping_strength=get("damping_strength", 1.0), output_dim=q,
         use_delta_reparameterization=get("use_delta_reparameterization", False))
+    model.precision = get("precision", "tf32")      # not an upstream key: "tf32" | "tf32x3"
+    return model

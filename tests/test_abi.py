@@ -31,9 +31,9 @@ def test_ctypes_structs_match_header_sizes():
     from st_dadk_b200 import _lib as L
     L.lib()   # raises on any sizeof mismatch between the ctypes structs and the compiled header
     assert ctypes.sizeof(L.Basis) == 32 and ctypes.sizeof(L.Points) == 64
-    assert ctypes.sizeof(L.Layer) == 48 and ctypes.sizeof(L.Dropout) == 32
+    assert ctypes.sizeof(L.Layer) == 56 and ctypes.sizeof(L.Dropout) == 32
     assert ctypes.sizeof(L.Head) == 24 + 8 + 32 + 16 + 24
-    assert ctypes.sizeof(L.FwdArgs) == 8 + 64 + 8 + 48 + 32 + 48
+    assert ctypes.sizeof(L.FwdArgs) == 8 + 64 + 8 + 56 + 32 + 48 + 16
 
 
 def test_product_never_imports_oracle():

@@ -43,7 +43,7 @@ def rel_err(a, b):
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
 
 
-def spec_from_oracle(m, learnable=False, dropout=0.0):
+def spec_from_oracle(m, learnable=False, dropout=0.0, precision="tf32"):
     L, ops, Executor, NetSpec, LossSpec = _mods()
     Wh, bh = m.head(np.float64)
     n_hidden = len(m.ln_gamma)
@@ -55,7 +55,7 @@ def spec_from_oracle(m, learnable=False, dropout=0.0):
         gammas=[T(g) if g is not None else None for g in m.ln_gamma],
         betas=[T(b) if b is not None else None for b in m.ln_beta],
         head_w=T(Wh), head_b=T(bh), basis_fn=m.basis_fn, p_cov=m.p, dropout=dropout, ln_eps=m.ln_eps,
-        learnable_basis=learnable)
+        learnable_basis=learnable, precision=precision)
 
 
 def test_library_loads_on_gpu():
@@ -217,16 +217,21 @@ CASES = [("small_mse", "wendland", "mse", None), ("small_mq", "wendland", "pinba
          ("small_delta", "wendland", "pinball", [0.1, 0.5, 0.9])]
 
 
+@pytest.mark.parametrize("precision", ["tf32", "tf32x3"])
 @pytest.mark.parametrize("name,fn,loss,taus", CASES)
-def test_network_forward_backward_vs_reference(name, fn, loss, taus):
+def test_network_forward_backward_vs_reference(name, fn, loss, taus, precision):
     """Whole chain (basis fused into block 1, tcgen05 blocks, fused head + loss, backward with basis
-    recompute, wgrad, knot gradients) against the reference module's FP64 outputs and autograd."""
+    recompute, wgrad, knot gradients) against the reference module's FP64 outputs and autograd.
+    precision "tf32x3" (three-pass operand split, FP32-faithful products): outputs to 2e-5, every gradient to 5e-4 of
+    the FP64 reference (MSE: 1e-4) -- the FP32 reference itself is no closer to its FP64 evaluation."""
     L, ops, Executor, NetSpec, LossSpec = _mods()
     g = golden(name)
     m = oracle_from_state(state_of(g), basis_fn=fn)
     learn = name == "small_learnable"
-    spec = spec_from_oracle(m, learnable=learn)
+    x3 = precision == "tf32x3"
+    spec = spec_from_oracle(m, learnable=learn, precision=precision)
     ex = Executor(spec)
+    ex.SAVE_X_MAX_ROWS = 0 if name in ("small_mq", "small_gauss") else ex.SAVE_X_MAX_ROWS   # also the recompute GEMM
     coords, t, y = T(g["coords"]), T(g["t"]), T(g["y"].reshape(-1))
     n = coords.shape[0]
     pts = ops.make_points(coords, t)
@@ -234,8 +239,10 @@ def test_network_forward_backward_vs_reference(name, fn, loss, taus):
     yhat = ex.forward(pts, train=True, y=y, loss=LossSpec(loss, taus or ()), inv_count=1.0 / (n * spec.q), save=True)
     torch.cuda.synchronize()
     yh = yhat.cpu().numpy()
-    assert rel_l2(yh, g["yhat64"]) < 1e-3 and rel_err(yh, g["yhat64"]) < 2e-3
-    assert abs(ex.loss_acc.item() - float(g["loss64"])) < 1e-3 * abs(float(g["loss64"]))
+    print(name, precision, "yhat rel_l2", rel_l2(yh, g["yhat64"]), "loss rel",
+          abs(ex.loss_acc.item() - float(g["loss64"])) / abs(float(g["loss64"])))
+    assert rel_l2(yh, g["yhat64"]) < (2e-5 if x3 else 1e-3) and rel_err(yh, g["yhat64"]) < (4e-5 if x3 else 2e-3)
+    assert abs(ex.loss_acc.item() - float(g["loss64"])) < (1e-5 if x3 else 1e-3) * abs(float(g["loss64"]))
     grads = ex.backward()
     torch.cuda.synchronize()
     ref = {k[5:]: g[k] for k in g.files if k.startswith("grad.")}
@@ -244,6 +251,8 @@ def test_network_forward_backward_vs_reference(name, fn, loss, taus):
     # gradients vs the FP64 reference: TF32 operand rounding gives ~5e-3 (measured, profiles/); the check-loss
     # gradient additionally jumps by 1/N when a residual changes sign under a 1e-3 perturbation of yhat
     tol = 4e-2 if loss == "mse" else 6e-2     # networks this narrow (32/16 units) average fewer rounding errors
+    if x3:
+        tol = 1e-4 if loss == "mse" else 5e-4
     nh = spec.n_hidden
     for li in range(nh):
         k = lin[li]
@@ -288,7 +297,9 @@ def _default_oracle_model(seed, q=1, fn="wendland", hidden=(256, 256, 128)):
 @pytest.mark.parametrize("q,loss,taus,p,fused_train", [(1, "mse", None, 0.0, False),
                                                        (5, "pinball", [0.05, 0.25, 0.5, 0.75, 0.95], 0.1, False),
                                                        (5, "pinball", [0.05, 0.25, 0.5, 0.75, 0.95], 0.1, True),
-                                                       (1, "mse", None, 0.0, True)])
+                                                       (1, "mse", None, 0.0, True),
+                                                       (1, "mse", None, 0.1, "x3"),
+                                                       (5, "pinball", [0.05, 0.25, 0.5, 0.75, 0.95], 0.1, "x3")])
 def test_default_size_network_with_dropout_vs_oracle(q, loss, taus, p, fused_train):
     """Default architecture 297-256-256-128-Q, ragged batch, dropout masks drawn in-kernel (Philox keyed on the
     global row) and replayed by the oracle: outputs, loss and all gradients."""
@@ -309,7 +320,9 @@ def test_default_size_network_with_dropout_vs_oracle(q, loss, taus, p, fused_tra
     # isolates implementation errors from precision (tolerance 3e-3 instead of 2e-2)
     yemu, cache_e = orc.forward(m, None, coords, t, train=True, keep_masks=masks, return_cache=True, rnd=orc.tf32_round)
     gemu = orc.backward(m, cache_e, orc.loss_and_grad(yemu, y, loss, taus)[1])
-    spec = spec_from_oracle(m, dropout=p)
+    x3 = fused_train == "x3"          # precision "tf32x3": compared with the FP64 oracle directly (no TF32 emulation)
+    fused_train = bool(fused_train) and not x3
+    spec = spec_from_oracle(m, dropout=p, precision="tf32x3" if x3 else "tf32")
     ex = Executor(spec)
     ex.fused_train = fused_train      # stdadk_train_fwd (whole forward in one launch) vs one layer_fwd per block
     ex.loss_acc.zero_()
@@ -319,10 +332,12 @@ def test_default_size_network_with_dropout_vs_oracle(q, loss, taus, p, fused_tra
     assert not fused_train or ex._fused_ok is True
     grads = ex.backward()
     torch.cuda.synchronize()
-    assert rel_err(yhat.cpu().numpy(), yref) < 1e-3
-    assert abs(ex.loss_acc.item() - lref) < 1e-3 * abs(lref)
-    assert rel_l2(yhat.cpu().numpy(), yemu) < 2e-4
-    for ref_g, tol in ((gref, 2e-2), (gemu, 3e-3)):
+    print("x3" if x3 else "tf32", "yhat err", rel_err(yhat.cpu().numpy(), yref), "dW0 err vs fp64",
+          rel_err(grads["weights"][0].cpu().numpy(), gref["weights"][0]))
+    assert rel_err(yhat.cpu().numpy(), yref) < (2e-5 if x3 else 1e-3)
+    assert abs(ex.loss_acc.item() - lref) < (1e-5 if x3 else 1e-3) * abs(lref)
+    assert x3 or rel_l2(yhat.cpu().numpy(), yemu) < 2e-4
+    for ref_g, tol in (((gref, 1e-4 if loss == "mse" else 1e-3),) if x3 else ((gref, 2e-2), (gemu, 3e-3))):
         for l in range(3):
             assert rel_err(grads["weights"][l].cpu().numpy(), ref_g["weights"][l]) < tol, f"dW{l} {tol}"
             assert rel_err(grads["biases"][l].cpu().numpy(), ref_g["biases"][l]) < tol

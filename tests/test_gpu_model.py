@@ -126,16 +126,20 @@ def test_reference_api_surface():
     assert np.max(np.abs(phi.cpu().numpy() - ref) / np.maximum(ref, 2e-2)) < 1e-5
 
 
-def test_training_engine_loss_curve_vs_reference():
+@pytest.mark.parametrize("precision", ["tf32x3", "tf32"])
+def test_training_engine_loss_curve_vs_reference(precision):
     """20 optimisation steps (MSE, AdamW + clip + EMA, warm-up written after the step) on the fixture's data:
     per-step loss and gradient norm vs the reference's FP32 CPU run.
 
-    Stated tolerance.  At matched weights the loss agrees to <1e-3 (first steps here; 4e-5 in the single-step
-    tests).  Over many steps at lr=2e-2 the two runs follow slightly different trajectories because TF32 operand
-    rounding perturbs each gradient by ~5e-3 (see test_default_size_network...: the same kernels match a
-    TF32-emulating oracle to 3e-3 and the FP64 one to 2e-2); the per-step loss then differs by up to ~1.6e-2 by
-    step 20.  The test pins: steps 0-3 within 1e-3, every step within 3e-2, the first 8 gradient norms within 3e-2, and the
-    final raw / EMA predictions within 2e-2 (relative L2)."""
+    precision "tf32x3" (the parity mode: three tensor-core passes per GEMM, FP32-faithful products): EVERY one of the
+    20 losses and gradient norms within 1e-3 relative of the reference run, and the final raw and EMA predictions
+    within 1e-3 (relative L2) -- the tolerance north_star states for loss curves.  (The reference's own FP32 run is
+    3e-5 from its FP64 run on this curve, 1.5e-4 on the EMA predictions.)
+
+    precision "tf32" (the throughput mode): at matched weights the loss agrees to <1e-3 (first steps here; 4e-5 in
+    the single-step tests), but over many steps at lr=2e-2 TF32 operand rounding (~5e-3 per gradient) moves the
+    trajectory: steps 0-3 within 1e-3, every step within 3e-2, the first 8 gradient norms within 3e-2, raw
+    predictions within 2e-2."""
     from stnf.models import STInterpMLP
     from stnf.dataio import ObservationTable
     from st_dadk_b200.trainer import Trainer
@@ -147,7 +151,9 @@ def test_training_engine_loss_curve_vs_reference():
     table = ObservationTable(torch.from_numpy(g["coords"]), torch.from_numpy(g["t"].reshape(-1)),
                              torch.from_numpy(g["y"].reshape(-1))).to(DEV)
     bpe = n // bs
-    cfg = dict(lr=lr, weight_decay=wd, grad_clip=clip, warmup_epochs=warm // bpe, epochs=100, regression_type="mean")
+    x3 = precision == "tf32x3"
+    cfg = dict(lr=lr, weight_decay=wd, grad_clip=clip, warmup_epochs=warm // bpe, epochs=100, regression_type="mean",
+               precision=precision)
     for graph in (False, True):
         torch.manual_seed(123)
         model = STInterpMLP(**DEFAULT)
@@ -164,9 +170,14 @@ def test_training_engine_loss_curve_vs_reference():
         losses, norms = np.array(losses), np.array(norms)
         rel = np.abs(losses - g["losses"]) / np.abs(g["losses"])
         nrel = np.abs(norms - g["grad_norms"]) / g["grad_norms"]
-        print("graph", graph, "loss rel", np.array2string(rel, precision=2), "norm rel", np.array2string(nrel, precision=2))
-        assert rel[:4].max() < 1e-3 and rel.max() < 3e-2, (graph, rel)
-        assert nrel[:8].max() < 3e-2, nrel     # later norms sit on a chaotic trajectory (lr 2e-2): not compared
+        print(precision, "graph", graph, "loss rel", np.array2string(rel, precision=2), "norm rel",
+              np.array2string(nrel, precision=2))
+        if x3:
+            assert rel.max() < 1e-3, (graph, rel)
+            assert nrel.max() < 1e-3, (graph, nrel)
+        else:
+            assert rel[:4].max() < 1e-3 and rel.max() < 3e-2, (graph, rel)
+            assert nrel[:8].max() < 3e-2, nrel     # later norms sit on a chaotic trajectory (lr 2e-2): not compared
         model.eval()
         X = torch.zeros(256, 0, device=DEV)
         with torch.no_grad():
@@ -176,8 +187,9 @@ def test_training_engine_loss_curve_vs_reference():
             ema = model(X, table.coords[:256], table.t[:256, None]).cpu().numpy()
             tr.flat.restore()
         print("raw", rel_l2(raw, g["yhat_raw"]), "ema vs reference run", rel_l2(ema, g["yhat_ema"]))
-        assert rel_l2(raw, g["yhat_raw"]) < 2e-2
-        # EMA weights: the fused kernel's shadow == decay*shadow + (1-decay)*p replayed on the host after every step,
+        assert rel_l2(raw, g["yhat_raw"]) < (1e-3 if x3 else 2e-2)
+        assert not x3 or rel_l2(ema, g["yhat_ema"]) < 1e-3
+        # EMA weights (TF32 mode): the fused kernel's shadow == decay*shadow + (1-decay)*p replayed on the host after every step,
         # and the forward under the swapped-in EMA weights == the oracle on those same weights.  (The reference run's
         # EMA *predictions* are not compared: after 20 steps at lr 2e-2 the averaged model's output is a cancellation
         # that amplifies the 1e-3 weight-trajectory difference to ~1e-1; measured and explained in DESIGN.md.)
