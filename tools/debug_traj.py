@@ -1,0 +1,52 @@
+"""Debug aid: per-step knot trajectory of a driver parity case vs the reference's (tests/golden/_debug_traj_*.npz)."""
+import importlib, os, sys, tempfile
+from pathlib import Path
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import driver_cases as dc
+name, prec = "config1_shipped", "tf32x3"
+g = np.load(os.path.join(ROOT, "tests/golden", f"driver_{name}.npz"))
+d = np.load(os.path.join(ROOT, "tests/golden", f"_debug_traj_{name}.npz"))
+drv = importlib.import_module("scripts.train_st_interp")
+from st_dadk_b200.trainer import Trainer
+orig_step, orig_create = Trainer.train_step, drv.create_model
+rec = {"c": [], "bw": [], "loss": [], "gc": []}
+def create(cfg, train_coords=None):
+    m = orig_create(cfg, train_coords=train_coords)
+    sb = m.spatial_basis
+    with torch.no_grad():
+        sb.centers.copy_(torch.from_numpy(g["centers0"])); sb.centers_init.copy_(torch.from_numpy(g["centers0"]))
+        sb.log_bandwidths.copy_(torch.from_numpy(g["bandwidths0"]).log())
+    return m
+def step(self, table, perm, row_begin, n_rows, *a, **k):
+    self.use_cuda_graph = False
+    self._push_hyper()
+    self._step_compute(table, perm, row_begin, n_rows, n_rows, 0)
+    pen = self._add_penalty_grads(); self._damp_center_grads()
+    sb = self.model.spatial_basis
+    rec["gc"].append(self.flat.gviews[id(sb.centers)].detach().cpu().numpy().copy())
+    # undo: recompute via the normal path is not possible after the adds, so finish the update by hand
+    from st_dadk_b200 import ops
+    fl, ex = self.flat, self.ex
+    if self.clip > 0: ops.grad_sqnorm(fl.g[:fl.n], fl.group_end, self.sqnorms, self._sqnorm_ws)
+    ops.adamw_ema_step(fl.p, fl.g[:fl.n], fl.m, fl.v, fl.shadow, fl.group_end, self.hyper, self.sqnorms if self.clip > 0 else None,
+                       self.step_count, ema_decay=self.ema_decay, zero_grad=True, loss_acc=ex.loss_acc, loss_sum=self.loss_sum, loss_last=self.loss_last)
+    self._g_clean = True
+    if self.global_step < self.warmup_steps:
+        f = (self.global_step + 1) / self.warmup_steps
+        for gq in self.opt.param_groups: gq["lr"] = gq["initial_lr"] * f
+    self.global_step += 1
+    rec["c"].append(sb.centers.detach().cpu().numpy().copy()); rec["bw"].append(sb.bandwidths.detach().cpu().numpy().copy())
+    rec["loss"].append(float(self.loss_last.item()))
+Trainer.train_step, drv.create_model = step, create
+with tempfile.TemporaryDirectory() as tmp:
+    csv = dc.case_csv(name, tmp)
+    config = dict(dc.CASES[name]["config"], data_file=csv, precision=prec)
+    drv._run_single_quantile_experiment(config, int(g["experiment_id"][0]), Path(tmp) / "e", "cuda", verbose=False)
+for s in range(len(rec["loss"])):
+    rl = abs(rec["loss"][s] - g["step_loss"][s]) / abs(g["step_loss"][s])
+    dc_ = np.abs(rec["c"][s] - d["centers"][s]).max(); dbw = np.abs(rec["bw"][s] - d["bw"][s]).max()
+    gr = d["gc"][s]; go = rec["gc"][s]
+    ge = np.abs(go - gr).max() / max(np.abs(gr).max(), 1e-30) if gr.shape == go.shape else -1
+    print(f"step {s:2d} lr {g['step_lr'][s]} loss rel {rl:.2e}  max|dc| {dc_:.2e} max|dbw| {dbw:.2e}  centre-grad relerr (post-damp, pre-clip vs ref post-clip) {ge:.2e} |gref| {np.abs(gr).max():.2e} |gours| {np.abs(go).max():.2e}")
