@@ -15,7 +15,9 @@ throughput (1M = T x S points, sharded by point), the end-to-end numbers through
 the dominant kernel and the CPU baseline.
 
   python bench.py --gpus N --steps K --warmup W            # our arm (torchrun for N > 1)
-  python bench.py --impl reference --gpus N ...            # CPU arm: the oracle port on the host cores (rank 0 only)
+  python bench.py --impl reference --gpus N ...            # CPU arm: the reference's own PyTorch path (oracle/_ref, the
+                                                           # unmodified `stnf` package) on the host cores, rank 0 only
+  python bench.py --config 1|3|4|5 [--gpus N]              # the other BASELINE configs, one JSON line each (profiles/)
 """
 import argparse
 import json
@@ -98,8 +100,106 @@ def oracle_train_step(m, state, coords, t, y, step):
     return loss
 
 
-def cpu_baseline(seconds=12.0, max_steps=8):
-    """Bounded sample of the same workload on the host cores: a few B=4096 oracle training steps."""
+def _ref_package():
+    """The reference's own `stnf` package, copied unmodified into oracle/_ref by oracle/Makefile (build container) and
+    shipped to the GPU box with the snapshot.  Returns the module pair or None when the copy is absent."""
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "stnf")):
+        return None
+    import importlib.util
+    saved = {k: v for k, v in sys.modules.items() if k == "stnf" or k.startswith("stnf.")}
+    for k in saved:
+        del sys.modules[k]
+    sys.path.insert(0, ref_dir)
+    try:
+        models = importlib.import_module("stnf.models.st_interp")
+        ema = importlib.import_module("stnf.utils.ema")
+    finally:
+        sys.path.remove(ref_dir)
+        for k in [k for k in sys.modules if k == "stnf" or k.startswith("stnf.")]:
+            del sys.modules[k]        # the reference modules stay referenced by the objects returned below only
+        sys.modules.update(saved)
+    assert os.path.realpath(models.__file__).startswith(os.path.realpath(ref_dir))
+    return models, ema
+
+
+class ReferenceArm:
+    """The reference's CPU PyTorch path for the bench workload: STInterpMLP (st_interp.py:599-882) + nn.MSELoss +
+    clip_grad_norm_ + optim.AdamW + ModelEMA, i.e. the loop body of train_model (train_st_interp.py:608-733) on
+    pre-batched tensors (its list-of-dict DataLoader, 16.6 ms per 4096-batch, is left out in the reference's favour)."""
+
+    def __init__(self):
+        import torch
+        mods = _ref_package()
+        if mods is None:
+            raise RuntimeError("oracle/_ref is absent")
+        models, ema = mods
+        self.torch = torch
+        torch.set_num_threads(os.cpu_count())       # torchrun exports OMP_NUM_THREADS=1: use every host core anyway
+        torch.manual_seed(2025)
+        self.model = models.STInterpMLP(k_spatial_centers=K_SPATIAL, k_temporal_centers=K_TEMPORAL, hidden_dims=HIDDEN,
+                                        dropout=0.1, layernorm=True, output_dim=1)
+        self.opt = torch.optim.AdamW(self.model.parameters(), lr=CFG["lr"], weight_decay=CFG["weight_decay"])
+        bpe = (N_TRAIN + BATCH - 1) // BATCH
+        self.ema = ema.ModelEMA(self.model, decay=1.0 - 1.0 / (10.0 * bpe))
+        self.crit = torch.nn.MSELoss()
+        _, coords, t, y = synth_dataset(2025, N_TRAIN)
+        self.c, self.t, self.y = torch.from_numpy(coords), torch.from_numpy(t)[:, None], torch.from_numpy(y)[:, None]
+        self.X = torch.zeros(BATCH, 0)
+        self.threads = torch.get_num_threads()
+
+    def step(self, i):
+        torch = self.torch
+        lo = (i * BATCH) % (N_TRAIN - BATCH)
+        self.model.train()
+        self.opt.zero_grad()
+        pred = self.model(self.X, self.c[lo:lo + BATCH], self.t[lo:lo + BATCH])
+        loss = self.crit(pred, self.y[lo:lo + BATCH])
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(self.model.parameters(), CFG["grad_clip"])
+        self.opt.step()
+        self.ema.update(self.model)
+        return loss.item()
+
+    def predict_points_per_s(self, n_p=32768):
+        torch = self.torch
+        self.model.eval()
+        g = torch.Generator().manual_seed(1)
+        pc, pt = torch.rand(n_p, 2, generator=g), torch.rand(n_p, 1, generator=g)
+        with torch.no_grad():
+            self.model(torch.zeros(n_p, 0), pc, pt)
+            t0 = time.perf_counter()
+            self.model(torch.zeros(n_p, 0), pc, pt)
+        return n_p / (time.perf_counter() - t0)
+
+
+def cpu_baseline(seconds=12.0, max_steps=40):
+    """Bounded sample of the same workload on the host cores.  The reference's own PyTorch CPU path when oracle/_ref is
+    present (kind "reference"); otherwise the numpy oracle port (kind "port")."""
+    try:
+        arm = ReferenceArm()
+    except Exception as e:        # noqa: BLE001 -- no copy of the reference on this box: fall back to the port, say so
+        print(f"[bench] reference package unavailable ({e!r}); cpu_baseline uses the oracle port", file=sys.stderr)
+        return cpu_baseline_port(seconds)
+    for i in range(2):
+        arm.step(i)
+    times = []
+    t_end = time.perf_counter() + seconds
+    s = 2
+    while len(times) < max_steps and (time.perf_counter() < t_end or len(times) < 3):
+        t0 = time.perf_counter()
+        arm.step(s)
+        times.append(time.perf_counter() - t0)
+        s += 1
+    per = float(np.median(times))
+    return {"value": BATCH / per, "unit": UNIT, "cores": arm.threads, "kind": "reference",
+            "sample": f"{len(times)} training steps of batch {BATCH} of the reference's own STInterpMLP + AdamW + clip + "
+                      f"ModelEMA on pre-batched CPU tensors (no DataLoader), median; predict sample 32768 points",
+            "ms_per_step": per * 1e3, "predict_points_per_s": arm.predict_points_per_s()}
+
+
+def cpu_baseline_port(seconds=12.0, max_steps=8):
+    """Fallback: a few B=4096 training steps of the numpy oracle port."""
     m = oracle_model()
     _, coords, t, y = synth_dataset(2025, N_TRAIN)
     state = {}
@@ -131,7 +231,34 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 100))     # each step is ~0.1-0.2 s of host BLAS: the arm stays within minutes
+    steps = max(1, min(args.steps, 100))     # each step is ~0.1 s of host work: the arm stays within minutes
+    try:
+        arm = ReferenceArm()
+    except Exception as e:        # noqa: BLE001
+        print(f"[bench] reference package unavailable ({e!r}); the reference arm times the oracle port", file=sys.stderr)
+        return run_reference_port(args, steps)
+    for w in range(max(1, min(args.warmup, 3))):
+        arm.step(w)
+    t0 = time.perf_counter()
+    for s in range(steps):
+        arm.step(s + 3)
+    dt = time.perf_counter() - t0
+    val = steps * BATCH / dt
+    cb = {"value": val, "unit": UNIT, "cores": arm.threads, "kind": "reference",
+          "sample": f"{steps} training steps of batch {BATCH}: the reference's own STInterpMLP + MSELoss + clip_grad_norm_ + "
+                    f"AdamW + ModelEMA (oracle/_ref, unmodified) on pre-batched CPU tensors, {arm.threads} threads",
+          "predict_points_per_s": arm.predict_points_per_s()}
+    emit({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+          "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+          "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+          "config": {"workload": WORKLOAD, "global_batch": BATCH, "l2": "n/a (CPU)", "cuda_graph": False,
+                     "parallelism": "single", "precision": "fp32",
+                     "note": "the reference's CPU PyTorch path on the host cores; one rank only (it has no multi-device path)"},
+          "cpu_baseline": cb,
+          "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+
+
+def run_reference_port(args, steps):
     m = oracle_model()
     _, coords, t, y = synth_dataset(2025, N_TRAIN)
     state = {}
@@ -194,6 +321,83 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def measure_tf32_peak(dev, seconds=1.0):
+    """Dense TF32 tensor-core throughput of this GPU measured the way MEASURED_PEAKS.json measures BF16: cuBLAS matmul
+    8192^3 with TF32 inputs / FP32 accumulate, best of 10 (burst) and back to back for `seconds` (sustained)."""
+    import torch
+    n = 8192
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        a = torch.randn(n, n, device=dev)
+        b = torch.randn(n, n, device=dev)
+        c = torch.empty(n, n, device=dev)
+        for _ in range(3):
+            torch.matmul(a, b, out=c)
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b, out=c)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        reps = max(10, int(seconds * 1e3 / best))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            torch.matmul(a, b, out=c)
+        e1.record()
+        torch.cuda.synchronize()
+        sus = e0.elapsed_time(e1) / reps
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    fl = 2.0 * n ** 3
+    del a, b, c
+    return {"tf32_tflops": fl / (best * 1e-3) / 1e12, "tf32_tflops_sustained": fl / (sus * 1e-3) / 1e12,
+            "how": f"torch.matmul fp32 with allow_tf32 (cuBLAS TF32) {n}^3: best of 10 and {reps} back to back"}
+
+
+def short_kernel_name(name: str) -> str:
+    """stdadk::layer_fwd_kernel<true, 4, 4, 1>(...) -> layer_fwd_kernel<true,4,4,1>"""
+    import re
+    m = re.search(r"stdadk::([A-Za-z0-9_]+)(<[^(]*>)?", name)
+    if m:
+        return m.group(1) + (m.group(2) or "").replace(" ", "")
+    return name.split("(")[0][-60:]
+
+
+def profile_kernels(fn, iters):
+    """Per-kernel device time of `iters` calls of fn(i) from a CUPTI trace (torch.profiler): the kernels are timed where
+    they run -- inside the replayed CUDA graph, back to back -- not with host-side event pairs around eager launches.
+    Returns {short name: {"us": average per launch, "per_call": launches per call of fn}} or None if CUPTI is closed."""
+    import torch
+    try:
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            for i in range(iters):
+                fn(i)
+            torch.cuda.synchronize()
+        out = {}
+        for ev in prof.key_averages():
+            dt = getattr(ev, "device_time_total", None)
+            if dt is None:
+                dt = getattr(ev, "cuda_time_total", 0.0)
+            if dt <= 0 or getattr(ev, "device_type", None) is None:
+                continue
+            if "DeviceType.CUDA" not in str(ev.device_type):
+                continue
+            nm = short_kernel_name(ev.key)
+            d = out.setdefault(nm, {"us_total": 0.0, "count": 0})
+            d["us_total"] += float(dt)
+            d["count"] += int(ev.count)
+        return {k: {"us": v["us_total"] / max(v["count"], 1), "per_call": v["count"] / iters} for k, v in out.items()} or None
+    except Exception as e:        # noqa: BLE001
+        print(f"[bench] kernel trace unavailable: {e!r}", file=sys.stderr)
+        return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -233,7 +437,7 @@ def run_ours(args):
     host = ObservationTable(torch.from_numpy(coords), torch.from_numpy(t), torch.from_numpy(y)).pin()
     table = host.to(dev)
     bpe = (N_TRAIN + BATCH - 1) // BATCH
-    tr = Trainer(model, CFG, dev, batches_per_epoch=bpe, use_cuda_graph=not args.no_graph)
+    tr = Trainer(model, dict(CFG, precision=args.precision), dev, batches_per_epoch=bpe, use_cuda_graph=not args.no_graph)
     perm = torch.randperm(N_TRAIN, generator=torch.Generator().manual_seed(7 + rank)).to(dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # 256 MB > 126 MB L2
     global_rows = BATCH * world
@@ -293,7 +497,23 @@ def run_ours(args):
     e2e_t = torch.tensor([time.perf_counter() - t0], device=dev)
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_val = args.steps * BATCH * world / float(e2e_t.item())
+    e2e_lagged = args.steps * BATCH * world / float(e2e_t.item())
+    # the same with upstream's semantics: the host waits for EVERY step's loss before it issues the next batch
+    # (loss.item() per step, train_st_interp.py:721) -- this is the headline e2e number
+    n_sync = min(args.steps, 400)
+    for i in range(3):
+        tr.train_step_host(host, (i % n_off) * BATCH, BATCH, global_rows, lagged=False)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(n_sync):
+        e2e_losses.append(tr.train_step_host(host, ((i + 9) % n_off) * BATCH, BATCH, global_rows, lagged=False))
+    torch.cuda.synchronize()
+    e2e_t = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_val = n_sync * BATCH * world / float(e2e_t.item())
 
     log("e2e done; prediction")
     # ---- dense prediction: T x S = 1M points (space-time field), sharded by point, no collective
@@ -342,70 +562,96 @@ def run_ours(args):
         dist.all_reduce(pred_e2e, op=dist.ReduceOp.MAX)
     pred_e2e_pps = n_pred / float(pred_e2e.item())
 
-    n_prof, lay = pr.profile_layers(1000, 1000, 1)
-    _, fus = pr.profile_fused(1000, 1000, 1)
-    log("prediction done; per-kernel profile")
-    # ---- per-kernel timing (eager, CUDA events around every libstdadk launch) -> roofline of the dominant kernel
-    roof = None
+    # ---- rooflines: kernels chosen BY NAME, timed where they run
+    log("prediction done; rooflines")
     traffic = {}
     try:
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")) as fh:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
             traffic = json.load(fh)      # DRAM bytes per launch from the committed ncu captures (not measured live)
     except OSError:
         pass
-    kt = tr.profile_step(table, perm, BATCH, global_rows, repeats=10)   # every rank: the step contains the all-reduce
+    tf32 = measure_tf32_peak(dev) if rank == 0 else None
+    # (a) the kernels of the timed training step, from a CUPTI trace of graph REPLAYS (no eager event pairs)
+    ktrace = profile_kernels(lambda i: one_step(i), 20)
+    # (b) fused basis + Linear1 + LayerNorm/ReLU forward in the throughput regime: 1M explicit points per launch
+    #     (12 B read + 1024 B written per point; the 1 GB it writes is 8x the L2, so no flush is needed between launches)
+    n_roof = 1 << 20
+    g = torch.Generator().manual_seed(5)
+    rc, rt = torch.rand(n_roof, 2, generator=g).to(dev), torch.rand(n_roof, generator=g).to(dev)
+    l1 = pr.profile_block1(rc, rt, repeats=5)
+    _, fus = pr.profile_fused(1000, 1000, 1)
+    roof = roof_gemm = None
     if rank == 0:
-        name, info = max(kt["kernels"].items(), key=lambda kv: kv[1]["ms"] * kv[1]["count"])
-        flops = info["flops"]
-        achieved = flops / (info["ms"] * 1e-3) / 1e12
-        roof = {"kernel": name, "bound": "tensor", "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s",
-                "frac": achieved / tc_peak, "traffic": traffic.get("train", {}).get(name),
-                "traffic_source": traffic.get("source"), "peak_source": peak_src + ", dense bf16 sustained; the "
-                "kernel runs TF32 (nominal half rate)", "note": "a 4096-row batch is ONE wave of 32 CTAs on 148 SMs: "
-                "this kernel is latency-bound, not roofline-bound; the throughput regime is in roofline_predict",
-                "launch_ms": kt["kernels"][name]["ms"],
-                "share_of_step": kt["kernels"][name]["ms"] * kt["kernels"][name]["count"] / max(kt["step_ms"], 1e-9),
-                "algorithmic_flops_per_launch": flops}
-    roof_pred = None
-    if rank == 0:
-        lid, d = max(lay.items(), key=lambda kv: kv[1]["ms"])
-        ach = d["bytes"] / (d["ms"] * 1e-3) / 1e9
-        roof_pred = {"kernel": f"layer_fwd[{lid}] (dense prediction, {n_prof} points per launch)", "bound": "hbm",
-                     "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                     "traffic": traffic.get("predict", {}).get(f"layer_fwd[{lid}]"), "algorithmic_bytes_per_launch": d["bytes"],
-                     "peak_source": peak_src, "launch_ms": d["ms"],
-                     "all_blocks": {f"layer_fwd[{k}]": {"ms": v["ms"], "GB/s": v["bytes"] / (v["ms"] * 1e-3) / 1e9,
-                                                        "TFLOP/s": v["flops"] / (v["ms"] * 1e-3) / 1e12}
-                                    for k, v in sorted(lay.items())},
-                     "note": "layer-by-layer kernels (training forward / shapes the fused kernel does not take)"}
+        ach = l1["bytes"] / (l1["ms"] * 1e-3) / 1e9
+        in_step = None
+        if ktrace:
+            k1 = [k for k in ktrace if k.startswith("layer_fwd_kernel<true")]
+            if k1:
+                us = ktrace[k1[0]]["us"]
+                in_step = {"kernel": k1[0], "launch_us": us, "rows": BATCH,
+                           "GB/s": BATCH * l1["bytes_per_row"] / (us * 1e-6) / 1e9,
+                           "note": "the same kernel inside the timed step: 32 tiles on 148 SMs, latency-bound"}
+        roof = {"kernel": "layer_fwd_kernel<BASIS> (basis generated in the operand + Linear1 on tcgen05 + LayerNorm/ReLU epilogue)",
+                "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                "traffic": traffic.get("predict", {}).get("layer_fwd[0]"), "traffic_source": traffic.get("source"),
+                "rows_per_launch": n_roof, "algorithmic_bytes_per_row": l1["bytes_per_row"],
+                "algorithmic_bytes_per_launch": l1["bytes"], "launch_ms": l1["ms"], "peak_source": peak_src,
+                "timing": "CUDA events around 5 back-to-back launches on the launching stream, after warm-up",
+                "in_step": in_step}
         if fus is not None:
-            tf = fus["flops"] / (fus["ms"] * 1e-3) / 1e12
-            roof_pred = {"kernel": f"predict_fused (whole network, {n_prof} points per launch)", "bound": "tensor",
-                         "achieved": tf, "peak": tc_peak_burst, "unit": "TFLOP/s", "frac": tf / tc_peak_burst,
+            tfl = fus["flops"] / (fus["ms"] * 1e-3) / 1e12
+            roof_gemm = {"kernel": f"{fus.get('kernel', 'predict_fused_kernel')} (whole network, {fus['points']} points per launch)",
+                         "bound": "tensor", "achieved": tfl, "peak": tf32["tf32_tflops"], "unit": "TFLOP/s",
+                         "frac": tfl / tf32["tf32_tflops"], "peak_source": "measured in this run: " + tf32["how"] + " (burst)",
+                         "frac_of_sustained_tf32": tfl / tf32["tf32_tflops_sustained"],
+                         "executed_flops_per_launch": fus["flops"], "dense_equivalent_flops_per_launch": fus.get("dense_flops"),
                          "traffic": traffic.get("predict", {}).get("predict_fused"),
-                         "algorithmic_bytes_per_launch": fus["bytes"], "algorithmic_flops_per_launch": fus["flops"],
-                         "hbm_GB/s": fus["bytes"] / (fus["ms"] * 1e-3) / 1e9, "launch_ms": fus["ms"],
-                         "peak_source": peak_src + ", dense bf16 burst (kernel timed alone); the kernel runs TF32 "
-                                        "(nominal half rate)",
-                         "layered_path": roof_pred}
+                         "algorithmic_bytes_per_launch": fus["bytes"], "launch_ms": fus["ms"],
+                         "tensor_pipe_pct_ncu": traffic.get("tensor_pipe_pct", {}).get("predict_fused")}
+    x3_ms = None
+    if rank == 0 and world == 1 and args.precision == "tf32":
+        # the FP32-faithful parity mode (three tensor-core passes per GEMM) on the same step, for the record
+        torch.manual_seed(2025)
+        m3 = STInterpMLP(k_spatial_centers=K_SPATIAL, k_temporal_centers=K_TEMPORAL, hidden_dims=HIDDEN, dropout=0.1,
+                         layernorm=True, output_dim=1)
+        t3 = Trainer(m3, dict(CFG, precision="tf32x3"), dev, batches_per_epoch=bpe, use_cuda_graph=not args.no_graph)
+        for i in range(5):
+            t3.train_step(table, perm, (i % n_off) * BATCH, BATCH, global_rows)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(50):
+            t3.train_step(table, perm, ((i + 5) % n_off) * BATCH, BATCH, global_rows)
+        e1.record()
+        torch.cuda.synchronize()
+        x3_ms = e0.elapsed_time(e1) / 50
+        del t3, m3
     if rank == 0:
         cb = cpu_baseline() if world == 1 else None
+        step_us = {k: round(v["us"] * v["per_call"], 2) for k, v in (ktrace or {}).items()}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "tf32 (fp32 accumulate, fp32 master weights)",
+                "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if args.precision == "tf32" else "tf32x3",
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "global_batch": global_rows, "l2": "flushed between timed steps "
-                           "(256 MB write)", "cuda_graph": not args.no_graph, "parallelism": f"dp{world}" if world > 1 else "single"},
+                           "(256 MB write)", "cuda_graph": not args.no_graph,
+                           "parallelism": f"dp{world}" if world > 1 else "single", "precision": args.precision},
                 "clocks": clocks, "gpu_launches": tr.launches_per_step * args.steps,
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": hb, "d2h_bytes_per_step": 4,
-                        "readback": "per-step loss, read one step behind (double-buffered staging)",
+                        "readback": "every step's loss read by the host before the next batch is issued (upstream's "
+                                    "loss.item() per step)", "steps": n_sync,
+                        "lagged_value": e2e_lagged, "lagged_readback": "loss read one step behind (double-buffered staging)",
                         "last_loss": e2e_losses[-1]},
+                "predict_points_per_s": pred_pps, "grid10M_points_per_s": grid_pps, "predict_e2e_points_per_s": pred_e2e_pps,
                 "predict": {"metric": "predict_points_per_s", "value": pred_pps, "unit": "points/s",
                             "workload": f"T x S = {n_pred} space-time points, sharded by point over {world} GPU(s)",
                             "e2e_value": pred_e2e_pps, "d2h_bytes": int(out.numel() * 4),
                             "grid10M_points_per_s": grid_pps},
-                "roofline": roof, "roofline_predict": roof_pred, "kernel_times_ms": {k: v["ms"] for k, v in kt.get("kernels", {}).items()},
-                "cpu_baseline": cb, "mean_train_loss": final_loss / max(1, args.steps + max(args.warmup, 3)), "wall_s_timed_region": wall}
+                "roofline": roof, "roofline_gemm": roof_gemm, "tf32_peak": tf32,
+                "kernel_us_per_step": step_us, "kernel_us_sum": round(sum(step_us.values()), 2),
+                "tf32x3_ms_per_step": x3_ms,
+                "cpu_baseline": cb, "mean_train_loss": final_loss / max(1, args.steps + max(args.warmup, 3)),
+                "wall_s_timed_region": wall}
         emit(line)
     if world > 1:
         dist.barrier()
@@ -439,12 +685,19 @@ def main():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "tf32x3"],
+                    help="tensor-core precision of the measured arm: tf32 = throughput mode, tf32x3 = FP32-faithful parity mode")
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5],
+                    help="BASELINE.json config (1-based; 2 = the headline workload, the default)")
     ap.add_argument("--no-graph", action="store_true",
                     help="launch every kernel eagerly (for ncu: kernel replay cannot run inside stream capture)")
     args = ap.parse_args()
     _quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config != 2:
+        import bench_extra
+        bench_extra.run_config(args.config, args, emit)
     else:
         run_ours(args)
 

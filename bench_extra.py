@@ -130,6 +130,126 @@ def config5(epochs=50, configs_per_gpu=(1, 4), out_root="/tmp/stdadk_cfg5"):
                           "stderr_tail": pr.stderr[-300:] if pr.returncode else ""}), flush=True)
 
 
+def _dist_setup():
+    import torch.distributed as dist
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        from datetime import timedelta
+        dist.init_process_group("nccl", device_id=dev, timeout=timedelta(seconds=300))
+        dist.barrier()
+    return rank, world, dev
+
+
+def _max_over_ranks(ms, dev, world):
+    import torch.distributed as dist
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def run_config3(args, emit):
+    """BASELINE config 3: 10M-point dense grid (1000 x 1000 x 10, generated on the device), point-sharded, Q=1 and Q=5."""
+    from stnf.models import STInterpMLP
+    from st_dadk_b200.predict import Predictor
+    rank, world, dev = _dist_setup()
+    res = {}
+    for q in (1, 5):
+        torch.manual_seed(0)
+        model = STInterpMLP(output_dim=q).to(dev).eval()
+        pr = Predictor(model, static_weights=True)
+        for _ in range(max(args.warmup, 1) if args.warmup < 5 else 3):
+            pr.grid(1000, 1000, 10, rank, world)
+        torch.cuda.synchronize()
+        reps = max(1, min(args.steps, 10))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            out, _ = pr.grid(1000, 1000, 10, rank, world)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = _max_over_ranks(e0.elapsed_time(e1) / reps, dev, world)
+        res[f"q{q}"] = {"ms": ms, "points_per_s": 1e7 / (ms * 1e-3), "kernel": "field" if pr.used_field_kernel else "generic"}
+    if rank == 0:
+        emit({"metric": "predict_points_per_s", "value": res["q1"]["points_per_s"], "unit": "points/s", "n_gpus": world,
+              "steps": reps, "warmup": args.warmup, "ms_per_step": res["q1"]["ms"], "higher_is_better": True,
+              "scaling": "strong", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+              "config": {"workload": "BASELINE config 3: 10,000,000-point dense grid 1000x1000x10 generated on device, "
+                                     "contiguous block sharding by point, default model", "q5": res["q5"], "q1": res["q1"],
+                         "l2": "output 40 MB x Q per pass; inputs generated (0 B)"}})
+
+
+def run_config4(args, emit):
+    """BASELINE config 4: training with the 3-level ~100k-knot basis (K_s = 99,812, W1 102 MB), data parallel over the
+    ranks with one all-reduce of the flat gradient (102.8 MB) per step; per-GPU batch 65,536."""
+    from stnf.models import STInterpMLP
+    from stnf.dataio import ObservationTable
+    from st_dadk_b200.trainer import Trainer
+    rank, world, dev = _dist_setup()
+    torch.manual_seed(0)
+    model = STInterpMLP(k_spatial_centers=[10000, 30276, 59536], k_temporal_centers=[10, 15, 45],
+                        hidden_dims=[256, 256, 128], dropout=0.1, layernorm=True, output_dim=1)
+    n = 50_000_000 // max(world, 8) if world > 1 else 6_250_000      # this rank's share of the 50M observations
+    rng = np.random.default_rng(2025 + rank)
+    coords = rng.random((n, 2), dtype=np.float32)
+    t = (rng.integers(0, 100, n) / 99.0).astype(np.float32)
+    y = (np.sin(2 * np.pi * (coords[:, 0] + t)) * np.cos(2 * np.pi * coords[:, 1])).astype(np.float32)
+    table = ObservationTable(torch.from_numpy(coords), torch.from_numpy(t), torch.from_numpy(y)).to(dev)
+    perm = torch.randperm(n, generator=torch.Generator().manual_seed(1 + rank)).to(dev)
+    tr = Trainer(model, dict(lr=1e-3, weight_decay=5e-4, grad_clip=10.0, regression_type="mean"), dev,
+                 batches_per_epoch=100, use_cuda_graph=True)
+    B = 65536
+    out = {}
+    for i in range(max(args.warmup, 3) if args.warmup < 8 else 4):
+        tr.train_step(table, perm, i * B, B, B * world)
+    torch.cuda.synchronize()
+    steps = max(1, min(args.steps, 30))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        tr.train_step(table, perm, ((i + 4) * B) % (n - B), B, B * world)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = _max_over_ranks(e0.elapsed_time(e1) / steps, dev, world)
+    ar_ms = None
+    if world > 1:
+        import torch.distributed as dist
+        g = tr.flat.g[:tr.flat.n_exchange]
+        for _ in range(3):
+            dist.all_reduce(g)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(10):
+            dist.all_reduce(g)
+        e1.record()
+        torch.cuda.synchronize()
+        ar_ms = _max_over_ranks(e0.elapsed_time(e1) / 10, dev, world)
+        tr.flat.g.zero_()
+    if rank == 0:
+        emit({"metric": "train_samples_per_s", "value": B * world / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
+              "steps": steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+              "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+              "config": {"workload": "BASELINE config 4: K_s = 99,812 knots (100^2 + 174^2 + 244^2), W1 102 MB, support-walking "
+                                     "block 1, 50M observations over 8 ranks (6.25M resident per GPU)", "global_batch": B * world,
+                         "params": tr.flat.n, "allreduce_bytes": 4 * tr.flat.n_exchange, "allreduce_ms_alone": ar_ms,
+                         "parallelism": f"dp{world}" if world > 1 else "single"}})
+
+
+def run_config(which, args, emit):
+    {1: run_config1, 3: run_config3, 4: run_config4, 5: run_config5}[which](args, emit)
+
+
+def run_config1(args, emit):
+    raise SystemExit("config 1: use `python bench_extra.py config1`")
+
+
+def run_config5(args, emit):
+    raise SystemExit("config 5: use `python bench_extra.py config5`")
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["config4"]
     for w in which:

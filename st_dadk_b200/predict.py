@@ -39,6 +39,7 @@ class Predictor:
         self.d2h_chunk_rows = 1 << 18      # field predictions delivered to the host: rows per overlapped D2H piece
         self._copy_stream = None
         self.host_copy_done = None
+        self.used_field_kernel = False     # the last grid / field call ran the site-tile x time-loop kernel
 
     def _prepare(self):
         if self.static_weights and self._prepared:
@@ -210,6 +211,37 @@ class Predictor:
         return n, res
 
     @torch.no_grad()
+    def profile_block1(self, coords: torch.Tensor, t: torch.Tensor, repeats: int = 5) -> dict:
+        """The fused basis + Linear1 + LayerNorm/ReLU forward kernel (layer_fwd, block 1) alone on explicit points:
+        average launch time (CUDA events on the launching stream) and its algorithmic HBM bytes, 12 B read (x, y, t) +
+        4 * pad32(n_out) B written per row."""
+        import ctypes as C
+        from . import _lib as L
+        self._prepare()
+        ex, s = self.ex, self.ex.spec
+        n = coords.shape[0]
+        ws = ex._workspace(n)
+        basis = ex._basis()
+        a = L.FwdArgs()
+        a.pts = ops.make_points(coords, t)
+        a.basis = C.pointer(basis)
+        a.layer = ex._layer(0)
+        a.drop = L.Dropout(0.0, 0, 0, None, 0)
+        a.out_img = ws.h[0].data_ptr()
+        if ex.x3:
+            a.out_img_lo = ws.h_lo[0].data_ptr()
+        ops.layer_fwd(a)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(repeats):
+            ops.layer_fwd(a)
+        e1.record()
+        torch.cuda.synchronize()
+        per_row = 12 + 4 * ops.pad32(s.weights[0].shape[0]) * (2 if ex.x3 else 1)
+        return {"ms": e0.elapsed_time(e1) / repeats, "rows": n, "bytes_per_row": per_row, "bytes": float(n) * per_row,
+                "flops": 2.0 * n * s.weights[0].shape[0] * s.weights[0].shape[1]}
+
+    @torch.no_grad()
     def profile_fused(self, nx: int, ny: int, nt: int, repeats: int = 5):
         """Average duration of the whole-network kernel over a grid prediction of min(nx*ny*nt, chunk) points, with
         its algorithmic work: 4Q bytes written per point (nothing read for a generated grid) and the dense FLOPs of
@@ -231,4 +263,5 @@ class Predictor:
         torch.cuda.synchronize()
         s = self.ex.spec
         flops = sum(2.0 * w.shape[0] * w.shape[1] for w in s.weights) + 2.0 * s.head_w.shape[0] * s.head_w.shape[1]
-        return n, {"ms": e0.elapsed_time(e1) / repeats, "bytes": 4.0 * n * self.model.output_dim, "flops": flops * n}
+        return n, {"ms": e0.elapsed_time(e1) / repeats, "bytes": 4.0 * n * self.model.output_dim, "flops": flops * n,
+                   "dense_flops": flops * n, "points": n, "kernel": "predict_fused_kernel"}
