@@ -214,7 +214,7 @@ int stdadk_version(void);
 const char* stdadk_last_error(void);
 /* sizeof() of the argument structs, for bindings to verify their layout:
  * 0 basis, 1 points, 2 layer, 3 dropout, 4 head, 5 fwd_args, 6 bwd_args, 7 wgrad_args, 8 knotgrad_args, 9 adamw_args,
- * 10 pack_desc, 11 sparse_args, 12 predict_args, 13 train_fwd_args, 14 peer_allreduce_args */
+ * 10 pack_desc, 11 sparse_args, 12 predict_args, 13 train_fwd_args, 14 peer_allreduce_args, 15 field_args */
 size_t stdadk_sizeof(int which);
 
 size_t stdadk_image_floats(int64_t rows, int64_t cols);
@@ -279,6 +279,33 @@ typedef struct {
 } stdadk_predict_args;
 int stdadk_predict_supported(const stdadk_predict_args* a);   /* 1 yes, 0 no (reason in stdadk_last_error) */
 int stdadk_predict(const stdadk_predict_args* a, void* stream);
+
+/* Space-time FIELD prediction: every site of a set (explicit sites, or the lattice grid_nx x grid_ny with site = i*ny + j)
+ * at the time steps k_begin .. k_end-1 of an n_times-step axis, t_k = k/(n_times-1) -- the T x S field of upstream's
+ * plot_spatial_mse loop (train_st_interp.py:1233-1248), plot_temporal_series (:1380-1394) and the dense grid of
+ * stdadk_points.  Same function as stdadk_predict on those points; the kernel exploits that the first Linear layer
+ * separates, W1 [phi(s) | psi(t)] + b1 = zs(s) + zt(t): a CTA evaluates the basis and block 1 once per tile of 128
+ * sites and loops over the time steps.  Needs p_cov == 0 and the limits of stdadk_predict.
+ *   layers[0].w_img : image of W1[:, 0:k_s] (n_1 x k_s), the spatial columns only; layers[0].n_in = k_s
+ *   w1 / strides    : W1 itself (n_1 x (k_s + k_t)), read for the temporal columns
+ *   yhat row of point (k, s) = k * n_sites + s - row_base     (the caller's shard of the (t, s) row-major field)
+ *   zt_ws           : workspace of n_times * pad32(n_1) floats */
+typedef struct {
+    const stdadk_basis* basis;
+    const float* sites;
+    int32_t grid_nx, grid_ny;
+    int64_t n_sites;
+    int32_t n_times, k_begin, k_end, n_layers;
+    int64_t site_begin, site_end;
+    stdadk_layer layers[STDADK_MAX_HIDDEN];
+    const float* w1;
+    int64_t w1_row_stride, w1_col_stride;
+    const stdadk_head* head;
+    int64_t row_base;
+    float* zt_ws;
+} stdadk_field_args;
+int stdadk_predict_field_supported(const stdadk_field_args* a);   /* 1 yes, 0 no (reason in stdadk_last_error) */
+int stdadk_predict_field(const stdadk_field_args* a, void* stream);
 
 /* Forward of a TRAINING step through the same whole-network kernel (STInterpMLP.forward in train mode + the loss of
  * train_st_interp.py:620-631): one launch instead of one stdadk_layer_fwd per block.  Besides y_hat it applies

@@ -97,6 +97,14 @@ class PredictArgs(C.Structure):
                 ("layers", Layer * MAX_HIDDEN), ("head", C.POINTER(Head))]
 
 
+class FieldArgs(C.Structure):
+    _fields_ = [("basis", C.POINTER(Basis)), ("sites", fp), ("grid_nx", C.c_int32), ("grid_ny", C.c_int32),
+                ("n_sites", C.c_int64), ("n_times", C.c_int32), ("k_begin", C.c_int32), ("k_end", C.c_int32),
+                ("n_layers", C.c_int32), ("site_begin", C.c_int64), ("site_end", C.c_int64),
+                ("layers", Layer * MAX_HIDDEN), ("w1", fp), ("w1_row_stride", C.c_int64), ("w1_col_stride", C.c_int64),
+                ("head", C.POINTER(Head)), ("row_base", C.c_int64), ("zt_ws", fp)]
+
+
 MAX_PEERS = 8
 
 
@@ -126,6 +134,8 @@ _PROTOS = {
     "stdadk_predict_supported": (C.c_int, [C.POINTER(PredictArgs)]),
     "stdadk_predict": (C.c_int, [C.POINTER(PredictArgs), fp]),
     "stdadk_train_fwd": (C.c_int, [C.POINTER(TrainFwdArgs), fp]),
+    "stdadk_predict_field_supported": (C.c_int, [C.POINTER(FieldArgs)]),
+    "stdadk_predict_field": (C.c_int, [C.POINTER(FieldArgs), fp]),
     "stdadk_peer_allreduce": (C.c_int, [C.POINTER(PeerAllreduceArgs), fp]),
     "stdadk_layer_fwd": (C.c_int, [C.POINTER(FwdArgs), fp]),
     "stdadk_layer_bwd": (C.c_int, [C.POINTER(BwdArgs), fp]),
@@ -156,7 +166,7 @@ def lib():
             fn.restype = res
             fn.argtypes = args
         structs = [Basis, Points, Layer, Dropout, Head, FwdArgs, BwdArgs, WgradArgs, KnotGradArgs, AdamWArgs, PackDesc, SparseArgs,
-                   PredictArgs, TrainFwdArgs, PeerAllreduceArgs]
+                   PredictArgs, TrainFwdArgs, PeerAllreduceArgs, FieldArgs]
         for i, st in enumerate(structs):
             if L.stdadk_sizeof(i) != C.sizeof(st):
                 raise RuntimeError(f"libstdadk ABI mismatch: {st.__name__} is {C.sizeof(st)} B in the binding, "

@@ -9,6 +9,7 @@
 #include "misc.cuh"
 #include "sparse.cuh"
 #include "predict.cuh"
+#include "field.cuh"
 
 using namespace stdadk;
 
@@ -167,6 +168,7 @@ size_t stdadk_sizeof(int which) {
         case 12: return sizeof(stdadk_predict_args);
         case 13: return sizeof(stdadk_train_fwd_args);
         case 14: return sizeof(stdadk_peer_allreduce_args);
+        case 15: return sizeof(stdadk_field_args);
         default: return 0;
     }
 }
@@ -414,6 +416,111 @@ int stdadk_predict(const stdadk_predict_args* a, void* stream) {
     const int grid = Kl.n_tiles < sms ? Kl.n_tiles : sms;
     predict_fused_kernel<false><<<grid, PF_NT, Kl.sm.total, (cudaStream_t)stream>>>(Kl);
     return check_launch("predict");
+}
+
+static int field_fill(const stdadk_field_args* a, FieldK* K) {
+    REQUIRE(a && a->basis && a->head, "predict_field: NULL args / basis / head");
+    REQUIRE(a->n_layers >= 1 && a->n_layers <= PF_MAX_LAYERS, "predict_field: %d hidden blocks outside [1,%d]", a->n_layers,
+            PF_MAX_LAYERS);
+    const stdadk_basis* b = a->basis;
+    REQUIRE(b->p_cov == 0, "predict_field: covariates (p_cov=%d) are per (site, time): use stdadk_predict", b->p_cov);
+    REQUIRE(b->k_s >= 1 && b->knots4 && (b->k_t == 0 || b->tknots2), "predict_field: basis tables missing");
+    REQUIRE(((reinterpret_cast<uintptr_t>(b->knots4)) & 15) == 0, "predict_field: knots4 must be 16-byte aligned");
+    REQUIRE(b->basis_fn >= 0 && b->basis_fn <= 2, "predict_field: unknown basis_fn %d", b->basis_fn);
+    REQUIRE(a->layers[0].n_in == b->k_s, "predict_field: layers[0] is the spatial part: n_in=%d != k_s=%d", a->layers[0].n_in,
+            b->k_s);
+    REQUIRE(a->n_sites >= 1 && a->n_times >= 1, "predict_field: n_sites / n_times");
+    REQUIRE(a->sites || (a->grid_nx > 0 && a->grid_ny > 0 && (int64_t)a->grid_nx * a->grid_ny == a->n_sites),
+            "predict_field: give sites or a lattice with nx*ny == n_sites");
+    REQUIRE(!a->sites || (reinterpret_cast<uintptr_t>(a->sites) & 7) == 0, "predict_field: sites must be 8-byte aligned");
+    REQUIRE(0 <= a->k_begin && a->k_begin <= a->k_end && a->k_end <= a->n_times, "predict_field: time range");
+    REQUIRE(0 <= a->site_begin && a->site_begin <= a->site_end && a->site_end <= a->n_sites, "predict_field: site range");
+    REQUIRE(a->head->q >= 1 && a->head->q <= STDADK_MAX_Q && a->head->w && a->head->b && a->head->yhat,
+            "predict_field: head q / w / b / yhat");
+    REQUIRE(a->w1 && a->zt_ws && (reinterpret_cast<uintptr_t>(a->zt_ws) & 15) == 0, "predict_field: w1 / zt_ws");
+    *K = FieldK{};
+    K->basis = to_basis(b);
+    K->basis.k_t = 0;
+    K->basis.tknots = nullptr;
+    K->sites = a->sites;
+    K->nx = a->grid_nx;
+    K->ny = a->grid_ny;
+    K->n_sites = a->n_sites;
+    K->site_begin = a->site_begin;
+    K->site_end = a->site_end;
+    K->k_begin = a->k_begin;
+    K->k_end = a->k_end;
+    K->n_layers = a->n_layers;
+    K->q = a->head->q;
+    K->head_w = a->head->w;
+    K->head_b = a->head->b;
+    K->yhat = a->head->yhat;
+    K->row_base = a->row_base;
+    K->zt = a->zt_ws;
+    for (int l = 0; l < a->n_layers; ++l) {
+        const stdadk_layer& y = a->layers[l];
+        if (int r = check_layer(y, "predict_field")) return r;
+        REQUIRE(l == 0 || y.n_in == a->layers[l - 1].n_out, "predict_field: block %d n_in=%d != previous n_out=%d", l, y.n_in,
+                a->layers[l - 1].n_out);
+        PredLayerP& L = K->L[l];
+        L.w_img = y.w_img;
+        L.bias = y.bias;
+        L.gamma = y.gamma;
+        L.beta = y.beta;
+        L.n_out = y.n_out;
+        L.n_pad = pad32(y.n_out);
+        L.k_slabs = pad32(y.n_in) / SLAB_K;
+        L.has_ln = y.gamma != nullptr;
+        L.eps = y.ln_eps;
+    }
+    REQUIRE(K->L[0].k_slabs <= PF_HSLABS, "predict_field: %d spatial knots exceed the resident operand (%d)", b->k_s,
+            PF_HSLABS * SLAB_K);
+    uint32_t bytes = plan_field(*K);
+    REQUIRE(bytes <= 227 * 1024, "predict_field: the kernel needs %u B of shared memory (> 227 KB) for this shape", bytes);
+    // work units: (tile of 128 sites) x (chunk of time steps).  Every unit pays the basis + block-1 GEMM of its tile
+    // (about one time step of work), so chunks are as long as the SM count allows: minimise waves * (chunk + 1).
+    const int sms = g_sm_count > 0 ? g_sm_count : 148;
+    const long long n_s = a->site_end - a->site_begin;
+    const int tk = a->k_end - a->k_begin;
+    K->n_site_tiles = (int)ceil_div64(n_s, TILE_M);
+    int best_chunk = tk > 0 ? tk : 1;
+    double best_cost = 1e30;
+    for (int chunk = 1; chunk <= tk; ++chunk) {
+        const long long units = (long long)K->n_site_tiles * ((tk + chunk - 1) / chunk);
+        const double cost = (double)ceil_div64(units, sms) * (chunk + 1.0);
+        if (cost < best_cost - 1e-9 || (cost < best_cost + 1e-9 && chunk > best_chunk)) {
+            best_cost = cost;
+            best_chunk = chunk;
+        }
+    }
+    K->k_chunk = best_chunk;
+    K->n_kchunks = tk > 0 ? (tk + best_chunk - 1) / best_chunk : 0;
+    const long long units = (long long)K->n_site_tiles * K->n_kchunks;
+    REQUIRE(units < (1ll << 31), "predict_field: too many work units");
+    K->n_units = (int)units;
+    return 0;
+}
+
+int stdadk_predict_field_supported(const stdadk_field_args* a) {
+    FieldK K;
+    return field_fill(a, &K) == 0 ? 1 : 0;
+}
+
+int stdadk_predict_field(const stdadk_field_args* a, void* stream) {
+    if (int r = check_device()) return r;
+    FieldK K;
+    if (int r = field_fill(a, &K)) return r;
+    if (K.n_units <= 0) return 0;
+    const int pad0 = K.L[0].n_pad, total = a->n_times * pad0;
+    field_zt_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        a->w1, a->w1_row_stride, a->w1_col_stride, a->basis->k_s, a->layers[0].bias,
+        reinterpret_cast<const float2*>(a->basis->tknots2), a->basis->k_t, K.L[0].n_out, pad0, a->n_times, a->zt_ws);
+    if (int r = check_launch("predict_field (zt)")) return r;
+    if (int r = set_smem(predict_field_kernel, K.sm.total)) return r;
+    const int sms = g_sm_count > 0 ? g_sm_count : 148;
+    const int grid = K.n_units < sms ? K.n_units : sms;
+    predict_field_kernel<<<grid, PF_NT, K.sm.total, (cudaStream_t)stream>>>(K);
+    return check_launch("predict_field");
 }
 
 int stdadk_train_fwd(const stdadk_train_fwd_args* a, void* stream) {

@@ -134,6 +134,10 @@ class Executor:
         # image anyway, and one CTA per SM leaves less parallelism than the per-block kernels.  Off by default.
         self.fused_train = False
         self._fused_ok = None
+        self._field_ok = None
+        self._w1sf_img = None
+        self._w1sf_key = None
+        self._zt_ws = None
 
     @property
     def x3(self) -> bool:
@@ -183,6 +187,8 @@ class Executor:
         self._pack_key = None
         self._knots_ready = False
         self._fused_ok = None
+        self._field_ok = None
+        self._w1sf_key = None
 
     def _key(self):
         s = self.spec
@@ -415,6 +421,77 @@ class Executor:
             return False
         ops.predict(a)
         return True
+
+    # ------------------------------------------------------------------ space-time field prediction
+    def _field_args(self, sites, grid, n_sites, n_times, k0, k1, s0, s1, yhat, row_base) -> L.FieldArgs:
+        s = self.spec
+        k_s = s.centers.shape[0]
+        w1 = s.weights[0]
+        key = (w1.data_ptr(), w1._version, self._pack_key)
+        if self._w1sf_key != key:      # image of the spatial columns of W1 (forward operand of the site GEMM)
+            self._w1sf_img = ops.pack_images([w1[:, s.p_cov:s.p_cov + k_s]], [self._w1sf_img])[0]
+            self._w1sf_key = key
+        if self._zt_ws is None or self._zt_ws.numel() < n_times * ops.pad32(w1.shape[0]):
+            self._zt_ws = torch.empty(n_times * ops.pad32(w1.shape[0]), dtype=torch.float32, device=self.device)
+        basis = ops.make_basis(self.knots4, self.tknots2, k_s, s.t_centers.shape[0], 0, s.basis_fn)
+        head = ops.make_head(s.head_w, s.head_b, s.q, yhat)
+        a = L.FieldArgs()
+        a.basis = C.pointer(basis)
+        if sites is not None:
+            a.sites = sites.data_ptr()
+        else:
+            a.grid_nx, a.grid_ny = grid
+        a.n_sites, a.n_times, a.k_begin, a.k_end = n_sites, n_times, k0, k1
+        a.site_begin, a.site_end = s0, s1
+        a.n_layers = s.n_hidden
+        for l in range(s.n_hidden):
+            a.layers[l] = self._layer(l)
+        a.layers[0] = ops.make_layer(self._w1sf_img, s.biases[0], s.gammas[0], s.betas[0], k_s, w1.shape[0], s.ln_eps, 0)
+        a.w1 = w1.data_ptr()
+        a.w1_row_stride, a.w1_col_stride = w1.stride(0), w1.stride(1)
+        a.head = C.pointer(head)
+        a.row_base = row_base
+        a.zt_ws = self._zt_ws.data_ptr()
+        return a
+
+    def field_supported(self) -> bool:
+        """Whether grid / space-time-field predictions of this network run the site-tile x time-loop kernel
+        (stdadk_predict_field): dense regime, TF32 mode, no covariates, shape within the kernel's shared memory."""
+        s = self.spec
+        if self.sparse or self.x3 or not self.fused_predict or s.p_cov != 0 or s.n_hidden > L.MAX_HIDDEN:
+            return False
+        if self._field_ok is None:
+            probe = torch.empty(1, s.q, dtype=torch.float32, device=self.device)
+            self._field_ok = ops.predict_field_supported(self._field_args(None, (1, 1), 1, 1, 0, 1, 0, 1, probe, 0))
+        return bool(self._field_ok)
+
+    def predict_field(self, yhat: torch.Tensor, begin: int, end: int, n_sites: int, n_times: int,
+                      sites: Optional[torch.Tensor] = None, grid: Optional[Tuple[int, int]] = None) -> int:
+        """Rows [begin, end) of the (t, s) row-major field (row = k * n_sites + s) into yhat[0 : end - begin].
+        The shard is cut into at most three (site range x time range) rectangles -- a partial first time step, whole
+        steps, a partial last step -- one launch each.  Returns the number of launches."""
+        S = n_sites
+        k0, k1 = begin // S, (end - 1) // S if end > begin else begin // S
+        rects = []
+        if end <= begin:
+            return 0
+        if k0 == k1:
+            rects.append((k0, k0 + 1, begin - k0 * S, end - k0 * S))
+        else:
+            lo = k0
+            if begin > k0 * S:
+                rects.append((k0, k0 + 1, begin - k0 * S, S))
+                lo = k0 + 1
+            hi = k1 + 1
+            if end < (k1 + 1) * S:
+                hi = k1
+            if hi > lo:
+                rects.append((lo, hi, 0, S))
+            if hi == k1:
+                rects.append((k1, k1 + 1, 0, end - k1 * S))
+        for (ka, kb, sa, sb) in rects:
+            ops.predict_field(self._field_args(sites, grid, S, n_times, ka, kb, sa, sb, yhat, begin))
+        return 2 * len(rects)
 
     # ------------------------------------------------------------------ backward
     def alloc_grads(self, flat: Optional[torch.Tensor] = None, views: Optional[dict] = None):

@@ -175,6 +175,15 @@ def predict(args: L.PredictArgs):
     L.check(L.lib().stdadk_predict(C.byref(args), _stream()), "predict")
 
 
+def predict_field_supported(args: L.FieldArgs) -> bool:
+    return bool(L.lib().stdadk_predict_field_supported(C.byref(args)))
+
+
+def predict_field(args: L.FieldArgs):
+    """Space-time field prediction: basis + block 1 once per tile of sites, loop over the time steps."""
+    L.check(L.lib().stdadk_predict_field(C.byref(args), _stream()), "predict_field")
+
+
 def train_fwd(args: L.TrainFwdArgs):
     """Forward of a training step (dropout, loss, saved tensors for the backward) in one launch."""
     L.check(L.lib().stdadk_train_fwd(C.byref(args), _stream()), "train_fwd")

@@ -40,6 +40,7 @@ class Predictor:
         self._copy_stream = None
         self.host_copy_done = None
         self.used_field_kernel = False     # the last grid / field call ran the site-tile x time-loop kernel
+        self.use_field_kernel = True       # False: grid / field calls go through the generic per-point kernel
 
     def _prepare(self):
         if self.static_weights and self._prepared:
@@ -83,6 +84,11 @@ class Predictor:
         dev = self.ex.device
         if out is None:
             out = torch.empty(end - begin, self.model.output_dim, device=dev)
+        self.used_field_kernel = self.use_field_kernel and self.ex.field_supported()
+        if self.used_field_kernel:
+            # every site of the nx x ny lattice at nt time steps: basis + block 1 once per tile of sites
+            self.launches += self.ex.predict_field(out, begin, end, nx * ny, nt, grid=(nx, ny))
+            return out, (begin, end)
         self._run(lambda b, r: ops.make_points(grid=(nx, ny, nt), row_begin=b, n_rows=r), begin, end, out)
         return out, (begin, end)
 
@@ -129,8 +135,11 @@ class Predictor:
                 order = torch.argsort(torch.floor(cf[:, 0] * 32.0) * 2.0 + cf[:, 1])
                 site = order[site]
             cc = cf.index_select(0, site).contiguous()
+            # the S sites in the order the field kernel visits them (space-filling when whole steps are owned)
+            self._field_sites = (cf.index_select(0, order) if order is not None else cf).contiguous()
             self._field_key, self._field_pts = key, (cc, tt, order)
         cc, tt, order = self._field_pts
+        self.used_field_kernel = self.use_field_kernel and self.ex.field_supported()
         out = torch.empty(end - begin, self.model.output_dim, device=dev)
         q = out.shape[1]
         res = torch.empty_like(out) if order is not None else out
@@ -148,9 +157,15 @@ class Predictor:
                 self._copy_stream = torch.cuda.Stream(device=dev)
                 self.host_copy_done = torch.cuda.Event()
         main = torch.cuda.current_stream()
+        sites_f = None
+        if self.used_field_kernel:
+            sites_f = self._field_sites
         for b0, r0 in pieces:
-            self._run(lambda b, r: ops.make_points(cc, tt, None, row_begin=b - begin, n_rows=r), begin + b0,
-                      begin + b0 + r0, out[b0:b0 + r0])
+            if self.used_field_kernel:
+                self.launches += self.ex.predict_field(out[b0:b0 + r0], begin + b0, begin + b0 + r0, S, T, sites=sites_f)
+            else:
+                self._run(lambda b, r: ops.make_points(cc, tt, None, row_begin=b - begin, n_rows=r), begin + b0,
+                          begin + b0 + r0, out[b0:b0 + r0])
             if order is not None:
                 res[b0:b0 + r0].view(-1, S, q).index_copy_(1, order, out[b0:b0 + r0].view(-1, S, q))
             if host_out is not None:

@@ -1,0 +1,78 @@
+"""GPU: the space-time FIELD kernel (stdadk_predict_field: basis + block 1 once per tile of sites, loop over time)
+against the generic per-point kernel, the oracle and itself under sharding."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import orc
+from test_gpu_kernels import rel_l2
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _model(q=1, hidden=(256, 256, 128), fn="wendland", ln=True, seed=3):
+    from stnf.models import STInterpMLP
+    from test_gpu_model import _perturb_ln
+    torch.manual_seed(seed)
+    m = STInterpMLP(hidden_dims=list(hidden), dropout=0.0, layernorm=ln, output_dim=q, spatial_basis_function=fn)
+    if ln:
+        _perturb_ln(m, seed)
+    return m.to(DEV).eval()
+
+
+def _oracle(model, coords, t):
+    st = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
+    from helpers import oracle_from_state
+    m = oracle_from_state(st, basis_fn=model.spatial_basis_function)
+    return orc.forward(m, None, coords, t)
+
+
+@pytest.mark.parametrize("q,hidden,fn,ln,S,T", [(1, (256, 256, 128), "wendland", True, 1000, 7),
+                                               (5, (256, 256, 128), "wendland", True, 333, 3),
+                                               (3, (64, 32), "triangular", False, 130, 12),
+                                               (1, (128,), "gaussian", True, 257, 1),
+                                               (2, (256, 160, 96, 32), "wendland", True, 500, 5)])
+def test_field_kernel_matches_generic_kernel_and_oracle(q, hidden, fn, ln, S, T):
+    from st_dadk_b200.predict import Predictor
+    model = _model(q, hidden, fn, ln)
+    g = torch.Generator().manual_seed(1)
+    sites = torch.rand(S, 2, generator=g).to(DEV)
+    pr = Predictor(model)
+    field, (b, e) = pr.space_time_field(sites, T)
+    assert pr.used_field_kernel and (b, e) == (0, S * T)
+    gen = Predictor(model)
+    gen.use_field_kernel = False
+    ref, _ = gen.space_time_field(sites, T)
+    assert not gen.used_field_kernel
+    # same function; the two kernels differ in the order of FP32 additions and in zt being FP32 instead of a TF32 GEMM
+    assert rel_l2(field.cpu().numpy(), ref.cpu().numpy()) < 3e-4
+    coords = sites.repeat(T, 1).cpu().numpy()
+    t = (torch.arange(T).repeat_interleave(S).float() / max(T - 1, 1)).numpy()[:, None]
+    want = _oracle(model, coords, t)
+    assert rel_l2(field.cpu().numpy(), want) < 1e-3
+    # sharding: any cut of the (t, s) row-major field gives the same bits (ragged shards = partial time steps)
+    for world in (2, 3, 7):
+        parts = [pr.space_time_field(sites, T, r, world)[0] for r in range(world)]
+        assert torch.equal(torch.cat(parts), field), world
+
+
+def test_field_kernel_grid_equals_explicit_sites_and_shards():
+    from st_dadk_b200.predict import Predictor
+    model = _model(q=2)
+    pr = Predictor(model)
+    nx, ny, nt = 37, 23, 4
+    out, _ = pr.grid(nx, ny, nt)
+    assert pr.used_field_kernel
+    ii, jj = torch.meshgrid(torch.arange(nx), torch.arange(ny), indexing="ij")
+    sites = torch.stack([ii.reshape(-1).float() / (nx - 1), jj.reshape(-1).float() / (ny - 1)], dim=1).to(DEV)
+    pr2 = Predictor(model)
+    f2, _ = pr2.space_time_field(sites, nt)
+    assert rel_l2(out.cpu().numpy(), f2.cpu().numpy()) < 1e-6
+    gen = Predictor(model)
+    gen.use_field_kernel = False
+    ref, _ = gen.grid(nx, ny, nt)
+    assert rel_l2(out.cpu().numpy(), ref.cpu().numpy()) < 3e-4
+    for world in (2, 5, 8):
+        parts = [pr.grid(nx, ny, nt, r, world)[0] for r in range(world)]
+        assert torch.equal(torch.cat(parts), out), world
