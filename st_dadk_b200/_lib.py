@@ -5,7 +5,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libstdadk.so")
+# STDADK_LIB: an alternative build of the same library (e.g. the -DSTDADK_PF_DEBUG profiling build of tools/)
+LIB_PATH = os.environ.get("STDADK_LIB") or os.path.join(_HERE, "libstdadk.so")
 MAX_Q = 8
 
 WENDLAND, GAUSSIAN, TRIANGULAR = 0, 1, 2

@@ -457,6 +457,7 @@ static int field_fill(const stdadk_field_args* a, FieldK* K) {
     K->yhat = a->head->yhat;
     K->row_base = a->row_base;
     K->zt = a->zt_ws;
+    K->dbg = g_predict_dbg;
     for (int l = 0; l < a->n_layers; ++l) {
         const stdadk_layer& y = a->layers[l];
         if (int r = check_layer(y, "predict_field")) return r;

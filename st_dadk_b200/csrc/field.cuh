@@ -11,8 +11,13 @@
 // only the order of two FP32 additions differs from the generic kernel (zs + zt instead of one accumulation).
 //
 // Roles as in predict.cuh: 16 worker warps (thread = row x 1/4 of the columns), one producer warp (weight slabs + zt
-// rows), one MMA-issuer warp.  TMEM: columns [0, 256) = zs of the current tile, [256, 512) = accumulator of blocks 2.. .
-// Per time step: E1 (zs + zt -> LN -> ReLU -> H slabs) -> MMA block 2 (starts per slab) -> E2 -> MMA block 3 -> E3 + head.
+// rows), one MMA-issuer warp.
+// The shared-memory pipe is what bounds this kind of kernel (weight slabs written by TMA and read back by the tensor
+// core every time step), so the hidden activations do NOT go through it: the normalised output H of a block is written
+// to TENSOR MEMORY (tcgen05.st, 32-column slabs, one mbarrier each) and the next block's MMAs take their A operand from
+// there.  TMEM: columns [0, 256) = accumulator (zs of the tile first, then blocks 2..), [256, 512) = H.  zs itself is
+// parked in shared memory in the slots the block-1 operand occupied -- every thread reads back only what it wrote.
+// Per time step: E1 (zs + zt -> LN -> ReLU -> H) -> MMA block 2 (starts per slab) -> E2 -> MMA block 3 -> E3 + head.
 #pragma once
 #include "predict.cuh"
 
@@ -39,6 +44,7 @@ struct FieldK {
     float* yhat;                        // row (k * S + site) - row_base
     long long row_base;
     int n_layers, q;
+    unsigned long long* dbg;            // optional cycle counters (-DSTDADK_PF_DEBUG builds), NULL in production
 };
 
 __host__ inline uint32_t plan_field(FieldK& K) {
@@ -83,6 +89,24 @@ __global__ void field_zt_kernel(const float* __restrict__ w1, long long w_row_st
         }
     }
     zt[idx] = acc;
+}
+
+// one thread's 32 consecutive columns of its row <-> its 128-byte row of an operand slab (conflict-free swizzle), FP32 as is
+__device__ __forceinline__ void pf_store_raw(const float (&v)[32], uint32_t slab_saddr, uint32_t rowoff, uint32_t rx) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        st_shared_v4(slab_saddr + rowoff + (((uint32_t)c ^ rx) << 4), v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+}
+__device__ __forceinline__ void pf_load_raw(float (&v)[32], uint32_t slab_saddr, uint32_t rowoff, uint32_t rx) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(v[4 * c]), "=f"(v[4 * c + 1]), "=f"(v[4 * c + 2]), "=f"(v[4 * c + 3])
+                     : "r"(slab_saddr + rowoff + (((uint32_t)c ^ rx) << 4)));
+}
+__device__ __forceinline__ void pf_round_tf32(float (&v)[32]) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = to_tf32(v[i]);
 }
 
 __global__ void __launch_bounds__(PF_NT, 1) predict_field_kernel(const __grid_constant__ FieldK P) {
@@ -189,14 +213,24 @@ __global__ void __launch_bounds__(PF_NT, 1) predict_field_kernel(const __grid_co
         // ---------------- MMA issuer
         if (lane == 0) {
             uint32_t wstage = 0, wphase = 0, hph = 0;
-            auto run_block = [&](const PredLayerP& Ly, uint32_t acc) {
+            PF_DBG(unsigned long long w_a = 0, w_w = 0; const long long t_begin = clock64();)
+            auto run_block = [&](const PredLayerP& Ly, bool a_in_tmem) {
                 const uint32_t idesc = umma_idesc_tf32((uint32_t)Ly.n_pad, 0, 0);
                 for (int s = 0; s < Ly.k_slabs; ++s) {
-                    mbar_wait(&hfull[s], (hph >> s) & 1u);
+                    PF_TIMED_WAIT(w_a, mbar_wait(&hfull[s], (hph >> s) & 1u));
                     hph ^= 1u << s;
-                    mbar_wait(&wfull[wstage], wphase);
+                    PF_TIMED_WAIT(w_w, mbar_wait(&wfull[wstage], wphase));
                     tc_fence_after();
-                    issue_slab_mma(acc, sH + (size_t)s * SLAB_FLOATS, sW + (size_t)wstage * MAX_N * SLAB_K, idesc, s == 0);
+                    const float* sB = sW + (size_t)wstage * MAX_N * SLAB_K;
+                    if (a_in_tmem) {          // A = H slab s in tensor memory: 32 columns, four K = 8 steps
+                        const uint64_t bd = umma_desc_sw128(smem_u32(sB), 16, 1024);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_tf32_ts(tmem_base, tmem_base + MAX_N + (uint32_t)(s * SLAB_K + k * 8), bd + (uint64_t)(k * 2), idesc,
+                                         (s == 0 && k == 0) ? 0u : 1u);
+                    } else {
+                        issue_slab_mma(tmem_base, sH + (size_t)s * SLAB_FLOATS, sB, idesc, s == 0);
+                    }
                     umma_commit(&wempty[wstage]);
                     if (++wstage == PF_WST) {
                         wstage = 0;
@@ -208,10 +242,15 @@ __global__ void __launch_bounds__(PF_NT, 1) predict_field_kernel(const __grid_co
             for (int u = blockIdx.x; u < P.n_units; u += gridDim.x) {
                 const int kc = u % P.n_kchunks;
                 const int k0 = P.k_begin + kc * P.k_chunk, k1 = min(P.k_end, k0 + P.k_chunk);
-                run_block(P.L[0], tmem_base);                                    // zs of this site tile
+                run_block(P.L[0], false);                                        // zs of this site tile (A = phi slabs in SMEM)
                 for (int k = k0; k < k1; ++k)
-                    for (int l = 1; l < nl; ++l) run_block(P.L[l], tmem_base + MAX_N);
+                    for (int l = 1; l < nl; ++l) run_block(P.L[l], true);
             }
+            PF_DBG(if (P.dbg) {
+                atomicAdd(&P.dbg[0], w_a);
+                atomicAdd(&P.dbg[1], w_w);
+                atomicAdd(&P.dbg[2], (unsigned long long)(clock64() - t_begin));
+            })
         }
         __syncwarp();
     } else {
@@ -222,6 +261,11 @@ __global__ void __launch_bounds__(PF_NT, 1) predict_field_kernel(const __grid_co
         const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16);
         const uint32_t sH_addr = smem_u32(sH);
         uint32_t accw = 0, zi = 0;              // accumulator-ready phases waited for; zt rows consumed
+#ifdef STDADK_PF_DEBUG
+        unsigned long long w_acc = 0, w_zt = 0, w_bar = 0, ph_gen = 0, ph_ld = 0, ph_norm = 0, ph_head = 0;
+        const long long t_begin = clock64();
+        long long t_last = t_begin;
+#endif
         mbar_wait(kbar, 0);
         for (int u = blockIdx.x; u < P.n_units; u += gridDim.x) {
             const int tile = u / P.n_kchunks, kc = u - tile * P.n_kchunks;
@@ -249,9 +293,26 @@ __global__ void __launch_bounds__(PF_NT, 1) predict_field_kernel(const __grid_co
                     mbar_arrive(&hfull[s]);
                 }
             }
-            mbar_wait(accf, accw & 1u);            // zs complete
+            PF_PHASE(ph_gen);
+            PF_TIMED_WAIT(w_acc, mbar_wait(accf, accw & 1u));            // zs complete
+            PF_DBG(if (P.dbg) t_last = clock64();)
             ++accw;
             tc_fence_after();
+            // park this thread's 64 columns of zs in the (now dead) operand slabs cg, cg + 4 of its own row; the accumulator
+            // columns are then free for blocks 2.. (the barrier below: every thread has read them before an MMA writes)
+            {
+                float z[32];
+                if (32 * cg < pad0) {
+                    tmem_ld32(trow + (uint32_t)(32 * cg), z);
+                    pf_store_raw(z, sH_addr + (uint32_t)cg * SLAB_BYTES, rowoff, rx);
+                }
+                if (32 * cg + 128 < pad0) {
+                    tmem_ld32(trow + (uint32_t)(32 * cg + 128), z);
+                    pf_store_raw(z, sH_addr + (uint32_t)(cg + 4) * SLAB_BYTES, rowoff, rx);
+                }
+            }
+            tc_fence_before();
+            worker_barrier(PF_NW);
             for (int k = k0; k < k1; ++k, ++zi) {
                 const uint32_t zs_slot = zi % FD_ZT_RING, zph = (zi / FD_ZT_RING) & 1u;
                 for (int l = 0; l < nl; ++l) {
@@ -263,32 +324,37 @@ __global__ void __launch_bounds__(PF_NT, 1) predict_field_kernel(const __grid_co
                     const bool ha = c0a < Ly.n_pad, hb = c0b < Ly.n_pad;
                     const int nva = min(32, Ly.n_out - c0a), nvb = min(32, Ly.n_out - c0b);
                     float4* redl = red;
-                    uint32_t acc = trow;                                   // block 1: zs (already complete)
                     const float* addv = szt + (size_t)zs_slot * pad0;      // block 1: "bias" = zt[k]
                     if (l == 0) {
-                        mbar_wait(&ztfull[zs_slot], zph);
+                        PF_TIMED_WAIT(w_zt, mbar_wait(&ztfull[zs_slot], zph));
+                        PF_DBG(if (P.dbg) t_last = clock64();)
                     } else {
-                        mbar_wait(accf, accw & 1u);
+                        PF_TIMED_WAIT(w_acc, mbar_wait(accf, accw & 1u));
+                        PF_DBG(if (P.dbg) t_last = clock64();)
                         ++accw;
                         tc_fence_after();
-                        acc = trow + MAX_N;
                         addv = sb;
                     }
                     float va[32], vb[32];
-                    if (ha) {
-                        tmem_ld32_issue(acc + (uint32_t)c0a, va);
+                    if (l == 0) {                 // zs from this thread's own shared-memory slots
+                        if (ha) pf_load_raw(va, sH_addr + (uint32_t)cg * SLAB_BYTES, rowoff, rx);
+                        if (hb) pf_load_raw(vb, sH_addr + (uint32_t)(cg + 4) * SLAB_BYTES, rowoff, rx);
                     } else {
+                        if (ha) tmem_ld32_issue(trow + (uint32_t)c0a, va);
+                        if (hb) tmem_ld32_issue(trow + (uint32_t)c0b, vb);
+                    }
+                    if (!ha) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) va[i] = 0.0f;
                     }
-                    if (hb) {
-                        tmem_ld32_issue(acc + (uint32_t)c0b, vb);
-                    } else {
+                    if (!hb) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) vb[i] = 0.0f;
                     }
-                    tmem_ld_wait(va);
-                    tmem_ld_wait(vb);
+                    if (l != 0) {
+                        tmem_ld_wait(va);
+                        tmem_ld_wait(vb);
+                    }
                     bool have = false;
                     float K = 0.0f, S1 = 0.0f, S2 = 0.0f;
                     if (ha) pf_bias_stats(va, addv + c0a, nva, have, K, S1, S2);
@@ -299,7 +365,9 @@ __global__ void __launch_bounds__(PF_NT, 1) predict_field_kernel(const __grid_co
                         redl[cg * TILE_M + row] = make_float4(K, S1, S2, cntv);
                     }
                     tc_fence_before();
-                    worker_barrier(PF_NW);        // LN partials visible; every thread has read this accumulator / zt row
+                    PF_PHASE(ph_ld);
+                    PF_TIMED_WAIT(w_bar, worker_barrier(PF_NW));   // LN partials visible; everyone has read this accumulator / zt row
+                    PF_DBG(if (P.dbg) t_last = clock64();)
                     if (l == 0 && tid == 0) mbar_arrive(&ztempty[zs_slot]);
                     if (Ly.has_ln && ha) {
                         const float inv_n = 1.0f / (float)Ly.n_out;
@@ -323,16 +391,21 @@ __global__ void __launch_bounds__(PF_NT, 1) predict_field_kernel(const __grid_co
                     if (l + 1 < nl) {
                         if (ha) {
                             pf_normalize(va, sg + c0a, sbt + c0a, Ly.has_ln != 0, rstd, nmr, nva);
-                            pf_store_slab(va, sH_addr + (uint32_t)cg * SLAB_BYTES, rowoff, rx);
-                            fence_proxy_async_smem();
+                            pf_round_tf32(va);
+                            tmem_st32(trow + MAX_N + (uint32_t)c0a, va);
+                            tmem_st_wait();
+                            tc_fence_before();
                             mbar_arrive(&hfull[cg]);
                         }
                         if (hb) {
                             pf_normalize(vb, sg + c0b, sbt + c0b, Ly.has_ln != 0, rstd, nmr, nvb);
-                            pf_store_slab(vb, sH_addr + (uint32_t)(cg + 4) * SLAB_BYTES, rowoff, rx);
-                            fence_proxy_async_smem();
+                            pf_round_tf32(vb);
+                            tmem_st32(trow + MAX_N + (uint32_t)c0b, vb);
+                            tmem_st_wait();
+                            tc_fence_before();
                             mbar_arrive(&hfull[cg + 4]);
                         }
+                        PF_PHASE(ph_norm);
                     } else {
                         float yh[STDADK_MAX_Q];
 #pragma unroll
@@ -365,10 +438,21 @@ __global__ void __launch_bounds__(PF_NT, 1) predict_field_kernel(const __grid_co
                         }
                         // the head scratch is read above by the cg == 0 warps only after the barrier, and rewritten only
                         // after the NEXT step's two LayerNorm barriers: no further synchronisation is needed
+                        PF_PHASE(ph_head);
                     }
                 }
             }
         }
+        PF_DBG(if (P.dbg && tid == 0) {
+            atomicAdd(&P.dbg[3], w_acc);
+            atomicAdd(&P.dbg[4], w_zt);
+            atomicAdd(&P.dbg[5], (unsigned long long)(clock64() - t_begin));
+            atomicAdd(&P.dbg[6], w_bar);
+            atomicAdd(&P.dbg[8], ph_gen);
+            atomicAdd(&P.dbg[9], ph_ld);
+            atomicAdd(&P.dbg[10], ph_norm);
+            atomicAdd(&P.dbg[11], ph_head);
+        })
         tc_fence_before();
     }
     __syncthreads();

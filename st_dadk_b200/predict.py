@@ -280,3 +280,29 @@ class Predictor:
         flops = sum(2.0 * w.shape[0] * w.shape[1] for w in s.weights) + 2.0 * s.head_w.shape[0] * s.head_w.shape[1]
         return n, {"ms": e0.elapsed_time(e1) / repeats, "bytes": 4.0 * n * self.model.output_dim, "flops": flops * n,
                    "dense_flops": flops * n, "points": n, "kernel": "predict_fused_kernel"}
+
+    @torch.no_grad()
+    def profile_field(self, nx: int, ny: int, nt: int, repeats: int = 3):
+        """Average duration of a full (nx, ny, nt) grid prediction through the space-time field kernel with the work it
+        EXECUTES (block 1 once per site: 2*k_s*n_1 per site; blocks 2.. and the head per point) next to the dense-equivalent
+        FLOPs of the per-point network.  None when the field kernel does not take this network."""
+        self._prepare()
+        if not (self.use_field_kernel and self.ex.field_supported()):
+            return None
+        n = nx * ny * nt
+        out = torch.empty(n, self.model.output_dim, device=self.ex.device)
+        self.grid(nx, ny, nt, out=out)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(repeats):
+            self.grid(nx, ny, nt, out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        s = self.ex.spec
+        k_s = s.centers.shape[0]
+        per_site = 2.0 * k_s * s.weights[0].shape[0]
+        per_point = sum(2.0 * w.shape[0] * w.shape[1] for w in s.weights[1:]) + 2.0 * s.head_w.shape[0] * s.head_w.shape[1]
+        dense = sum(2.0 * w.shape[0] * w.shape[1] for w in s.weights) + 2.0 * s.head_w.shape[0] * s.head_w.shape[1]
+        return {"ms": e0.elapsed_time(e1) / repeats, "bytes": 4.0 * n * self.model.output_dim,
+                "flops": per_site * nx * ny + per_point * n, "dense_flops": dense * n, "points": n,
+                "kernel": "predict_field_kernel"}
