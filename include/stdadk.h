@@ -334,21 +334,25 @@ int stdadk_grad_sqnorm(const float* g, int64_t n, int n_groups, const int64_t* g
 int stdadk_adamw_ema_step(const stdadk_adamw_args* a, void* stream);
 
 /* Data-parallel training (one sum of the flat gradient per step; upstream itself is single
- * device): one-shot all-reduce over peer memory.  src[r] / flags[r] are rank r's gradient buffer and flag block as
- * mapped into THIS process (CUDA VMM / symmetric memory, own rank included); flags[r] points at 2*STDADK_MAX_PEERS
- * zero-initialised uint32.  out[i] = sum_r src[r][i] added in rank order (identical bits on every rank).  n must be
- * a multiple of 4, all pointers 16-byte aligned.  The kernel returns only after every peer has finished reading
- * src[rank], so the caller may overwrite it next.  Barrier ids derive from *step_count (equal on all ranks, must
- * grow by one between calls -- the AdamW step counter).  ticket: one zero-initialised local uint32. */
+ * device): one-shot all-reduce over NVLink peer memory, low-latency protocol (every 8-byte packet carries its own epoch
+ * flag), result IN PLACE in g, optionally fused with the gradient norm of stdadk_grad_sqnorm.
+ *   recv[p]  rank p's receive area as mapped into THIS process (CUDA VMM / symmetric memory, own rank included):
+ *            2 * world * (n / 2) packets of 16 bytes, zero-initialised once before the first call
+ *   n        floats, a multiple of 4; g 16-byte aligned
+ *   step_count  device counter, equal on all ranks, must grow by exactly one between calls (the AdamW step counter)
+ *   n_groups > 0: sqnorms[k] = sum of squares of the REDUCED g[0 : n_norm) over group k (bitwise deterministic);
+ *            workspace = (148 * 8 + 8) zero-initialised floats */
 #define STDADK_MAX_PEERS 8
 typedef struct {
     int32_t world, rank;
-    const float* src[STDADK_MAX_PEERS];
-    uint32_t* flags[STDADK_MAX_PEERS];
-    float* out;
+    float* g;
     int64_t n;
+    void* recv[STDADK_MAX_PEERS];
     const int32_t* step_count;
-    uint32_t* ticket;
+    int32_t n_groups, _pad;
+    const int64_t* group_end;   /* host array (n_groups), last entry = n_norm */
+    float* sqnorms;
+    float* workspace;
 } stdadk_peer_allreduce_args;
 int stdadk_peer_allreduce(const stdadk_peer_allreduce_args* a, void* stream);
 

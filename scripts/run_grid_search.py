@@ -5,8 +5,10 @@ configurations are independent jobs dealt to the ranks of a torchrun launch (one
 `--configs_per_gpu C` each rank additionally splits its share over C worker PROCESSES on the same GPU.  A 50-epoch
 run of the default model is ~0.1 s of GPU time and ~0.5 s of host work (CSV, knot placement, evaluation, artefact
 files), so what packing buys is host parallelism; worker threads inside one interpreter were measured slower than
-sequential (GIL, serialised graph captures), separate processes are not.  Outputs keep upstream's file names:
-grid_search_summary.csv, grid_search_detail.csv, grid_search_configs.json.
+sequential (GIL, serialised graph captures), separate processes are not.  Outputs are upstream's (:102-237): ONE
+grid_search_summary.csv, grid_search_detail.csv, grid_search_configs.json / .csv per launch with the same columns, and
+summary_statistics.json + all_experiments.csv inside every config directory -- merged by whichever rank finishes last
+from the per-experiment results.json files (the ranks never communicate).
 
     torchrun --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 scripts/run_grid_search.py --config ... --configs_per_gpu 2
 """
@@ -26,7 +28,8 @@ import torch
 import yaml
 
 sys.path.append(str(Path(__file__).resolve().parent.parent))
-from scripts.train_st_interp import run_single_experiment   # noqa: E402
+from scripts.train_st_interp import (run_single_experiment, aggregate_results, collect_experiment_results,   # noqa: E402
+                                     launch_directory)
 
 # the sweep of BASELINE config 5 (64 = 4 x 2 x 2 x 2 x 2); upstream hard-codes its own grid at :257-274
 DEFAULT_GRID = {
@@ -78,6 +81,63 @@ def _run_config(cfg, out_dir, device, results):
     print(f"[grid] config {cfg['config_id']} ({cfg['tag']}) done in {time.time() - t0:.1f}s", flush=True)
 
 
+STAT_METRICS = ("test_rmse", "test_mae", "test_mse", "valid_rmse", "valid_mae", "valid_mse", "train_rmse", "train_mae",
+                "train_mse", "total_time_seconds")
+CONFIG_COLUMNS = ("spatial_basis_function", "spatial_init_method", "spatial_learnable", "obs_method", "obs_ratio",
+                  "obs_spatial_pattern")
+
+
+def save_experiment_results(all_results, output_dir):
+    """grid_search_summary.csv (one row per config: mean / std / min / max / median of every metric),
+    grid_search_detail.csv (one row per config x experiment), grid_search_configs.json / .csv -- upstream's files and
+    columns (:102-237)."""
+    output_dir = Path(output_dir)
+    summary_rows, detail_rows, configs, index = [], [], {}, []
+    for res in all_results:
+        if res is None or res.get("summary") is None:
+            continue
+        cfg, summ = res["config"], res["summary"]
+        base = {"config_id": cfg["config_id"], "tag": cfg["tag"],
+                **{k: cfg.get(k, "wendland" if k == "spatial_basis_function" else None) for k in CONFIG_COLUMNS}}
+        row = dict(base, n_experiments=summ["n_experiments"])
+        for m in STAT_METRICS:
+            st = summ["statistics"].get(m)
+            if st is not None:
+                for k in ("mean", "std", "min", "max", "median"):
+                    row[f"{m}_{k}"] = st[k]
+        summary_rows.append(row)
+        n_exp = summ["n_experiments"]
+        for e in range(n_exp):
+            d = {"config_id": cfg["config_id"], "tag": cfg["tag"], "experiment_id": e + 1,
+                 **{k: base[k] for k in CONFIG_COLUMNS}}
+            for m in STAT_METRICS:
+                if m in summ["statistics"]:
+                    d[m] = summ["statistics"][m]["values"][e]
+            detail_rows.append(d)
+        configs[str(cfg["config_id"])] = cfg
+        index.append({"config_id": cfg["config_id"], "tag": cfg["tag"]})
+    df_summary, df_detail = pd.DataFrame(summary_rows), pd.DataFrame(detail_rows)
+    df_summary.to_csv(output_dir / "grid_search_summary.csv", index=False)
+    df_detail.to_csv(output_dir / "grid_search_detail.csv", index=False)
+    with open(output_dir / "grid_search_configs.json", "w", encoding="utf-8") as f:
+        json.dump(configs, f, indent=2, ensure_ascii=False, default=str)
+    pd.DataFrame(index).to_csv(output_dir / "grid_search_configs.csv", index=False)
+    return df_summary, df_detail
+
+
+def merge_outputs(configs, out):
+    """Per-config aggregation (summary_statistics.json, all_experiments.csv in the config directory, as upstream's
+    run_multiple_experiments leaves them) and the launch-level CSVs, from the results.json files on disk."""
+    all_results = []
+    for cfg in configs:
+        cdir = Path(out) / f"config_{cfg['config_id']:03d}"
+        ids = list(range(1, int(cfg.get("n_experiments", 1)) + 1))
+        rs = collect_experiment_results(cdir, ids) if cdir.exists() else None
+        rs = [r for r in (rs or []) if isinstance(r, dict) and "total_time_seconds" in r]
+        all_results.append({"config": cfg, "summary": aggregate_results(rs, cdir) if rs else None})
+    return save_experiment_results(all_results, out)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="configs/config_st_interp.yaml")
@@ -99,7 +159,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     device = f"cuda:{local}"
-    out = Path(args.output_dir or Path("results") / f"grid_{datetime.now().strftime('%Y%m%d_%H%M%S')}")
+    out = Path(args.output_dir) if args.output_dir else launch_directory("grid_search")   # one directory per launch
     out.mkdir(parents=True, exist_ok=True)
     mine = configs[rank::world]
     n_workers = max(1, args.configs_per_gpu)
@@ -117,14 +177,6 @@ def main():
             base_cmd += ["--epochs", str(args.epochs)]
         procs = [subprocess.Popen(base_cmd + ["--worker_slice", f"{i}:{n_workers}"]) for i in range(n_workers)]
         rcs = [p.wait() for p in procs]
-        parts = [out / f"grid_search_detail_rank{rank}_w{i}.csv" for i in range(n_workers)]
-        frames = []
-        for f in parts:
-            try:
-                frames.append(pd.read_csv(f))
-            except (FileNotFoundError, pd.errors.EmptyDataError):
-                pass
-        results = pd.concat(frames).to_dict("records") if frames else []
         if any(rcs):
             print(f"[grid] worker exit codes: {rcs}", flush=True)
     else:
@@ -136,19 +188,15 @@ def main():
             _run_config(cfg, out, device, results)
         torch.cuda.synchronize()
         if args.worker_slice is not None:
-            pd.DataFrame(results).to_csv(out / f"grid_search_detail_rank{rank}_w{wi}.csv", index=False)
-            return
+            return            # the parent of this rank merges from the results.json files
     wall = time.time() - t0
-    detail = pd.DataFrame(results)
-    detail.to_csv(out / f"grid_search_detail_rank{rank}.csv", index=False)
-    if len(detail):
-        summary = detail.groupby(["config_id", "tag"]).agg(["mean", "std"]).reset_index()
-        summary.columns = ["_".join(c).strip("_") for c in summary.columns]
-        summary.to_csv(out / f"grid_search_summary_rank{rank}.csv", index=False)
-    if rank == 0:
-        json.dump([{k: v for k, v in c.items()} for c in configs], open(out / "grid_search_configs.json", "w"), indent=1,
-                  default=str)
-    print(json.dumps({"rank": rank, "configs": len(mine), "wall_s": wall, "configs_per_gpu": n_workers}))
+    (out / f".rank{rank}.done").write_text(f"{wall:.3f}")
+    merged = False
+    if all((out / f".rank{r}.done").exists() for r in range(world)):
+        # every rank's share is on disk: whoever sees that merges (identical content if two ranks do)
+        merge_outputs(configs, out)
+        merged = True
+    print(json.dumps({"rank": rank, "configs": len(mine), "wall_s": wall, "configs_per_gpu": n_workers, "merged": merged}))
 
 
 if __name__ == "__main__":

@@ -4,6 +4,9 @@ scripts/train_st_interp.py; artefact names `results.json`, `training_history.csv
 
     python scripts/train_st_interp.py --config configs/config_st_interp.yaml [--data_file ...] [--n_experiments N]
     torchrun --nproc-per-node 8 scripts/train_st_interp.py --config ...   # independent experiments packed per GPU
+    torchrun --nproc-per-node 8 scripts/train_st_interp.py --config ... --data_parallel
+                                   # ONE model trained by all GPUs: each global batch split over the ranks, one gradient
+                                   # exchange per step over NVLink (st_dadk_b200/peer.py), rank 0 writes the artefacts
 
 The per-batch Python of upstream (list-of-dict dataset, collate, per-step .to(device)/.item()) is replaced by the
 device-resident ObservationTable + st_dadk_b200.trainer.fit; observation / split masks are drawn with the same numpy
@@ -257,6 +260,8 @@ def _run_single_quantile_experiment(config, experiment_id, output_dir, device, v
         res["quantile_levels"] = config.get("quantile_levels")
     if config.get("regression_type") == "quantile":
         res["quantile_level"] = config.get("current_quantile")
+    if _dp_rank() != 0:          # data parallel: the replicas are identical, rank 0 writes
+        return res
     save_results(res, output_dir)
     torch.save(model.state_dict(), output_dir / "model_final.pt")
     field = predict_field(model, coords, z_full.shape[0], device, cfg)
@@ -265,6 +270,12 @@ def _run_single_quantile_experiment(config, experiment_id, output_dir, device, v
     np.savez(output_dir / "basis_info.npz", centers=sb.centers.detach().cpu().numpy(),
              bandwidths=sb.bandwidths.detach().cpu().numpy())
     return res
+
+
+def _dp_rank() -> int:
+    """Rank inside a data-parallel group (torch.distributed initialised by --data_parallel), else 0."""
+    import torch.distributed as dist
+    return dist.get_rank() if (dist.is_available() and dist.is_initialized()) else 0
 
 
 def run_single_experiment(config, experiment_id, output_dir, device, verbose=True, parallel_mode=False,
@@ -292,6 +303,9 @@ def run_multiple_experiments(config, base_output_dir, device, parallel=False, st
     n = config.get("n_experiments", 10)
     ids = list(range(start_exp_id or 1, (end_exp_id or n) + 1))
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        rank, world = 0, 1        # data parallel: every rank takes part in every experiment
     results = []
     for i in ids[rank::world]:
         d = Path(base_output_dir) / f"experiment_{i:03d}"
@@ -302,6 +316,61 @@ def run_multiple_experiments(config, base_output_dir, device, parallel=False, st
             (d / "error.txt").write_text(repr(e))
             print(f"[ERROR] experiment {i}: {e!r}")
     return results
+
+
+METRIC_KEYS = ("train_mse", "train_mae", "train_rmse", "valid_mse", "valid_mae", "valid_rmse", "test_mse", "test_mae",
+               "test_rmse", "total_time_seconds")
+
+
+def aggregate_results(all_results: list, summary_dir):
+    """summary_statistics.json (mean / std / min / max / median / values per metric) and all_experiments.csv with
+    upstream's names and columns (upstream :2790-2908; its spatial-MSE plots are left to the offline tools)."""
+    import pandas as pd
+    summary_dir = Path(summary_dir)
+    data = {k: [] for k in METRIC_KEYS}
+    for r in all_results:
+        for k in METRIC_KEYS[:-1]:
+            split, metric = k.split("_", 1)
+            data[k].append(r["metrics"][split][metric] if "metrics" in r else r.get(k, 0))
+        data["total_time_seconds"].append(r["total_time_seconds"])
+    summary = {"n_experiments": len(all_results), "statistics": {}}
+    for k, vals in data.items():
+        a = np.array(vals, dtype=float)
+        summary["statistics"][k] = {"mean": float(np.mean(a)), "std": float(np.std(a)), "min": float(np.min(a)),
+                                    "max": float(np.max(a)), "median": float(np.median(a)), "values": [float(v) for v in vals]}
+    with open(summary_dir / "summary_statistics.json", "w") as f:
+        json.dump(summary, f, indent=2)
+    cols = {"experiment_id": [r.get("experiment_id", i + 1) for i, r in enumerate(all_results)]}
+    if all_results and "experiment_seed" in all_results[0]:
+        cols["experiment_seed"] = [r["experiment_seed"] for r in all_results]
+    cols.update(data)
+    pd.DataFrame(cols).to_csv(summary_dir / "all_experiments.csv", index=False)
+    return summary
+
+
+def collect_experiment_results(base_output_dir, ids):
+    """results.json of every finished experiment under `base_output_dir`, ordered by experiment id (the experiments of
+    one launch are dealt to the ranks; whoever sees them all complete aggregates)."""
+    out = []
+    for i in ids:
+        f = Path(base_output_dir) / f"experiment_{i:03d}" / "results.json"
+        if not f.exists():
+            return None
+        out.append(json.load(open(f)))
+    return out
+
+
+def launch_directory(tag: str) -> Path:
+    """results/<date>/<time>_<tag>, ONE directory per launch: under torchrun every rank derives it from the start time
+    of the common parent (the elastic agent), not from its own clock."""
+    t = datetime.now()
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        try:
+            import psutil
+            t = datetime.fromtimestamp(psutil.Process(os.getppid()).create_time())
+        except Exception:      # noqa: BLE001 -- no psutil: whole minutes of the local clock
+            t = t.replace(second=0, microsecond=0)
+    return Path("results") / t.strftime("%Y%m%d") / f"{t.strftime('%H%M%S')}_{tag}"
 
 
 def main():
@@ -315,6 +384,9 @@ def main():
     ap.add_argument("--start_exp_id", type=int, default=None)
     ap.add_argument("--end_exp_id", type=int, default=None)
     ap.add_argument("--skip-existing", action="store_true")
+    ap.add_argument("--data_parallel", action="store_true",
+                    help="under torchrun: train ONE model on all GPUs (global batches split over the ranks) instead of "
+                         "dealing independent experiments to them")
     args = ap.parse_args()
     with open(args.config) as f:
         config = yaml.safe_load(f)
@@ -324,17 +396,27 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     device = f"cuda:{local}"         # the yaml's `device: cpu` cannot be honoured: this implementation is CUDA-only
     torch.cuda.set_device(local)
-    out = Path("results") / datetime.now().strftime("%Y%m%d") / f"{datetime.now().strftime('%H%M%S')}_{config.get('tag', 'default')}"
+    if args.data_parallel and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(device))
+    out = launch_directory(config.get("tag", "default"))
     out.mkdir(parents=True, exist_ok=True)
-    yaml.safe_dump(config, open(out / "config.yaml", "w"))
-    res = run_multiple_experiments(config, out, device, args.parallel, args.start_exp_id, args.end_exp_id,
-                                   args.skip_existing)
-    flat = [r for r in res if isinstance(r, dict) and "test_rmse" in r]
-    if flat:
-        summ = {k: {"mean": float(np.mean([r[k] for r in flat])), "std": float(np.std([r[k] for r in flat]))}
-                for k in ("train_rmse", "valid_rmse", "test_rmse", "test_mae", "total_time_seconds")}
-        json.dump(summ, open(out / f"summary_statistics_rank{os.environ.get('RANK', '0')}.json", "w"), indent=2)
-        print(json.dumps(summ, indent=2))
+    rank = int(os.environ.get("RANK", "0"))
+    if rank == 0:
+        yaml.safe_dump(config, open(out / "config.yaml", "w"))
+    run_multiple_experiments(config, out, device, args.parallel, args.start_exp_id, args.end_exp_id, args.skip_existing)
+    n = config.get("n_experiments", 10)
+    ids = list(range(args.start_exp_id or 1, (args.end_exp_id or n) + 1))
+    (out / f".rank{rank}.done").write_text("done")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if _dp_rank() == 0 and all((out / f".rank{r}.done").exists() for r in range(1 if args.data_parallel else world)):
+        # the last rank to finish (or any rank that sees every marker) merges: same content whoever writes it
+        allr = collect_experiment_results(out, ids)
+        flat = [r for r in (allr or []) if isinstance(r, dict) and "total_time_seconds" in r]
+        if flat:
+            summ = aggregate_results(flat, out)
+            print(json.dumps({k: {"mean": v["mean"], "std": v["std"]} for k, v in summ["statistics"].items()}, indent=2))
 
 
 if __name__ == "__main__":

@@ -110,8 +110,9 @@ MAX_PEERS = 8
 
 
 class PeerAllreduceArgs(C.Structure):
-    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("src", fp * MAX_PEERS), ("flags", fp * MAX_PEERS),
-                ("out", fp), ("n", C.c_int64), ("step_count", fp), ("ticket", fp)]
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("g", fp), ("n", C.c_int64), ("recv", fp * MAX_PEERS),
+                ("step_count", fp), ("n_groups", C.c_int32), ("_pad", C.c_int32), ("group_end", C.POINTER(C.c_int64)),
+                ("sqnorms", fp), ("workspace", fp)]
 
 
 class TrainFwdArgs(C.Structure):

@@ -804,29 +804,34 @@ __global__ void step_inc_kernel(int* c) { *c += 1; }
 
 int stdadk_peer_allreduce(const stdadk_peer_allreduce_args* a, void* stream) {
     if (int r = check_device()) return r;
-    REQUIRE(a && a->out && a->step_count && a->ticket, "peer_allreduce: NULL argument");
+    REQUIRE(a && a->g && a->step_count, "peer_allreduce: NULL argument");
     REQUIRE(a->world >= 2 && a->world <= PEER_MAX && a->rank >= 0 && a->rank < a->world,
             "peer_allreduce: world=%d rank=%d outside [2,%d]", a->world, a->rank, PEER_MAX);
     REQUIRE(a->n > 0 && a->n % 4 == 0, "peer_allreduce: n=%lld must be a positive multiple of 4", (long long)a->n);
     static_assert(PEER_MAX == STDADK_MAX_PEERS, "peer limits differ");
+    REQUIRE((reinterpret_cast<uintptr_t>(a->g) & 15) == 0, "peer_allreduce: g must be 16-byte aligned");
     PeerK K{};
     for (int r = 0; r < a->world; ++r) {
-        REQUIRE(a->src[r] && a->flags[r], "peer_allreduce: rank %d buffer / flags not mapped", r);
-        REQUIRE((reinterpret_cast<uintptr_t>(a->src[r]) & 15) == 0, "peer_allreduce: buffers must be 16-byte aligned");
-        K.src[r] = a->src[r];
-        K.flags[r] = a->flags[r];
+        REQUIRE(a->recv[r] && (reinterpret_cast<uintptr_t>(a->recv[r]) & 15) == 0,
+                "peer_allreduce: rank %d receive area not mapped / not 16-byte aligned", r);
+        K.recv[r] = static_cast<uint4*>(a->recv[r]);
     }
-    REQUIRE((reinterpret_cast<uintptr_t>(a->out) & 15) == 0, "peer_allreduce: out must be 16-byte aligned");
-    K.out = a->out;
-    K.n4 = a->n / 4;
+    K.g = a->g;
+    K.n2 = a->n / 2;
     K.step_count = a->step_count;
-    K.ticket = a->ticket;
     K.rank = a->rank;
     K.world = a->world;
-    // every block of every rank waits on flags: keep the grid small enough to be co-resident (it always is: <= 148)
-    long long blocks = (K.n4 + PEER_THREADS * 4 - 1) / (PEER_THREADS * 4);
-    const int sms = g_sm_count > 0 ? g_sm_count : 148;
-    if (blocks > sms) blocks = sms;
+    if (a->n_groups > 0) {
+        REQUIRE(a->group_end && a->sqnorms && a->workspace, "peer_allreduce: fused norm needs group_end / sqnorms / workspace");
+        K.n_norm = a->group_end[a->n_groups - 1];
+        REQUIRE(K.n_norm <= a->n, "peer_allreduce: norm range exceeds n");
+        if (int r = make_groups(a->n_groups, a->group_end, K.n_norm, &K.G)) return r;
+        K.sq_out = a->sqnorms;
+        K.ws = a->workspace;
+    }
+    // grid: a function of n alone (the norm's summation order must not depend on the device), at most one block per SM
+    long long blocks = (K.n2 + PEER_THREADS * 2 - 1) / (PEER_THREADS * 2);
+    if (blocks > 148) blocks = 148;
     if (blocks < 1) blocks = 1;
     peer_allreduce_kernel<<<(int)blocks, PEER_THREADS, 0, (cudaStream_t)stream>>>(K);
     return check_launch("peer_allreduce");

@@ -202,68 +202,127 @@ __global__ void sqnorm_kernel(const float* __restrict__ g, long long n, GroupsP 
 }
 
 // ---------------------------------------------------------------- data-parallel gradient exchange over peer memory
-// One-shot all-reduce of the flat gradient between the GPUs of one box (NVLink / NVSwitch), replacing the NCCL call
-// of a data-parallel step: every rank's gradient buffer lives in symmetric memory that all ranks have mapped, so each
-// rank simply reads all W buffers and adds them in RANK ORDER (the result is bitwise identical on every rank) into a
-// local output.  Two flag barriers through the same mappings: "ready" (my gradient is complete, you may read it) and
-// "done" (I have finished reading yours; the kernel does not end before every peer has said so, so the next kernel may
-// overwrite the buffer).  Barrier ids come from the device-side step counter (2s+1, 2s+2: monotonic, graph-replay
-// safe).  Waits are bounded: a missing peer traps after ~2 s instead of hanging the GPU.
+// One-shot all-reduce of the flat gradient between the GPUs of one box (NVLink 5 / NVSwitch), fused with the gradient
+// norm that follows it in a step, replacing {graph boundary, ncclAllReduce, graph boundary, sqnorm launch}.
+//
+// Low-latency protocol (flag travels WITH the data, as in NCCL's LL): every rank pushes its gradient to every peer's
+// receive area with 16-byte remote stores {v0, epoch, v1, epoch} -- two self-validating 8-byte packets -- and then
+// reduces: for each element it reads the W - 1 packets that the peers pushed into ITS receive area (local memory),
+// spinning on the epoch, and adds them to its own value in RANK ORDER, so every rank forms bit-identical sums.  No
+// separate barrier, no second pass, the result is written in place.  Receive areas are double-buffered by epoch
+// parity: a rank can only be one exchange ahead of its slowest peer (it cannot finish exchange e+1 before every peer
+// has pushed e+1, which a peer does after it finished reading e), so parity e+2 never overwrites unread data.
+// epoch = *step_count + 1 (device-side, equal on all ranks, grows by one per step: graph-replay safe, never 0).
+// Traffic per rank: 8 B x n x (W - 1) pushed (0.7 MB gradient, 8 ranks: 10 MB, ~13 us at NVLink rate); waits are
+// bounded (trap after ~2 s instead of hanging the GPU).
 constexpr int PEER_MAX = 8;
 struct PeerK {
-    const float* src[PEER_MAX];       // rank r's gradient buffer as mapped in this process (own buffer at [rank])
-    unsigned int* flags[PEER_MAX];    // rank r's flag block: [0, PEER_MAX) ready, [PEER_MAX, 2 PEER_MAX) done
-    float* out;
-    long long n4;                     // float4 elements
+    float* g;                         // this rank's gradient, reduced in place
+    long long n2;                     // float pairs
+    uint4* recv[PEER_MAX];            // rank p's receive area as mapped here: [2 parities][W sources][n2] packets
     const int* step_count;
-    unsigned int* ticket;             // local, zero-initialised
     int rank, world;
+    GroupsP G;                        // fused squared norm of g[0 : n_norm) per group (G.n == 0: no norm)
+    long long n_norm;
+    float* sq_out;
+    float* ws;                        // gridDim.x * 8 partials + ticket
 };
-__device__ __forceinline__ void peer_signal(unsigned int* p, unsigned int v) {
-    __threadfence_system();
-    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_sys_v4(uint4* p, uint4 v) {
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-__device__ __forceinline__ void peer_wait(const unsigned int* p, unsigned int v) {
-    unsigned int cur;
-    unsigned long long t0 = 0, now;
-    for (;;) {
-        asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(cur) : "l"(p) : "memory");
-        if ((int)(cur - v) >= 0) break;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-        if (t0 == 0) t0 = now;
-        else if (now - t0 > 2000000000ull) __trap();
-        __nanosleep(100);
-    }
-    __threadfence_system();
+__device__ __forceinline__ uint4 ld_sys_v4(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
 }
 constexpr int PEER_THREADS = 256;
 __global__ void __launch_bounds__(PEER_THREADS) peer_allreduce_kernel(const __grid_constant__ PeerK P) {
-    const unsigned int id = 2u * (unsigned int)(*P.step_count) + 1u;
-    __shared__ bool last;
-    if (blockIdx.x == 0 && threadIdx.x < P.world) peer_signal(&P.flags[threadIdx.x][P.rank], id);
-    if (threadIdx.x < P.world) peer_wait(&P.flags[P.rank][threadIdx.x], id);
-    __syncthreads();
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < P.n4; i += (long long)gridDim.x * blockDim.x) {
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const unsigned int epoch = (unsigned int)(*P.step_count) + 1u;
+    const long long par_off = (long long)(epoch & 1u) * P.world;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    float2* g2 = reinterpret_cast<float2*>(P.g);
+    // ---- push my gradient into every peer's receive area
+    for (long long i = i0; i < P.n2; i += stride) {
+        const float2 v = g2[i];
+        const uint4 pkt = make_uint4(__float_as_uint(v.x), epoch, __float_as_uint(v.y), epoch);
 #pragma unroll
-        for (int r = 0; r < PEER_MAX; ++r)
-            if (r < P.world) {
-                const float4 v = __ldcg(reinterpret_cast<const float4*>(P.src[r]) + i);
-                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        for (int p = 0; p < PEER_MAX; ++p)
+            if (p < P.world && p != P.rank) st_sys_v4(P.recv[p] + (par_off + P.rank) * P.n2 + i, pkt);
+    }
+    // ---- reduce in rank order what the peers pushed into mine
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.0f;
+    const uint4* mine = P.recv[P.rank];
+    for (long long i = i0; i < P.n2; i += stride) {
+        const float2 own = g2[i];
+        float2 sum = make_float2(0.0f, 0.0f);
+#pragma unroll
+        for (int s = 0; s < PEER_MAX; ++s)
+            if (s < P.world) {
+                float2 v = own;
+                if (s != P.rank) {
+                    const uint4* src = mine + (par_off + s) * P.n2 + i;
+                    uint4 q = ld_sys_v4(src);
+                    if (q.y != epoch || q.w != epoch) {
+                        unsigned long long t0 = 0, now;
+                        do {
+                            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                            if (t0 == 0) t0 = now;
+                            else if (now - t0 > 2000000000ull) __trap();
+                            q = ld_sys_v4(src);
+                        } while (q.y != epoch || q.w != epoch);
+                    }
+                    v = make_float2(__uint_as_float(q.x), __uint_as_float(q.z));
+                }
+                sum.x += v.x;
+                sum.y += v.y;
             }
-        reinterpret_cast<float4*>(P.out)[i] = acc;
+        g2[i] = sum;
+        if (P.G.n > 0) {
+            const long long e = i << 1;
+            const float vv[2] = {sum.x, sum.y};
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+                if (e + j < P.n_norm) {
+                    const int gi = group_of(P.G, e + j);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (k == gi) acc[k] = fmaf(vv[j], vv[j], acc[k]);
+                }
+        }
+    }
+    if (P.G.n == 0) return;
+    // ---- deterministic finish of the norm: ordered in-block reduction, last block adds the partials in block order
+    __shared__ float wsum[PEER_THREADS / 32][8];
+    __shared__ bool last;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        float s = warp_sum(acc[k]);
+        if (lane == 0) wsum[warp][k] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        float s = 0.0f;
+        for (int w = 0; w < PEER_THREADS / 32; ++w) s += wsum[w][threadIdx.x];
+        P.ws[blockIdx.x * 8 + threadIdx.x] = s;
     }
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
-        const unsigned int t = atomicAdd(P.ticket, 1u);
+        unsigned int* ticket = reinterpret_cast<unsigned int*>(P.ws + gridDim.x * 8);
+        unsigned int t = atomicAdd(ticket, 1u);
         last = (t == gridDim.x - 1);
-        if (last) *P.ticket = 0u;
+        if (last) *ticket = 0u;
     }
     __syncthreads();
-    if (last && threadIdx.x < P.world) {
-        peer_signal(&P.flags[threadIdx.x][PEER_MAX + P.rank], id + 1u);
-        peer_wait(&P.flags[P.rank][PEER_MAX + threadIdx.x], id + 1u);
+    if (last && threadIdx.x < P.G.n) {
+        __threadfence();
+        float s = 0.0f;
+        for (unsigned int b = 0; b < gridDim.x; ++b) s += P.ws[b * 8 + threadIdx.x];
+        P.sq_out[threadIdx.x] = s;
     }
 }
 

@@ -1,14 +1,17 @@
 """Data-parallel gradient exchange over NVLink peer memory (one box).
 
-The flat gradient buffer of every rank is allocated in symmetric memory (torch.distributed._symmetric_memory: CUDA VMM
-allocations that all ranks of the group map), so a rank can read its peers' gradients with ordinary loads.  One kernel
-(`stdadk_peer_allreduce`) then replaces the NCCL all-reduce of a step: two flag barriers through the same mappings and
-a rank-ordered sum.  Being a plain kernel it is captured in the step's CUDA graph, which removes the graph boundary the
-NCCL call needs.  If symmetric memory cannot be set up the trainer keeps the NCCL path.
+Every rank owns a receive area in symmetric memory (torch.distributed._symmetric_memory: CUDA VMM allocations that all
+ranks of the group map).  One kernel (`stdadk_peer_allreduce`, low-latency protocol: each 8-byte packet carries its own
+epoch flag) pushes the rank's flat gradient into every peer's area, reduces what the peers pushed into its own in rank
+order -- in place, bit-identical on all ranks -- and can finish with the gradient norm of the reduced vector.  Being a
+plain kernel it is captured in the step's single CUDA graph: no NCCL call, no graph boundary, no separate barrier.
+If symmetric memory cannot be set up, or the gradient is too large for the double-buffered areas, the trainer keeps the
+NCCL all-reduce (bandwidth-bound exchanges are NCCL's home ground; this path is for the latency-bound small model).
 """
 from __future__ import annotations
 
 import ctypes as C
+from typing import Optional, Sequence
 
 import torch
 import torch.distributed as dist
@@ -16,44 +19,47 @@ import torch.distributed as dist
 from . import _lib as L
 from . import ops
 
-FLAG_WORDS = 64          # 2 * MAX_PEERS barrier words (+ padding), behind the gradient in the same allocation
+MAX_FLOATS = 1 << 22          # 4M floats: 16 * world * n bytes of receive area (512 MB at 8 ranks); beyond that: NCCL
 
 
 class PeerExchange:
-    def __init__(self, device):
+    def __init__(self, device, n_floats: int):
+        import torch.distributed._symmetric_memory as sm
         self.device = torch.device(device)
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         if self.world > L.MAX_PEERS:
             raise RuntimeError(f"peer exchange supports at most {L.MAX_PEERS} ranks, got {self.world}")
-        self.buf = None
-
-    def alloc(self, size: int) -> torch.Tensor:
-        """Symmetric allocation holding `size` floats of gradient (+ the barrier words); returns the gradient view."""
-        import torch.distributed._symmetric_memory as sm
-        self.size = int(size)
-        self.n_pad = (self.size + 3) // 4 * 4
-        self.buf = sm.empty(self.n_pad + FLAG_WORDS, dtype=torch.float32, device=self.device)
-        self.buf.zero_()
-        self.handle = sm.rendezvous(self.buf, dist.group.WORLD)
+        self.n = (int(n_floats) + 3) // 4 * 4
+        if self.n > MAX_FLOATS:
+            raise RuntimeError(f"gradient of {self.n} floats exceeds the peer-exchange limit ({MAX_FLOATS})")
+        # [2 parities][world sources][n / 2] packets of 16 bytes = 4 floats
+        self.recv = sm.empty(2 * self.world * (self.n // 2) * 4, dtype=torch.float32, device=self.device)
+        self.recv.zero_()
+        self.handle = sm.rendezvous(self.recv, dist.group.WORLD)
         torch.cuda.synchronize(self.device)
-        self.handle.barrier()                      # every rank's buffer (and its barrier words) is zero before first use
-        self.out = torch.zeros(self.n_pad, dtype=torch.float32, device=self.device)
-        self.ticket = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.handle.barrier()                      # every rank's area is zero (epoch 0 = "nothing yet") before first use
+        self.ws = torch.zeros(148 * 8 + 8, dtype=torch.float32, device=self.device)
         a = L.PeerAllreduceArgs()
-        a.world, a.rank = self.world, self.rank
+        a.world, a.rank, a.n = self.world, self.rank, self.n
         for r, p in enumerate(self.handle.buffer_ptrs):
-            a.src[r] = p
-            a.flags[r] = p + 4 * self.n_pad
-        a.out = self.out.data_ptr()
-        a.n = self.n_pad
-        a.ticket = self.ticket.data_ptr()
+            a.recv[r] = p
         self._args = a
-        return self.buf[:self.size]
+        self._keep = None
 
-    def allreduce(self, step_count: torch.Tensor):
-        """Sum over ranks of every rank's buf[:n_pad], written back into this rank's buffer.  `step_count` is the
-        device-side step counter (identical on all ranks, incremented once per step after this call)."""
-        self._args.step_count = step_count.data_ptr()
-        ops.peer_allreduce(self._args)
-        # the kernel returned only after every peer finished reading this rank's buffer: it may be overwritten now
-        self.buf[:self.n_pad].copy_(self.out)
+    def allreduce(self, g: torch.Tensor, step_count: torch.Tensor, group_end: Optional[Sequence[int]] = None,
+                  sqnorms: Optional[torch.Tensor] = None):
+        """g[:n] <- sum over ranks, in place (g must hold at least n floats, 16-byte aligned).  `step_count`: the
+        device-side step counter (identical on all ranks, incremented once per step after this call).  With
+        `group_end` / `sqnorms` the squared norm per group of the reduced gradient is produced by the same kernel."""
+        a = self._args
+        if g.numel() < self.n:
+            raise RuntimeError("peer exchange: gradient buffer shorter than the padded exchange length")
+        a.g = g.data_ptr()
+        a.step_count = step_count.data_ptr()
+        if group_end is not None:
+            arr = (C.c_int64 * len(group_end))(*group_end)
+            a.n_groups, a.group_end, a.sqnorms, a.workspace = len(group_end), arr, sqnorms.data_ptr(), self.ws.data_ptr()
+            self._keep = arr
+        else:
+            a.n_groups = 0
+        ops.peer_allreduce(a)

@@ -47,7 +47,7 @@ class FlatState:
     is coalesced; the Parameter seen by PyTorch is the `.t()` view with the upstream (out, in) shape.
     """
 
-    def __init__(self, model, device, alloc_g=None):
+    def __init__(self, model, device):
         self.model = model
         blocks = model.hidden_blocks()
         entries = []   # (param, stored_shape, transposed)
@@ -76,11 +76,11 @@ class FlatState:
         self.n_scratch = q * d + q if model.delta_params is not None else 0
         mk = lambda extra=0: torch.zeros(n + extra, dtype=torch.float32, device=device)
         # g carries, behind the parameter gradients, the scratch head gradient of the delta parameterisation and ONE
-        # more float: the step's loss accumulator, so that a data-parallel step needs a single all-reduce
+        # more float: the step's loss accumulator, so that a data-parallel step needs a single exchange (the buffer is
+        # padded to a multiple of four floats: the peer-memory exchange moves 16-byte packets)
         self.p, self.m, self.v, self.shadow = mk(), mk(), mk(), mk()
-        # (a data-parallel trainer places g in symmetric memory so that peers can read it: alloc_g)
-        self.g = mk(self.n_scratch + 1) if alloc_g is None else alloc_g(n + self.n_scratch + 1)
         self.n_exchange = n + self.n_scratch + 1
+        self.g = mk(self.n_scratch + 1 + (-self.n_exchange) % 4)
         self.loss_slot = self.g[n + self.n_scratch:n + self.n_scratch + 1]
         self.views: Dict[int, torch.Tensor] = {}
         self.gviews: Dict[int, torch.Tensor] = {}
@@ -149,27 +149,25 @@ class Trainer:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("st_dadk_b200.Trainer runs on CUDA (sm_100) only; there is no CPU training path")
-        # Data parallel over NCCL ranks of one box, optional (STDADK_PEER_ALLREDUCE=1): the gradient lives in symmetric
-        # memory and the per-step exchange is one peer-memory kernel inside the step graph (st_dadk_b200/peer.py).
-        # Results equal the NCCL path (replicas bit-identical, |dp| 2e-7), but on 2 GPUs it measured 0.206 ms per step
-        # against 0.193 ms with NCCL's low-latency all-reduce between two graphs, so NCCL stays the default.
+        self.flat = FlatState(self.model, self.device)
+        # Data parallel over the GPUs of one box: the per-step gradient exchange is ONE kernel over NVLink peer memory
+        # (st_dadk_b200/peer.py: low-latency packets, rank-ordered in-place sum, fused gradient norm), captured inside
+        # the step's single CUDA graph.  NCCL's all-reduce between two graphs remains for gradients too large for the
+        # receive areas (the 100k-knot model: bandwidth-bound, NCCL's home ground), for non-NCCL groups, when symmetric
+        # memory cannot be set up, or on request (STDADK_PEER_ALLREDUCE=0).
         self._peer = None
-        if _dist_on() and dist.get_backend() == "nccl" and os.environ.get("STDADK_PEER_ALLREDUCE", "0") == "1":
+        if _dist_on() and dist.get_backend() == "nccl" and os.environ.get("STDADK_PEER_ALLREDUCE", "1") != "0":
             ok = torch.ones(1, device=self.device)
             try:
                 from .peer import PeerExchange
-                peer = PeerExchange(self.device)
-                self.flat = FlatState(self.model, self.device, alloc_g=peer.alloc)
-                self._peer = peer
+                self._peer = PeerExchange(self.device, self.flat.n_exchange)
             except Exception as e:       # noqa: BLE001 -- any set-up failure falls back to NCCL, loudly
-                warnings.warn(f"peer-memory gradient exchange unavailable ({e!r}); using the NCCL all-reduce")
+                if "exceeds the peer-exchange limit" not in str(e):
+                    warnings.warn(f"peer-memory gradient exchange unavailable ({e!r}); using the NCCL all-reduce")
                 ok.zero_()
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)       # all ranks must agree on the exchange path
             if float(ok.item()) == 0.0:
                 self._peer = None
-                self.flat = FlatState(self.model, self.device)
-        else:
-            self.flat = FlatState(self.model, self.device)
         m = self.model
         self.learnable = bool(m.spatial_basis.learnable)
         self.q = m.output_dim
@@ -199,6 +197,12 @@ class Trainer:
         self._host_perm = None
         self.world = dist.get_world_size() if _dist_on() else 1
         self.rank = dist.get_rank() if _dist_on() else 0
+        c = self.cfg
+        self._param_terms_possible = bool(
+            self.learnable
+            or (c.get("sparsity_penalty_type", "none") != "none"
+                and (float(c.get("sparsity_lambda_l1", 0.001)) != 0.0 or float(c.get("sparsity_lambda_group", 0.01)) != 0.0))
+            or (c.get("use_delta_reparameterization", False) and float(c.get("non_crossing_lambda", 0.0)) > 0))
         self.kernel_launches = 0
 
     # ------------------------------------------------------------------ configuration
@@ -404,17 +408,23 @@ class Trainer:
     def _step_exchange(self):
         """The one data-parallel exchange of a step: sum of the flat gradient (and of the loss) over ranks."""
         if self.world > 1:
-            if self._peer is not None:
-                self._peer.allreduce(self.step_count)                # one kernel over NVLink peer memory
+            if self._peer is not None:                               # one kernel over NVLink peer memory (+ the norm)
+                fuse = self._norm_fused()
+                self._peer.allreduce(self.flat.g, self.step_count, self.flat.group_end if fuse else None, self.sqnorms)
             else:
                 dist.all_reduce(self.flat.g[:self.flat.n_exchange])  # gradients + loss accumulator in one call
+
+    def _norm_fused(self) -> bool:
+        """The exchange kernel also produces the clip norm when nothing is added to the gradient between the exchange
+        and the clip (parameter-only penalties, knot-gradient damping)."""
+        return self._peer is not None and self.world > 1 and self.clip > 0 and not self._param_terms_possible
 
     def _step_update(self):
         """Replicated tail: parameter-only penalties, damping, gradient norm, fused clip + AdamW + EMA."""
         ex, fl = self.ex, self.flat
         pen = self._add_penalty_grads()
         self._damp_center_grads()
-        if self.clip > 0:
+        if self.clip > 0 and not self._norm_fused():
             ops.grad_sqnorm(fl.g[:fl.n], fl.group_end, self.sqnorms, self._sqnorm_ws)
         scratch_tail = fl.n_scratch > 0          # scratch gradients behind the parameters are not seen by the kernel
         ops.adamw_ema_step(fl.p, fl.g[:fl.n], fl.m, fl.v, fl.shadow, fl.group_end, self.hyper,
@@ -462,12 +472,9 @@ class Trainer:
                     self._step_body(table, self._stage_idx, 0, n_rows, global_rows, key_offset)
                     torch.cuda.current_stream().synchronize()
                     mode = dict(capture_error_mode="thread_local")
-                    # Data parallel over NCCL: the collective stays between two graphs (the peer-memory exchange is a
-                    # plain kernel and is captured with the rest).  Capturing the NCCL all-reduce as a node
-                    # of one graph (STDADK_DDP_ONE_GRAPH=1) was measured: 0.2412 vs 0.2427 ms per step on 2 GPUs -- no
-                    # gain -- and the process then hung in teardown, so it is not the default.
-                    one_graph = self.world == 1 or self._peer is not None or (
-                        dist.get_backend() == "nccl" and os.environ.get("STDADK_DDP_ONE_GRAPH", "0") == "1")
+                    # Data parallel: the peer-memory exchange is a plain kernel and is captured with the rest of the
+                    # step; an NCCL all-reduce stays between two graphs (the collective outside stream capture).
+                    one_graph = self.world == 1 or self._peer is not None
                     if one_graph:
                         g1 = torch.cuda.CUDAGraph()
                         with torch.cuda.graph(g1, **mode):
@@ -566,7 +573,9 @@ class Trainer:
         n += (1 if fused else nh) + nh + nh   # forward (one whole-network launch, or one per block), layer_bwd, wgrad
         if self.learnable:
             n += 3                          # knot + temporal tables (knots move), knot_grad
-        n += (1 if self.clip > 0 else 0) + 2   # grad_sqnorm, step counter, adamw_ema
+        n += (1 if (self.clip > 0 and not self._norm_fused()) else 0) + 2   # grad_sqnorm, step counter, adamw_ema
+        if self._peer is not None and self.world > 1:
+            n += 1                          # peer-memory exchange kernel
         return n
 
     def profile_step(self, table, perm, n_rows: int, global_rows: int, repeats: int = 10) -> dict:
@@ -697,7 +706,12 @@ def fit(model, train_table, val_table, config: dict, device, output_dir=None, ba
     """Epoch loop with the semantics of upstream `train_model` (scripts/train_st_interp.py:463-881): per-epoch
     permutation drawn like DataLoader(shuffle=True), EMA-weight validation, cosine/warm-up/unfreeze schedule, best
     checkpoint = EMA weights at the lowest validation loss, early stopping on `patience`, training_history.csv.
-    Returns (model, history, basis_centers_history)."""
+    Returns (model, history, basis_centers_history).
+
+    Data parallel: when torch.distributed is initialised (world > 1) every rank holds the tables, draws the SAME
+    permutation (same seed => same global-RNG draws) and takes its contiguous block of every global batch of
+    `batch_size` samples; one gradient exchange per step; replicas stay bit-identical, so every rank evaluates the
+    same validation loss and takes the same early-stopping decision.  Rank 0 alone writes files."""
     dev = torch.device(device)
     train_table, val_table = train_table.to(dev), val_table.to(dev)
     n = len(train_table)
@@ -721,7 +735,12 @@ def fit(model, train_table, val_table, config: dict, device, output_dir=None, ba
         perm = epoch_permutation(n, dev, shuffle)
         for b in range(bpe):
             lo = b * batch_size
-            tr.train_step(train_table, perm, lo, min(batch_size, n - lo))
+            nb = min(batch_size, n - lo)
+            if tr.world > 1:       # this rank's block of the global batch (loss and dropout keys are global)
+                r0, r1 = shard_rows(nb, tr.rank, tr.world)
+                tr.train_step(train_table, perm, lo + r0, r1 - r0, nb, key_offset=r0)
+            else:
+                tr.train_step(train_table, perm, lo, nb)
         train_loss = tr.pop_loss_sum() / bpe
         if math.isnan(train_loss):
             print(f"\n[WARNING] NaN detected in epoch {epoch + 1}!")
@@ -752,14 +771,14 @@ def fit(model, train_table, val_table, config: dict, device, output_dir=None, ba
             best, bad = val_loss, 0
             tr.flat.apply_shadow()
             best_state = tr.state_for_checkpoint()
-            if best_path is not None:
+            if best_path is not None and tr.rank == 0:
                 torch.save(best_state, best_path)
             tr.flat.restore()
             msg += " [Best]"
         else:
             bad += 1
             msg += f" ({bad}/{patience})"
-        if verbose:
+        if verbose and tr.rank == 0:
             print(msg)
         if tr.learnable and (epoch + 1) % 100 == 0:
             centers_hist.append((epoch + 1, model.spatial_basis.centers.detach().cpu().numpy().copy()))
@@ -773,7 +792,7 @@ def fit(model, train_table, val_table, config: dict, device, output_dir=None, ba
             print(f"\nTraining Complete! Best Val Loss: {best:.6f} (EMA model)")
     else:
         tr.flat.p.copy_(tr.flat.shadow)
-    if output_dir is not None:
+    if output_dir is not None and tr.rank == 0:
         import pandas as pd
         pd.DataFrame({"epoch": list(range(1, len(history["train_loss"]) + 1)), **history}).to_csv(
             os.path.join(str(output_dir), "training_history.csv"), index=False)
