@@ -83,3 +83,34 @@ def test_peer_memory_exchange_matches_nccl_two_gpus():
                         "--master-addr", "127.0.0.1", "--master-port", str(port),
                         os.path.join(root, "tools", "check_peer_allreduce.py")], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs of one box")
+@pytest.mark.parametrize("learnable", ["0", "1"])
+def test_fit_data_parallel_equals_single_gpu(tmp_path, learnable):
+    """trainer.fit under torchrun on 2 GPUs (global batches split over the ranks, peer-memory gradient exchange inside
+    the step graph) follows the single-GPU run: same per-epoch training / validation losses and learning rates,
+    replicas bit-identical.  (Sums of the two half-batch gradients differ from the full-batch sum in rounding only;
+    dropout masks are keyed by the global row.)"""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = os.path.join(root, "tools", "check_fit_ddp.py")
+    env = dict(os.environ, LEARNABLE=learnable)
+    one = subprocess.run([sys.executable, script, str(tmp_path / "one.json")], capture_output=True, text=True, timeout=300,
+                         env={k: v for k, v in env.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
+    assert one.returncode == 0 and "FIT OK" in one.stdout, one.stdout[-1500:] + one.stderr[-1500:]
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    two = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port), script, str(tmp_path / "two.json")],
+                         capture_output=True, text=True, timeout=300, env=env)
+    assert two.returncode == 0 and "FIT OK" in two.stdout, two.stdout[-1500:] + two.stderr[-1500:]
+    a, b = json.load(open(tmp_path / "one.json")), json.load(open(tmp_path / "two.json"))
+    assert b["world"] == 2 and b["replicas_identical"] and b["peer_exchange"]
+    assert a["history"]["lr"] == b["history"]["lr"]
+    for k in ("train_loss", "val_loss", "val_rmse"):
+        assert np.allclose(a["history"][k], b["history"][k], rtol=2e-3), (k, a["history"][k], b["history"][k])
+    assert abs(a["p_sq"] - b["p_sq"]) < 2e-3 * a["p_sq"]

@@ -23,6 +23,7 @@ for mode in ("0", "1"):
     torch.manual_seed(3)
     tr = Trainer(STInterpMLP(dropout=0.1), cfg, dev, batches_per_epoch=20, use_cuda_graph=True)
     assert (tr._peer is not None) == (mode == "1"), "exchange path not as requested"
+    assert mode == "0" or tr._norm_fused(), "the peer exchange should also produce the clip norm here"
     lo, hi = shard_rows(B, rank, world)
     losses = []
     for s in range(8):
