@@ -242,11 +242,22 @@ typedef struct {
 } stdadk_pack_desc;
 int stdadk_pack_images(const stdadk_pack_desc* descs, int n, void* stream);
 
-/* Large-knot regime of block 1 (uniform lattices, fixed knots, K_s up to ~1e5+; BASELINE config 4): walk only the knots
- * in each point's compact support.  knot j of level l sits at lattice node (j / side, j % side) (st_interp.py:152-185).
+/* Large-knot regime of block 1 (K_s up to ~1e5+; BASELINE config 4): walk only the knots in each point's compact
+ * support.
  *   fwd  : zs[n,:]  = sum_{j in supp(s_n)} phi_j(s_n) * w1t[p_cov + j, :]
- *   wgrad: dw1t[p_cov + j, :] += phi_j(s_n) * dz1[n,:]
- * w1t / dw1t: first Linear layer stored knot-major, (n_in x n_out) contiguous. */
+ *   wgrad: dw1t[p_cov + j, :] += phi_j(s_n) * dz1[n,:]; with d_centers / d_log_bw also the knot gradients
+ *          (st_interp.py:94-108, closed form of SURVEY.md 9.1)
+ * w1t / dw1t: first Linear layer stored knot-major, (n_in x n_out) contiguous.
+ * Candidate knots per level: the fixed uniform lattice (knot j of level l at node (j / side, j % side),
+ * st_interp.py:152-185) is walked in closed form; ANY other knot set (gmm / random_site / kmeans_balanced placement,
+ * learnable knots: st_interp.py:187-431) goes through a cell list built on the device by stdadk_celllist_build
+ * (per level: cells of edge >= the level's largest theta', knots counting-sorted by cell; rebuilt every step when the
+ * knots move).  No limit on the number of knots inside a support. */
+size_t stdadk_celllist_ws_bytes(int32_t k_s, int32_t n_levels);
+/* level_begin: HOST array of n_levels + 1 knot offsets (levels are contiguous knot ranges); ws: device workspace of
+ * stdadk_celllist_ws_bytes() bytes, 16-byte aligned */
+int stdadk_celllist_build(const float* knots4, int32_t k_s, const int32_t* level_begin, int32_t n_levels, void* ws,
+                          size_t ws_bytes, void* stream);
 #define STDADK_MAX_LEVELS 8
 typedef struct {
     stdadk_points pts;
@@ -259,6 +270,11 @@ typedef struct {
     float* zs;                /* fwd out (rows x n_out) */
     const float* dz_img;      /* wgrad in: image (rows x n_out) */
     float* dw1t;              /* wgrad out, += */
+    const void* celllist;     /* workspace filled by stdadk_celllist_build for these knots (then side/offset/thetap are
+                                 not read; n_levels and celllist_k_s must be the values it was built with), or NULL */
+    int32_t celllist_k_s, _pad;
+    float* d_centers;         /* wgrad, learnable knots: (k_s x 2) +=, or NULL */
+    float* d_log_bw;          /* (k_s) += */
 } stdadk_sparse_args;
 int stdadk_sparse_l1_fwd(const stdadk_sparse_args* a, void* stream);
 int stdadk_sparse_l1_wgrad(const stdadk_sparse_args* a, void* stream);

@@ -82,7 +82,8 @@ MAX_LEVELS = 8
 class SparseArgs(C.Structure):
     _fields_ = [("pts", Points), ("knots4", fp), ("n_levels", C.c_int32), ("basis_fn", C.c_int32), ("n_out", C.c_int32),
                 ("p_cov", C.c_int32), ("side", C.c_int32 * MAX_LEVELS), ("offset", C.c_int32 * MAX_LEVELS),
-                ("thetap", C.c_float * MAX_LEVELS), ("w1t", fp), ("zs", fp), ("dz_img", fp), ("dw1t", fp)]
+                ("thetap", C.c_float * MAX_LEVELS), ("w1t", fp), ("zs", fp), ("dz_img", fp), ("dw1t", fp),
+                ("celllist", fp), ("celllist_k_s", C.c_int32), ("_pad", C.c_int32), ("d_centers", fp), ("d_log_bw", fp)]
 
 
 class PackDesc(C.Structure):
@@ -146,6 +147,8 @@ _PROTOS = {
     "stdadk_sqnorm_ws_floats": (C.c_size_t, []),
     "stdadk_grad_sqnorm": (C.c_int, [fp, C.c_int64, C.c_int, C.POINTER(C.c_int64), fp, fp, fp]),
     "stdadk_adamw_ema_step": (C.c_int, [C.POINTER(AdamWArgs), fp]),
+    "stdadk_celllist_ws_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "stdadk_celllist_build": (C.c_int, [fp, C.c_int32, C.POINTER(C.c_int32), C.c_int32, fp, C.c_size_t, fp]),
     "stdadk_sparse_l1_fwd": (C.c_int, [C.POINTER(SparseArgs), fp]),
     "stdadk_sparse_l1_wgrad": (C.c_int, [C.POINTER(SparseArgs), fp]),
 }

@@ -732,12 +732,26 @@ static int sparse_fill(const stdadk_sparse_args* a, SparseK* K, bool wgrad) {
     }
     K->pts = to_points(a->pts);
     K->lat.n_levels = a->n_levels;
-    for (int l = 0; l < a->n_levels; ++l) {
-        REQUIRE(a->side[l] >= 1 && a->thetap[l] > 0.0f, "sparse_l1: level %d side=%d theta'=%f", l, a->side[l], a->thetap[l]);
-        K->lat.side[l] = a->side[l];
-        K->lat.offset[l] = a->offset[l];
-        K->lat.thetap[l] = a->thetap[l];
+    if (a->celllist) {
+        REQUIRE((reinterpret_cast<uintptr_t>(a->celllist) & 15) == 0 && a->celllist_k_s >= 1, "sparse_l1: cell list workspace");
+        const int* wsi = static_cast<const int*>(a->celllist);
+        K->cl.desc = wsi;
+        K->cl.starts = wsi + 8 * SP_MAX_LEVELS;
+        K->cl.order = K->cl.starts + (size_t)a->n_levels * (CL_GMAX * CL_GMAX + 1) + (size_t)a->n_levels * CL_GMAX * CL_GMAX;
+        size_t ib = (celllist_ints(a->celllist_k_s, a->n_levels) * 4 + 15) & ~(size_t)15;
+        K->cl.sorted = reinterpret_cast<const float4*>(static_cast<const uint8_t*>(a->celllist) + ib);
+        K->cl.n_levels = a->n_levels;
+    } else {
+        for (int l = 0; l < a->n_levels; ++l) {
+            REQUIRE(a->side[l] >= 1 && a->thetap[l] > 0.0f, "sparse_l1: level %d side=%d theta'=%f", l, a->side[l], a->thetap[l]);
+            K->lat.side[l] = a->side[l];
+            K->lat.offset[l] = a->offset[l];
+            K->lat.thetap[l] = a->thetap[l];
+        }
     }
+    REQUIRE((a->d_centers == nullptr) == (a->d_log_bw == nullptr), "sparse_l1: give d_centers and d_log_bw together");
+    K->d_centers = wgrad ? a->d_centers : nullptr;
+    K->d_log_bw = wgrad ? a->d_log_bw : nullptr;
     K->knots = reinterpret_cast<const float4*>(a->knots4);
     K->w1t = a->w1t;
     K->zs = a->zs;
@@ -759,6 +773,36 @@ static int make_groups(int n_groups, const int64_t* group_end, int64_t n, Groups
     REQUIRE(prev == n, "optimizer: last group_end (%lld) != n (%lld)", (long long)prev, (long long)n);
     G->n = n_groups;
     return 0;
+}
+
+size_t stdadk_celllist_ws_bytes(int32_t k_s, int32_t n_levels) {
+    if (k_s < 0 || n_levels < 1 || n_levels > SP_MAX_LEVELS) return 0;
+    return celllist_bytes(k_s, n_levels);
+}
+
+int stdadk_celllist_build(const float* knots4, int32_t k_s, const int32_t* level_begin, int32_t n_levels, void* ws,
+                          size_t ws_bytes, void* stream) {
+    if (int r = check_device()) return r;
+    REQUIRE(knots4 && level_begin && ws && k_s >= 1, "celllist_build: NULL argument / no knots");
+    REQUIRE(n_levels >= 1 && n_levels <= SP_MAX_LEVELS, "celllist_build: 1..%d levels, got %d", SP_MAX_LEVELS, n_levels);
+    REQUIRE(((reinterpret_cast<uintptr_t>(ws) | reinterpret_cast<uintptr_t>(knots4)) & 15) == 0,
+            "celllist_build: knots4 / workspace must be 16-byte aligned");
+    REQUIRE(ws_bytes >= celllist_bytes(k_s, n_levels), "celllist_build: workspace of %zu B, need %zu B", ws_bytes,
+            celllist_bytes(k_s, n_levels));
+    CellBuildK K{};
+    K.knots = reinterpret_cast<const float4*>(knots4);
+    K.k_s = k_s;
+    K.n_levels = n_levels;
+    for (int l = 0; l <= n_levels; ++l) {
+        REQUIRE(level_begin[l] >= (l ? level_begin[l - 1] : 0) && level_begin[l] <= k_s, "celllist_build: level_begin not monotone");
+        K.level_begin[l] = level_begin[l];
+    }
+    REQUIRE(level_begin[0] == 0 && level_begin[n_levels] == k_s, "celllist_build: levels must cover [0, k_s)");
+    K.ws = static_cast<int*>(ws);
+    size_t ib = (celllist_ints(k_s, n_levels) * 4 + 15) & ~(size_t)15;
+    K.sorted = reinterpret_cast<float4*>(static_cast<uint8_t*>(ws) + ib);
+    celllist_build_kernel<<<1, CL_THREADS, 0, (cudaStream_t)stream>>>(K);
+    return check_launch("celllist_build");
 }
 
 size_t stdadk_sqnorm_ws_floats(void) { return (size_t)SQNORM_BLOCKS * 8 + 8; }

@@ -40,6 +40,7 @@ class NetSpec:
     ln_eps: float = 1e-5
     learnable_basis: bool = False
     lattice_sides: Optional[List[int]] = None  # knots per axis of each level when the knots are the fixed uniform lattice
+    level_sizes: Optional[List[int]] = None    # knots per resolution level (contiguous ranges of `centers`); None = one level
     # "tf32": one tensor-core pass on TF32-rounded operands (throughput mode; outputs within 1e-3 of the FP32 reference).
     # "tf32x3": every operand is split into tf32(x) + tf32(x - tf32(x)) and every GEMM runs hi*hi + hi*lo + lo*hi into
     # the same FP32 accumulator: FP32-faithful products, for runs that must track the reference's FP32 trajectory.
@@ -135,6 +136,7 @@ class Executor:
         self.fused_train = False
         self._fused_ok = None
         self._field_ok = None
+        self._cell_ws = None
         self._w1sf_img = None
         self._w1sf_key = None
         self._zt_ws = None
@@ -149,31 +151,41 @@ class Executor:
         k_s = spec.centers.shape[0]
         want = self.force_sparse or k_s > self.DENSE_MAX_KNOTS
         self.sparse = False
+        self.lat = None
+        self.level_begin = None
         if not want:
             return
         problems = []
-        if spec.lattice_sides is None or spec.learnable_basis:
-            problems.append("the support walk needs the fixed uniform lattice (spatial_init_method='uniform', not learnable)")
         if spec.basis_fn == "gaussian":
             problems.append("the gaussian basis is not compactly supported")
         if spec.p_cov != 0:
             problems.append("covariates are not supported together with the support walk")
         if spec.weights[0].shape[0] % 4:
             problems.append("first hidden width must be a multiple of 4")
+        sizes = [int(v) for v in (spec.level_sizes or [k_s])]
+        if sum(sizes) != k_s or len(sizes) > 8:
+            problems.append("level_sizes must be at most 8 contiguous ranges adding up to the number of knots")
         if problems:
             if self.force_sparse or k_s * 16 > 96 * 1024:
                 raise RuntimeError(f"{k_s} spatial knots need the support-walking path, but " + "; ".join(problems))
             return
-        sides = [int(v) for v in spec.lattice_sides]
-        offs, o = [], 0
-        for sd in sides:
-            offs.append(o)
-            o += sd * sd
-        assert o == k_s, "lattice_sides do not add up to the number of knots"
-        bw = spec.bandwidths[torch.tensor(offs, device=spec.bandwidths.device)].float().cpu().numpy()
-        import numpy as _np
-        calib = _np.float32(L.CALIBRATION[spec.basis_fn])
-        self.lat = (sides, offs, [float(_np.float32(b) * calib) for b in bw])
+        if spec.lattice_sides is not None and not spec.learnable_basis:
+            # fixed uniform lattice: candidate windows in closed form
+            sides = [int(v) for v in spec.lattice_sides]
+            offs, o = [], 0
+            for sd in sides:
+                offs.append(o)
+                o += sd * sd
+            assert o == k_s, "lattice_sides do not add up to the number of knots"
+            bw = spec.bandwidths[torch.tensor(offs, device=spec.bandwidths.device)].float().cpu().numpy()
+            import numpy as _np
+            calib = _np.float32(L.CALIBRATION[spec.basis_fn])
+            self.lat = (sides, offs, [float(_np.float32(b) * calib) for b in bw])
+        else:
+            # any other knot set (gmm / random_site / kmeans_balanced, learnable knots): per-level cell list on the device
+            self.level_begin = [0]
+            for n in sizes:
+                self.level_begin.append(self.level_begin[-1] + n)
         self.sparse = True
 
     # ------------------------------------------------------------------ operand preparation
@@ -206,6 +218,8 @@ class Executor:
             ops.knots_prepare(s.centers, s.bandwidths if s.log_bandwidths is None else None, s.log_bandwidths,
                               s.basis_fn, out=self.knots4)
             ops.tknots_prepare(s.t_centers, s.t_bandwidths, out=self.tknots2)   # fixed buffers: only the first time
+            if self.sparse and self.level_begin is not None:      # the knots moved (or first use): rebuild the cell list
+                self._cell_ws = ops.celllist_build(self.knots4, self.level_begin, self._cell_ws)
             self._knots_ready = True
         srcs, outs, slots, parts = [], [], [], []
         x3 = self.x3
@@ -229,7 +243,7 @@ class Executor:
                 add(w, "w", l)
             if for_backward and l > 0:
                 add(w.t(), "wt", l)
-        if for_backward and s.learnable_basis:
+        if for_backward and s.learnable_basis and not self.sparse:
             add(s.weights[0][:, s.p_cov:s.p_cov + s.centers.shape[0]].t(), "w1s", 0)   # (K_s, n_out)
         for (kind, l, part), img in zip(slots, ops.pack_images(srcs, outs, parts)):   # one launch per 8 images
             if kind == "w":
@@ -272,8 +286,11 @@ class Executor:
 
     def _sparse_args(self, pts, ws, **kw) -> L.SparseArgs:
         s = self.spec
-        sides, offs, ths = self.lat
-        return ops.make_sparse_args(pts, self.knots4, s.basis_fn, s.weights[0].shape[0], s.p_cov, sides, offs, ths, **kw)
+        if self.lat is not None:
+            sides, offs, ths = self.lat
+            return ops.make_sparse_args(pts, self.knots4, s.basis_fn, s.weights[0].shape[0], s.p_cov, sides, offs, ths, **kw)
+        return ops.make_sparse_args(pts, self.knots4, s.basis_fn, s.weights[0].shape[0], s.p_cov, celllist=self._cell_ws,
+                                    n_levels=len(self.level_begin) - 1, **kw)
 
     # ------------------------------------------------------------------ forward
     def forward(self, pts: L.Points, train: bool = False, step: int = 0, seed: int = 0,
@@ -556,7 +573,10 @@ class Executor:
             ops.wgrad(a)
             if gw.stride(0) != 1 or gw.stride(1) != w.shape[0]:
                 raise RuntimeError("support-walk wgrad needs the first-layer gradient stored (in, out)-contiguous")
-            ops.sparse_l1_wgrad(self._sparse_args(pts, ws, dz_img=ws.dz[0], dw1t=gw))   # ... spatial rows scattered
+            kg = {}
+            if s.learnable_basis:       # knot gradients from the same walk (closed-form chain rule per (point, knot))
+                kg = dict(d_centers=g["centers"], d_log_bw=g["log_bandwidths"])
+            ops.sparse_l1_wgrad(self._sparse_args(pts, ws, dz_img=ws.dz[0], dw1t=gw, **kg))   # ... spatial rows scattered
             return
         a.dw = gw.data_ptr()
         a.stride_o, a.stride_i = gw.stride(0), gw.stride(1)
@@ -624,7 +644,7 @@ class Executor:
             with torch.cuda.stream(side):
                 self._wgrad_block(l, pts, ws, basis, g)
         main.wait_stream(side)      # join: every weight gradient is complete before the caller continues
-        if s.learnable_basis:
+        if s.learnable_basis and not self.sparse:
             a = L.KnotGradArgs()
             a.basis = C.pointer(basis)
             a.pts = pts

@@ -233,16 +233,38 @@ def peer_allreduce(args: L.PeerAllreduceArgs):
     L.check(L.lib().stdadk_peer_allreduce(C.byref(args), _stream()), "peer_allreduce")
 
 
-def make_sparse_args(pts: L.Points, knots4, basis_fn: str, n_out: int, p_cov: int, sides, offsets, thetaps, w1t=None,
-                     zs=None, dz_img=None, dw1t=None) -> L.SparseArgs:
+def make_sparse_args(pts: L.Points, knots4, basis_fn: str, n_out: int, p_cov: int, sides=None, offsets=None,
+                     thetaps=None, w1t=None, zs=None, dz_img=None, dw1t=None, celllist=None, n_levels=None,
+                     d_centers=None, d_log_bw=None) -> L.SparseArgs:
+    """Lattice mode: sides / offsets / thetaps per level.  Cell-list mode: `celllist` (workspace filled by
+    celllist_build for these knots) and `n_levels`."""
     a = L.SparseArgs()
     a.pts = pts
     a.knots4 = _ptr(knots4)
-    a.n_levels, a.basis_fn, a.n_out, a.p_cov = len(sides), L.BASIS_CODE[basis_fn], n_out, p_cov
-    for i, (sd, of, th) in enumerate(zip(sides, offsets, thetaps)):
-        a.side[i], a.offset[i], a.thetap[i] = int(sd), int(of), float(th)
+    a.basis_fn, a.n_out, a.p_cov = L.BASIS_CODE[basis_fn], n_out, p_cov
+    if celllist is not None:
+        a.n_levels, a.celllist, a.celllist_k_s = int(n_levels), _ptr(celllist), int(knots4.shape[0])
+    else:
+        a.n_levels = len(sides)
+        for i, (sd, of, th) in enumerate(zip(sides, offsets, thetaps)):
+            a.side[i], a.offset[i], a.thetap[i] = int(sd), int(of), float(th)
     a.w1t, a.zs, a.dz_img, a.dw1t = _ptr(w1t), _ptr(zs), _ptr(dz_img), _ptr(dw1t)
+    a.d_centers, a.d_log_bw = _ptr(d_centers), _ptr(d_log_bw)
     return a
+
+
+def celllist_build(knots4: torch.Tensor, level_begin: Sequence[int], ws: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Per-level cell list of an arbitrary knot set (knots4 rows: cx, cy, theta'^2, 1/theta'); levels are the contiguous
+    knot ranges level_begin[l] : level_begin[l + 1].  Returns the (reusable) workspace tensor."""
+    k_s, nl = int(knots4.shape[0]), len(level_begin) - 1
+    need = L.lib().stdadk_celllist_ws_bytes(k_s, nl)
+    if need == 0:
+        raise RuntimeError(f"celllist_build: unsupported shape (k_s={k_s}, levels={nl})")
+    if ws is None or ws.numel() * 4 < need:
+        ws = torch.empty((need + 3) // 4, dtype=torch.int32, device=knots4.device)
+    arr = (C.c_int32 * (nl + 1))(*[int(v) for v in level_begin])
+    L.check(L.lib().stdadk_celllist_build(_ptr(knots4), k_s, arr, nl, _ptr(ws), ws.numel() * 4, _stream()), "celllist_build")
+    return ws
 
 
 def sparse_l1_fwd(args: L.SparseArgs):

@@ -267,7 +267,7 @@ class STInterpMLP(nn.Module):
             ln_eps=blocks[0][1].eps if blocks and blocks[0][1] is not None else 1e-5, learnable_basis=sb.learnable,
             lattice_sides=[int(math.sqrt(k)) for k in sb.n_centers]
             if (sb.init_method == "uniform" and not sb.learnable) else None,
-            precision=getattr(self, "precision", "tf32"))
+            level_sizes=[int(k) for k in sb.n_centers], precision=getattr(self, "precision", "tf32"))
 
     def _executor(self, head_w=None, head_b=None):
         spec = self.net_spec(head_w, head_b)

@@ -621,3 +621,104 @@ def test_large_batch_stored_operand_matches_regenerated_basis():
     # and against the oracle on a subset of rows' worth of statistics: the loss
     yref = orc.forward(m, None, coords[:2000], t[:2000])
     assert rel_l2(y0[:2000].cpu().numpy(), yref) < 1e-3
+
+
+def _small_net(rng, k_s, k_t=25, hidden=(64, 32)):
+    dims = [k_s + k_t, *hidden]
+    ws = [(rng.standard_normal((dims[i + 1], dims[i])) / np.sqrt(40)).astype(np.float32) for i in range(len(hidden))]
+    bs = [rng.standard_normal(dims[i + 1]).astype(np.float32) * 0.1 for i in range(len(hidden))]
+    gs = [(1 + 0.1 * rng.standard_normal(dims[i + 1])).astype(np.float32) for i in range(len(hidden))]
+    be = [(0.1 * rng.standard_normal(dims[i + 1])).astype(np.float32) for i in range(len(hidden))]
+    ws.append((rng.standard_normal((1, hidden[-1])) / 6).astype(np.float32))
+    bs.append(np.zeros(1, np.float32))
+    return ws, bs, gs, be
+
+
+@pytest.mark.parametrize("fn,learnable", [("wendland", True), ("triangular", False), ("wendland", False)])
+def test_cell_list_regime_arbitrary_and_learnable_knots_vs_oracle(fn, learnable):
+    """Support walk over a NON-lattice knot set (data-adaptive placement: clustered centres, per-knot bandwidths, some
+    knots outside [0,1]^2 as drifted learnable knots are) through the device-built per-level cell list: forward, loss,
+    every gradient -- including d centres / d log-bandwidths from the same walk -- vs the FP64 oracle, and the dense
+    path on the same model.  One level is crowded on purpose (> 300 knots inside a support): nothing is truncated."""
+    L, ops, Executor, NetSpec, LossSpec = _mods()
+    rng = np.random.default_rng(33)
+    sizes = [60, 400, 900]
+    cen, bw = [], []
+    for li, k in enumerate(sizes):
+        if li == 1:      # crowded level: clustered knots with wide supports
+            c = 0.5 + 0.08 * rng.standard_normal((k, 2))
+            b = rng.uniform(0.25, 0.4, k)
+        else:
+            c = rng.random((k, 2)) * 1.1 - 0.05             # a few centres outside the unit square
+            b = rng.uniform(0.6, 1.0, k) * 2.5 / np.sqrt(k)
+        cen.append(c)
+        bw.append(b)
+    c, b = np.concatenate(cen).astype(np.float32), np.concatenate(bw).astype(np.float32)
+    tc, tb = orc.temporal_knots([10, 15])
+    ws, bs, gs, be = _small_net(rng, c.shape[0])
+    m = orc.OracleModel(centers=c, bandwidths=b, t_centers=tc, t_bandwidths=tb, weights=ws, biases=bs, ln_gamma=gs,
+                        ln_beta=be, basis_fn=fn)
+    n = 600
+    coords = rng.random((n, 2)).astype(np.float32)
+    coords[:4] = [[0, 0], [1, 1], [0.5, 0.5], [1, 0]]
+    t = rng.random((n, 1)).astype(np.float32)
+    y = rng.standard_normal(n).astype(np.float32)
+    y64, cache = orc.forward(m, None, coords, t, return_cache=True)
+    lref, dy = orc.loss_and_grad(y64, y, "mse")
+    gref = orc.backward(m, cache, dy, coords=coords, want_knot_grads=learnable)
+    assert orc.support_mask_f32(coords, c, b, fn).sum(axis=1).max() > 300
+    spec = spec_from_oracle(m, learnable=learnable)
+    spec.level_sizes = sizes
+    ex = Executor(spec, force_sparse=True)
+    assert ex.sparse and ex.lat is None and ex.level_begin == [0, 60, 460, 1360]
+    ex.loss_acc.zero_()
+    pts = ops.make_points(T(coords), T(t))
+    yhat = ex.forward(pts, train=True, y=T(y), loss=LossSpec("mse"), inv_count=1.0 / n, save=True)
+    grads = ex.backward()
+    torch.cuda.synchronize()
+    assert rel_l2(yhat.cpu().numpy(), y64) < 1e-3
+    assert abs(ex.loss_acc.item() - lref) < 1e-3 * abs(lref)
+    for l in range(2):
+        assert rel_err(grads["weights"][l].cpu().numpy(), gref["weights"][l]) < 2e-2, f"dW{l}"
+        assert rel_err(grads["biases"][l].cpu().numpy(), gref["biases"][l]) < 2e-2
+    if learnable:
+        assert rel_err(grads["centers"].cpu().numpy(), gref["centers"]) < 2e-2
+        assert rel_err(grads["log_bandwidths"].cpu().numpy(), gref["log_bandwidths"]) < 2e-2
+    exd = Executor(spec_from_oracle(m, learnable=learnable))
+    assert not exd.sparse
+    assert rel_l2(ex.forward(pts, train=False).cpu().numpy(), exd.forward(pts, train=False).cpu().numpy()) < 1e-3
+    gw = grads["weights"][0].cpu().numpy()[:, :c.shape[0]]
+    mask = orc.support_mask_f32(coords, c, b, fn).any(axis=0)
+    assert np.all(gw[:, ~mask] == 0) and np.all(np.abs(gw[:, mask]).sum(axis=0) > 0)      # index sets
+
+
+def test_support_walk_at_real_size_99812_knots_vs_oracle():
+    """BASELINE config 4 shape at REAL size: 3-level lattice 100^2 + 174^2 + 244^2 = 99,812 knots (W1 = 256 x 99,882,
+    102 MB), default hidden widths; 512 rows against the dense FP64 oracle (a 512 x 99,812 basis matrix on the host),
+    through both candidate sources -- the closed-form lattice window and the device-built cell list."""
+    L, ops, Executor, NetSpec, LossSpec = _mods()
+    rng = np.random.default_rng(5)
+    n_centers = [10000, 30276, 59536]
+    c, b = orc.uniform_spatial_knots(n_centers)
+    tc, tb = orc.temporal_knots([10, 15, 45])
+    ws, bs, gs, be = _small_net(rng, c.shape[0], k_t=70, hidden=(256, 256, 128))
+    m = orc.OracleModel(centers=c, bandwidths=b, t_centers=tc, t_bandwidths=tb, weights=ws, biases=bs, ln_gamma=gs,
+                        ln_beta=be, basis_fn="wendland")
+    n = 512
+    coords = rng.random((n, 2)).astype(np.float32)
+    coords[:3] = [[0, 0], [1, 1], [0.5, 0.5]]
+    t = rng.random((n, 1)).astype(np.float32)
+    y64 = orc.forward(m, None, coords, t)
+    spec = spec_from_oracle(m)
+    spec.lattice_sides, spec.level_sizes = [100, 174, 244], n_centers
+    ex = Executor(spec)
+    assert ex.sparse and ex.lat is not None
+    pts = ops.make_points(T(coords), T(t))
+    ya = ex.forward(pts, train=False).cpu().numpy()
+    assert rel_l2(ya, y64) < 1e-3
+    spec2 = spec_from_oracle(m)
+    spec2.level_sizes = n_centers                     # no lattice information: the cell list takes over
+    ex2 = Executor(spec2)
+    assert ex2.sparse and ex2.lat is None
+    yb = ex2.forward(pts, train=False).cpu().numpy()
+    assert rel_l2(yb, y64) < 1e-3 and rel_l2(ya, yb) < 1e-5
