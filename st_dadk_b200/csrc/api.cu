@@ -750,6 +750,8 @@ static int sparse_fill(const stdadk_sparse_args* a, SparseK* K, bool wgrad) {
         }
     }
     REQUIRE((a->d_centers == nullptr) == (a->d_log_bw == nullptr), "sparse_l1: give d_centers and d_log_bw together");
+    REQUIRE(!(wgrad && a->d_centers) || (a->w1t && (reinterpret_cast<uintptr_t>(a->w1t) & 15) == 0),
+            "sparse_l1_wgrad: knot gradients need w1t (G = dz1 . W1t row)");
     K->d_centers = wgrad ? a->d_centers : nullptr;
     K->d_log_bw = wgrad ? a->d_log_bw : nullptr;
     K->knots = reinterpret_cast<const float4*>(a->knots4);

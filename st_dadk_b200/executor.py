@@ -103,9 +103,10 @@ class Executor:
     SAVE_FEAT_MIN_ROWS = SAVE_X_MAX_ROWS + 1
     store_basis_operand = False
 
-    def __init__(self, spec: NetSpec, force_sparse: bool = False):
+    def __init__(self, spec: NetSpec, force_sparse: bool = False, force_dense: bool = False):
         self.spec = spec
         self.force_sparse = force_sparse
+        self.force_dense = force_dense        # keep the dense operand even above DENSE_MAX_KNOTS (while it fits in SMEM)
         self._setup_regime(spec)
         dev = spec.centers.device
         if dev.type != "cuda":
@@ -149,7 +150,7 @@ class Executor:
         if spec.precision not in ("tf32", "tf32x3"):
             raise ValueError(f"precision must be 'tf32' or 'tf32x3', got {spec.precision!r}")
         k_s = spec.centers.shape[0]
-        want = self.force_sparse or k_s > self.DENSE_MAX_KNOTS
+        want = (self.force_sparse or k_s > self.DENSE_MAX_KNOTS) and not self.force_dense
         self.sparse = False
         self.lat = None
         self.level_begin = None
@@ -575,7 +576,7 @@ class Executor:
                 raise RuntimeError("support-walk wgrad needs the first-layer gradient stored (in, out)-contiguous")
             kg = {}
             if s.learnable_basis:       # knot gradients from the same walk (closed-form chain rule per (point, knot))
-                kg = dict(d_centers=g["centers"], d_log_bw=g["log_bandwidths"])
+                kg = dict(d_centers=g["centers"], d_log_bw=g["log_bandwidths"], w1t=self._w1t)
             ops.sparse_l1_wgrad(self._sparse_args(pts, ws, dz_img=ws.dz[0], dw1t=gw, **kg))   # ... spatial rows scattered
             return
         a.dw = gw.data_ptr()

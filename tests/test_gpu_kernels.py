@@ -453,7 +453,7 @@ def test_large_knot_regime_support_walk_vs_oracle(fn, sides):
         assert rel_err(grads["weights"][l].cpu().numpy(), gref["weights"][l]) < 1e-2, f"dW{l}"
         assert rel_err(grads["biases"][l].cpu().numpy(), gref["biases"][l]) < 1e-2
     # dense path on the same model gives the same prediction
-    exd = Executor(spec_from_oracle(m))
+    exd = Executor(spec_from_oracle(m), force_dense=True)
     assert not exd.sparse
     yd = exd.forward(pts, train=False).cpu().numpy()
     ys = ex.forward(pts, train=False).cpu().numpy()
@@ -634,8 +634,9 @@ def _small_net(rng, k_s, k_t=25, hidden=(64, 32)):
     return ws, bs, gs, be
 
 
-@pytest.mark.parametrize("fn,learnable", [("wendland", True), ("triangular", False), ("wendland", False)])
-def test_cell_list_regime_arbitrary_and_learnable_knots_vs_oracle(fn, learnable):
+@pytest.mark.parametrize("fn,learnable,precision", [("wendland", True, "tf32x3"), ("wendland", True, "tf32"),
+                                                   ("triangular", False, "tf32"), ("wendland", False, "tf32")])
+def test_cell_list_regime_arbitrary_and_learnable_knots_vs_oracle(fn, learnable, precision):
     """Support walk over a NON-lattice knot set (data-adaptive placement: clustered centres, per-knot bandwidths, some
     knots outside [0,1]^2 as drifted learnable knots are) through the device-built per-level cell list: forward, loss,
     every gradient -- including d centres / d log-bandwidths from the same walk -- vs the FP64 oracle, and the dense
@@ -667,8 +668,9 @@ def test_cell_list_regime_arbitrary_and_learnable_knots_vs_oracle(fn, learnable)
     lref, dy = orc.loss_and_grad(y64, y, "mse")
     gref = orc.backward(m, cache, dy, coords=coords, want_knot_grads=learnable)
     assert orc.support_mask_f32(coords, c, b, fn).sum(axis=1).max() > 300
-    spec = spec_from_oracle(m, learnable=learnable)
+    spec = spec_from_oracle(m, learnable=learnable, precision=precision)
     spec.level_sizes = sizes
+    x3 = precision == "tf32x3"
     ex = Executor(spec, force_sparse=True)
     assert ex.sparse and ex.lat is None and ex.level_begin == [0, 60, 460, 1360]
     ex.loss_acc.zero_()
@@ -676,15 +678,20 @@ def test_cell_list_regime_arbitrary_and_learnable_knots_vs_oracle(fn, learnable)
     yhat = ex.forward(pts, train=True, y=T(y), loss=LossSpec("mse"), inv_count=1.0 / n, save=True)
     grads = ex.backward()
     torch.cuda.synchronize()
-    assert rel_l2(yhat.cpu().numpy(), y64) < 1e-3
-    assert abs(ex.loss_acc.item() - lref) < 1e-3 * abs(lref)
+    assert rel_l2(yhat.cpu().numpy(), y64) < (2e-5 if x3 else 1e-3)
+    assert abs(ex.loss_acc.item() - lref) < (1e-5 if x3 else 1e-3) * abs(lref)
+    # TF32 mode: operand rounding moves pre-activations by ~5e-4, which flips a few ReLUs of this narrow net; knot
+    # gradients are sums of large cancelling terms and take that hardest.  tf32x3 shows the kernels themselves are exact.
+    tol = 2e-4 if x3 else 2e-2
     for l in range(2):
-        assert rel_err(grads["weights"][l].cpu().numpy(), gref["weights"][l]) < 2e-2, f"dW{l}"
-        assert rel_err(grads["biases"][l].cpu().numpy(), gref["biases"][l]) < 2e-2
+        assert rel_err(grads["weights"][l].cpu().numpy(), gref["weights"][l]) < tol, f"dW{l}"
+        assert rel_err(grads["biases"][l].cpu().numpy(), gref["biases"][l]) < tol
     if learnable:
-        assert rel_err(grads["centers"].cpu().numpy(), gref["centers"]) < 2e-2
-        assert rel_err(grads["log_bandwidths"].cpu().numpy(), gref["log_bandwidths"]) < 2e-2
-    exd = Executor(spec_from_oracle(m, learnable=learnable))
+        ec = rel_err(grads["centers"].cpu().numpy(), gref["centers"])
+        eb = rel_err(grads["log_bandwidths"].cpu().numpy(), gref["log_bandwidths"])
+        print(precision, "knot gradient errors", ec, eb)
+        assert ec < (1e-3 if x3 else 2e-1) and eb < (1e-3 if x3 else 2e-1)
+    exd = Executor(spec_from_oracle(m, learnable=learnable, precision=precision), force_dense=True)
     assert not exd.sparse
     assert rel_l2(ex.forward(pts, train=False).cpu().numpy(), exd.forward(pts, train=False).cpu().numpy()) < 1e-3
     gw = grads["weights"][0].cpu().numpy()[:, :c.shape[0]]
@@ -721,4 +728,4 @@ def test_support_walk_at_real_size_99812_knots_vs_oracle():
     ex2 = Executor(spec2)
     assert ex2.sparse and ex2.lat is None
     yb = ex2.forward(pts, train=False).cpu().numpy()
-    assert rel_l2(yb, y64) < 1e-3 and rel_l2(ya, yb) < 1e-5
+    assert rel_l2(yb, y64) < 1e-3 and rel_l2(ya, yb) < 1e-4      # same index sets, different FP32 summation order
