@@ -208,6 +208,11 @@ typedef struct {
     float* loss_acc;          /* optional pair (device scalars): *loss_sum += *loss_acc; *loss_acc = 0 -- the running */
     float* loss_sum;          /* epoch loss of train_st_interp.py:721 kept on the device                              */
     float* loss_last;         /* optional: receives this step's loss (what loss.item() returns upstream, :721)        */
+    int32_t fuse_norm;        /* != 0: ONE launch for the whole step tail -- the kernel forms the squared gradient norms
+                                 itself (two phases around a grid barrier; bitwise deterministic), writes them to sqnorms
+                                 (which then only needs to be non-NULL when clipping is on), and advances step_count */
+    int32_t _pad;
+    float* norm_ws;           /* fuse_norm: (148 * 8 + 8) floats, zero-initialised once */
 } stdadk_adamw_args;
 
 int stdadk_version(void);

@@ -73,7 +73,8 @@ class AdamWArgs(C.Structure):
     _fields_ = [("p", fp), ("g", fp), ("m", fp), ("v", fp), ("shadow", fp), ("n", C.c_int64),
                 ("n_groups", C.c_int32), ("zero_grad", C.c_int32), ("group_end", C.POINTER(C.c_int64)), ("hyper", fp),
                 ("sqnorms", fp), ("step_count", fp), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
-                ("ema_decay", C.c_float), ("loss_acc", fp), ("loss_sum", fp), ("loss_last", fp)]
+                ("ema_decay", C.c_float), ("loss_acc", fp), ("loss_sum", fp), ("loss_last", fp), ("fuse_norm", C.c_int32),
+                ("_pad", C.c_int32), ("norm_ws", fp)]
 
 
 MAX_LEVELS = 8

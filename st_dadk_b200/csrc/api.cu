@@ -908,8 +908,22 @@ int stdadk_adamw_ema_step(const stdadk_adamw_args* a, void* stream) {
     REQUIRE(((reinterpret_cast<uintptr_t>(a->p) | reinterpret_cast<uintptr_t>(a->g) | reinterpret_cast<uintptr_t>(a->m) |
               reinterpret_cast<uintptr_t>(a->v) | reinterpret_cast<uintptr_t>(a->shadow)) & 15) == 0,
             "adamw: buffers must be 16-byte aligned");
+    if (a->fuse_norm) {
+        REQUIRE(a->norm_ws, "adamw: fuse_norm needs norm_ws");
+        K.sq_out = const_cast<float*>(a->sqnorms);
+        K.norm_ws = a->norm_ws;
+        K.step_rw = a->step_count;
+        // every block must be resident for the grid barrier: at most one block per SM; the grid is a function of n only
+        long long blocks = ((a->n + 3) / 4 + 255) / 256;
+        if (blocks > 148) blocks = 148;
+        const int sms = g_sm_count > 0 ? g_sm_count : 148;
+        if (blocks > sms) blocks = sms;
+        if (blocks < 1) blocks = 1;
+        adamw_ema_kernel<true><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(K);
+        return check_launch("adamw_ema_step (fused tail)");
+    }
     step_inc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(a->step_count);     // only once every argument check has passed
-    adamw_ema_kernel<<<grid_for((a->n + 3) / 4, 256, 8), 256, 0, (cudaStream_t)stream>>>(K);
+    adamw_ema_kernel<false><<<grid_for((a->n + 3) / 4, 256, 8), 256, 0, (cudaStream_t)stream>>>(K);
     return check_launch("adamw_ema_step");
 }
 

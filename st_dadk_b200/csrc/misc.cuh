@@ -342,11 +342,94 @@ struct AdamK {
     float* loss_acc;       // optional: *loss_sum += *loss_acc; *loss_acc = 0 (one thread), saves two tiny launches
     float* loss_sum;
     float* loss_last;      // optional: the step's loss before the accumulator is cleared
+    // fused step tail (adamw_fused_kernel): the kernel itself forms the squared gradient norms (written to sq_out),
+    // and advances the step counter -- one launch instead of {sqnorm, step counter, adamw}
+    float* sq_out;
+    float* norm_ws;        // gridDim.x * 8 partials, then two uint32: arrival counter, generation
+    int* step_rw;
 };
 // torch.optim.AdamW (decoupled decay, bias correction) + clip_grad_norm_ coefficient + ModelEMA.update
 // in one pass: 20 B read + 16 B written per parameter (28 B without EMA).
-__global__ void adamw_ema_kernel(AdamK A) {
-    const int step = *A.step_count;
+template <bool FUSED>
+__global__ void __launch_bounds__(256) adamw_ema_kernel(AdamK A) {
+    __shared__ float s_sq[8];
+    int step;
+    if (FUSED) {
+        // ---- phase 1: squared norm per group.  Deterministic: the element -> thread map is a function of the grid
+        // (itself a function of n), in-block reduction and the sum over blocks are ordered.
+        step = *A.step_count + 1;                       // read BEFORE the grid barrier; block 0 publishes it after
+        float acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = 0.0f;
+        if (A.sqnorms) {                                // (sqnorms != NULL <=> clipping is on)
+            const long long n4q = A.n >> 2;
+            const float4* gq = reinterpret_cast<const float4*>(A.g);
+            for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4q; i += (long long)gridDim.x * blockDim.x) {
+                const float4 v = __ldg(gq + i);
+                const long long e = i << 2;
+                const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int gi = group_of(A.G, e + j);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (k == gi) acc[k] = fmaf(vv[j], vv[j], acc[k]);
+                }
+            }
+            if (blockIdx.x == 0 && threadIdx.x < (A.n & 3)) {
+                const long long i = (n4q << 2) + threadIdx.x;
+                const float v = A.g[i];
+                const int gi = group_of(A.G, i);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (k == gi) acc[k] = fmaf(v, v, acc[k]);
+            }
+        }
+        __shared__ float wsum[8][8];
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float sk = warp_sum(acc[k]);
+            if (lane == 0) wsum[warp][k] = sk;
+        }
+        __syncthreads();
+        if (threadIdx.x < 8) {
+            float sk = 0.0f;
+            for (int w = 0; w < 8; ++w) sk += wsum[w][threadIdx.x];
+            A.norm_ws[blockIdx.x * 8 + threadIdx.x] = sk;
+        }
+        // ---- grid barrier (the grid is at most one block per SM and every block is resident): arrival counter +
+        // generation word; bounded wait
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned int* cnt = reinterpret_cast<unsigned int*>(A.norm_ws + gridDim.x * 8);
+            volatile unsigned int* gen = cnt + 1;
+            const unsigned int my_gen = *gen;
+            if (atomicAdd(cnt, 1u) == gridDim.x - 1) {
+                *cnt = 0u;
+                __threadfence();
+                atomicAdd(const_cast<unsigned int*>(gen), 1u);
+            } else {
+                long long t0 = clock64();
+                while (*gen == my_gen) {
+                    if (clock64() - t0 > 4000000000LL) __trap();
+                }
+            }
+            __threadfence();
+        }
+        __syncthreads();
+        if (threadIdx.x < 8) {
+            float sk = 0.0f;
+            for (unsigned int b = 0; b < gridDim.x; ++b) sk += __ldcg(&A.norm_ws[b * 8 + threadIdx.x]);
+            s_sq[threadIdx.x] = sk;
+            if (blockIdx.x == 0 && A.sq_out && threadIdx.x < A.G.n) A.sq_out[threadIdx.x] = sk;
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) *A.step_rw = step;
+        __syncthreads();
+    } else {
+        step = *A.step_count;
+    }
     const float bc1 = 1.0f - powf(A.beta1, (float)step);
     const float bc2 = 1.0f - powf(A.beta2, (float)step);
     const float inv_sqrt_bc2 = 1.0f / sqrtf(bc2);
@@ -359,7 +442,7 @@ __global__ void adamw_ema_kernel(AdamK A) {
             lr[k] = A.hyper[4 * k];
             wd[k] = A.hyper[4 * k + 1];
             float mx = A.hyper[4 * k + 2];
-            if (A.sqnorms && mx > 0.0f) clip[k] = fminf(1.0f, mx / (sqrtf(A.sqnorms[k]) + 1e-6f));
+            if (A.sqnorms && mx > 0.0f) clip[k] = fminf(1.0f, mx / (sqrtf(FUSED ? s_sq[k] : A.sqnorms[k]) + 1e-6f));
         }
     }
     auto update = [&](long long i, float g, float& p, float& m, float& v, float& sh) {

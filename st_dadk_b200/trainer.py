@@ -186,6 +186,7 @@ class Trainer:
         # own reduction workspace (partials + ticket): trainers of different configurations run concurrently on
         # separate streams of one GPU and must not share it
         self._sqnorm_ws = torch.zeros(L.lib().stdadk_sqnorm_ws_floats(), device=self.device)
+        self._tail_ws = torch.zeros(148 * 8 + 8, device=self.device)      # fused step tail: norm partials + grid barrier
         self.seed = int(torch.initial_seed() & (2 ** 63 - 1))
         self.loss_sum = torch.zeros(1, device=self.device)      # running sum of per-step losses (one sync / epoch)
         self.loss_last = torch.zeros(1, device=self.device)     # loss of the most recent step (written by AdamW)
@@ -424,12 +425,14 @@ class Trainer:
         ex, fl = self.ex, self.flat
         pen = self._add_penalty_grads()
         self._damp_center_grads()
-        if self.clip > 0 and not self._norm_fused():
-            ops.grad_sqnorm(fl.g[:fl.n], fl.group_end, self.sqnorms, self._sqnorm_ws)
+        # Step tail.  The exchange kernel of a data-parallel step may already have produced the clip norm; otherwise the
+        # update kernel forms it itself (one launch for {norm, step counter, clip + AdamW + EMA}).
+        fused_tail = not self._norm_fused()
         scratch_tail = fl.n_scratch > 0          # scratch gradients behind the parameters are not seen by the kernel
         ops.adamw_ema_step(fl.p, fl.g[:fl.n], fl.m, fl.v, fl.shadow, fl.group_end, self.hyper,
                            self.sqnorms if self.clip > 0 else None, self.step_count, ema_decay=self.ema_decay,
-                           zero_grad=True, loss_acc=ex.loss_acc, loss_sum=self.loss_sum, loss_last=self.loss_last)
+                           zero_grad=True, loss_acc=ex.loss_acc, loss_sum=self.loss_sum, loss_last=self.loss_last,
+                           norm_ws=self._tail_ws if fused_tail else None)
         if scratch_tail:
             fl.g[fl.n:fl.n + fl.n_scratch].zero_()
         self._g_clean = True
@@ -573,7 +576,7 @@ class Trainer:
         n += (1 if fused else nh) + nh + nh   # forward (one whole-network launch, or one per block), layer_bwd, wgrad
         if self.learnable:
             n += 3                          # knot + temporal tables (knots move), knot_grad
-        n += (1 if (self.clip > 0 and not self._norm_fused()) else 0) + 2   # grad_sqnorm, step counter, adamw_ema
+        n += 1 if not self._norm_fused() else 2    # fused tail {norm, step counter, clip + AdamW + EMA}; or step counter + update
         if self._peer is not None and self.world > 1:
             n += 1                          # peer-memory exchange kernel
         return n

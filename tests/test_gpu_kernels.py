@@ -372,7 +372,10 @@ def test_prediction_sharding_and_grid_bit_exact():
     assert rel_err(full.cpu().numpy(), orc.forward(m, None, coords, t)) < 1e-3
 
 
-def test_adamw_ema_and_sqnorm_vs_oracle():
+@pytest.mark.parametrize("fused", [False, True])
+def test_adamw_ema_and_sqnorm_vs_oracle(fused):
+    """clip_grad_norm_ coefficient + AdamW + EMA (train_st_interp.py:696-718, ema.py:52-66) vs the oracle; `fused`: the
+    whole step tail in one launch (norm, step counter, update around a grid barrier) instead of three."""
     L, ops, *_ = _mods()
     rng = np.random.default_rng(1)
     n = 100_003
@@ -383,11 +386,16 @@ def test_adamw_ema_and_sqnorm_vs_oracle():
     hyper = T([[2e-2, 5e-4, 10.0, 0], [1e-3, 5e-4, 1.0, 0]])
     sq = torch.zeros(2, device=DEV)
     stepc = torch.zeros(1, dtype=torch.int32, device=DEV)
+    tail_ws = torch.zeros(148 * 8 + 8, device=DEV)
     for step in range(1, 5):
         gnp = (rng.standard_normal(n) * (3.0 if step == 2 else 0.01)).astype(np.float32)
         g = T(gnp)
-        ops.grad_sqnorm(g, ends, sq)
-        ops.adamw_ema_step(p, g, m, v, sh, ends, hyper, sq, stepc, ema_decay=0.95)
+        if fused:
+            ops.adamw_ema_step(p, g, m, v, sh, ends, hyper, sq, stepc, ema_decay=0.95, norm_ws=tail_ws, zero_grad=True)
+            assert float(g.abs().max()) == 0.0
+        else:
+            ops.grad_sqnorm(g, ends, sq)
+            ops.adamw_ema_step(p, g, m, v, sh, ends, hyper, sq, stepc, ema_decay=0.95)
         lo = 0
         for gi, hi in enumerate(ends):
             norm, coef = orc.clip_coef([gnp[lo:hi]], float(hyper[gi, 2]))

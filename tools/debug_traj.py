@@ -29,9 +29,8 @@ def step(self, table, perm, row_begin, n_rows, *a, **k):
     # undo: recompute via the normal path is not possible after the adds, so finish the update by hand
     from st_dadk_b200 import ops
     fl, ex = self.flat, self.ex
-    if self.clip > 0: ops.grad_sqnorm(fl.g[:fl.n], fl.group_end, self.sqnorms, self._sqnorm_ws)
     ops.adamw_ema_step(fl.p, fl.g[:fl.n], fl.m, fl.v, fl.shadow, fl.group_end, self.hyper, self.sqnorms if self.clip > 0 else None,
-                       self.step_count, ema_decay=self.ema_decay, zero_grad=True, loss_acc=ex.loss_acc, loss_sum=self.loss_sum, loss_last=self.loss_last)
+                       self.step_count, ema_decay=self.ema_decay, zero_grad=True, loss_acc=ex.loss_acc, loss_sum=self.loss_sum, loss_last=self.loss_last, norm_ws=self._tail_ws)
     self._g_clean = True
     if self.global_step < self.warmup_steps:
         f = (self.global_step + 1) / self.warmup_steps
