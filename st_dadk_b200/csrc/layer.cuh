@@ -313,6 +313,109 @@ __device__ __forceinline__ float row_loss(const HeadP& H, const float* yh, float
     return loss;
 }
 
+// ---------------------------------------------------------------- register-resident epilogue pieces (32-column chunks)
+// bias add + shifted moments of one 32-column chunk held in registers (nv valid columns); packed FP32 throughout
+__device__ __forceinline__ void pf_bias_stats(float (&v)[32], const float* sb, int nv, bool& have, float& K, float& S1,
+                                              float& S2) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float4 b = *reinterpret_cast<const float4*>(sb + 4 * c);
+        const float2 lo = add2(make_float2(v[4 * c], v[4 * c + 1]), make_float2(b.x, b.y));
+        const float2 hi = add2(make_float2(v[4 * c + 2], v[4 * c + 3]), make_float2(b.z, b.w));
+        v[4 * c] = lo.x; v[4 * c + 1] = lo.y; v[4 * c + 2] = hi.x; v[4 * c + 3] = hi.y;
+    }
+    if (!have) {
+        K = v[0];
+        have = true;
+    }
+    if (nv >= 32) {
+        // two independent packed accumulator pairs (= four scalar chains): with four warps per scheduler a single
+        // 32-long FADD chain would stall
+        const float2 nk = make_float2(-K, -K);
+        float2 a1[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, a2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+            const float2 d = add2(make_float2(v[i], v[i + 1]), nk);
+            a1[(i >> 1) & 1] = add2(a1[(i >> 1) & 1], d);
+            a2[(i >> 1) & 1] = fma2(d, d, a2[(i >> 1) & 1]);
+        }
+        S1 += (a1[0].x + a1[0].y) + (a1[1].x + a1[1].y);
+        S2 += (a2[0].x + a2[0].y) + (a2[1].x + a2[1].y);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (i < nv) {
+                const float d = v[i] - K;
+                S1 += d;
+                S2 = fmaf(d, d, S2);
+            }
+    }
+}
+
+// v <- relu(LayerNorm(v)) (or relu(v)); columns >= nv forced to zero
+__device__ __forceinline__ void pf_normalize(float (&v)[32], const float* sg, const float* sbt, bool has_ln, float rstd,
+                                             float nmr, int nv) {
+    if (has_ln) {
+        const float2 r2 = make_float2(rstd, rstd), n2 = make_float2(nmr, nmr);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float4 g = *reinterpret_cast<const float4*>(sg + 4 * c);
+            const float4 b = *reinterpret_cast<const float4*>(sbt + 4 * c);
+            const float2 y0 = fma2(fma2(make_float2(v[4 * c], v[4 * c + 1]), r2, n2), make_float2(g.x, g.y),
+                                   make_float2(b.x, b.y));
+            const float2 y1 = fma2(fma2(make_float2(v[4 * c + 2], v[4 * c + 3]), r2, n2), make_float2(g.z, g.w),
+                                   make_float2(b.z, b.w));
+            v[4 * c] = fmaxf(y0.x, 0.0f);
+            v[4 * c + 1] = fmaxf(y0.y, 0.0f);
+            v[4 * c + 2] = fmaxf(y1.x, 0.0f);
+            v[4 * c + 3] = fmaxf(y1.y, 0.0f);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+    }
+    if (nv < 32) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (i >= nv) v[i] = 0.0f;
+    }
+}
+
+// keep bits of one 32-column chunk: four Philox calls (same keys as layer_fwd_kernel).  Computed BEFORE the accumulator
+// is pulled into registers -- while the MMAs are still running -- so the calls neither sit on the critical path nor
+// force the 64 accumulator registers to be saved around them.
+__device__ __forceinline__ uint32_t pf_keep_mask(unsigned long long seed, uint32_t step, uint32_t layer,
+                                                 unsigned long long key_row, int c0, uint32_t thresh16) {
+    uint32_t keep = 0;
+#pragma unroll 1
+    for (int b = 0; b < 4; ++b) keep |= dropout_keep8(seed, step, layer, key_row, (uint32_t)(c0 / 8 + b), thresh16) << (8 * b);
+    return keep;
+}
+__device__ __forceinline__ void pf_dropout(float (&v)[32], uint32_t keep, float scale) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = ((keep >> i) & 1u) ? v[i] * scale : 0.0f;
+}
+__device__ __forceinline__ void pf_head_partial(const float (&v)[32], const float* shw, int n_pad, int c0, int q,
+                                                float (&yh)[STDADK_MAX_Q]) {
+#pragma unroll 1
+    for (int k = 0; k < q; ++k) {
+        const float* wk = shw + k * n_pad + c0;
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float4 w = *reinterpret_cast<const float4*>(wk + 4 * c);
+            a0 = fmaf(v[4 * c], w.x, a0);
+            a1 = fmaf(v[4 * c + 1], w.y, a1);
+            a2 = fmaf(v[4 * c + 2], w.z, a2);
+            a3 = fmaf(v[4 * c + 3], w.w, a3);
+        }
+        const float acc = (a0 + a1) + (a2 + a3);
+#pragma unroll
+        for (int kk = 0; kk < STDADK_MAX_Q; ++kk)
+            if (kk == k) yh[kk] += acc;
+    }
+}
+
 // =============================================================================================
 // Forward
 // =============================================================================================
@@ -331,7 +434,9 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
     uint64_t* accf = full + 2 * NSTAGE;
     uint64_t* kbar = accf + 1;                                       // knot tables have landed (BASIS)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + sp.tmem_off);
-    float4* sprm = reinterpret_cast<float4*>(smem + sp.vec_off);   // per column (bias, gamma, beta, 0): one LDS.128
+    float* sbias = reinterpret_cast<float*>(smem + sp.vec_off);    // per column bias | gamma | beta (one LDS.128 per 4 columns)
+    float* sgam = sbias + P.n_pad;
+    float* sbet = sgam + P.n_pad;
     float* shw = reinterpret_cast<float*>(smem + sp.headw_off);
     float* shb = shw + (P.has_head ? P.head.q * P.n_pad : 0);
     float4* sk = reinterpret_cast<float4*>(smem + sp.knots_off);
@@ -362,8 +467,9 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
     }
     for (int i = tid; i < n_pad; i += NT) {
         bool ok = i < n_out;
-        sprm[i] = make_float4(ok ? P.L.bias[i] : 0.0f, (ok && has_ln) ? P.L.gamma[i] : 1.0f,
-                              (ok && has_ln) ? P.L.beta[i] : 0.0f, 0.0f);
+        sbias[i] = ok ? P.L.bias[i] : 0.0f;
+        sgam[i] = (ok && has_ln) ? P.L.gamma[i] : 1.0f;
+        sbet[i] = (ok && has_ln) ? P.L.beta[i] : 0.0f;
     }
     if (P.has_head) {
         for (int i = tid; i < P.head.q * n_pad; i += NT) {
@@ -443,7 +549,8 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
                 mbar_arrive(&full[stage]);
             }
         }
-        // ---------------- epilogue
+        // ---------------- epilogue: two passes over the accumulator (a thread owns 256 / CG columns, more than the
+        // register file holds at two CTAs per SM), each on whole 32-column chunks in registers with packed FP32 math
         mbar_wait(accf, 0);
         tc_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16);
@@ -452,9 +559,9 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
         float v[32];
         float mean = 0.0f, rstd = 1.0f;
         if (has_ln) {
-            // One pass over the accumulator: sums of (x - K) and (x - K)^2 with a per-thread shift K (the thread's
-            // first value), which removes the cancellation of the raw-moment formula; the CG column groups of a row
-            // publish (K, S1, S2, count) and every thread combines them exactly:
+            // pass 1: shifted moments of x = A W^T + b (+ addend): per-thread shift K (the thread's first value) removes
+            // the cancellation of the raw-moment formula; the CG column groups of a row publish (K, S1, S2, count) and
+            // every thread combines them exactly:
             //   mean = sum_g (n_g K_g + S1_g) / n,   M2 = sum_g [S2_g - 2 (mean - K_g) S1_g + n_g (mean - K_g)^2]
             float K = 0.0f, S1 = 0.0f, S2 = 0.0f, cntv = 0.0f;
             bool have = false;
@@ -463,28 +570,8 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
                 if (nv <= 0) break;
                 tmem_ld32(trow + c0, v);
                 if (arow) add_addend_chunk(v, arow, c0, n_out);
-                if (!have) {
-                    K = v[0] + sprm[c0].x;
-                    have = true;
-                }
-                if (nv >= 32) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        float d = v[i] + sprm[c0 + i].x - K;
-                        S1 += d;
-                        S2 = fmaf(d, d, S2);
-                    }
-                    cntv += 32.0f;
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (i < nv) {
-                            float d = v[i] + sprm[c0 + i].x - K;
-                            S1 += d;
-                            S2 = fmaf(d, d, S2);
-                        }
-                    cntv += (float)nv;
-                }
+                pf_bias_stats(v, sbias + c0, min(nv, 32), have, K, S1, S2);
+                cntv += (float)min(nv, 32);
             }
             const float inv_n = 1.0f / (float)n_out;
             if (CG > 1) {
@@ -515,54 +602,33 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
                 P.stats[2 * lrow + 1] = rstd;
             }
         }
+        const float nmr = -mean * rstd;
         float yh[STDADK_MAX_Q];
 #pragma unroll
         for (int k = 0; k < STDADK_MAX_Q; ++k) yh[k] = 0.0f;
         const bool drop = P.L.drop_p > 0.0f;
         const unsigned int drop_step = drop ? dropout_step(P.L) : 0u;
+        // pass 2: x -> LayerNorm -> ReLU -> dropout -> operand image (+ head partials, + x image for the backward)
         for (int c0 = 32 * cg; c0 < n_pad; c0 += 32 * CG) {
+            uint32_t keep = 0xFFFFFFFFu;
+            if (drop)       // masks first: the Philox calls neither sit behind the TMEM load nor hold 32 live values
+                keep = pf_keep_mask(P.L.seed, drop_step, (uint32_t)P.L.layer_id, P.L.key_offset + (unsigned long long)lrow, c0,
+                                    P.thresh16);
             tmem_ld32(trow + c0, v);
             if (arow) add_addend_chunk(v, arow, c0, n_out);
-            uint32_t keep = 0xFFFFFFFFu;
-            if (drop) {
-                keep = 0;
-#pragma unroll 1
-                for (int b = 0; b < 4; ++b)
-                    keep |= dropout_keep8(P.L.seed, drop_step, (uint32_t)P.L.layer_id, P.L.key_offset + (unsigned long long)lrow,
-                                          (uint32_t)(c0 / 8 + b), P.thresh16)
-                            << (8 * b);
-            }
-            if (P.x_img && tile_valid) {          // training with a single wave of tiles: keep x for the backward
-                float xs[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) xs[i] = v[i] + sprm[c0 + i].x;
-                image_store_chunk(P.x_img, tile, n_pad / SLAB_K, c0, (uint32_t)row, xs);
+            for (int c = 0; c < 8; ++c) {
+                const float4 b = *reinterpret_cast<const float4*>(sbias + c0 + 4 * c);
+                const float2 lo = add2(make_float2(v[4 * c], v[4 * c + 1]), make_float2(b.x, b.y));
+                const float2 hi = add2(make_float2(v[4 * c + 2], v[4 * c + 3]), make_float2(b.z, b.w));
+                v[4 * c] = lo.x; v[4 * c + 1] = lo.y; v[4 * c + 2] = hi.x; v[4 * c + 3] = hi.y;
             }
-            const bool chunk_ok = rvalid && (c0 + 32 <= n_out);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const int col = c0 + i;
-                const float4 q = sprm[col];
-                // y = ((v + b) - mean) * rstd * gamma + beta  as one FFMA on v:  a = rstd*gamma, c = (b - mean)*a + beta
-                const float sc = has_ln ? rstd * q.y : 1.0f;
-                const float sh = has_ln ? fmaf(q.x - mean, sc, q.z) : q.x;
-                float a = fmaxf(fmaf(v[i], sc, sh), 0.0f);
-                if (drop) a = ((keep >> i) & 1u) ? a * P.drop_scale : 0.0f;
-                if (!chunk_ok && (col >= n_out || !rvalid)) a = 0.0f;
-                v[i] = a;
-            }
-            if (P.has_head) {
-#pragma unroll 1
-                for (int k = 0; k < P.head.q; ++k) {     // runtime loop: Q is 1 or a handful; keeps the code small
-                    float acc = 0.0f;
-                    const float* wk = shw + k * n_pad + c0;
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) acc = fmaf(v[i], wk[i], acc);
-#pragma unroll
-                    for (int kk = 0; kk < STDADK_MAX_Q; ++kk)
-                        if (kk == k) yh[kk] += acc;
-                }
-            }
+            if (P.x_img && tile_valid)            // training with a single wave of tiles: keep x for the backward
+                image_store_chunk(P.x_img, tile, n_pad / SLAB_K, c0, (uint32_t)row, v);
+            const int nv = rvalid ? min(32, max(n_out - c0, 0)) : 0;      // padding rows / columns -> 0
+            pf_normalize(v, sgam + c0, sbet + c0, has_ln, rstd, nmr, nv);
+            if (drop) pf_dropout(v, keep, P.drop_scale);
+            if (P.has_head) pf_head_partial(v, shw, n_pad, c0, P.head.q, yh);
             if (P.out_img && tile_valid)
                 store_operand_chunk(P.out_img, P.out_img_lo, tile, n_pad / SLAB_K, c0, (uint32_t)row, v);
         }

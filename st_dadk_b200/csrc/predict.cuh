@@ -115,87 +115,6 @@ __device__ __forceinline__ void pf_gen_slab(const BasisP& B, const float4* sk, c
     }
 }
 
-// bias add + shifted moments of one 32-column chunk held in registers (nv valid columns); packed FP32 throughout
-__device__ __forceinline__ void pf_bias_stats(float (&v)[32], const float* sb, int nv, bool& have, float& K, float& S1,
-                                              float& S2) {
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const float4 b = *reinterpret_cast<const float4*>(sb + 4 * c);
-        const float2 lo = add2(make_float2(v[4 * c], v[4 * c + 1]), make_float2(b.x, b.y));
-        const float2 hi = add2(make_float2(v[4 * c + 2], v[4 * c + 3]), make_float2(b.z, b.w));
-        v[4 * c] = lo.x; v[4 * c + 1] = lo.y; v[4 * c + 2] = hi.x; v[4 * c + 3] = hi.y;
-    }
-    if (!have) {
-        K = v[0];
-        have = true;
-    }
-    if (nv >= 32) {
-        // two independent packed accumulator pairs (= four scalar chains): with four warps per scheduler a single
-        // 32-long FADD chain would stall
-        const float2 nk = make_float2(-K, -K);
-        float2 a1[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, a2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-            const float2 d = add2(make_float2(v[i], v[i + 1]), nk);
-            a1[(i >> 1) & 1] = add2(a1[(i >> 1) & 1], d);
-            a2[(i >> 1) & 1] = fma2(d, d, a2[(i >> 1) & 1]);
-        }
-        S1 += (a1[0].x + a1[0].y) + (a1[1].x + a1[1].y);
-        S2 += (a2[0].x + a2[0].y) + (a2[1].x + a2[1].y);
-    } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-            if (i < nv) {
-                const float d = v[i] - K;
-                S1 += d;
-                S2 = fmaf(d, d, S2);
-            }
-    }
-}
-
-// v <- relu(LayerNorm(v)) (or relu(v)); columns >= nv forced to zero
-__device__ __forceinline__ void pf_normalize(float (&v)[32], const float* sg, const float* sbt, bool has_ln, float rstd,
-                                             float nmr, int nv) {
-    if (has_ln) {
-        const float2 r2 = make_float2(rstd, rstd), n2 = make_float2(nmr, nmr);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const float4 g = *reinterpret_cast<const float4*>(sg + 4 * c);
-            const float4 b = *reinterpret_cast<const float4*>(sbt + 4 * c);
-            const float2 y0 = fma2(fma2(make_float2(v[4 * c], v[4 * c + 1]), r2, n2), make_float2(g.x, g.y),
-                                   make_float2(b.x, b.y));
-            const float2 y1 = fma2(fma2(make_float2(v[4 * c + 2], v[4 * c + 3]), r2, n2), make_float2(g.z, g.w),
-                                   make_float2(b.z, b.w));
-            v[4 * c] = fmaxf(y0.x, 0.0f);
-            v[4 * c + 1] = fmaxf(y0.y, 0.0f);
-            v[4 * c + 2] = fmaxf(y1.x, 0.0f);
-            v[4 * c + 3] = fmaxf(y1.y, 0.0f);
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
-    }
-    if (nv < 32) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-            if (i >= nv) v[i] = 0.0f;
-    }
-}
-
-// keep bits of one 32-column chunk: four Philox calls (same keys as layer_fwd_kernel).  Computed BEFORE the accumulator
-// is pulled into registers -- while the MMAs are still running -- so the calls neither sit on the critical path nor
-// force the 64 accumulator registers to be saved around them.
-__device__ __forceinline__ uint32_t pf_keep_mask(unsigned long long seed, uint32_t step, uint32_t layer,
-                                                 unsigned long long key_row, int c0, uint32_t thresh16) {
-    uint32_t keep = 0;
-#pragma unroll 1
-    for (int b = 0; b < 4; ++b) keep |= dropout_keep8(seed, step, layer, key_row, (uint32_t)(c0 / 8 + b), thresh16) << (8 * b);
-    return keep;
-}
-__device__ __forceinline__ void pf_dropout(float (&v)[32], uint32_t keep, float scale) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = ((keep >> i) & 1u) ? v[i] * scale : 0.0f;
-}
 // the TF32-rounded chunk into a global operand image (what the next block / wgrad of the layered path read)
 __device__ __forceinline__ void pf_store_image_tf32(float* img, int tile, int slabs, int c0, uint32_t row, const float (&v)[32]) {
     uint8_t* dst = reinterpret_cast<uint8_t*>(img + ((size_t)tile * slabs + (c0 / SLAB_K)) * SLAB_FLOATS);
@@ -210,27 +129,6 @@ __device__ __forceinline__ void pf_store_slab(const float (&v)[32], uint32_t sla
     for (int c = 0; c < 8; ++c)
         st_shared_v4(slab_saddr + rowoff + (((uint32_t)c ^ rx) << 4), to_tf32(v[4 * c]), to_tf32(v[4 * c + 1]),
                      to_tf32(v[4 * c + 2]), to_tf32(v[4 * c + 3]));
-}
-
-__device__ __forceinline__ void pf_head_partial(const float (&v)[32], const float* shw, int n_pad, int c0, int q,
-                                                float (&yh)[STDADK_MAX_Q]) {
-#pragma unroll 1
-    for (int k = 0; k < q; ++k) {
-        const float* wk = shw + k * n_pad + c0;
-        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const float4 w = *reinterpret_cast<const float4*>(wk + 4 * c);
-            a0 = fmaf(v[4 * c], w.x, a0);
-            a1 = fmaf(v[4 * c + 1], w.y, a1);
-            a2 = fmaf(v[4 * c + 2], w.z, a2);
-            a3 = fmaf(v[4 * c + 3], w.w, a3);
-        }
-        const float acc = (a0 + a1) + (a2 + a3);
-#pragma unroll
-        for (int kk = 0; kk < STDADK_MAX_Q; ++kk)
-            if (kk == k) yh[kk] += acc;
-    }
 }
 
 // TRAIN = false: prediction (eval mode, nothing but y_hat leaves the SM).  TRAIN = true: the forward of a training
