@@ -419,6 +419,154 @@ __device__ __forceinline__ void pf_head_partial(const float (&v)[32], const floa
 // =============================================================================================
 // Forward
 // =============================================================================================
+// Epilogue of a forward block for one thread = (row, column group): two passes over the accumulator in tensor memory
+// (a thread owns 256 / CG columns, more than the register file holds at two CTAs per SM), each on whole 32-column chunks
+// in registers with packed FP32 math.  Shared by layer_fwd_kernel and layer_fwd_lattice_kernel.
+struct EpiCtx {
+    const float* sbias;
+    const float* sgam;
+    const float* sbet;
+    const float* shw;
+    const float* shb;
+    float* red;                    // CG x 128 x RED_STRIDE floats of scratch
+    uint32_t trow;                 // accumulator address of this warp's lane quarter
+    int tile, row, cg, lane;
+    long long lrow, grow;
+    bool rvalid, tile_valid;
+};
+template <int CG>
+__device__ __forceinline__ void fwd_epilogue(const FwdK& P, const EpiCtx& E) {
+    constexpr int NW = n_work(CG);
+    const float* sbias = E.sbias;
+    const float* sgam = E.sgam;
+    const float* sbet = E.sbet;
+    const float* shw = E.shw;
+    const float* shb = E.shb;
+    float* red = E.red;
+    const uint32_t trow = E.trow;
+    const int tile = E.tile, row = E.row, cg = E.cg, lane = E.lane;
+    const long long lrow = E.lrow, grow = E.grow;
+    const bool rvalid = E.rvalid, tile_valid = E.tile_valid;
+    const int n_pad = P.n_pad, n_out = P.L.n_out;
+    const bool has_ln = P.L.gamma != nullptr;
+    float* myred = red + ((size_t)cg * TILE_M + row) * RED_STRIDE;
+    const float* arow = (P.addend && rvalid) ? P.addend + (size_t)lrow * n_out : nullptr;
+    float v[32];
+    float mean = 0.0f, rstd = 1.0f;
+    if (has_ln) {
+        // pass 1: shifted moments of x = A W^T + b (+ addend): per-thread shift K (the thread's first value) removes
+        // the cancellation of the raw-moment formula; the CG column groups of a row publish (K, S1, S2, count) and
+        // every thread combines them exactly:
+        //   mean = sum_g (n_g K_g + S1_g) / n,   M2 = sum_g [S2_g - 2 (mean - K_g) S1_g + n_g (mean - K_g)^2]
+        float K = 0.0f, S1 = 0.0f, S2 = 0.0f, cntv = 0.0f;
+        bool have = false;
+        for (int c0 = 32 * cg; c0 < n_pad; c0 += 32 * CG) {
+            const int nv = n_out - c0;
+            if (nv <= 0) break;
+            tmem_ld32(trow + c0, v);
+            if (arow) add_addend_chunk(v, arow, c0, n_out);
+            pf_bias_stats(v, sbias + c0, min(nv, 32), have, K, S1, S2);
+            cntv += (float)min(nv, 32);
+        }
+        const float inv_n = 1.0f / (float)n_out;
+        if (CG > 1) {
+            *reinterpret_cast<float4*>(myred) = make_float4(K, S1, S2, cntv);
+            worker_barrier(NW);
+            float4 part[CG];
+            float tot = 0.0f;
+#pragma unroll
+            for (int g = 0; g < CG; ++g) {
+                part[g] = *reinterpret_cast<const float4*>(red + ((size_t)g * TILE_M + row) * RED_STRIDE);
+                tot += fmaf(part[g].w, part[g].x, part[g].y);
+            }
+            mean = tot * inv_n;
+            float m2 = 0.0f;
+#pragma unroll
+            for (int g = 0; g < CG; ++g) {
+                float dk = mean - part[g].x;
+                m2 += part[g].z - 2.0f * dk * part[g].y + part[g].w * dk * dk;
+            }
+            rstd = 1.0f / sqrtf(fmaxf(m2 * inv_n, 0.0f) + P.L.eps);
+        } else {
+            float m1 = S1 * inv_n;
+            mean = K + m1;
+            rstd = 1.0f / sqrtf(fmaxf(S2 * inv_n - m1 * m1, 0.0f) + P.L.eps);
+        }
+        if (P.stats && rvalid && cg == 0) {
+            P.stats[2 * lrow] = mean;
+            P.stats[2 * lrow + 1] = rstd;
+        }
+    }
+    const float nmr = -mean * rstd;
+    float yh[STDADK_MAX_Q];
+#pragma unroll
+    for (int k = 0; k < STDADK_MAX_Q; ++k) yh[k] = 0.0f;
+    const bool drop = P.L.drop_p > 0.0f;
+    const unsigned int drop_step = drop ? dropout_step(P.L) : 0u;
+    // pass 2: x -> LayerNorm -> ReLU -> dropout -> operand image (+ head partials, + x image for the backward)
+    for (int c0 = 32 * cg; c0 < n_pad; c0 += 32 * CG) {
+        uint32_t keep = 0xFFFFFFFFu;
+        if (drop)       // masks first: the Philox calls neither sit behind the TMEM load nor hold 32 live values
+            keep = pf_keep_mask(P.L.seed, drop_step, (uint32_t)P.L.layer_id, P.L.key_offset + (unsigned long long)lrow, c0,
+                                P.thresh16);
+        tmem_ld32(trow + c0, v);
+        if (arow) add_addend_chunk(v, arow, c0, n_out);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float4 b = *reinterpret_cast<const float4*>(sbias + c0 + 4 * c);
+            const float2 lo = add2(make_float2(v[4 * c], v[4 * c + 1]), make_float2(b.x, b.y));
+            const float2 hi = add2(make_float2(v[4 * c + 2], v[4 * c + 3]), make_float2(b.z, b.w));
+            v[4 * c] = lo.x; v[4 * c + 1] = lo.y; v[4 * c + 2] = hi.x; v[4 * c + 3] = hi.y;
+        }
+        if (P.x_img && tile_valid)            // training with a single wave of tiles: keep x for the backward
+            image_store_chunk(P.x_img, tile, n_pad / SLAB_K, c0, (uint32_t)row, v);
+        const int nv = rvalid ? min(32, max(n_out - c0, 0)) : 0;      // padding rows / columns -> 0
+        pf_normalize(v, sgam + c0, sbet + c0, has_ln, rstd, nmr, nv);
+        if (drop) pf_dropout(v, keep, P.drop_scale);
+        if (P.has_head) pf_head_partial(v, shw, n_pad, c0, P.head.q, yh);
+        if (P.out_img && tile_valid)
+            store_operand_chunk(P.out_img, P.out_img_lo, tile, n_pad / SLAB_K, c0, (uint32_t)row, v);
+    }
+    if (P.has_head) {
+        if (CG > 1) {
+#pragma unroll
+            for (int k = 0; k < STDADK_MAX_Q; ++k)
+                if (k < P.head.q) myred[2 + k] = yh[k];
+            worker_barrier(NW);
+        }
+        if (cg == 0) {
+            float loss = 0.0f;
+            if (rvalid) {
+                float dy[STDADK_MAX_Q];
+#pragma unroll
+                for (int k = 0; k < STDADK_MAX_Q; ++k)
+                    if (k < P.head.q) {
+                        if (CG > 1) {
+                            float acc = 0.0f;
+#pragma unroll
+                            for (int g = 0; g < CG; ++g) acc += red[((size_t)g * TILE_M + row) * RED_STRIDE + 2 + k];
+                            yh[k] = acc;
+                        }
+                        yh[k] += shb[k];
+                        P.head.yhat[lrow * P.head.q + k] = yh[k];
+                    }
+                if (P.head.loss_type != STDADK_LOSS_NONE) {
+                    loss = row_loss(P.head, yh, P.head.y[sample_of(P.pts, grow)], dy);
+                    if (P.head.dyhat) {
+#pragma unroll
+                        for (int k = 0; k < STDADK_MAX_Q; ++k)
+                            if (k < P.head.q) P.head.dyhat[lrow * P.head.q + k] = dy[k];
+                    }
+                }
+            }
+            if (P.head.loss_type != STDADK_LOSS_NONE) {
+                loss = warp_sum(loss);
+                if (lane == 0) atomicAdd(P.head.loss_acc, loss);
+            }
+        }
+    }
+}
+
 template <bool BASIS, int CG, int NS, int CL>
 __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kernel(const __grid_constant__ FwdK P) {
     constexpr int NW = n_work(CG), NT = n_threads(CG), NSTAGE = NS;
@@ -549,127 +697,12 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
                 mbar_arrive(&full[stage]);
             }
         }
-        // ---------------- epilogue: two passes over the accumulator (a thread owns 256 / CG columns, more than the
-        // register file holds at two CTAs per SM), each on whole 32-column chunks in registers with packed FP32 math
+        // ---------------- epilogue
         mbar_wait(accf, 0);
         tc_fence_after();
-        const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16);
-        float* myred = red + ((size_t)cg * TILE_M + row) * RED_STRIDE;
-        const float* arow = (P.addend && rvalid) ? P.addend + (size_t)lrow * n_out : nullptr;
-        float v[32];
-        float mean = 0.0f, rstd = 1.0f;
-        if (has_ln) {
-            // pass 1: shifted moments of x = A W^T + b (+ addend): per-thread shift K (the thread's first value) removes
-            // the cancellation of the raw-moment formula; the CG column groups of a row publish (K, S1, S2, count) and
-            // every thread combines them exactly:
-            //   mean = sum_g (n_g K_g + S1_g) / n,   M2 = sum_g [S2_g - 2 (mean - K_g) S1_g + n_g (mean - K_g)^2]
-            float K = 0.0f, S1 = 0.0f, S2 = 0.0f, cntv = 0.0f;
-            bool have = false;
-            for (int c0 = 32 * cg; c0 < n_pad; c0 += 32 * CG) {
-                const int nv = n_out - c0;
-                if (nv <= 0) break;
-                tmem_ld32(trow + c0, v);
-                if (arow) add_addend_chunk(v, arow, c0, n_out);
-                pf_bias_stats(v, sbias + c0, min(nv, 32), have, K, S1, S2);
-                cntv += (float)min(nv, 32);
-            }
-            const float inv_n = 1.0f / (float)n_out;
-            if (CG > 1) {
-                *reinterpret_cast<float4*>(myred) = make_float4(K, S1, S2, cntv);
-                worker_barrier(NW);
-                float4 part[CG];
-                float tot = 0.0f;
-#pragma unroll
-                for (int g = 0; g < CG; ++g) {
-                    part[g] = *reinterpret_cast<const float4*>(red + ((size_t)g * TILE_M + row) * RED_STRIDE);
-                    tot += fmaf(part[g].w, part[g].x, part[g].y);
-                }
-                mean = tot * inv_n;
-                float m2 = 0.0f;
-#pragma unroll
-                for (int g = 0; g < CG; ++g) {
-                    float dk = mean - part[g].x;
-                    m2 += part[g].z - 2.0f * dk * part[g].y + part[g].w * dk * dk;
-                }
-                rstd = 1.0f / sqrtf(fmaxf(m2 * inv_n, 0.0f) + P.L.eps);
-            } else {
-                float m1 = S1 * inv_n;
-                mean = K + m1;
-                rstd = 1.0f / sqrtf(fmaxf(S2 * inv_n - m1 * m1, 0.0f) + P.L.eps);
-            }
-            if (P.stats && rvalid && cg == 0) {
-                P.stats[2 * lrow] = mean;
-                P.stats[2 * lrow + 1] = rstd;
-            }
-        }
-        const float nmr = -mean * rstd;
-        float yh[STDADK_MAX_Q];
-#pragma unroll
-        for (int k = 0; k < STDADK_MAX_Q; ++k) yh[k] = 0.0f;
-        const bool drop = P.L.drop_p > 0.0f;
-        const unsigned int drop_step = drop ? dropout_step(P.L) : 0u;
-        // pass 2: x -> LayerNorm -> ReLU -> dropout -> operand image (+ head partials, + x image for the backward)
-        for (int c0 = 32 * cg; c0 < n_pad; c0 += 32 * CG) {
-            uint32_t keep = 0xFFFFFFFFu;
-            if (drop)       // masks first: the Philox calls neither sit behind the TMEM load nor hold 32 live values
-                keep = pf_keep_mask(P.L.seed, drop_step, (uint32_t)P.L.layer_id, P.L.key_offset + (unsigned long long)lrow, c0,
-                                    P.thresh16);
-            tmem_ld32(trow + c0, v);
-            if (arow) add_addend_chunk(v, arow, c0, n_out);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const float4 b = *reinterpret_cast<const float4*>(sbias + c0 + 4 * c);
-                const float2 lo = add2(make_float2(v[4 * c], v[4 * c + 1]), make_float2(b.x, b.y));
-                const float2 hi = add2(make_float2(v[4 * c + 2], v[4 * c + 3]), make_float2(b.z, b.w));
-                v[4 * c] = lo.x; v[4 * c + 1] = lo.y; v[4 * c + 2] = hi.x; v[4 * c + 3] = hi.y;
-            }
-            if (P.x_img && tile_valid)            // training with a single wave of tiles: keep x for the backward
-                image_store_chunk(P.x_img, tile, n_pad / SLAB_K, c0, (uint32_t)row, v);
-            const int nv = rvalid ? min(32, max(n_out - c0, 0)) : 0;      // padding rows / columns -> 0
-            pf_normalize(v, sgam + c0, sbet + c0, has_ln, rstd, nmr, nv);
-            if (drop) pf_dropout(v, keep, P.drop_scale);
-            if (P.has_head) pf_head_partial(v, shw, n_pad, c0, P.head.q, yh);
-            if (P.out_img && tile_valid)
-                store_operand_chunk(P.out_img, P.out_img_lo, tile, n_pad / SLAB_K, c0, (uint32_t)row, v);
-        }
-        if (P.has_head) {
-            if (CG > 1) {
-#pragma unroll
-                for (int k = 0; k < STDADK_MAX_Q; ++k)
-                    if (k < P.head.q) myred[2 + k] = yh[k];
-                worker_barrier(NW);
-            }
-            if (cg == 0) {
-                float loss = 0.0f;
-                if (rvalid) {
-                    float dy[STDADK_MAX_Q];
-#pragma unroll
-                    for (int k = 0; k < STDADK_MAX_Q; ++k)
-                        if (k < P.head.q) {
-                            if (CG > 1) {
-                                float acc = 0.0f;
-#pragma unroll
-                                for (int g = 0; g < CG; ++g) acc += red[((size_t)g * TILE_M + row) * RED_STRIDE + 2 + k];
-                                yh[k] = acc;
-                            }
-                            yh[k] += shb[k];
-                            P.head.yhat[lrow * P.head.q + k] = yh[k];
-                        }
-                    if (P.head.loss_type != STDADK_LOSS_NONE) {
-                        loss = row_loss(P.head, yh, P.head.y[sample_of(P.pts, grow)], dy);
-                        if (P.head.dyhat) {
-#pragma unroll
-                            for (int k = 0; k < STDADK_MAX_Q; ++k)
-                                if (k < P.head.q) P.head.dyhat[lrow * P.head.q + k] = dy[k];
-                        }
-                    }
-                }
-                if (P.head.loss_type != STDADK_LOSS_NONE) {
-                    loss = warp_sum(loss);
-                    if (lane == 0) atomicAdd(P.head.loss_acc, loss);
-                }
-            }
-        }
+        EpiCtx E{sbias, sgam, sbet, shw, shb, red, tmem_base + ((uint32_t)(q4 * 32) << 16), tile, row, cg, lane, lrow, grow,
+                 rvalid, tile_valid};
+        fwd_epilogue<CG>(P, E);
         tc_fence_before();
     }
     __syncthreads();
