@@ -125,14 +125,6 @@ typedef struct {
                                 when the batch is a single wave of tiles and latency, not bandwidth, is the limit. */
     const float* a_img_lo;   /* tf32x3 (layer.w_img_lo != NULL): residual image of a_img */
     float* out_img_lo;       /* tf32x3: residual image of out_img (written together with it) */
-    /* Optional, block 1 only: the knots are upstream's FIXED UNIFORM LATTICE (st_interp.py:152-185: level l has
-     * lat_side[l]^2 knots, knot j at node (j / side, j % side), bandwidth theta'_l).  The kernel then walks each
-     * point's support window per level in closed form instead of testing every knot (same values and index sets).
-     * lat_levels = 0: not a lattice / unknown -> every knot is tested. */
-    int32_t lat_levels;
-    int32_t lat_side[4];
-    float lat_thetap[4];
-    int32_t _pad2;
 } stdadk_fwd_args;
 
 /* Backward of one hidden block: recomputes z = A W^T (for block 1 this recomputes the basis),

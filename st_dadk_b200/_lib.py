@@ -47,8 +47,7 @@ class Head(C.Structure):
 class FwdArgs(C.Structure):
     _fields_ = [("basis", C.POINTER(Basis)), ("pts", Points), ("a_img", fp), ("layer", Layer), ("drop", Dropout),
                 ("out_img", fp), ("stats", fp), ("head", C.POINTER(Head)), ("addend", fp), ("feat_img", fp), ("x_img", fp),
-                ("a_img_lo", fp), ("out_img_lo", fp), ("lat_levels", C.c_int32), ("lat_side", C.c_int32 * 4),
-                ("lat_thetap", C.c_float * 4), ("_pad2", C.c_int32)]
+                ("a_img_lo", fp), ("out_img_lo", fp)]
 
 
 class BwdArgs(C.Structure):

@@ -10,7 +10,6 @@
 #include "sparse.cuh"
 #include "predict.cuh"
 #include "field.cuh"
-#include "lattice.cuh"
 
 using namespace stdadk;
 
@@ -316,46 +315,6 @@ int stdadk_layer_fwd(const stdadk_fwd_args* a, void* stream) {
     REQUIRE(sp.total <= 227 * 1024, "layer_fwd: needs %u B of shared memory (> 227 KB): too many knots for the dense path",
             sp.total);
     K.n_tiles = tiles;
-    // Fixed uniform lattice (upstream's default knots): the support-walking block-1 kernel, persistent, one CTA per SM.
-    if (basis && a->lat_levels >= 1 && a->lat_levels <= LT_MAX_LEVELS && !x3 && !a->feat_img && a->basis->p_cov == 0 &&
-        a->basis->basis_fn != STDADK_GAUSSIAN && a->basis->k_s < 8192 && getenv("STDADK_NO_LATTICE_WALK") == nullptr) {
-        LatP Lt{};
-        Lt.n_levels = a->lat_levels;
-        int off = 0;
-        bool ok = true;
-        for (int l = 0; l < a->lat_levels; ++l) {
-            const int side = a->lat_side[l];
-            const float th = a->lat_thetap[l];
-            ok = ok && side >= 2 && side <= LT_AXIS && th > 0.0f && th * (float)(side - 1) <= 2.5f + 1e-3f;
-            Lt.side[l] = side;
-            Lt.offset[l] = off;
-            Lt.th2[l] = th * th;              // same FP32 products as knots_prepare_kernel
-            Lt.inv_th[l] = 1.0f / th;
-            Lt.thg[l] = th * (float)(side - 1);
-            off += side * side;
-        }
-        ok = ok && off == a->basis->k_s;
-        if (ok) {
-            Lt.ks_aligned = (a->basis->k_s / 4) * 4;
-            int ns = 3;
-            LatSmem ls = plan_lattice(K.n_pad, K.has_head ? K.head.q : 0, K.basis.k_s, K.basis.k_t, ns);
-            if (ls.total > 227 * 1024) {
-                ns = 2;
-                ls = plan_lattice(K.n_pad, K.has_head ? K.head.q : 0, K.basis.k_s, K.basis.k_t, ns);
-            }
-            if (ls.total <= 227 * 1024) {
-                const int grid = tiles < sms ? tiles : sms;
-                if (a->basis->basis_fn == STDADK_WENDLAND) {
-                    if (int r = set_smem(layer_fwd_lattice_kernel<STDADK_WENDLAND>, ls.total)) return r;
-                    layer_fwd_lattice_kernel<STDADK_WENDLAND><<<grid, LT_NT, ls.total, (cudaStream_t)stream>>>(K, Lt, ns);
-                } else {
-                    if (int r = set_smem(layer_fwd_lattice_kernel<STDADK_TRIANGULAR>, ls.total)) return r;
-                    layer_fwd_lattice_kernel<STDADK_TRIANGULAR><<<grid, LT_NT, ls.total, (cudaStream_t)stream>>>(K, Lt, ns);
-                }
-                return check_launch("layer_fwd (lattice walk)");
-            }
-        }
-    }
     // Optional (STDADK_CLUSTER=1): clusters of 4 CTAs share every weight slab by multicast (L2 -> SM weight traffic / 4).
     // Bit-identical output, but measured SLOWER on B200 (1M-point prediction 2.25 ms vs 2.03 ms): the kernels are
     // issue/latency-bound, not L2-bound, and the cluster couples four tiles' pipelines.  Kept for L2-bound shapes.

@@ -138,7 +138,6 @@ class Executor:
         self._fused_ok = None
         self._field_ok = None
         self._cell_ws = None
-        self._lat_host = None
         self._w1sf_img = None
         self._w1sf_key = None
         self._zt_ws = None
@@ -203,7 +202,6 @@ class Executor:
         self._fused_ok = None
         self._field_ok = None
         self._w1sf_key = None
-        self._lat_host = None
 
     def _key(self):
         s = self.spec
@@ -277,32 +275,6 @@ class Executor:
         k_s = 0 if self.sparse else s.centers.shape[0]     # sparse regime: the tensor-core operand holds [X | psi] only
         return ops.make_basis(self.knots4, self.tknots2, k_s, s.t_centers.shape[0], s.p_cov, s.basis_fn)
 
-    def _set_lattice(self, a):
-        """Tell block 1 that the knots are upstream's fixed uniform lattice (sides, theta' per level), so that the kernel
-        can walk each point's support window in closed form."""
-        s = self.spec
-        if s.lattice_sides is None or s.learnable_basis or s.bandwidths is None or len(s.lattice_sides) > 4:
-            return
-        if self._lat_host is None:
-            import numpy as _np
-            sides = [int(v) for v in s.lattice_sides]
-            offs, o = [], 0
-            for sd in sides:
-                offs.append(o)
-                o += sd * sd
-            if o != s.centers.shape[0]:
-                self._lat_host = False
-                return
-            bw = s.bandwidths[torch.tensor(offs, device=s.bandwidths.device)].float().cpu().numpy()
-            calib = _np.float32(L.CALIBRATION[s.basis_fn])
-            self._lat_host = (sides, [float(_np.float32(b) * calib) for b in bw])
-        if not self._lat_host:
-            return
-        sides, ths = self._lat_host
-        a.lat_levels = len(sides)
-        for i, (sd, th) in enumerate(zip(sides, ths)):
-            a.lat_side[i], a.lat_thetap[i] = sd, th
-
     def _n_in(self, l: int) -> int:
         w = self.spec.weights[l]
         return w.shape[1] - (self.spec.centers.shape[0] if (l == 0 and self.sparse) else 0)
@@ -360,8 +332,6 @@ class Executor:
                 a.basis = C.pointer(basis)
                 if self.sparse:
                     a.addend = ws.zs.data_ptr()
-                else:
-                    self._set_lattice(a)
                 if save and ws.feat is not None:
                     a.feat_img = ws.feat.data_ptr()
             else:

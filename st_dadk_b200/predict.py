@@ -241,7 +241,6 @@ class Predictor:
         a.pts = ops.make_points(coords, t)
         a.basis = C.pointer(basis)
         a.layer = ex._layer(0)
-        ex._set_lattice(a)
         a.drop = L.Dropout(0.0, 0, 0, None, 0)
         a.out_img = ws.h[0].data_ptr()
         if ex.x3:

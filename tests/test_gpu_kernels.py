@@ -737,40 +737,3 @@ def test_support_walk_at_real_size_99812_knots_vs_oracle():
     assert ex2.sparse and ex2.lat is None
     yb = ex2.forward(pts, train=False).cpu().numpy()
     assert rel_l2(yb, y64) < 1e-3 and rel_l2(ya, yb) < 1e-4      # same index sets, different FP32 summation order
-
-
-@pytest.mark.parametrize("fn,n,q,p", [("wendland", 1000, 1, 0.1), ("triangular", 333, 3, 0.0), ("wendland", 70_001, 1, 0.0)])
-def test_lattice_walk_block1_equals_dense_generator_bit_for_bit(fn, n, q, p):
-    """Block 1 on upstream's fixed uniform lattice: the support-walking kernel (closed-form 6 x 6 window per level,
-    per-row lists scattered into zero-filled operand slabs, persistent CTAs) must produce the operand the dense generator
-    produces -- same predicate, same knot coordinates, same polynomial -- so outputs, loss and every gradient of a
-    training step are identical bit for bit (dropout on, ragged last tile, several tiles per CTA at 70,001 rows)."""
-    L, ops, Executor, NetSpec, LossSpec = _mods()
-    m = _default_oracle_model(7 + q, q=q, fn=fn)
-    rng = np.random.default_rng(2)
-    coords = rng.random((n, 2)).astype(np.float32)
-    coords[:6] = [[0, 0], [1, 1], [0.5, 0.5], [1, 0], [0.25, 0.75], [0.1, 0.9]]      # on knots / lattice lines / corners
-    t = rng.random((n, 1)).astype(np.float32)
-    y = rng.standard_normal(n).astype(np.float32)
-    taus = [0.1, 0.5, 0.9] if q == 3 else None
-    loss = LossSpec("pinball", taus) if q == 3 else LossSpec("mse")
-    outs = []
-    for lattice in (True, False):
-        spec = spec_from_oracle(m, dropout=p)
-        spec.lattice_sides = [5, 9, 11] if lattice else None
-        ex = Executor(spec)
-        ex.loss_acc.zero_()
-        pts = ops.make_points(T(coords), T(t))
-        yhat = ex.forward(pts, train=True, step=3, seed=99, y=T(y), loss=loss, inv_count=1.0 / (n * q), save=True).clone()
-        g = ex.backward()
-        torch.cuda.synchronize()
-        outs.append((yhat, ex.loss_acc.clone(), g["weights"][0].clone(), g["biases"][0].clone(), g["weights"][2].clone()))
-    (ya, la, wa, ba, w2a), (yb, lb, wb, bb, w2b) = outs
-    assert torch.equal(ya, yb)
-    assert abs(la.item() - lb.item()) <= 1e-6 * abs(lb.item())          # the loss is accumulated with atomics
-    # gradients: same inputs to the same backward kernels; only atomic accumulation order differs
-    for a, b in ((wa, wb), (ba, bb), (w2a, w2b)):
-        assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max())
-    yref = orc.forward(m, None, coords[:2000], t[:2000], train=True,
-                       keep_masks=[orc.dropout_keep_mask(min(n, 2000), w.shape[0], p, 99, 3, l, 0) for l, w in enumerate(m.weights[:-1])])
-    assert rel_err(ya[:2000].cpu().numpy(), yref) < 1e-3
