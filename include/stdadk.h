@@ -324,6 +324,9 @@ typedef struct {
     const stdadk_head* head;
     int64_t row_base;
     float* zt_ws;
+    int64_t out_k_stride;     /* rows of yhat between consecutive time steps: point (k, site) is written to row
+                                 k * out_k_stride + site - row_base.  0 = n_sites (the (t, s) row-major field).  A site-sharded
+                                 rank passes its own site count and row_base = site_begin: a dense (n_times, sites) block */
 } stdadk_field_args;
 int stdadk_predict_field_supported(const stdadk_field_args* a);   /* 1 yes, 0 no (reason in stdadk_last_error) */
 int stdadk_predict_field(const stdadk_field_args* a, void* stream);
@@ -370,7 +373,10 @@ typedef struct {
     int64_t n;
     void* recv[STDADK_MAX_PEERS];
     const int32_t* step_count;
-    int32_t n_groups, _pad;
+    int32_t n_groups;
+    int32_t mode;               /* 0 = automatic, 1 = one-shot (every rank pushes everything to every peer, one NVLink
+                                   traversal), 2 = two-phase (chunk owners reduce and publish: ~4x fewer bytes at 8 ranks,
+                                   two traversals; automatic choice from 4 ranks on).  Same bits either way. */
     const int64_t* group_end;   /* host array (n_groups), last entry = n_norm */
     float* sqnorms;
     float* workspace;

@@ -105,7 +105,7 @@ class FieldArgs(C.Structure):
                 ("n_sites", C.c_int64), ("n_times", C.c_int32), ("k_begin", C.c_int32), ("k_end", C.c_int32),
                 ("n_layers", C.c_int32), ("site_begin", C.c_int64), ("site_end", C.c_int64),
                 ("layers", Layer * MAX_HIDDEN), ("w1", fp), ("w1_row_stride", C.c_int64), ("w1_col_stride", C.c_int64),
-                ("head", C.POINTER(Head)), ("row_base", C.c_int64), ("zt_ws", fp)]
+                ("head", C.POINTER(Head)), ("row_base", C.c_int64), ("zt_ws", fp), ("out_k_stride", C.c_int64)]
 
 
 MAX_PEERS = 8
@@ -113,7 +113,7 @@ MAX_PEERS = 8
 
 class PeerAllreduceArgs(C.Structure):
     _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("g", fp), ("n", C.c_int64), ("recv", fp * MAX_PEERS),
-                ("step_count", fp), ("n_groups", C.c_int32), ("_pad", C.c_int32), ("group_end", C.POINTER(C.c_int64)),
+                ("step_count", fp), ("n_groups", C.c_int32), ("mode", C.c_int32), ("group_end", C.POINTER(C.c_int64)),
                 ("sqnorms", fp), ("workspace", fp)]
 
 

@@ -311,7 +311,8 @@ int stdadk_layer_fwd(const stdadk_fwd_args* a, void* stream) {
     const int sms = g_sm_count > 0 ? g_sm_count : 148;
     const int cg = tiles >= 2 * sms ? 2 : 4;
     const int ns = cg == 2 ? 2 : 4;   // 1 CTA/SM in the latency configuration: spend the shared memory on pipeline depth
-    SmemPlan sp = plan_smem(K.n_pad, K.has_head ? K.head.q : 0, basis ? K.basis.k_s : 0, basis ? K.basis.k_t : 0, false, cg, ns);
+    SmemPlan sp = plan_smem(K.n_pad, K.has_head ? K.head.q : 0, basis ? K.basis.k_s : 0, basis ? K.basis.k_t : 0, false, cg, ns,
+                            basis ? K.k_slabs * 8 : 0);
     REQUIRE(sp.total <= 227 * 1024, "layer_fwd: needs %u B of shared memory (> 227 KB): too many knots for the dense path",
             sp.total);
     K.n_tiles = tiles;
@@ -435,6 +436,7 @@ static int field_fill(const stdadk_field_args* a, FieldK* K) {
     REQUIRE(!a->sites || (reinterpret_cast<uintptr_t>(a->sites) & 7) == 0, "predict_field: sites must be 8-byte aligned");
     REQUIRE(0 <= a->k_begin && a->k_begin <= a->k_end && a->k_end <= a->n_times, "predict_field: time range");
     REQUIRE(0 <= a->site_begin && a->site_begin <= a->site_end && a->site_end <= a->n_sites, "predict_field: site range");
+    REQUIRE(a->out_k_stride >= 0, "predict_field: out_k_stride");
     REQUIRE(a->head->q >= 1 && a->head->q <= STDADK_MAX_Q && a->head->w && a->head->b && a->head->yhat,
             "predict_field: head q / w / b / yhat");
     REQUIRE(a->w1 && a->zt_ws && (reinterpret_cast<uintptr_t>(a->zt_ws) & 15) == 0, "predict_field: w1 / zt_ws");
@@ -456,6 +458,7 @@ static int field_fill(const stdadk_field_args* a, FieldK* K) {
     K->head_b = a->head->b;
     K->yhat = a->head->yhat;
     K->row_base = a->row_base;
+    K->out_k_stride = a->out_k_stride > 0 ? a->out_k_stride : a->n_sites;
     K->zt = a->zt_ws;
     K->dbg = g_predict_dbg;
     for (int l = 0; l < a->n_layers; ++l) {
@@ -867,6 +870,8 @@ int stdadk_peer_allreduce(const stdadk_peer_allreduce_args* a, void* stream) {
     K.step_count = a->step_count;
     K.rank = a->rank;
     K.world = a->world;
+    REQUIRE(a->mode >= 0 && a->mode <= 2, "peer_allreduce: mode=%d (0 automatic, 1 one-shot, 2 two-phase)", a->mode);
+    K.two_phase = a->mode == 2 || (a->mode == 0 && a->world >= 4);
     if (a->n_groups > 0) {
         REQUIRE(a->group_end && a->sqnorms && a->workspace, "peer_allreduce: fused norm needs group_end / sqnorms / workspace");
         K.n_norm = a->group_end[a->n_groups - 1];

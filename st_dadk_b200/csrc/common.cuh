@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 
 #include "../../include/stdadk.h"
 #include "ptx.cuh"

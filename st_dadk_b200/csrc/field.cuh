@@ -41,8 +41,8 @@ struct FieldK {
     const float* zt;                    // (T, n_pad of block 1): W1[:, temporal] psi(t_k) + b1, zero in the padding columns
     const float* head_w;
     const float* head_b;
-    float* yhat;                        // row (k * S + site) - row_base
-    long long row_base;
+    float* yhat;                        // row k * out_k_stride + site - row_base
+    long long row_base, out_k_stride;
     int n_layers, q;
     unsigned long long* dbg;            // optional cycle counters (-DSTDADK_PF_DEBUG builds), NULL in production
 };
@@ -426,7 +426,7 @@ __global__ void __launch_bounds__(PF_NT, 1) predict_field_kernel(const __grid_co
                         }
                         worker_barrier(PF_NW);
                         if (cg == 0 && rvalid) {
-                            float* dst = P.yhat + ((long long)k * P.n_sites + site - P.row_base) * P.q;
+                            float* dst = P.yhat + ((long long)k * P.out_k_stride + site - P.row_base) * P.q;
 #pragma unroll
                             for (int kk = 0; kk < STDADK_MAX_Q; ++kk)
                                 if (kk < P.q) {

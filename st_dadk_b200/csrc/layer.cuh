@@ -29,7 +29,10 @@ __device__ __forceinline__ void worker_barrier(int nw) { asm volatile("bar.sync 
 struct SmemPlan {
     uint32_t a_off, b_off, bar_off, tmem_off, vec_off, headw_off, knots_off, tknots_off, colsum_off, red_off, total;
 };
-__host__ __device__ inline SmemPlan plan_smem(int n_pad, int q, int k_s, int k_t, bool bwd, int cg = 1, int ns = 2) {
+// tab_chunks > 0 (forward kernel of block 1): the knot tables are the chunk-indexed SoA tables of gen_basis_slab_soa
+// (64 bytes per 4-feature chunk) instead of the knots4 / tknots2 copies.
+__host__ __device__ inline SmemPlan plan_smem(int n_pad, int q, int k_s, int k_t, bool bwd, int cg = 1, int ns = 2,
+                                              int tab_chunks = 0) {
     SmemPlan s;
     uint32_t o = 0;
     s.a_off = o; o += ns * SLAB_BYTES;
@@ -39,8 +42,8 @@ __host__ __device__ inline SmemPlan plan_smem(int n_pad, int q, int k_s, int k_t
     s.vec_off = o; o += 4u * n_pad * 4u;                 // per column (bias, gamma, beta, -)
     s.headw_off = o; o += (uint32_t)(q > 0 ? (q * n_pad + STDADK_MAX_Q) * 4 : 0);
     o = (o + 15u) & ~15u;
-    s.knots_off = o; o += (uint32_t)k_s * 16u;
-    s.tknots_off = o; o += (uint32_t)k_t * 8u;
+    s.knots_off = o; o += tab_chunks > 0 ? (uint32_t)tab_chunks * 64u : (uint32_t)k_s * 16u;
+    s.tknots_off = o; o += tab_chunks > 0 ? 0u : (uint32_t)k_t * 8u;
     o = (o + 15u) & ~15u;
     s.colsum_off = o; o += bwd ? (uint32_t)((3 + q) * n_pad + STDADK_MAX_Q) * 4u : 0u;
     s.red_off = s.a_off;   // epilogue scratch reuses the operand stages, which are dead once the last MMA committed
@@ -143,6 +146,113 @@ __device__ __forceinline__ float4 feature_chunk(const BasisP& B, const float4* s
                        tf32_part(feature_value(B, sk, st, f + 1, x, y, t, xrow), lo),
                        tf32_part(feature_value(B, sk, st, f + 2, x, y, t, xrow), lo),
                        tf32_part(feature_value(B, sk, st, f + 3, x, y, t, xrow), lo));
+}
+
+// ---- chunk-indexed tables of the forward generator.  Entry ci (64 bytes) describes features [4 ci, 4 ci + 4) when they
+// are all spatial (cx[4], cy[4], theta'^2[4], 1/theta'[4]) or all temporal (c[4], 1/bw[4], -, -): structure-of-arrays,
+// so that one LDS.128 fills a register quad that the packed FP32 instructions (two values per issue slot) consume
+// directly.  Mixed chunks (block boundaries, at most three per row) go through feature_value on the global tables.
+__device__ __forceinline__ int chunk_kind(const BasisP& B, int f) {
+    const int s0 = B.p_cov, s1 = s0 + B.k_s, t1 = s1 + B.k_t;
+    if (f >= s0 && f + 4 <= s1) return 0;
+    if (f >= s1 && f + 4 <= t1) return 1;
+    if (f >= t1) return 2;
+    return 3;
+}
+__device__ __forceinline__ void build_chunk_tables(const BasisP& B, float4* tab, int n_chunks, int tid, int nt) {
+    for (int ci = tid; ci < n_chunks; ci += nt) {
+        const int f = 4 * ci, kind = chunk_kind(B, f);
+        float4* g = tab + 4 * ci;
+        if (kind == 0) {
+            const float4* kp = B.knots + (f - B.p_cov);
+            const float4 k0 = kp[0], k1 = kp[1], k2 = kp[2], k3 = kp[3];
+            g[0] = make_float4(k0.x, k1.x, k2.x, k3.x);
+            g[1] = make_float4(k0.y, k1.y, k2.y, k3.y);
+            g[2] = make_float4(k0.z, k1.z, k2.z, k3.z);
+            g[3] = make_float4(k0.w, k1.w, k2.w, k3.w);
+        } else if (kind == 1) {
+            const float2* tp = B.tknots + (f - B.p_cov - B.k_s);
+            const float2 t0 = tp[0], t1 = tp[1], t2 = tp[2], t3 = tp[3];
+            g[0] = make_float4(t0.x, t1.x, t2.x, t3.x);
+            g[1] = make_float4(t0.y, t1.y, t2.y, t3.y);
+        }
+    }
+}
+// Same arithmetic, operation by operation, as spatial_chunk / phi_from_d2 (the packed instructions round like the
+// scalar ones), so the operand is bit-identical to what the backward and the prediction kernels regenerate.
+template <int FN, bool LO>
+__device__ __forceinline__ float4 spatial_chunk_soa(const float4* g, float2 xx, float2 yy) {
+    constexpr bool lo = LO;
+    const float4 cx = g[0], cy = g[1], th2 = g[2], ith = g[3];
+    const float2 dxa = sub2(xx, make_float2(cx.x, cx.y)), dxb = sub2(xx, make_float2(cx.z, cx.w));
+    const float2 dya = sub2(yy, make_float2(cy.x, cy.y)), dyb = sub2(yy, make_float2(cy.z, cy.w));
+    // the sums stay scalar: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (seen in SASS, CUDA 12.9), which
+    // would change d2 -- and with it the support predicate -- in the last bit
+    const float2 pxa = mul2(dxa, dxa), pya = mul2(dya, dya), pxb = mul2(dxb, dxb), pyb = mul2(dyb, dyb);
+    const float2 d2a = make_float2(__fadd_rn(pxa.x, pya.x), __fadd_rn(pxa.y, pya.y));
+    const float2 d2b = make_float2(__fadd_rn(pxb.x, pyb.x), __fadd_rn(pxb.y, pyb.y));
+    const bool i0 = d2a.x < th2.x, i1 = d2a.y < th2.y, i2 = d2b.x < th2.z, i3 = d2b.y < th2.w;
+    if (FN == STDADK_GAUSSIAN) {
+        const float2 ia = make_float2(ith.x, ith.y), ib = make_float2(ith.z, ith.w);
+        const float2 kk = make_float2(-0.72134752044448170f, -0.72134752044448170f);
+        const float2 ea = mul2(kk, mul2(mul2(d2a, ia), ia)), eb = mul2(kk, mul2(mul2(d2b, ib), ib));
+        return make_float4(tf32_part(ex2_approx(ea.x), lo), tf32_part(ex2_approx(ea.y), lo), tf32_part(ex2_approx(eb.x), lo),
+                           tf32_part(ex2_approx(eb.y), lo));
+    }
+    // ordered points (grids, sorted sites): most chunks are outside every row's support -> one vote, no evaluation
+    if (!__any_sync(__activemask(), i0 | i1 | i2 | i3)) return make_float4(0.f, 0.f, 0.f, 0.f);
+    const float2 qa = make_float2(rsqrt_approx(fmaxf(d2a.x, 1e-30f)), rsqrt_approx(fmaxf(d2a.y, 1e-30f)));
+    const float2 qb = make_float2(rsqrt_approx(fmaxf(d2b.x, 1e-30f)), rsqrt_approx(fmaxf(d2b.y, 1e-30f)));
+    const float2 ra = mul2(mul2(d2a, qa), make_float2(ith.x, ith.y)), rb = mul2(mul2(d2b, qb), make_float2(ith.z, ith.w));
+    const float2 one = make_float2(1.0f, 1.0f);
+    float2 ua = sub2(one, ra), ub = sub2(one, rb);
+    ua = make_float2(fmaxf(ua.x, 0.0f), fmaxf(ua.y, 0.0f));
+    ub = make_float2(fmaxf(ub.x, 0.0f), fmaxf(ub.y, 0.0f));
+    float2 va = ua, vb = ub;
+    if (FN == STDADK_WENDLAND) {
+        const float2 c35 = make_float2(35.0f / 3.0f, 35.0f / 3.0f), c6 = make_float2(6.0f, 6.0f);
+        const float2 u2a = mul2(ua, ua), u2b = mul2(ub, ub);
+        va = mul2(mul2(mul2(u2a, u2a), u2a), fma2(fma2(c35, ra, c6), ra, one));
+        vb = mul2(mul2(mul2(u2b, u2b), u2b), fma2(fma2(c35, rb, c6), rb, one));
+    }
+    return make_float4(tf32_part(i0 ? va.x : 0.0f, lo), tf32_part(i1 ? va.y : 0.0f, lo), tf32_part(i2 ? vb.x : 0.0f, lo),
+                       tf32_part(i3 ? vb.y : 0.0f, lo));
+}
+template <bool LO>
+__device__ __forceinline__ float4 temporal_chunk_soa(const float4* g, float2 tt) {
+    constexpr bool lo = LO;
+    const float4 c = g[0], ib = g[1];
+    const float2 kk = make_float2(-0.72134752044448170f, -0.72134752044448170f);
+    const float2 sa = mul2(sub2(tt, make_float2(c.x, c.y)), make_float2(ib.x, ib.y));
+    const float2 sb = mul2(sub2(tt, make_float2(c.z, c.w)), make_float2(ib.z, ib.w));
+    const float2 ea = mul2(mul2(kk, sa), sa), eb = mul2(mul2(kk, sb), sb);
+    return make_float4(tf32_part(ex2_approx(ea.x), lo), tf32_part(ex2_approx(ea.y), lo), tf32_part(ex2_approx(eb.x), lo),
+                       tf32_part(ex2_approx(eb.y), lo));
+}
+// chunks [c_begin, c_end) of operand slab `slab` of row r, from the chunk tables (forward kernel)
+template <int FN, bool LO>
+__device__ __forceinline__ void gen_basis_slab_soa(const BasisP& B, const float4* tab, int slab, float x, float y, float t,
+                                                   const float* xrow, uint32_t slab_saddr, uint32_t r, int c_begin, int c_end,
+                                                   float* gslab) {
+    constexpr bool lo = LO;
+    const float2 xx = make_float2(x, x), yy = make_float2(y, y), tt = make_float2(t, t);
+    const uint32_t rbase = slab_saddr + r * 128u, r7 = r & 7u;
+    uint8_t* grow = gslab ? reinterpret_cast<uint8_t*>(gslab) + r * 128u : nullptr;
+#pragma unroll 1
+    for (int c = c_begin; c < c_end; ++c) {
+        const int f = slab * SLAB_K + 4 * c, kind = chunk_kind(B, f);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kind == 0) v = spatial_chunk_soa<FN, LO>(tab + f, xx, yy);
+        else if (kind == 1) v = temporal_chunk_soa<LO>(tab + f, tt);
+        else if (kind == 3)
+            v = make_float4(tf32_part(feature_value(B, B.knots, B.tknots, f + 0, x, y, t, xrow), lo),
+                            tf32_part(feature_value(B, B.knots, B.tknots, f + 1, x, y, t, xrow), lo),
+                            tf32_part(feature_value(B, B.knots, B.tknots, f + 2, x, y, t, xrow), lo),
+                            tf32_part(feature_value(B, B.knots, B.tknots, f + 3, x, y, t, xrow), lo));
+        const uint32_t so = ((uint32_t)c ^ r7) << 4;
+        st_shared_v4(rbase + so, v.x, v.y, v.z, v.w);
+        if (grow) *reinterpret_cast<float4*>(grow + so) = v;
+    }
 }
 
 // Generate chunks [c_begin, c_end) of one 128-row x 32-feature operand slab (this thread = row r) into swizzled SMEM.
@@ -574,21 +684,19 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = align_smem(smem_raw);
     const SmemPlan sp = plan_smem(P.n_pad, P.has_head ? P.head.q : 0, BASIS ? P.basis.k_s : 0,
-                                  BASIS ? P.basis.k_t : 0, false, CG, NS);
+                                  BASIS ? P.basis.k_t : 0, false, CG, NS, BASIS ? P.k_slabs * 8 : 0);
     float* sA = reinterpret_cast<float*>(smem + sp.a_off);
     float* sB = reinterpret_cast<float*>(smem + sp.b_off);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + sp.bar_off);
     uint64_t* empty = full + NSTAGE;
     uint64_t* accf = full + 2 * NSTAGE;
-    uint64_t* kbar = accf + 1;                                       // knot tables have landed (BASIS)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + sp.tmem_off);
     float* sbias = reinterpret_cast<float*>(smem + sp.vec_off);    // per column bias | gamma | beta (one LDS.128 per 4 columns)
     float* sgam = sbias + P.n_pad;
     float* sbet = sgam + P.n_pad;
     float* shw = reinterpret_cast<float*>(smem + sp.headw_off);
     float* shb = shw + (P.has_head ? P.head.q * P.n_pad : 0);
-    float4* sk = reinterpret_cast<float4*>(smem + sp.knots_off);
-    float2* st = reinterpret_cast<float2*>(smem + sp.tknots_off);
+    float4* ctab = reinterpret_cast<float4*>(smem + sp.knots_off);  // chunk tables of the generator (BASIS)
     float* red = reinterpret_cast<float*>(smem + sp.red_off);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -605,14 +713,13 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
             mbar_init(&empty[s], CL);        // every CTA of the cluster must have consumed the stage
         }
         mbar_init(accf, 1);
-        mbar_init(kbar, 1);
         mbar_fence_init();
-        if (BASIS) stage_knots_async(P.basis, sk, st, kbar);
     }
     if (warp == 4 * CG) {
         __syncwarp();
         tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
     }
+    if (BASIS) build_chunk_tables(P.basis, ctab, P.k_slabs * 8, tid, NT);
     for (int i = tid; i < n_pad; i += NT) {
         bool ok = i < n_out;
         sbias[i] = ok ? P.L.bias[i] : 0.0f;
@@ -683,19 +790,30 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
                 load_point(P.pts, grow, x, y, t);
                 if (P.basis.p_cov > 0 && P.pts.xcov) xrow = P.pts.xcov + sample_of(P.pts, grow) * P.basis.p_cov;
             }
-            mbar_wait(kbar, 0);
-            const int n_virt = P.k_slabs * P.passes;
-            for (int v = 0; v < n_virt; ++v) {
-                const int s = v / P.passes, p = v - s * P.passes;
-                int stage = v % NSTAGE, it = v / NSTAGE;
-                if (it > 0) mbar_wait(&empty[stage], (it - 1) & 1);
-                gen_basis_slab(P.basis, sk, st, s, x, y, t, xrow, smem_u32(sA + (size_t)stage * SLAB_FLOATS),
-                               (uint32_t)row, cg * (8 / CG), (cg + 1) * (8 / CG),
-                               (P.feat_img && tile_valid && p == 0) ? P.feat_img + ((size_t)tile * P.k_slabs + s) * SLAB_FLOATS : nullptr,
-                               pass_a_lo(p));
-                fence_proxy_async_smem();
-                mbar_arrive(&full[stage]);
-            }
+            // one instantiation of the slab loop per basis function: the generator's inner code has no runtime switch
+            auto gen_all = [&](auto fn_tag) {
+                constexpr int FN = decltype(fn_tag)::value;
+                int stage = 0, it = 0;
+                for (int s = 0; s < P.k_slabs; ++s) {
+                    float* gslab = (P.feat_img && tile_valid) ? P.feat_img + ((size_t)tile * P.k_slabs + s) * SLAB_FLOATS : nullptr;
+                    for (int p = 0; p < P.passes; ++p) {
+                        if (it > 0) mbar_wait(&empty[stage], (it - 1) & 1);
+                        const uint32_t sa = smem_u32(sA + (size_t)stage * SLAB_FLOATS);
+                        if (pass_a_lo(p))
+                            gen_basis_slab_soa<FN, true>(P.basis, ctab, s, x, y, t, xrow, sa, (uint32_t)row, cg * (8 / CG),
+                                                         (cg + 1) * (8 / CG), nullptr);
+                        else
+                            gen_basis_slab_soa<FN, false>(P.basis, ctab, s, x, y, t, xrow, sa, (uint32_t)row, cg * (8 / CG),
+                                                          (cg + 1) * (8 / CG), p == 0 ? gslab : nullptr);
+                        fence_proxy_async_smem();
+                        mbar_arrive(&full[stage]);
+                        if (++stage == NSTAGE) { stage = 0; ++it; }
+                    }
+                }
+            };
+            if (P.basis.fn == STDADK_WENDLAND) gen_all(std::integral_constant<int, STDADK_WENDLAND>{});
+            else if (P.basis.fn == STDADK_TRIANGULAR) gen_all(std::integral_constant<int, STDADK_TRIANGULAR>{});
+            else gen_all(std::integral_constant<int, STDADK_GAUSSIAN>{});
         }
         // ---------------- epilogue
         mbar_wait(accf, 0);

@@ -239,6 +239,16 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) {
         : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
     return d;
 }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "mul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+// a - b with the subtraction's own single rounding: b * (-1) is exact inside the fma
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return fma2(b, make_float2(-1.0f, -1.0f), a); }
 __device__ __forceinline__ void st_shared_v4(uint32_t saddr, float a, float b, float c, float d) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }

@@ -441,7 +441,7 @@ class Executor:
         return True
 
     # ------------------------------------------------------------------ space-time field prediction
-    def _field_args(self, sites, grid, n_sites, n_times, k0, k1, s0, s1, yhat, row_base) -> L.FieldArgs:
+    def _field_args(self, sites, grid, n_sites, n_times, k0, k1, s0, s1, yhat, row_base, out_k_stride=0) -> L.FieldArgs:
         s = self.spec
         k_s = s.centers.shape[0]
         w1 = s.weights[0]
@@ -469,6 +469,7 @@ class Executor:
         a.w1_row_stride, a.w1_col_stride = w1.stride(0), w1.stride(1)
         a.head = C.pointer(head)
         a.row_base = row_base
+        a.out_k_stride = out_k_stride
         a.zt_ws = self._zt_ws.data_ptr()
         return a
 
@@ -510,6 +511,17 @@ class Executor:
         for (ka, kb, sa, sb) in rects:
             ops.predict_field(self._field_args(sites, grid, S, n_times, ka, kb, sa, sb, yhat, begin))
         return 2 * len(rects)
+
+    def predict_field_sites(self, yhat: torch.Tensor, site_begin: int, site_end: int, n_sites: int, n_times: int,
+                            sites: Optional[torch.Tensor] = None, grid: Optional[Tuple[int, int]] = None) -> int:
+        """Sites [site_begin, site_end) at ALL n_times steps into yhat viewed as (n_times, site_end - site_begin, Q):
+        one rectangle, one launch pair.  The sharding for several GPUs: the per-site work (basis + spatial part of
+        block 1) is done once per site on exactly one rank, as on a single GPU."""
+        if site_end <= site_begin:
+            return 0
+        ops.predict_field(self._field_args(sites, grid, n_sites, n_times, 0, n_times, site_begin, site_end, yhat,
+                                           site_begin, site_end - site_begin))
+        return 2
 
     # ------------------------------------------------------------------ backward
     def alloc_grads(self, flat: Optional[torch.Tensor] = None, views: Optional[dict] = None):

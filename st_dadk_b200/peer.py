@@ -11,6 +11,7 @@ NCCL all-reduce (bandwidth-bound exchanges are NCCL's home ground; this path is 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence
 
 import torch
@@ -41,6 +42,7 @@ class PeerExchange:
         self.ws = torch.zeros(148 * 8 + 8, dtype=torch.float32, device=self.device)
         a = L.PeerAllreduceArgs()
         a.world, a.rank, a.n = self.world, self.rank, self.n
+        a.mode = int(os.environ.get("STDADK_PEER_MODE", "0"))     # 0 automatic, 1 one-shot, 2 two-phase (include/stdadk.h)
         for r, p in enumerate(self.handle.buffer_ptrs):
             a.recv[r] = p
         self._args = a

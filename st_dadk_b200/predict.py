@@ -93,6 +93,28 @@ class Predictor:
         return out, (begin, end)
 
     @torch.no_grad()
+    def grid_by_sites(self, nx: int, ny: int, nt: int, rank: int = 0, world: int = 1, out: Optional[torch.Tensor] = None):
+        """The same (nt, nx, ny) grid sharded by SITE: this rank's sites [s0, s1) of the nx*ny lattice at all nt time steps;
+        returns (yhat (nt, s1 - s0, Q), (s0, s1)) -- concatenating the ranks' results along dim 1 gives the (nt, nx*ny, Q)
+        field.  Every point is computed by exactly one rank and has the value `grid` gives it.  With contiguous point
+        blocks (`grid`) a rank of an 8-GPU job owns ~nt/8 time steps of every site and repeats the per-site work of
+        the field kernel (basis + spatial part of block 1) that a single GPU does once for all nt steps; by sites the
+        work per point is the single-GPU one at every world size."""
+        self._prepare()
+        S = nx * ny
+        s0, s1 = shard_range(S, rank, world)
+        q = self.model.output_dim
+        if out is None:
+            out = torch.empty(nt, s1 - s0, q, device=self.ex.device)
+        self.used_field_kernel = self.use_field_kernel and self.ex.field_supported()
+        if self.used_field_kernel:
+            self.launches += self.ex.predict_field_sites(out, s0, s1, S, nt, grid=(nx, ny))
+            return out, (s0, s1)
+        for k in range(nt):       # generic kernels: one block of rows per time step
+            self._run(lambda b, r: ops.make_points(grid=(nx, ny, nt), row_begin=b, n_rows=r), k * S + s0, k * S + s1, out[k])
+        return out, (s0, s1)
+
+    @torch.no_grad()
     def points(self, coords: torch.Tensor, t: torch.Tensor, X: Optional[torch.Tensor] = None, rank: int = 0,
                world: int = 1, out: Optional[torch.Tensor] = None):
         """This rank's block of an explicit point set (coords (N,2), t (N,) or (N,1)) resident on the device."""
@@ -178,6 +200,40 @@ class Predictor:
             self.host_copy_done.record(self._copy_stream)
             res.record_stream(self._copy_stream)
         return res, (begin, end)
+
+    @torch.no_grad()
+    def space_time_field_by_sites(self, coords: torch.Tensor, T: int, rank: int = 0, world: int = 1):
+        """The (T, S) field sharded by SITE: this rank's sites [s0, s1) (in the caller's order) at all T time steps;
+        returns (yhat (T, s1 - s0, Q), (s0, s1)); the ranks' results concatenated along dim 1 are the field.  Same values
+        as `space_time_field`; the per-site work of the field kernel is not repeated across ranks (see grid_by_sites)."""
+        self._prepare()
+        S = coords.shape[0]
+        s0, s1 = shard_range(S, rank, world)
+        n, q, dev = s1 - s0, self.model.output_dim, coords.device
+        key = ("by_sites", coords.data_ptr(), coords._version, S, T, s0, s1)
+        if self._field_key != key:
+            cf = coords[s0:s1].float()
+            # neighbours in a warp share their support (one vote skips a knot chunk): visit the sites in x strips
+            order = torch.argsort(torch.floor(cf[:, 0] * 32.0) * 2.0 + cf[:, 1]) if n >= 256 else None
+            self._field_sites = (cf.index_select(0, order) if order is not None else cf).contiguous()
+            self._field_key, self._field_pts = key, (None, None, order)
+        order = self._field_pts[2]
+        self.used_field_kernel = self.use_field_kernel and self.ex.field_supported()
+        out = torch.empty(T, n, q, device=dev)
+        if n == 0:
+            return out, (s0, s1)
+        if self.used_field_kernel:
+            self.launches += self.ex.predict_field_sites(out, 0, n, n, T, sites=self._field_sites)
+        else:
+            cc = self._field_sites.repeat(T, 1)
+            tt = (torch.arange(T, device=dev).repeat_interleave(n).float() / float(T - 1)) if T > 1 else \
+                torch.zeros(T * n, device=dev)
+            self._run(lambda b, r: ops.make_points(cc, tt, None, row_begin=b, n_rows=r), 0, T * n, out.view(T * n, q))
+        if order is None:
+            return out, (s0, s1)
+        res = torch.empty_like(out)
+        res.index_copy_(1, order, out)
+        return res, (s0, s1)
 
     @torch.no_grad()
     def profile_layers(self, nx: int, ny: int, nt: int, repeats: int = 3):

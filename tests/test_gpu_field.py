@@ -57,6 +57,13 @@ def test_field_kernel_matches_generic_kernel_and_oracle(q, hidden, fn, ln, S, T)
     for world in (2, 3, 7):
         parts = [pr.space_time_field(sites, T, r, world)[0] for r in range(world)]
         assert torch.equal(torch.cat(parts), field), world
+    # sharded by site: the same bits as a (T, S, Q) field
+    for world in (1, 3):
+        parts = [pr.space_time_field_by_sites(sites, T, r, world)[0] for r in range(world)]
+        assert pr.used_field_kernel
+        assert torch.equal(torch.cat(parts, dim=1), field.view(T, S, q)), world
+    parts = [gen.space_time_field_by_sites(sites, T, r, 2)[0] for r in range(2)]
+    assert torch.equal(torch.cat(parts, dim=1), ref.view(T, S, q))
 
 
 def test_field_kernel_grid_equals_explicit_sites_and_shards():
@@ -78,3 +85,13 @@ def test_field_kernel_grid_equals_explicit_sites_and_shards():
     for world in (2, 5, 8):
         parts = [pr.grid(nx, ny, nt, r, world)[0] for r in range(world)]
         assert torch.equal(torch.cat(parts), out), world
+    # sharded by SITE (every rank: its sites at all time steps): the same bits, as an (nt, S, Q) field
+    field = out.view(nt, nx * ny, 2)
+    for world in (1, 3, 8):
+        parts = [pr.grid_by_sites(nx, ny, nt, r, world) for r in range(world)]
+        assert parts[0][1][0] == 0 and parts[-1][1][1] == nx * ny
+        assert all(parts[i][1][1] == parts[i + 1][1][0] for i in range(world - 1))
+        assert torch.equal(torch.cat([p[0] for p in parts], dim=1), field), world
+    # ... and through the generic kernels (field kernel off)
+    parts = [gen.grid_by_sites(nx, ny, nt, r, 3)[0] for r in range(3)]
+    assert torch.equal(torch.cat(parts, dim=1), ref.view(nt, nx * ny, 2))
