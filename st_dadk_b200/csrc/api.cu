@@ -258,6 +258,7 @@ static int check_layer(const stdadk_layer& l, const char* who) {
     return 0;
 }
 
+static unsigned long long* g_predict_dbg = nullptr;   // stdadk_debug_counters (profiling builds)
 int stdadk_layer_fwd(const stdadk_fwd_args* a, void* stream) {
     if (int r = check_device()) return r;
     REQUIRE(a, "layer_fwd: NULL args");
@@ -296,6 +297,7 @@ int stdadk_layer_fwd(const stdadk_fwd_args* a, void* stream) {
     K.addend = a->addend;
     K.x_img = a->x_img;
     K.feat_img = a->basis ? a->feat_img : nullptr;
+    K.dbg = g_predict_dbg;
     K.out_img = a->out_img;
     K.stats = a->stats;
     K.has_head = a->head ? 1 : 0;
@@ -359,7 +361,6 @@ int stdadk_layer_fwd(const stdadk_fwd_args* a, void* stream) {
     return check_launch("layer_fwd");
 }
 
-static unsigned long long* g_predict_dbg = nullptr;
 // Development aid (not part of include/stdadk.h): 16 device counters of cycles the fused prediction kernel's roles spend
 // waiting; see tools/prof_predict.py.
 extern "C" void stdadk_debug_counters(void* dev_u64x16) { g_predict_dbg = static_cast<unsigned long long*>(dev_u64x16); }

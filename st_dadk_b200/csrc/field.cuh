@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(PF_NT, 1) predict_field_kernel(const __grid_co
             mbar_init(&wfull[s], 1);
             mbar_init(&wempty[s], 1);
         }
-        for (int s = 0; s < PF_HSLABS; ++s) mbar_init(&hfull[s], TILE_M);
+        for (int s = 0; s < PF_HSLABS; ++s) mbar_init(&hfull[s], TILE_M / 32);
         mbar_init(accf, 1);
         mbar_init(kbar, 1);
         for (int s = 0; s < FD_ZT_RING; ++s) {
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(PF_NT, 1) predict_field_kernel(const __grid_co
                 for (int s = cg; s < P.L[0].k_slabs; s += PF_CG) {
                     pf_gen_slab(P.basis, sk, st, s, x, y, 0.0f, nullptr, sH_addr + (uint32_t)s * SLAB_BYTES + rowoff, rx);
                     fence_proxy_async_smem();
-                    mbar_arrive(&hfull[s]);
+                    mbar_arrive_warp(&hfull[s]);
                 }
             }
             PF_PHASE(ph_gen);
@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(PF_NT, 1) predict_field_kernel(const __grid_co
                             tmem_st32(trow + MAX_N + (uint32_t)c0a, va);
                             tmem_st_wait();
                             tc_fence_before();
-                            mbar_arrive(&hfull[cg]);
+                            mbar_arrive_warp(&hfull[cg]);
                         }
                         if (hb) {
                             pf_normalize(vb, sg + c0b, sbt + c0b, Ly.has_ln != 0, rstd, nmr, nvb);
@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(PF_NT, 1) predict_field_kernel(const __grid_co
                             tmem_st32(trow + MAX_N + (uint32_t)c0b, vb);
                             tmem_st_wait();
                             tc_fence_before();
-                            mbar_arrive(&hfull[cg + 4]);
+                            mbar_arrive_warp(&hfull[cg + 4]);
                         }
                         PF_PHASE(ph_norm);
                     } else {

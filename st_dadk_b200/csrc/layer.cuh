@@ -69,7 +69,34 @@ struct FwdK {
     unsigned int thresh16;
     float drop_scale;
     int n_tiles, passes;        // passes: 1 (TF32) or 3 (tf32x3)
+    unsigned long long* dbg;    // optional phase timers of -DSTDADK_PF_DEBUG builds (stdadk_debug_counters), else NULL
 };
+// Development aid: globaltimer nanoseconds between the phases of a tile's life, summed over CTAs by one worker thread
+// (dbg[0..7] phase sums, dbg[8] = CTAs).  Production builds carry none of it.
+#ifdef STDADK_PF_DEBUG
+#define FWD_T(slot)                                                       \
+    do {                                                                  \
+        if (P.dbg && tid == 0) {                                          \
+            unsigned long long now_;                                      \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now_));      \
+            atomicAdd(P.dbg + (slot), now_ - t_prev_);                    \
+            t_prev_ = now_;                                               \
+        }                                                                 \
+    } while (0)
+#define FWD_WAIT(slot, stmt)                                               \
+    do {                                                                   \
+        unsigned long long w0_ = 0, w1_;                                   \
+        if (P.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(w0_)); \
+        stmt;                                                              \
+        if (P.dbg) {                                                       \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(w1_));        \
+            atomicAdd(P.dbg + (slot), w1_ - w0_);                          \
+        }                                                                  \
+    } while (0)
+#else
+#define FWD_T(slot)
+#define FWD_WAIT(slot, stmt) stmt
+#endif
 
 struct BwdK {
     BasisP basis;
@@ -180,43 +207,72 @@ __device__ __forceinline__ void build_chunk_tables(const BasisP& B, float4* tab,
 }
 // Same arithmetic, operation by operation, as spatial_chunk / phi_from_d2 (the packed instructions round like the
 // scalar ones), so the operand is bit-identical to what the backward and the prediction kernels regenerate.
-template <int FN, bool LO>
-__device__ __forceinline__ float4 spatial_chunk_soa(const float4* g, float2 xx, float2 yy) {
+// NC consecutive chunks at once: NC x 4 independent evaluations in flight per thread (a worker warp runs one dependent
+// chain per chunk otherwise, and with ~4 worker warps per scheduler the LDS / MUFU latencies were exposed: ncu showed
+// 10.7 cycles per issued instruction per warp), one support vote for the group.
+template <int FN, bool LO, int NC>
+__device__ __forceinline__ void spatial_chunks_soa(const float4* g, float2 xx, float2 yy, float4 (&out)[NC]) {
     constexpr bool lo = LO;
-    const float4 cx = g[0], cy = g[1], th2 = g[2], ith = g[3];
-    const float2 dxa = sub2(xx, make_float2(cx.x, cx.y)), dxb = sub2(xx, make_float2(cx.z, cx.w));
-    const float2 dya = sub2(yy, make_float2(cy.x, cy.y)), dyb = sub2(yy, make_float2(cy.z, cy.w));
-    // the sums stay scalar: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (seen in SASS, CUDA 12.9), which
-    // would change d2 -- and with it the support predicate -- in the last bit
-    const float2 pxa = mul2(dxa, dxa), pya = mul2(dya, dya), pxb = mul2(dxb, dxb), pyb = mul2(dyb, dyb);
-    const float2 d2a = make_float2(__fadd_rn(pxa.x, pya.x), __fadd_rn(pxa.y, pya.y));
-    const float2 d2b = make_float2(__fadd_rn(pxb.x, pyb.x), __fadd_rn(pxb.y, pyb.y));
-    const bool i0 = d2a.x < th2.x, i1 = d2a.y < th2.y, i2 = d2b.x < th2.z, i3 = d2b.y < th2.w;
+    float2 d2a[NC], d2b[NC];
+    float4 th2[NC], ith[NC];
+    bool in = false;
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+        const float4 cx = g[4 * k], cy = g[4 * k + 1];
+        th2[k] = g[4 * k + 2];
+        ith[k] = g[4 * k + 3];
+        const float2 dxa = sub2(xx, make_float2(cx.x, cx.y)), dxb = sub2(xx, make_float2(cx.z, cx.w));
+        const float2 dya = sub2(yy, make_float2(cy.x, cy.y)), dyb = sub2(yy, make_float2(cy.z, cy.w));
+        // the sums stay scalar: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (seen in SASS, CUDA 12.9),
+        // which would change d2 -- and with it the support predicate -- in the last bit
+        const float2 pxa = mul2(dxa, dxa), pya = mul2(dya, dya), pxb = mul2(dxb, dxb), pyb = mul2(dyb, dyb);
+        d2a[k] = make_float2(__fadd_rn(pxa.x, pya.x), __fadd_rn(pxa.y, pya.y));
+        d2b[k] = make_float2(__fadd_rn(pxb.x, pyb.x), __fadd_rn(pxb.y, pyb.y));
+        in |= (d2a[k].x < th2[k].x) | (d2a[k].y < th2[k].y) | (d2b[k].x < th2[k].z) | (d2b[k].y < th2[k].w);
+    }
     if (FN == STDADK_GAUSSIAN) {
-        const float2 ia = make_float2(ith.x, ith.y), ib = make_float2(ith.z, ith.w);
         const float2 kk = make_float2(-0.72134752044448170f, -0.72134752044448170f);
-        const float2 ea = mul2(kk, mul2(mul2(d2a, ia), ia)), eb = mul2(kk, mul2(mul2(d2b, ib), ib));
-        return make_float4(tf32_part(ex2_approx(ea.x), lo), tf32_part(ex2_approx(ea.y), lo), tf32_part(ex2_approx(eb.x), lo),
-                           tf32_part(ex2_approx(eb.y), lo));
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            const float2 ia = make_float2(ith[k].x, ith[k].y), ib = make_float2(ith[k].z, ith[k].w);
+            const float2 ea = mul2(kk, mul2(mul2(d2a[k], ia), ia)), eb = mul2(kk, mul2(mul2(d2b[k], ib), ib));
+            out[k] = make_float4(tf32_part(ex2_approx(ea.x), lo), tf32_part(ex2_approx(ea.y), lo),
+                                 tf32_part(ex2_approx(eb.x), lo), tf32_part(ex2_approx(eb.y), lo));
+        }
+        return;
     }
     // ordered points (grids, sorted sites): most chunks are outside every row's support -> one vote, no evaluation
-    if (!__any_sync(__activemask(), i0 | i1 | i2 | i3)) return make_float4(0.f, 0.f, 0.f, 0.f);
-    const float2 qa = make_float2(rsqrt_approx(fmaxf(d2a.x, 1e-30f)), rsqrt_approx(fmaxf(d2a.y, 1e-30f)));
-    const float2 qb = make_float2(rsqrt_approx(fmaxf(d2b.x, 1e-30f)), rsqrt_approx(fmaxf(d2b.y, 1e-30f)));
-    const float2 ra = mul2(mul2(d2a, qa), make_float2(ith.x, ith.y)), rb = mul2(mul2(d2b, qb), make_float2(ith.z, ith.w));
-    const float2 one = make_float2(1.0f, 1.0f);
-    float2 ua = sub2(one, ra), ub = sub2(one, rb);
-    ua = make_float2(fmaxf(ua.x, 0.0f), fmaxf(ua.y, 0.0f));
-    ub = make_float2(fmaxf(ub.x, 0.0f), fmaxf(ub.y, 0.0f));
-    float2 va = ua, vb = ub;
-    if (FN == STDADK_WENDLAND) {
-        const float2 c35 = make_float2(35.0f / 3.0f, 35.0f / 3.0f), c6 = make_float2(6.0f, 6.0f);
-        const float2 u2a = mul2(ua, ua), u2b = mul2(ub, ub);
-        va = mul2(mul2(mul2(u2a, u2a), u2a), fma2(fma2(c35, ra, c6), ra, one));
-        vb = mul2(mul2(mul2(u2b, u2b), u2b), fma2(fma2(c35, rb, c6), rb, one));
+    if (!__any_sync(__activemask(), in)) {
+#pragma unroll
+        for (int k = 0; k < NC; ++k) out[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
     }
-    return make_float4(tf32_part(i0 ? va.x : 0.0f, lo), tf32_part(i1 ? va.y : 0.0f, lo), tf32_part(i2 ? vb.x : 0.0f, lo),
-                       tf32_part(i3 ? vb.y : 0.0f, lo));
+    const float2 one = make_float2(1.0f, 1.0f);
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+        const float2 qa = make_float2(rsqrt_approx(fmaxf(d2a[k].x, 1e-30f)), rsqrt_approx(fmaxf(d2a[k].y, 1e-30f)));
+        const float2 qb = make_float2(rsqrt_approx(fmaxf(d2b[k].x, 1e-30f)), rsqrt_approx(fmaxf(d2b[k].y, 1e-30f)));
+        const float2 ra = mul2(mul2(d2a[k], qa), make_float2(ith[k].x, ith[k].y));
+        const float2 rb = mul2(mul2(d2b[k], qb), make_float2(ith[k].z, ith[k].w));
+        float2 ua = sub2(one, ra), ub = sub2(one, rb);
+        ua = make_float2(fmaxf(ua.x, 0.0f), fmaxf(ua.y, 0.0f));
+        ub = make_float2(fmaxf(ub.x, 0.0f), fmaxf(ub.y, 0.0f));
+        float2 va = ua, vb = ub;
+        if (FN == STDADK_WENDLAND) {
+            const float2 c35 = make_float2(35.0f / 3.0f, 35.0f / 3.0f), c6 = make_float2(6.0f, 6.0f);
+            const float2 u2a = mul2(ua, ua), u2b = mul2(ub, ub);
+            va = mul2(mul2(mul2(u2a, u2a), u2a), fma2(fma2(c35, ra, c6), ra, one));
+            vb = mul2(mul2(mul2(u2b, u2b), u2b), fma2(fma2(c35, rb, c6), rb, one));
+        }
+        out[k] = make_float4(tf32_part(d2a[k].x < th2[k].x ? va.x : 0.0f, lo), tf32_part(d2a[k].y < th2[k].y ? va.y : 0.0f, lo),
+                             tf32_part(d2b[k].x < th2[k].z ? vb.x : 0.0f, lo), tf32_part(d2b[k].y < th2[k].w ? vb.y : 0.0f, lo));
+    }
+}
+template <int FN, bool LO>
+__device__ __forceinline__ float4 spatial_chunk_soa(const float4* g, float2 xx, float2 yy) {
+    float4 o[1];
+    spatial_chunks_soa<FN, LO, 1>(g, xx, yy, o);
+    return o[0];
 }
 template <bool LO>
 __device__ __forceinline__ float4 temporal_chunk_soa(const float4* g, float2 tt) {
@@ -230,7 +286,7 @@ __device__ __forceinline__ float4 temporal_chunk_soa(const float4* g, float2 tt)
                        tf32_part(ex2_approx(eb.y), lo));
 }
 // chunks [c_begin, c_end) of operand slab `slab` of row r, from the chunk tables (forward kernel)
-template <int FN, bool LO>
+template <int FN, bool LO, int NC>
 __device__ __forceinline__ void gen_basis_slab_soa(const BasisP& B, const float4* tab, int slab, float x, float y, float t,
                                                    const float* xrow, uint32_t slab_saddr, uint32_t r, int c_begin, int c_end,
                                                    float* gslab) {
@@ -238,17 +294,40 @@ __device__ __forceinline__ void gen_basis_slab_soa(const BasisP& B, const float4
     const float2 xx = make_float2(x, x), yy = make_float2(y, y), tt = make_float2(t, t);
     const uint32_t rbase = slab_saddr + r * 128u, r7 = r & 7u;
     uint8_t* grow = gslab ? reinterpret_cast<uint8_t*>(gslab) + r * 128u : nullptr;
+    auto chunk_value = [&](int kind, int f) -> float4 {
+        if (kind == 0) return spatial_chunk_soa<FN, LO>(tab + f, xx, yy);
+        if (kind == 1) return temporal_chunk_soa<LO>(tab + f, tt);
+        if (kind == 3)
+            return make_float4(tf32_part(feature_value(B, B.knots, B.tknots, f + 0, x, y, t, xrow), lo),
+                               tf32_part(feature_value(B, B.knots, B.tknots, f + 1, x, y, t, xrow), lo),
+                               tf32_part(feature_value(B, B.knots, B.tknots, f + 2, x, y, t, xrow), lo),
+                               tf32_part(feature_value(B, B.knots, B.tknots, f + 3, x, y, t, xrow), lo));
+        return make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    int c = c_begin;
 #pragma unroll 1
-    for (int c = c_begin; c < c_end; ++c) {
-        const int f = slab * SLAB_K + 4 * c, kind = chunk_kind(B, f);
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (kind == 0) v = spatial_chunk_soa<FN, LO>(tab + f, xx, yy);
-        else if (kind == 1) v = temporal_chunk_soa<LO>(tab + f, tt);
-        else if (kind == 3)
-            v = make_float4(tf32_part(feature_value(B, B.knots, B.tknots, f + 0, x, y, t, xrow), lo),
-                            tf32_part(feature_value(B, B.knots, B.tknots, f + 1, x, y, t, xrow), lo),
-                            tf32_part(feature_value(B, B.knots, B.tknots, f + 2, x, y, t, xrow), lo),
-                            tf32_part(feature_value(B, B.knots, B.tknots, f + 3, x, y, t, xrow), lo));
+    for (; c + NC <= c_end; c += NC) {     // groups of NC chunks: the common case is all spatial (or all temporal)
+        const int f = slab * SLAB_K + 4 * c;
+        bool all_spatial = true;
+#pragma unroll
+        for (int k = 0; k < NC; ++k) all_spatial &= chunk_kind(B, f + 4 * k) == 0;
+        float4 v[NC];
+        if (all_spatial) {
+            spatial_chunks_soa<FN, LO, NC>(tab + f, xx, yy, v);
+        } else {
+#pragma unroll
+            for (int k = 0; k < NC; ++k) v[k] = chunk_value(chunk_kind(B, f + 4 * k), f + 4 * k);
+        }
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            const uint32_t so = ((uint32_t)(c + k) ^ r7) << 4;
+            st_shared_v4(rbase + so, v[k].x, v[k].y, v[k].z, v[k].w);
+            if (grow) *reinterpret_cast<float4*>(grow + so) = v[k];
+        }
+    }
+    for (; c < c_end; ++c) {
+        const int f = slab * SLAB_K + 4 * c;
+        const float4 v = chunk_value(chunk_kind(B, f), f);
         const uint32_t so = ((uint32_t)c ^ r7) << 4;
         st_shared_v4(rbase + so, v.x, v.y, v.z, v.w);
         if (grow) *reinterpret_cast<float4*>(grow + so) = v;
@@ -700,6 +779,13 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
     float* red = reinterpret_cast<float*>(smem + sp.red_off);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef STDADK_PF_DEBUG
+    unsigned long long t_prev_ = 0;
+    if (P.dbg && tid == 0) {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_prev_));
+        atomicAdd(P.dbg + 8, 1ull);
+    }
+#endif
     const bool tile_valid = (int)blockIdx.x < P.n_tiles;       // a cluster may be padded with a tile-less CTA
     const int tile = tile_valid ? (int)blockIdx.x : P.n_tiles - 1;
     const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
@@ -709,7 +795,7 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
 
     if (tid == NW) {
         for (int s = 0; s < NSTAGE; ++s) {
-            mbar_init(&full[s], BASIS ? 1 + NW : 1);
+            mbar_init(&full[s], BASIS ? 1 + NW / 32 : 1);
             mbar_init(&empty[s], CL);        // every CTA of the cluster must have consumed the stage
         }
         mbar_init(accf, 1);
@@ -738,6 +824,7 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
     if (CL > 1) cluster_sync_all();                // peers' barriers are initialised before anything remote arrives
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    FWD_T(0);       // prologue
 
     if (warp == 4 * CG) {
         // ---------------- producer
@@ -747,7 +834,7 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
             for (int v = 0; v < n_virt; ++v) {
                 const int s = v / P.passes, p = v - s * P.passes;
                 int stage = v % NSTAGE, it = v / NSTAGE;
-                if (it > 0) mbar_wait(&empty[stage], (it - 1) & 1);
+                if (it > 0) FWD_WAIT(7, mbar_wait(&empty[stage], (it - 1) & 1));
                 const float* w_src = pass_b_lo(p) ? P.L.w_img_lo : P.L.w_img;
                 const float* a_tile = BASIS ? nullptr : (pass_a_lo(p) ? P.a_img_lo : P.a_img) + a_off;
                 if (CL > 1)
@@ -766,7 +853,7 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
             const int n_virt = P.k_slabs * P.passes;
             for (int s = 0; s < n_virt; ++s) {
                 int stage = s % NSTAGE, it = s / NSTAGE;
-                mbar_wait(&full[stage], it & 1);
+                FWD_WAIT(6, mbar_wait(&full[stage], it & 1));
                 tc_fence_after();
                 issue_slab_mma(tmem_base, sA + (size_t)stage * SLAB_FLOATS, sB + stage * b_stage_floats, idesc,
                                s == 0);
@@ -797,16 +884,19 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
                 for (int s = 0; s < P.k_slabs; ++s) {
                     float* gslab = (P.feat_img && tile_valid) ? P.feat_img + ((size_t)tile * P.k_slabs + s) * SLAB_FLOATS : nullptr;
                     for (int p = 0; p < P.passes; ++p) {
-                        if (it > 0) mbar_wait(&empty[stage], (it - 1) & 1);
+                        if (it > 0) {
+                            if (tid == 0) FWD_WAIT(5, mbar_wait(&empty[stage], (it - 1) & 1));
+                            else mbar_wait(&empty[stage], (it - 1) & 1);
+                        }
                         const uint32_t sa = smem_u32(sA + (size_t)stage * SLAB_FLOATS);
                         if (pass_a_lo(p))
-                            gen_basis_slab_soa<FN, true>(P.basis, ctab, s, x, y, t, xrow, sa, (uint32_t)row, cg * (8 / CG),
+                            gen_basis_slab_soa<FN, true, 2>(P.basis, ctab, s, x, y, t, xrow, sa, (uint32_t)row, cg * (8 / CG),
                                                          (cg + 1) * (8 / CG), nullptr);
                         else
-                            gen_basis_slab_soa<FN, false>(P.basis, ctab, s, x, y, t, xrow, sa, (uint32_t)row, cg * (8 / CG),
+                            gen_basis_slab_soa<FN, false, 2>(P.basis, ctab, s, x, y, t, xrow, sa, (uint32_t)row, cg * (8 / CG),
                                                           (cg + 1) * (8 / CG), p == 0 ? gslab : nullptr);
                         fence_proxy_async_smem();
-                        mbar_arrive(&full[stage]);
+                        mbar_arrive_warp(&full[stage]);
                         if (++stage == NSTAGE) { stage = 0; ++it; }
                     }
                 }
@@ -815,17 +905,21 @@ __global__ void __launch_bounds__(n_threads(CG), CG <= 2 ? 2 : 1) layer_fwd_kern
             else if (P.basis.fn == STDADK_TRIANGULAR) gen_all(std::integral_constant<int, STDADK_TRIANGULAR>{});
             else gen_all(std::integral_constant<int, STDADK_GAUSSIAN>{});
         }
+        FWD_T(1);   // operand generated (incl. waits for free stages)
         // ---------------- epilogue
         mbar_wait(accf, 0);
         tc_fence_after();
+        FWD_T(2);   // wait for the accumulator
         EpiCtx E{sbias, sgam, sbet, shw, shb, red, tmem_base + ((uint32_t)(q4 * 32) << 16), tile, row, cg, lane, lrow, grow,
                  rvalid, tile_valid};
         fwd_epilogue<CG>(P, E);
         tc_fence_before();
+        FWD_T(3);   // epilogue
     }
     __syncthreads();
     if (CL > 1) cluster_sync_all();                // no peer may still multicast into / arrive on this CTA's memory
     if (warp == 4 * CG) tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+    FWD_T(4);       // tail
 }
 
 // g[i] = sum_k dyh[k] * head_w[k, c0 + i]: the gradient entering the last hidden block, formed per row from the
@@ -890,7 +984,7 @@ __global__ void __launch_bounds__(n_threads(CG), 1) layer_bwd_kernel(const __gri
 
     if (tid == NW) {
         for (int s = 0; s < NSTAGE; ++s) {
-            mbar_init(&full[s], BASIS ? 1 + NW : 1);
+            mbar_init(&full[s], BASIS ? 1 + NW / 32 : 1);
             mbar_init(&empty[s], 1);
         }
         mbar_init(accf, 1);
@@ -979,7 +1073,7 @@ __global__ void __launch_bounds__(n_threads(CG), 1) layer_bwd_kernel(const __gri
                                    (uint32_t)row, cg * (8 / CG), (cg + 1) * (8 / CG), nullptr, pass_a_lo(p));
                     fence_proxy_async_smem();
                 }
-                mbar_arrive(&full[stage]);
+                mbar_arrive_warp(&full[stage]);
             }
         }
         mbar_wait(accf, 0);
@@ -1247,7 +1341,7 @@ __global__ void __launch_bounds__(n_threads(CG), 1) wgrad_kernel(const __grid_co
 
     if (tid == NW) {
         for (int s = 0; s < WG_NSTAGE; ++s) {
-            mbar_init(&full[s], NW);
+            mbar_init(&full[s], NW / 32);
             mbar_init(&empty[s], 1);
         }
         mbar_init(accf, 1);
@@ -1332,7 +1426,7 @@ __global__ void __launch_bounds__(n_threads(CG), 1) wgrad_kernel(const __grid_co
                         }
                     }
                     fence_proxy_async_smem();
-                    mbar_arrive(&full[stage]);
+                    mbar_arrive_warp(&full[stage]);
                 }
             mbar_wait(accf, 0);
             tc_fence_after();

@@ -166,10 +166,10 @@ __global__ void __launch_bounds__(PF_NT, 1) predict_fused_kernel(const __grid_co
             mbar_init(&wempty[s], 1);
         }
         for (int s = 0; s < PF_AST; ++s) {
-            mbar_init(&afull[s], TILE_M);
+            mbar_init(&afull[s], TILE_M / 32);
             mbar_init(&aempty[s], 1);
         }
-        for (int s = 0; s < PF_HSLABS; ++s) mbar_init(&hfull[s], TILE_M);
+        for (int s = 0; s < PF_HSLABS; ++s) mbar_init(&hfull[s], TILE_M / 32);
         for (int s = 0; s < PF_AST; ++s) mbar_init(&hfree[s], 1);
         mbar_init(&accf[0], 1);
         mbar_init(&accf[1], 1);
@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(PF_NT, 1) predict_fused_kernel(const __grid_co
                                 pf_gen_slab(P.basis, sk, st, s, x, y, t, xrow,
                                             sH_addr + astage * (uint32_t)SLAB_BYTES + rowoff, rx);
                                 fence_proxy_async_smem();
-                                mbar_arrive(&afull[astage]);
+                                mbar_arrive_warp(&afull[astage]);
                             }
                             if (++astage == PF_AST) {
                                 astage = 0;
@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(PF_NT, 1) predict_fused_kernel(const __grid_co
                         pf_store_slab(va, sH_addr + (uint32_t)cg * SLAB_BYTES, rowoff, rx);
                         fence_proxy_async_smem();
                         tc_fence_before();
-                        mbar_arrive(&hfull[cg]);
+                        mbar_arrive_warp(&hfull[cg]);
                     }
                     if (hb) {
                         pf_normalize(vb, sg + c0b, sbt + c0b, Ly.has_ln != 0, rstd, nmr, nvb_e);
@@ -460,7 +460,7 @@ __global__ void __launch_bounds__(PF_NT, 1) predict_fused_kernel(const __grid_co
                         pf_store_slab(vb, sH_addr + (uint32_t)(cg + 4) * SLAB_BYTES, rowoff, rx);
                         fence_proxy_async_smem();
                         tc_fence_before();
-                        mbar_arrive(&hfull[cg + 4]);
+                        mbar_arrive_warp(&hfull[cg + 4]);
                     }
                     PF_PHASE(ph_norm);
                 } else {
