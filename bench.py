@@ -419,7 +419,7 @@ def run_ours(args):
     from stnf.dataio import ObservationTable
     from st_dadk_b200 import ops
     from st_dadk_b200.trainer import Trainer
-    from st_dadk_b200.predict import Predictor
+    from st_dadk_b200.predict import Predictor, shard_range
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -556,7 +556,8 @@ def run_ours(args):
         dist.all_reduce(gms, op=dist.ReduceOp.MAX)
     grid_pps = 10_000_000 / (float(gms.item()) * 1e-3)
     # e2e prediction: result copied back to pinned host memory
-    hout = torch.empty(out.shape, dtype=torch.float32).pin_memory()
+    rb, re_ = shard_range(n_pred, rank, world)          # the host-delivery path shards the (t, s) rows
+    hout = torch.empty(re_ - rb, model.output_dim, dtype=torch.float32).pin_memory()
     pr.space_time_field(sites_d, T_STEPS, rank, world, host_out=hout)       # warm (copy stream, events)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -611,7 +612,8 @@ def run_ours(args):
                          "frac": tfl / tf32["tf32_tflops"], "peak_source": "measured in this run: " + tf32["how"] + " (burst)",
                          "frac_of_sustained_tf32": tfl / tf32["tf32_tflops_sustained"],
                          "executed_flops_per_launch": fus["flops"], "dense_equivalent_flops_per_launch": fus.get("dense_flops"),
-                         "traffic": traffic.get("predict", {}).get("predict_fused"),
+                         "traffic": traffic.get("predict", {}).get(
+                             "predict_field" if fus.get("kernel") == "predict_field_kernel" else "predict_fused"),
                          "algorithmic_bytes_per_launch": fus["bytes"], "launch_ms": fus["ms"],
                          "tensor_pipe_pct_ncu": traffic.get("tensor_pipe_pct", {}).get(fus.get("kernel")),
                          "points_per_s": fus["points"] / (fus["ms"] * 1e-3),

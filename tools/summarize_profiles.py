@@ -85,7 +85,7 @@ def train_names(name, k):
     return None
 
 
-def main():
+def main_r1():
     src = os.path.join(OUT, "launches_r1_final.csv")
     if os.path.exists(src):
         shutil.copy(src, os.path.join(PROF, "r1_launches_bench_nograph.csv"))
@@ -114,6 +114,63 @@ def main():
     json.dump(traffic, open(os.path.join(PROF, "traffic.json"), "w"), indent=1)
     print(open(os.path.join(PROF, "r1_ncu_summary.md")).read())
 
+
+def tensor_pct(rep):
+    r = raw(rep)
+    h = r[0]
+    i = h.index("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")
+    return float(r[2][i])
+
+
+def main_r2():
+    """profiles/r2_*: the round-2 captures of tools/profile_round2.sh."""
+    src = os.path.join(OUT, "launches_r2.csv")
+    if os.path.exists(src):
+        shutil.copy(src, os.path.join(PROF, "r2_launches_bench_nograph.csv"))
+    traffic = {"source": "ncu --set full --clock-control none (tools/profile_round2.sh): dram__bytes_read.sum + "
+                         "dram__bytes_write.sum per launch; training kernels from `bench.py --steps 5 --warmup 3 "
+                         "--no-graph`, block 1 alone from `tools/prof_block1.py` (1M explicit random points), field kernel "
+                         "from `tools/prof_field.py` (10M-point grid), whole-network kernel from `tools/prof_predict.py` "
+                         "(1M grid points); summary in profiles/r2_ncu_summary.md"}
+    with open(os.path.join(PROF, "r2_ncu_summary.md"), "w") as f:
+        f.write("# Round-2 ncu summaries (B200, `ncu --set full --clock-control none --import-source on`)\n\n"
+                "Produced by `tools/profile_round2.sh` (each command first run plain, exit 0) and "
+                "`tools/summarize_profiles.py r2`; the reports stay in `gpurun_out/`.  Launch list of the bench command: "
+                "`profiles/r2_launches_bench_nograph.csv` (cold-cache, serialised per-launch times: compare shares, not "
+                "absolutes).  Template arguments: `layer_fwd_kernel<BASIS, CG, NS, CL>`, `layer_bwd_kernel<BASIS, CG, NS, "
+                "LN, HEAD>`, `wgrad_kernel<BASIS, CG>`, `adamw_ema_kernel<FUSED>`.\n\n")
+        traffic["train"] = section(f, "training step, batch 4096 = 32 tiles: one wave, latency-bound",
+                                   os.path.join(OUT, "prof_train_r2.ncu-rep"), train_names)
+        b1 = section(f, "fused basis + Linear1 + LayerNorm/ReLU forward alone, 1M explicit random points (bench.py `roofline`)",
+                     os.path.join(OUT, "prof_block1_r2.ncu-rep"), lambda n, k: "layer_fwd[0]")
+        fd = section(f, "space-time field kernel, 10M-point grid (bench.py `roofline_gemm`, BASELINE config 3)",
+                     os.path.join(OUT, "prof_field_r2.ncu-rep"), lambda n, k: "predict_field")
+        fu = section(f, "whole-network kernel for explicit points, 1M grid points (stdadk_predict)",
+                     os.path.join(OUT, "prof_fused_r2.ncu-rep"), lambda n, k: "predict_fused")
+        traffic["predict"] = {**b1, **fd, **fu}
+        traffic["tensor_pipe_pct"] = {"predict_field_kernel": tensor_pct(os.path.join(OUT, "prof_field_r2.ncu-rep")),
+                                      "predict_fused_kernel": tensor_pct(os.path.join(OUT, "prof_fused_r2.ncu-rep"))}
+        f.write(NOTES_R2)
+    json.dump(traffic, open(os.path.join(PROF, "traffic.json"), "w"), indent=1)
+    print(open(os.path.join(PROF, "r2_ncu_summary.md")).read())
+
+
+def main():
+    return main_r2() if sys.argv[1:] == ["r2"] else main_r1()
+
+
+NOTES_R2 = """## Reading
+
+* Training kernels run ONE wave of 32 CTAs on 148 SMs: the time is the serial latency of one tile; per-kernel times
+  inside the replayed graph come from CUPTI (`bench.py: kernel_us_per_step`).
+* Block 1 alone: 388 warp instructions per row (round 1: 639) at ~46 % issue utilisation; DRAM write = the h1 image
+  (1.02 GB), read = weights and points: traffic / algorithmic = 1.0.  No pipe above 40 %: the kernel is bound by per-warp
+  latency with 4-5 warps per scheduler (DESIGN.md section 4 has the phase timers).
+* Field kernel: DRAM traffic is y_hat plus weights; tensor pipe ~23 %: the worker warps' epilogues (LayerNorm over
+  TMEM loads, TF32 rounding, tcgen05.st of the next operand) take ~2.6x the MMA time per (tile, time step).
+* SASS evidence of the instruction mix: `profiles/r2_sass_mnemonics.txt`, checked by
+  `tests/test_abi.py::test_sass_is_blackwell_native`.
+"""
 
 NOTES = """## Reading
 
