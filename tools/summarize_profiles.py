@@ -31,6 +31,9 @@ def raw(rep):
 
 
 def section(f, title, rep, names):
+    if not os.path.exists(rep):
+        print("missing report, section skipped:", rep)
+        return {}
     r = raw(rep)
     h, u = r[0], r[1]
     f.write(f"## {title}\n\n| kernel | " + " | ".join(s for _, s in WANT) + " |\n|" + "---|" * (len(WANT) + 1) + "\n")
@@ -148,8 +151,9 @@ def main_r2():
         fu = section(f, "whole-network kernel for explicit points, 1M grid points (stdadk_predict)",
                      os.path.join(OUT, "prof_fused_r2.ncu-rep"), lambda n, k: "predict_fused")
         traffic["predict"] = {**b1, **fd, **fu}
-        traffic["tensor_pipe_pct"] = {"predict_field_kernel": tensor_pct(os.path.join(OUT, "prof_field_r2.ncu-rep")),
-                                      "predict_fused_kernel": tensor_pct(os.path.join(OUT, "prof_fused_r2.ncu-rep"))}
+        traffic["tensor_pipe_pct"] = {k: tensor_pct(os.path.join(OUT, r)) for k, r in
+                                      (("predict_field_kernel", "prof_field_r2.ncu-rep"),
+                                       ("predict_fused_kernel", "prof_fused_r2.ncu-rep")) if os.path.exists(os.path.join(OUT, r))}
         f.write(NOTES_R2)
     json.dump(traffic, open(os.path.join(PROF, "traffic.json"), "w"), indent=1)
     print(open(os.path.join(PROF, "r2_ncu_summary.md")).read())
