@@ -402,7 +402,7 @@ def run_config5(args, emit):
                        "wall_s": wall, "configs_per_gpu": per_gpu, "results_json_files": n_done, "failed_configs": errs,
                        "rank_failed": failed_rank, "merged_summary": os.path.exists(os.path.join(out, "grid_search_summary.csv")),
                        "stderr_tail": pr.stderr[-300:] if pr.returncode else ""}}
-    if _ref_available():
+    if _ref_available() and not os.environ.get("STDADK_SKIP_REFERENCE_LEG"):
         from joblib import Parallel, delayed
         sys.path.insert(0, os.path.join(ROOT, "scripts"))
         import run_grid_search as gs

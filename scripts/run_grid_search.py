@@ -163,6 +163,21 @@ def main():
     out.mkdir(parents=True, exist_ok=True)
     mine = configs[rank::world]
     n_workers = max(1, args.configs_per_gpu)
+    # Host side of a sweep: the work per configuration is host-bound (driver, scikit-learn knot placement), so the host
+    # cores are shared out among the processes of the box (torchrun pins OMP_NUM_THREADS=1, which makes every mixture
+    # fit 5-10x slower), and mixture fits are shared between processes through files (knot_init._gmm_fit_shared).
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    threads = max(1, (os.cpu_count() or 1) // max(1, local_world * n_workers))
+    os.environ.setdefault("STDADK_GMM_CACHE_DIR", str(out / ".gmm_cache"))
+    if args.worker_slice is None:
+        for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+            os.environ[k] = str(threads)            # inherited by the worker processes (read when numpy / torch load)
+    try:
+        torch.set_num_threads(threads)
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=threads)
+    except Exception:
+        pass
     t0 = time.time()
     if n_workers > 1 and args.worker_slice is None:
         # parent of this rank: C worker processes on the same GPU, each with every C-th configuration of the share

@@ -640,7 +640,7 @@ __device__ __forceinline__ void fwd_epilogue(const FwdK& P, const EpiCtx& E) {
     const bool has_ln = P.L.gamma != nullptr;
     float* myred = red + ((size_t)cg * TILE_M + row) * RED_STRIDE;
     const float* arow = (P.addend && rvalid) ? P.addend + (size_t)lrow * n_out : nullptr;
-    float v[32], w[32];
+    float v[32];
     float mean = 0.0f, rstd = 1.0f;
     if (has_ln) {
         // pass 1: shifted moments of x = A W^T + b (+ addend): per-thread shift K (the thread's first value) removes
@@ -649,23 +649,13 @@ __device__ __forceinline__ void fwd_epilogue(const FwdK& P, const EpiCtx& E) {
         //   mean = sum_g (n_g K_g + S1_g) / n,   M2 = sum_g [S2_g - 2 (mean - K_g) S1_g + n_g (mean - K_g)^2]
         float K = 0.0f, S1 = 0.0f, S2 = 0.0f, cntv = 0.0f;
         bool have = false;
-        // two chunks per round trip to tensor memory: both loads are in flight before the (single) wait
-        for (int c0 = 32 * cg; c0 < n_pad; c0 += 64 * CG) {
-            const int c1 = c0 + 32 * CG, nv = n_out - c0, nw = n_out - c1;
+        for (int c0 = 32 * cg; c0 < n_pad; c0 += 32 * CG) {
+            const int nv = n_out - c0;
             if (nv <= 0) break;
-            const bool two = c1 < n_pad && nw > 0;
-            tmem_ld32_issue(trow + c0, v);
-            if (two) tmem_ld32_issue(trow + c1, w);
-            tmem_ld_wait(v);
+            tmem_ld32(trow + c0, v);
             if (arow) add_addend_chunk(v, arow, c0, n_out);
             pf_bias_stats(v, sbias + c0, min(nv, 32), have, K, S1, S2);
             cntv += (float)min(nv, 32);
-            if (two) {
-                tmem_ld_wait(w);
-                if (arow) add_addend_chunk(w, arow, c1, n_out);
-                pf_bias_stats(w, sbias + c1, min(nw, 32), have, K, S1, S2);
-                cntv += (float)min(nw, 32);
-            }
         }
         const float inv_n = 1.0f / (float)n_out;
         if (CG > 1) {
@@ -703,41 +693,28 @@ __device__ __forceinline__ void fwd_epilogue(const FwdK& P, const EpiCtx& E) {
     const bool drop = P.L.drop_p > 0.0f;
     const unsigned int drop_step = drop ? dropout_step(P.L) : 0u;
     // pass 2: x -> LayerNorm -> ReLU -> dropout -> operand image (+ head partials, + x image for the backward)
-    auto finish_chunk = [&](float (&u)[32], int c0, uint32_t keep) {
-        if (arow) add_addend_chunk(u, arow, c0, n_out);
+    for (int c0 = 32 * cg; c0 < n_pad; c0 += 32 * CG) {
+        uint32_t keep = 0xFFFFFFFFu;
+        if (drop)       // masks first: the Philox calls neither sit behind the TMEM load nor hold 32 live values
+            keep = pf_keep_mask(P.L.seed, drop_step, (uint32_t)P.L.layer_id, P.L.key_offset + (unsigned long long)lrow, c0,
+                                P.thresh16);
+        tmem_ld32(trow + c0, v);
+        if (arow) add_addend_chunk(v, arow, c0, n_out);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             const float4 b = *reinterpret_cast<const float4*>(sbias + c0 + 4 * c);
-            const float2 lo = add2(make_float2(u[4 * c], u[4 * c + 1]), make_float2(b.x, b.y));
-            const float2 hi = add2(make_float2(u[4 * c + 2], u[4 * c + 3]), make_float2(b.z, b.w));
-            u[4 * c] = lo.x; u[4 * c + 1] = lo.y; u[4 * c + 2] = hi.x; u[4 * c + 3] = hi.y;
+            const float2 lo = add2(make_float2(v[4 * c], v[4 * c + 1]), make_float2(b.x, b.y));
+            const float2 hi = add2(make_float2(v[4 * c + 2], v[4 * c + 3]), make_float2(b.z, b.w));
+            v[4 * c] = lo.x; v[4 * c + 1] = lo.y; v[4 * c + 2] = hi.x; v[4 * c + 3] = hi.y;
         }
         if (P.x_img && tile_valid)            // training with a single wave of tiles: keep x for the backward
-            image_store_chunk(P.x_img, tile, n_pad / SLAB_K, c0, (uint32_t)row, u);
+            image_store_chunk(P.x_img, tile, n_pad / SLAB_K, c0, (uint32_t)row, v);
         const int nv = rvalid ? min(32, max(n_out - c0, 0)) : 0;      // padding rows / columns -> 0
-        pf_normalize(u, sgam + c0, sbet + c0, has_ln, rstd, nmr, nv);
-        if (drop) pf_dropout(u, keep, P.drop_scale);
-        if (P.has_head) pf_head_partial(u, shw, n_pad, c0, P.head.q, yh);
+        pf_normalize(v, sgam + c0, sbet + c0, has_ln, rstd, nmr, nv);
+        if (drop) pf_dropout(v, keep, P.drop_scale);
+        if (P.has_head) pf_head_partial(v, shw, n_pad, c0, P.head.q, yh);
         if (P.out_img && tile_valid)
-            store_operand_chunk(P.out_img, P.out_img_lo, tile, n_pad / SLAB_K, c0, (uint32_t)row, u);
-    };
-    for (int c0 = 32 * cg; c0 < n_pad; c0 += 64 * CG) {
-        const int c1 = c0 + 32 * CG;
-        const bool two = c1 < n_pad;
-        uint32_t keep0 = 0xFFFFFFFFu, keep1 = 0xFFFFFFFFu;
-        if (drop) {     // masks first: the Philox calls neither sit behind the TMEM loads nor hold live accumulator values
-            const unsigned long long key_row = P.L.key_offset + (unsigned long long)lrow;
-            keep0 = pf_keep_mask(P.L.seed, drop_step, (uint32_t)P.L.layer_id, key_row, c0, P.thresh16);
-            if (two) keep1 = pf_keep_mask(P.L.seed, drop_step, (uint32_t)P.L.layer_id, key_row, c1, P.thresh16);
-        }
-        tmem_ld32_issue(trow + c0, v);
-        if (two) tmem_ld32_issue(trow + c1, w);
-        tmem_ld_wait(v);
-        finish_chunk(v, c0, keep0);
-        if (two) {
-            tmem_ld_wait(w);
-            finish_chunk(w, c1, keep1);
-        }
+            store_operand_chunk(P.out_img, P.out_img_lo, tile, n_pad / SLAB_K, c0, (uint32_t)row, v);
     }
     if (P.has_head) {
         if (CG > 1) {

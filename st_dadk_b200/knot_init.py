@@ -8,7 +8,9 @@ from __future__ import annotations
 
 import hashlib
 import math
+import os
 import threading
+import time
 from typing import Sequence, Tuple
 
 import numpy as np
@@ -68,7 +70,6 @@ _GMM_CACHE_MAX = 32
 
 
 def _gmm_fit(sub: np.ndarray, k: int):
-    from sklearn.mixture import GaussianMixture
     key = (hashlib.sha1(np.ascontiguousarray(sub).tobytes()).hexdigest(), int(k))
     with _GMM_LOCK:
         slot = _GMM_CACHE.get(key)
@@ -78,10 +79,56 @@ def _gmm_fit(sub: np.ndarray, k: int):
             slot = _GMM_CACHE[key] = {"lock": threading.Lock(), "value": None}
     with slot["lock"]:
         if slot["value"] is None:
-            gm = GaussianMixture(n_components=k, covariance_type="spherical", random_state=42, max_iter=100, n_init=3,
-                                 init_params="k-means++", reg_covar=1e-6, tol=1e-3, verbose=0).fit(sub)
-            slot["value"] = (gm.means_.copy(), gm.covariances_.copy())
+            slot["value"] = _gmm_fit_shared(sub, k, key)
     return slot["value"]
+
+
+def _gmm_fit_shared(sub: np.ndarray, k: int, key):
+    """The fit itself, shared between PROCESSES through files when STDADK_GMM_CACHE_DIR is set (run_grid_search.py sets
+    it to a directory of the sweep: the worker processes of all ranks of a box fit every (sample, k) once).  The first
+    process to create `<key>.lock` fits and publishes `<key>.npz` atomically; the others wait for the file (and fit
+    themselves if it does not appear: a crashed owner must not stall the sweep)."""
+    from sklearn.mixture import GaussianMixture
+
+    def fit():
+        gm = GaussianMixture(n_components=k, covariance_type="spherical", random_state=42, max_iter=100, n_init=3,
+                             init_params="k-means++", reg_covar=1e-6, tol=1e-3, verbose=0).fit(sub)
+        return gm.means_.copy(), gm.covariances_.copy()
+
+    cache_dir = os.environ.get("STDADK_GMM_CACHE_DIR")
+    if not cache_dir:
+        return fit()
+    os.makedirs(cache_dir, exist_ok=True)
+    base = os.path.join(cache_dir, f"{key[0]}_{key[1]}")
+
+    def load():
+        try:
+            with np.load(base + ".npz") as z:
+                return z["means"].copy(), z["cov"].copy()
+        except (OSError, ValueError, KeyError):
+            return None
+
+    got = load()
+    if got is not None:
+        return got
+    try:
+        fd = os.open(base + ".lock", os.O_CREAT | os.O_EXCL | os.O_WRONLY)
+        os.close(fd)
+        owner = True
+    except FileExistsError:
+        owner = False
+    if not owner:
+        deadline = time.time() + 180.0
+        while time.time() < deadline:
+            got = load()
+            if got is not None:
+                return got
+            time.sleep(0.05)
+    means, cov = fit()
+    tmp = f"{base}.{os.getpid()}.tmp.npz"
+    np.savez(tmp, means=means, cov=cov)
+    os.replace(tmp, base + ".npz")
+    return means, cov
 
 
 def gmm_knots(n_centers: Sequence[int], train_coords: np.ndarray):

@@ -192,3 +192,25 @@ def test_aggregated_artefacts_have_upstream_names_and_columns(tmp_path):
     assert sorted(cj) == ["1", "2", "3"] and (tmp_path / "grid_search_configs.csv").exists()
     v = s1["statistics"]["test_mae"]["values"]
     assert abs(summ.loc[summ.config_id == 1, "test_mae_mean"].item() - np.mean(v)) < 1e-12
+
+
+def test_gmm_fit_is_shared_between_processes_through_files(tmp_path, monkeypatch):
+    """Sweeps: every (sample, k) mixture fit is done once per box; other processes read the published file."""
+    import numpy as np
+    from st_dadk_b200 import knot_init as ki
+    monkeypatch.setenv("STDADK_GMM_CACHE_DIR", str(tmp_path))
+    ki._GMM_CACHE.clear()
+    rng = np.random.default_rng(0)
+    sub = rng.random((400, 2))
+    m1, c1 = ki._gmm_fit(sub, 9)
+    files = sorted(p.name for p in tmp_path.iterdir())
+    assert any(f.endswith("_9.npz") for f in files) and any(f.endswith("_9.lock") for f in files)
+    ki._GMM_CACHE.clear()                      # "another process": no in-memory memo, must come from the file
+    calls = []
+    import sklearn.mixture as sm
+    orig = sm.GaussianMixture.fit
+    monkeypatch.setattr(sm.GaussianMixture, "fit", lambda self, X: calls.append(1) or orig(self, X))
+    m2, c2 = ki._gmm_fit(sub, 9)
+    assert not calls and np.array_equal(m1, m2) and np.array_equal(c1, c2)
+    m3, _ = ki._gmm_fit(sub, 4)                 # a different k is a different fit
+    assert calls and m3.shape == (4, 2)
