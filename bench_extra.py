@@ -383,8 +383,10 @@ def run_config5(args, emit):
     t0 = time.time()
     pr = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "run_grid_search.py"), "--config",
                          os.path.join(out_root, "base.yaml"), "--output_dir", os.path.join(out_root, "sweep"),
-                         "--configs_per_gpu", str(per_gpu)], capture_output=True, text=True)
+                         "--configs_per_gpu", str(per_gpu)], capture_output=True, text=True,
+                        env=dict(os.environ, STDADK_SWEEP_T0=str(t0)))
     wall = time.time() - t0
+    timeline = [ln for ln in pr.stdout.splitlines() if ln.startswith("[grid] rank") and "since launch" in ln]
     t = torch.tensor([wall, float(pr.returncode != 0)], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -400,7 +402,7 @@ def run_config5(args, emit):
             "config": {"workload": "BASELINE config 5: 64-configuration sweep on a 2a-shaped file (S=1000 x T=100), "
                                    f"{epochs} epochs each, run_grid_search.py, configurations packed {per_gpu} per GPU",
                        "wall_s": wall, "configs_per_gpu": per_gpu, "results_json_files": n_done, "failed_configs": errs,
-                       "rank_failed": failed_rank, "merged_summary": os.path.exists(os.path.join(out, "grid_search_summary.csv")),
+                       "rank_failed": failed_rank, "rank0_timeline": timeline, "merged_summary": os.path.exists(os.path.join(out, "grid_search_summary.csv")),
                        "stderr_tail": pr.stderr[-300:] if pr.returncode else ""}}
     if _ref_available() and not os.environ.get("STDADK_SKIP_REFERENCE_LEG"):
         from joblib import Parallel, delayed

@@ -2,7 +2,8 @@
 
 Upstream fans configurations out to CPU worker processes with joblib (scripts/run_grid_search.py:329-387).  Here the
 configurations are independent jobs dealt to the ranks of a torchrun launch (one process per GPU); with
-`--configs_per_gpu C` each rank additionally splits its share over C worker PROCESSES on the same GPU.  A 50-epoch
+`--configs_per_gpu C` each rank additionally splits its share over C worker PROCESSES on the same GPU (forked before
+the rank touches CUDA, so a worker costs no second interpreter / torch start-up).  A 50-epoch
 run of the default model is ~0.1 s of GPU time and ~0.5 s of host work (CSV, knot placement, evaluation, artefact
 files), so what packing buys is host parallelism; worker threads inside one interpreter were measured slower than
 sequential (GIL, serialised graph captures), separate processes are not.  Outputs are upstream's (:102-237): ONE
@@ -12,6 +13,8 @@ from the per-experiment results.json files (the ranks never communicate).
 
     torchrun --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 scripts/run_grid_search.py --config ... --configs_per_gpu 2
 """
+import time as _time
+_T_PROCESS = _time.time()          # for the start-up timeline printed at the end (imports below are part of it)
 import argparse
 import copy
 import itertools
@@ -146,7 +149,6 @@ def main():
     ap.add_argument("--configs_per_gpu", type=int, default=1)
     ap.add_argument("--n_experiments", type=int, default=None)
     ap.add_argument("--epochs", type=int, default=None)
-    ap.add_argument("--worker_slice", default=None, help="internal: 'i:C' = this process is worker i of C of its rank")
     args = ap.parse_args()
     base = yaml.safe_load(open(args.config))
     if args.n_experiments is not None:
@@ -157,8 +159,8 @@ def main():
     configs = generate_config_combinations(base, grid)
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
     device = f"cuda:{local}"
+    t_launch = float(os.environ.get("STDADK_SWEEP_T0", str(_T_PROCESS)))     # when the launcher started this sweep
     out = Path(args.output_dir) if args.output_dir else launch_directory("grid_search")   # one directory per launch
     out.mkdir(parents=True, exist_ok=True)
     mine = configs[rank::world]
@@ -169,41 +171,45 @@ def main():
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
     threads = max(1, (os.cpu_count() or 1) // max(1, local_world * n_workers))
     os.environ.setdefault("STDADK_GMM_CACHE_DIR", str(out / ".gmm_cache"))
-    if args.worker_slice is None:
-        for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
-            os.environ[k] = str(threads)            # inherited by the worker processes (read when numpy / torch load)
-    try:
-        torch.set_num_threads(threads)
-        from threadpoolctl import threadpool_limits
-        threadpool_limits(limits=threads)
-    except Exception:
-        pass
+    for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        os.environ[k] = str(threads)
+
+    def run_share(share, tag):
+        """One worker: its configurations one after the other on this rank's GPU (own CUDA context, own streams)."""
+        try:
+            torch.set_num_threads(threads)
+            from threadpoolctl import threadpool_limits
+            threadpool_limits(limits=threads)
+        except Exception:
+            pass
+        torch.cuda.set_device(local)
+        t_start = time.time()
+        results, t_first = [], None
+        for cfg in share:
+            _run_config(cfg, out, device, results)
+            if t_first is None:
+                t_first = time.time()
+        torch.cuda.synchronize()
+        print(f"[grid] {tag}: {len(share)} configurations; since launch: worker started +{t_start - t_launch:.1f} s, first "
+              f"configuration done +{(t_first or t_start) - t_launch:.1f} s, all done +{time.time() - t_launch:.1f} s", flush=True)
+
     t0 = time.time()
-    if n_workers > 1 and args.worker_slice is None:
-        # parent of this rank: C worker processes on the same GPU, each with every C-th configuration of the share
-        import subprocess
-        base_cmd = [sys.executable, os.path.abspath(__file__), "--config", args.config, "--output_dir", str(out),
-                    "--configs_per_gpu", str(n_workers)]
-        if args.grid:
-            base_cmd += ["--grid", args.grid]
-        if args.n_experiments is not None:
-            base_cmd += ["--n_experiments", str(args.n_experiments)]
-        if args.epochs is not None:
-            base_cmd += ["--epochs", str(args.epochs)]
-        procs = [subprocess.Popen(base_cmd + ["--worker_slice", f"{i}:{n_workers}"]) for i in range(n_workers)]
-        rcs = [p.wait() for p in procs]
+    if n_workers > 1:
+        # C worker processes on the same GPU, each with every C-th configuration of the share.  They are FORKED from
+        # this process before it touches CUDA (the interpreter and the imported torch are shared copy-on-write: a
+        # worker costs no second start-up, which at this problem size is longer than its share of the sweep).
+        import multiprocessing as mp
+        ctx = mp.get_context("fork")
+        procs = [ctx.Process(target=run_share, args=(mine[i::n_workers], f"rank {rank} worker {i}")) for i in range(n_workers)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join()
+        rcs = [p.exitcode for p in procs]
         if any(rcs):
             print(f"[grid] worker exit codes: {rcs}", flush=True)
     else:
-        results = []
-        if args.worker_slice is not None:
-            wi, wc = (int(v) for v in args.worker_slice.split(":"))
-            mine = mine[wi::wc]
-        for cfg in mine:
-            _run_config(cfg, out, device, results)
-        torch.cuda.synchronize()
-        if args.worker_slice is not None:
-            return            # the parent of this rank merges from the results.json files
+        run_share(mine, f"rank {rank}")
     wall = time.time() - t0
     (out / f".rank{rank}.done").write_text(f"{wall:.3f}")
     merged = False
