@@ -20,7 +20,8 @@ RUNS = [("b_1_final.json", "python bench.py  (1 GPU, defaults: BASELINE config 2
         ("c4_1.json", "python bench.py --config 4"),
         ("c4_8.json", "torchrun --nproc-per-node 8 bench.py --gpus 8 --config 4"),
         ("c5_1.json", "STDADK_CONFIGS_PER_GPU=4 python bench.py --config 5 --steps 50"),
-        ("c5_8.json", "STDADK_CONFIGS_PER_GPU=2 torchrun --nproc-per-node 8 bench.py --gpus 8 --config 5 --steps 50")]
+        ("c5_8.json", "STDADK_CONFIGS_PER_GPU=2 torchrun --nproc-per-node 8 bench.py --gpus 8 --config 5 --steps 50  (before the workers were forked / shared the host cores; with the reference leg)"),
+        ("c5_8b.json", "STDADK_SKIP_REFERENCE_LEG=1 STDADK_CONFIGS_PER_GPU=2 torchrun --nproc-per-node 8 bench.py --gpus 8 --config 5 --steps 50")]
 
 
 def main():
