@@ -95,3 +95,33 @@ def test_field_kernel_grid_equals_explicit_sites_and_shards():
     # ... and through the generic kernels (field kernel off)
     parts = [gen.grid_by_sites(nx, ny, nt, r, 3)[0] for r in range(3)]
     assert torch.equal(torch.cat(parts, dim=1), ref.view(nt, nx * ny, 2))
+
+
+def test_full_size_10M_point_grid_sample_vs_oracle_and_world8_shards():
+    """BASELINE config 3 at its real size: the 1000 x 1000 x 10 grid generated on the device (10,000,000 points).  A
+    4,096-row sample (plus corner / boundary rows) is checked against the oracle; the 8-way shardings -- contiguous
+    blocks of the row index and by site -- reproduce the single-launch field bit for bit."""
+    from st_dadk_b200.predict import Predictor
+    model = _model(q=1)
+    pr = Predictor(model, static_weights=True)
+    nx, ny, nt = 1000, 1000, 10
+    S, n = nx * ny, nx * ny * nt
+    out, (b, e) = pr.grid(nx, ny, nt)
+    assert pr.used_field_kernel and (b, e) == (0, n) and bool(torch.isfinite(out).all())
+    rng = np.random.default_rng(5)
+    rows = np.unique(np.concatenate([rng.integers(0, n, 4096), [0, ny - 1, S - 1, S, n - S, n - 1, 1_250_000, 1_249_999]]))
+    k, site = rows // S, rows % S
+    i, j = site // ny, site % ny
+    f32 = np.float32          # the grid generator's arithmetic: FP32 division of the FP32 indices
+    coords = np.stack([i.astype(f32) / f32(nx - 1), j.astype(f32) / f32(ny - 1)], axis=1)
+    t = (k.astype(f32) / f32(nt - 1))[:, None]
+    assert coords.dtype == np.float32 and t.dtype == np.float32
+    want = _oracle(model, coords, t)
+    got = out[torch.from_numpy(rows).to(DEV)].cpu().numpy()
+    assert rel_l2(got, want) < 1e-3
+    parts = [pr.grid(nx, ny, nt, r, 8) for r in range(8)]
+    assert parts[0][1][0] == 0 and parts[-1][1][1] == n and all(parts[r][1][1] == parts[r + 1][1][0] for r in range(7))
+    assert torch.equal(torch.cat([p[0] for p in parts]), out)
+    del parts
+    parts = [pr.grid_by_sites(nx, ny, nt, r, 8) for r in range(8)]
+    assert torch.equal(torch.cat([p[0] for p in parts], dim=1), out.view(nt, S, 1))
