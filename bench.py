@@ -693,11 +693,15 @@ def emit(obj):
 
 
 def main():
+    global BATCH, N_TRAIN, WORKLOAD
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH,
+                    help="per-GPU batch (default 4096 = the BASELINE config; e.g. 65536 for the throughput regime: the "
+                         "resident training set then grows to 4 batches per GPU)")
     ap.add_argument("--precision", default="tf32", choices=["tf32", "tf32x3"],
                     help="tensor-core precision of the measured arm: tf32 = throughput mode, tf32x3 = FP32-faithful parity mode")
     ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5],
@@ -705,6 +709,10 @@ def main():
     ap.add_argument("--no-graph", action="store_true",
                     help="launch every kernel eagerly (for ncu: kernel replay cannot run inside stream capture)")
     args = ap.parse_args()
+    if args.batch != BATCH:
+        WORKLOAD = WORKLOAD.replace(f"batch {BATCH}/GPU", f"batch {args.batch}/GPU").replace(
+            "80k train samples", f"{max(N_TRAIN, 4 * args.batch)} train samples")
+        BATCH, N_TRAIN = args.batch, max(N_TRAIN, 4 * args.batch)
     _quiet_stdout()
     if args.impl == "reference":
         run_reference(args)

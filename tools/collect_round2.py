@@ -14,6 +14,8 @@ RUNS = [("b_1_final.json", "python bench.py  (1 GPU, defaults: BASELINE config 2
         ("b_1_ref.json", "python bench.py --impl reference  (the reference's PyTorch CPU path on the box's host cores)"),
         ("b_2b.json", "torchrun --nproc-per-node 2 bench.py --gpus 2 --steps 50 --warmup 5"),
         ("b_8c.json", "torchrun --nproc-per-node 8 bench.py --gpus 8 --steps 50 --warmup 5"),
+        ("b64k_1.json", "python bench.py --batch 65536 --steps 100 --warmup 5"),
+        ("b64k_8.json", "torchrun --nproc-per-node 8 bench.py --gpus 8 --batch 65536 --steps 50 --warmup 5"),
         ("c1_1.json", "python bench.py --config 1 --steps 20"),
         ("c3_1.json", "python bench.py --config 3"),
         ("c3_8b.json", "torchrun --nproc-per-node 8 bench.py --gpus 8 --config 3"),
