@@ -616,7 +616,8 @@ int stdadk_layer_bwd(const stdadk_bwd_args* a, void* stream) {
     K.drop_scale = a->drop.p > 0.0f ? 1.0f / (1.0f - a->drop.p) : 1.0f;
     const bool basis = a->basis != nullptr && a->x_img == nullptr;
     constexpr int BCG = 2, BNS = 4;
-    SmemPlan sp = plan_smem(K.n_pad, K.has_head ? K.head.q : 0, basis ? K.basis.k_s : 0, basis ? K.basis.k_t : 0, true, BCG, BNS);
+    SmemPlan sp = plan_smem(K.n_pad, K.has_head ? K.head.q : 0, basis ? K.basis.k_s : 0, basis ? K.basis.k_t : 0, true, BCG, BNS,
+                            basis ? K.k_slabs * 8 : 0);
     REQUIRE(sp.total <= 227 * 1024, "layer_bwd: needs %u B of shared memory (> 227 KB)", sp.total);
     int tiles = (int)ceil_div64(a->pts.n_rows, TILE_M);
     const bool ln = a->layer.gamma != nullptr, hd = a->head != nullptr;

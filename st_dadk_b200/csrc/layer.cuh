@@ -952,20 +952,19 @@ __global__ void __launch_bounds__(n_threads(CG), 1) layer_bwd_kernel(const __gri
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = align_smem(smem_raw);
     const int q = HEAD ? P.head.q : 0;
-    const SmemPlan sp = plan_smem(P.n_pad, q, BASIS ? P.basis.k_s : 0, BASIS ? P.basis.k_t : 0, true, CG, NS);
+    const SmemPlan sp = plan_smem(P.n_pad, q, BASIS ? P.basis.k_s : 0, BASIS ? P.basis.k_t : 0, true, CG, NS,
+                                  BASIS ? P.k_slabs * 8 : 0);
     float* sA = reinterpret_cast<float*>(smem + sp.a_off);
     float* sB = reinterpret_cast<float*>(smem + sp.b_off);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + sp.bar_off);
     uint64_t* empty = full + NSTAGE;
     uint64_t* accf = full + 2 * NSTAGE;
-    uint64_t* kbar = accf + 1;                                       // knot tables have landed (BASIS)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + sp.tmem_off);
     float* sbias = reinterpret_cast<float*>(smem + sp.vec_off);
     float* sgam = sbias + P.n_pad;
     float* sbet = sgam + P.n_pad;
     float* shw = reinterpret_cast<float*>(smem + sp.headw_off);
-    float4* sk = reinterpret_cast<float4*>(smem + sp.knots_off);
-    float2* st = reinterpret_cast<float2*>(smem + sp.tknots_off);
+    float4* ctab = reinterpret_cast<float4*>(smem + sp.knots_off);  // chunk tables of the generator (BASIS)
     float* cs_bias = reinterpret_cast<float*>(smem + sp.colsum_off);
     float* cs_gam = cs_bias + P.n_pad;
     float* cs_bet = cs_gam + P.n_pad;
@@ -988,14 +987,13 @@ __global__ void __launch_bounds__(n_threads(CG), 1) layer_bwd_kernel(const __gri
             mbar_init(&empty[s], 1);
         }
         mbar_init(accf, 1);
-        mbar_init(kbar, 1);
         mbar_fence_init();
-        if (BASIS) stage_knots_async(P.basis, sk, st, kbar);
     }
     if (warp == 4 * CG) {
         __syncwarp();
         tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
     }
+    if (BASIS) build_chunk_tables(P.basis, ctab, P.k_slabs * 8, tid, NT);
     for (int i = tid; i < n_pad; i += NT) {
         bool ok = i < n_out;
         sbias[i] = ok ? P.L.bias[i] : 0.0f;
@@ -1063,18 +1061,29 @@ __global__ void __launch_bounds__(n_threads(CG), 1) layer_bwd_kernel(const __gri
                 load_point(P.pts, grow, x, y, t);
                 if (P.basis.p_cov > 0 && P.pts.xcov) xrow = P.pts.xcov + sample_of(P.pts, grow) * P.basis.p_cov;
             }
-            mbar_wait(kbar, 0);
-            for (int v = 0; v < total_slabs; ++v) {
-                int stage = v % NSTAGE, it = v / NSTAGE;
-                if (it > 0) mbar_wait(&empty[stage], (it - 1) & 1);
-                if (v < virt1) {
-                    const int s = v / P.passes, p = v - s * P.passes;
-                    gen_basis_slab(P.basis, sk, st, s, x, y, t, xrow, smem_u32(sA + (size_t)stage * SLAB_FLOATS),
-                                   (uint32_t)row, cg * (8 / CG), (cg + 1) * (8 / CG), nullptr, pass_a_lo(p));
-                    fence_proxy_async_smem();
+            // the forward's generator (chunk tables, packed FP32): the regenerated operand is the forward's bit for bit
+            auto gen_all = [&](auto fn_tag) {
+                constexpr int FN = decltype(fn_tag)::value;
+                for (int v = 0; v < total_slabs; ++v) {
+                    int stage = v % NSTAGE, it = v / NSTAGE;
+                    if (it > 0) mbar_wait(&empty[stage], (it - 1) & 1);
+                    if (v < virt1) {
+                        const int s = v / P.passes, p = v - s * P.passes;
+                        const uint32_t sa = smem_u32(sA + (size_t)stage * SLAB_FLOATS);
+                        if (pass_a_lo(p))
+                            gen_basis_slab_soa<FN, true, 2>(P.basis, ctab, s, x, y, t, xrow, sa, (uint32_t)row, cg * (8 / CG),
+                                                            (cg + 1) * (8 / CG), nullptr);
+                        else
+                            gen_basis_slab_soa<FN, false, 2>(P.basis, ctab, s, x, y, t, xrow, sa, (uint32_t)row, cg * (8 / CG),
+                                                             (cg + 1) * (8 / CG), nullptr);
+                        fence_proxy_async_smem();
+                    }
+                    mbar_arrive_warp(&full[stage]);
                 }
-                mbar_arrive_warp(&full[stage]);
-            }
+            };
+            if (P.basis.fn == STDADK_WENDLAND) gen_all(std::integral_constant<int, STDADK_WENDLAND>{});
+            else if (P.basis.fn == STDADK_TRIANGULAR) gen_all(std::integral_constant<int, STDADK_TRIANGULAR>{});
+            else gen_all(std::integral_constant<int, STDADK_GAUSSIAN>{});
         }
         mbar_wait(accf, 0);
         tc_fence_after();
