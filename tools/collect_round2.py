@@ -13,6 +13,7 @@ OUT, PROF = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 RUNS = [("b_1_final.json", "python bench.py  (1 GPU, defaults: BASELINE config 2 shape)"),
         ("b_1_ref.json", "python bench.py --impl reference  (the reference's PyTorch CPU path on the box's host cores)"),
         ("b_2b.json", "torchrun --nproc-per-node 2 bench.py --gpus 2 --steps 50 --warmup 5"),
+        ("b_4.json", "torchrun --nproc-per-node 4 bench.py --gpus 4 --steps 50 --warmup 5"),
         ("b_8c.json", "torchrun --nproc-per-node 8 bench.py --gpus 8 --steps 50 --warmup 5"),
         ("b64k_1.json", "python bench.py --batch 65536 --steps 100 --warmup 5"),
         ("b64k_8.json", "torchrun --nproc-per-node 8 bench.py --gpus 8 --batch 65536 --steps 50 --warmup 5"),
