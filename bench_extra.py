@@ -208,7 +208,7 @@ def run_config4(args, emit):
     table = ObservationTable(torch.from_numpy(coords), torch.from_numpy(t), torch.from_numpy(y)).to(dev)
     perm = torch.randperm(n, generator=torch.Generator().manual_seed(1 + rank)).to(dev)
     tr = Trainer(model, dict(lr=1e-3, weight_decay=5e-4, grad_clip=10.0, regression_type="mean"), dev,
-                 batches_per_epoch=100, use_cuda_graph=True)
+                 batches_per_epoch=100, use_cuda_graph=not getattr(args, "no_graph", False))
     B = 65536
     out = {}
     for i in range(max(args.warmup, 3) if args.warmup < 8 else 4):

@@ -10,4 +10,6 @@ timeout 200 python tools/prof_block1.py || exit 1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:layer_fwd_kernel -s 2 -c 1 -o gpurun_out/prof_block1_r2 -f python tools/prof_block1.py > gpurun_out/ncu_block1_r2.log 2>&1
 timeout 200 python tools/prof_predict.py || exit 1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:predict_fused -s 2 -c 1 -o gpurun_out/prof_fused_r2 -f python tools/prof_predict.py > gpurun_out/ncu_fused_r2.log 2>&1
+timeout 300 python bench.py --config 4 --no-graph --steps 6 --warmup 3 > gpurun_out/c4_nograph_r2.json || exit 1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:sparse_spatial -s 8 -c 2 -o gpurun_out/prof_sparse_r2 -f python bench.py --config 4 --no-graph --steps 6 --warmup 3 > gpurun_out/ncu_sparse_r2.log 2>&1
 ls -la gpurun_out/*_r2.ncu-rep

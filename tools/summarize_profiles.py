@@ -21,6 +21,7 @@ WANT = [("gpu__time_duration.sum", "time"), ("launch__grid_size", "grid"), ("lau
         ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM %"),
         ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "L1 pipe: LSU shared %"),
         ("l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "L1 pipe: tensor operands %"),
+        ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 %"),
         ("smsp__inst_executed.sum", "warp instr")]
 MUL = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
@@ -150,7 +151,11 @@ def main_r2():
                      os.path.join(OUT, "prof_field_r2.ncu-rep"), lambda n, k: "predict_field")
         fu = section(f, "whole-network kernel for explicit points, 1M grid points (stdadk_predict)",
                      os.path.join(OUT, "prof_fused_r2.ncu-rep"), lambda n, k: "predict_fused")
+        sp = section(f, "support-walking block 1 at BASELINE config 4's size (K_s = 99,812, W1 102 MB, batch 65,536): forward gather and wgrad scatter",
+                     os.path.join(OUT, "prof_sparse_r2.ncu-rep"),
+                     lambda n, k: "sparse_fwd" if "fwd" in n else "sparse_wgrad")
         traffic["predict"] = {**b1, **fd, **fu}
+        traffic["config4"] = sp
         traffic["tensor_pipe_pct"] = {k: tensor_pct(os.path.join(OUT, r)) for k, r in
                                       (("predict_field_kernel", "prof_field_r2.ncu-rep"),
                                        ("predict_fused_kernel", "prof_fused_r2.ncu-rep")) if os.path.exists(os.path.join(OUT, r))}
@@ -172,6 +177,10 @@ NOTES_R2 = """## Reading
   latency with 4-5 warps per scheduler (DESIGN.md section 4 has the phase timers).
 * Field kernel: DRAM traffic is y_hat plus weights; tensor pipe ~23 %: the worker warps' epilogues (LayerNorm over
   TMEM loads, TF32 rounding, tcgen05.st of the next operand) take ~2.6x the MMA time per (tile, time step).
+* Support walk at config 4's size: the forward gathers ~59 knot rows of 1 KB per point (3.9 GB per 65,536-point launch)
+  out of the 102 MB W1, ~80 % of it from L2 (DRAM read 0.81 GB; L2 43 %, DRAM 26 % of peak; 65 % of the warp samples wait
+  on those loads); the wgrad scatters the same rows back with 16-byte vector atomics (L2 63 %, DRAM write 1.15 GB,
+  `mio_throttle` 25 %: the atomics queue).
 * SASS evidence of the instruction mix: `profiles/r2_sass_mnemonics.txt`, checked by
   `tests/test_abi.py::test_sass_is_blackwell_native`.
 """
