@@ -21,6 +21,8 @@ RUNS = [("b_1_final.json", "python bench.py  (1 GPU, defaults: BASELINE config 2
         ("c3_1.json", "python bench.py --config 3"),
         ("c3_8b.json", "torchrun --nproc-per-node 8 bench.py --gpus 8 --config 3"),
         ("c4_1.json", "python bench.py --config 4"),
+        ("c4_2.json", "torchrun --nproc-per-node 2 bench.py --gpus 2 --config 4"),
+        ("c4_4.json", "torchrun --nproc-per-node 4 bench.py --gpus 4 --config 4"),
         ("c4_8.json", "torchrun --nproc-per-node 8 bench.py --gpus 8 --config 4"),
         ("c5_1.json", "STDADK_CONFIGS_PER_GPU=4 python bench.py --config 5 --steps 50"),
         ("c5_8.json", "STDADK_CONFIGS_PER_GPU=2 torchrun --nproc-per-node 8 bench.py --gpus 8 --config 5 --steps 50  (before the workers were forked / shared the host cores; with the reference leg)"),
