@@ -537,15 +537,24 @@ class Trainer:
         st = self._host_stage[k]
         sl = slice(row_begin, row_begin + n_rows)
         main = torch.cuda.current_stream()
-        with torch.cuda.stream(self._host_copy_stream):
-            self._host_copy_stream.wait_event(self._host_done[k])       # the step two calls ago has released buffer k
+
+        def copy_batch():
             st.coords[:n_rows].copy_(host_table.coords[sl], non_blocking=True)
             st.t[:n_rows].copy_(host_table.t[sl], non_blocking=True)
             st.y[:n_rows].copy_(host_table.y[sl], non_blocking=True)
             if st.X is not None:
                 st.X[:n_rows].copy_(host_table.X[sl], non_blocking=True)
-            self._host_ready[k].record(self._host_copy_stream)
-        main.wait_event(self._host_ready[k])
+
+        if lagged or self._host_pending is not None:
+            with torch.cuda.stream(self._host_copy_stream):
+                self._host_copy_stream.wait_event(self._host_done[k])   # the step two calls ago has released buffer k
+                copy_batch()
+                self._host_ready[k].record(self._host_copy_stream)
+            main.wait_event(self._host_ready[k])
+        else:
+            # one synchronisation per step: nothing can overlap, so the copies go on the launching stream itself (no
+            # stream switch, no event pair: ~15 us of host time per step that would sit on the critical path)
+            copy_batch()
         self.train_step(st, self._host_perm, 0, n_rows, global_rows)
         self._host_loss[k].copy_(self.loss_last, non_blocking=True)
         self._host_done[k].record(main)
