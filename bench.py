@@ -420,7 +420,6 @@ def run_ours(args):
         dist.barrier()
     from stnf.models import STInterpMLP
     from stnf.dataio import ObservationTable
-    from st_dadk_b200 import ops
     from st_dadk_b200.trainer import Trainer
     from st_dadk_b200.predict import Predictor, shard_range
     peaks = {}

@@ -22,10 +22,8 @@ import json
 import os
 import sys
 import time
-from datetime import datetime
 from pathlib import Path
 
-import numpy as np
 import pandas as pd
 import torch
 import yaml

@@ -12,7 +12,7 @@ mirroring STInterpMLP.forward (stnf/models/st_interp.py:827-882) and its autogra
 from __future__ import annotations
 
 import ctypes as C
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch

@@ -8,7 +8,7 @@ device from the linear index, so a grid prediction reads 0 bytes of input per po
 """
 from __future__ import annotations
 
-from typing import Optional, Sequence, Tuple
+from typing import Optional, Tuple
 
 import torch
 

@@ -11,7 +11,7 @@ CUDA (sm_100) only: a CPU tensor raises -- there is no fallback path.
 from __future__ import annotations
 
 import math
-from typing import List, Optional, Sequence
+from typing import List, Optional
 
 import numpy as np
 import torch
