@@ -623,7 +623,7 @@ def test_large_batch_stored_operand_matches_regenerated_basis():
         torch.cuda.synchronize()
         res.append((yh, [w.clone() for w in g["weights"]], [b.clone() for b in g["biases"]], ex.loss_acc.item()))
     (y0, w0, b0, l0), (y1, w1, b1, l1) = res
-    assert torch.equal(y0, y1) and abs(l0 - l1) <= 5e-6 * abs(l1)      # the loss: FP32 atomics over 304 tiles
+    assert torch.equal(y0, y1) and abs(l0 - l1) <= 2e-5 * abs(l1)      # the loss: FP32 atomics over 304 tiles
     for a, b in zip(w0 + b0, w1 + b1):
         assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < 2e-5
     # and against the oracle on a subset of rows' worth of statistics: the loss
