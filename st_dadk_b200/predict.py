@@ -284,7 +284,7 @@ class Predictor:
     @torch.no_grad()
     def profile_block1(self, coords: torch.Tensor, t: torch.Tensor, repeats: int = 5) -> dict:
         """The fused basis + Linear1 + LayerNorm/ReLU forward kernel (layer_fwd, block 1) alone on explicit points:
-        average launch time (CUDA events on the launching stream) and its algorithmic HBM bytes, 12 B read (x, y, t) +
+        median launch time (a CUDA event pair per launch on the launching stream) and its algorithmic HBM bytes, 12 B read (x, y, t) +
         4 * pad32(n_out) B written per row."""
         import ctypes as C
         from . import _lib as L
@@ -302,14 +302,15 @@ class Predictor:
         if ex.x3:
             a.out_img_lo = ws.h_lo[0].data_ptr()
         ops.layer_fwd(a)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(repeats):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(repeats)]
+        for e0, e1 in ev:
+            e0.record()
             ops.layer_fwd(a)
-        e1.record()
+            e1.record()
         torch.cuda.synchronize()
+        times = sorted(e0.elapsed_time(e1) for e0, e1 in ev)       # median: one disturbed launch must not move the figure
         per_row = 12 + 4 * ops.pad32(s.weights[0].shape[0]) * (2 if ex.x3 else 1)
-        return {"ms": e0.elapsed_time(e1) / repeats, "rows": n, "bytes_per_row": per_row, "bytes": float(n) * per_row,
+        return {"ms": times[len(times) // 2], "ms_all": times, "rows": n, "bytes_per_row": per_row, "bytes": float(n) * per_row,
                 "flops": 2.0 * n * s.weights[0].shape[0] * s.weights[0].shape[1]}
 
     @torch.no_grad()
@@ -339,7 +340,7 @@ class Predictor:
 
     @torch.no_grad()
     def profile_field(self, nx: int, ny: int, nt: int, repeats: int = 3):
-        """Average duration of a full (nx, ny, nt) grid prediction through the space-time field kernel with the work it
+        """Median duration of a full (nx, ny, nt) grid prediction through the space-time field kernel with the work it
         EXECUTES (block 1 once per site: 2*k_s*n_1 per site; blocks 2.. and the head per point) next to the dense-equivalent
         FLOPs of the per-point network.  None when the field kernel does not take this network."""
         self._prepare()
@@ -348,17 +349,18 @@ class Predictor:
         n = nx * ny * nt
         out = torch.empty(n, self.model.output_dim, device=self.ex.device)
         self.grid(nx, ny, nt, out=out)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(repeats):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(repeats)]
+        for e0, e1 in ev:
+            e0.record()
             self.grid(nx, ny, nt, out=out)
-        e1.record()
+            e1.record()
         torch.cuda.synchronize()
+        ms = sorted(e0.elapsed_time(e1) for e0, e1 in ev)[repeats // 2]       # median of the repetitions
         s = self.ex.spec
         k_s = s.centers.shape[0]
         per_site = 2.0 * k_s * s.weights[0].shape[0]
         per_point = sum(2.0 * w.shape[0] * w.shape[1] for w in s.weights[1:]) + 2.0 * s.head_w.shape[0] * s.head_w.shape[1]
         dense = sum(2.0 * w.shape[0] * w.shape[1] for w in s.weights) + 2.0 * s.head_w.shape[0] * s.head_w.shape[1]
-        return {"ms": e0.elapsed_time(e1) / repeats, "bytes": 4.0 * n * self.model.output_dim,
+        return {"ms": ms, "bytes": 4.0 * n * self.model.output_dim,
                 "flops": per_site * nx * ny + per_point * n, "dense_flops": dense * n, "points": n,
                 "kernel": "predict_field_kernel"}
